@@ -1,0 +1,366 @@
+"""Benchmark of the RetinaNet anchor + detection-head path on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): the training-target path on a batch of 16 pages of 800x1333, 1 class,
+<= 20 GT tables per page -- K1 (anchor generation + IoU matching + targets) then K2 (focal + smooth-L1
+forward and backward).  One "step" = one batch per GPU; per-GPU work is fixed as N grows (weak scaling),
+pages shard by image, the only collective is the all-reduce of the positive-anchor count.
+
+`value`  = pages/s with the batch's inputs resident in HBM (GT block + head outputs), CUDA events.
+`e2e`    = pages/s through the public Python API with HOST inputs every step: the ragged GT list is packed
+           and copied, the head outputs are copied from pinned memory, the three loss scalars are read back.
+`roofline` = K2 (the dominant kernel): algorithmic bytes / its mean duration (CUDA events inside the timed
+           region) against the measured HBM peak in MEASURED_PEAKS.json.
+`cpu_baseline` = the oracle (numpy port of the reference) on this host's cores, bounded sample.
+`inference` (extra) = BASELINE configs[2]: 64 pages, fused decode + clip + threshold + sort + NMS.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import synthetic  # noqa: E402
+
+CFG = 2
+HW = synthetic.CONFIGS[CFG]['hw']
+PAGES_PER_GPU = synthetic.CONFIGS[CFG]['batch']
+GMAX = synthetic.CONFIGS[CFG]['gmax'] + 2          # +2: the adversarial snapped duplicates
+CLASSES = 1
+METRIC = "pages/sec (anchor targets + focal/smooth-L1 fwd+bwd) @800x1333"
+WORKLOAD = "configs[1]: training-target path, 16 pages/GPU of 800x1333, 1 class, <=20 GT, 200700 anchors/page"
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (NVML) -- runs during warm-up + timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.ok = index, [], False, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max_sm = None
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            try:
+                sm = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                rs = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self, t0, t1):
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": [], "samples": 0}
+        bits = 0
+        for s in inside:
+            bits |= s[2]
+        reasons = [n for b, n in self.REASONS.items() if bits & b and n != "gpu_idle"]
+        return {"sm_mhz": float(np.median([s[1] for s in inside])), "sm_max_mhz": self.max_sm,
+                "reasons": reasons, "samples": len(inside)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (numpy port of the reference) on the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_page(args):
+    """One page of the training-target path on the CPU: targets + both losses forward and backward."""
+    page, = args
+    from oracle import anchors_np as OA
+    from oracle import losses_np as OL
+    anchors = _cpu_page.anchors
+    img = synthetic.PageShape(HW + (3,))
+    ann = synthetic.gt_for_page(CFG, page, anchors=anchors)
+    reg, lab = OA.anchor_targets_bbox(anchors, [img], [ann], CLASSES)
+    cls, rp = synthetic.training_predictions(CFG, 1, anchors.shape[0], classes=CLASSES, first_page=page)
+    npos = float((lab[:, :, -1] == 1).sum())
+    # the batch-global normaliser needs every page's count first; per page the arithmetic is identical,
+    # so the worker uses its own count (same work, documented in DESIGN.md)
+    lf, gf = OL.focal()(lab, cls, return_grad=True, normalizer=max(1.0, npos))
+    ls, gs = OL.smooth_l1()(reg, rp, return_grad=True, normalizer=max(1.0, npos))
+    return npos, float(lf), float(ls)
+
+
+def _cpu_init():
+    from oracle import anchors_np as OA
+    _cpu_page.anchors = OA.anchors_for_shape(HW + (3,))
+    os.environ["OMP_NUM_THREADS"] = "1"
+
+
+class CpuPool(object):
+    def __init__(self):
+        import multiprocessing as mp
+        self.cores = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init)
+
+    def run(self, pages):
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_page, [(p,) for p in pages], chunksize=1)
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_baseline_leg(budget_s=20.0):
+    pool = CpuPool()
+    try:
+        pool.run(range(min(pool.cores, PAGES_PER_GPU)))                 # warm-up (imports, anchors)
+        pages, elapsed, reps = 0, 0.0, 0
+        while elapsed < budget_s / 2 and reps < 4:
+            elapsed += pool.run(range(PAGES_PER_GPU))
+            pages += PAGES_PER_GPU
+            reps += 1
+        return {"value": pages / elapsed, "unit": "pages/s", "cores": pool.cores, "kind": "port",
+                "sample": "%d x the 16-page batch (targets + losses fwd+bwd per page), numpy oracle, "
+                          "multiprocessing.Pool(%d), %.1f s" % (reps, pool.cores, elapsed)}
+    finally:
+        pool.close()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (numpy oracle port: the reference is
+    Python/TF and cannot travel to the GPU box) on all host cores; each step a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pool = CpuPool()
+    try:
+        t_full = pool.run(range(PAGES_PER_GPU))                          # also warms the workers
+        budget = 150.0
+        per_step = int(max(1, min(PAGES_PER_GPU, PAGES_PER_GPU * budget / max(1e-9, t_full * (args.steps + args.warmup)))))
+        for _ in range(args.warmup):
+            pool.run(range(per_step))
+        t = 0.0
+        for _ in range(args.steps):
+            t += pool.run(range(per_step))
+        value = per_step * args.steps / t
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32",
+                "data": "synthetic", "config": {"workload": WORKLOAD, "pages_per_step": per_step},
+                "cpu_baseline": {"value": value, "unit": "pages/s", "cores": pool.cores, "kind": "port",
+                                 "sample": "%d pages per step through multiprocessing.Pool(%d), numpy oracle port of "
+                                           "model/anchors.py + model/losses.py (fwd+bwd)" % (per_step, pool.cores)},
+                "e2e": {"value": value, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+    finally:
+        pool.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    import retinanet_b200 as rn
+    rn._lib.load()
+
+    B, C = PAGES_PER_GPU, CLASSES
+    anchors = rn.anchors_for_shape(HW + (3,))
+    N = anchors.shape[0]
+    first = rank * B
+    images, anns = synthetic.training_batch(CFG, batch=B, anchors=np.asarray(anchors), first_page=first)
+    cls_np, reg_np = synthetic.training_predictions(CFG, B, N, classes=C, first_page=first)
+    cls_host = torch.from_numpy(cls_np).pin_memory()
+    reg_host = torch.from_numpy(reg_np).pin_memory()
+
+    step = rn.pipeline.TargetLossStep(HW + (3,), B, GMAX, C)
+    gt_bytes = step.load_annotations(images, anns)
+    step.load_predictions(cls_host, reg_host)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident: `value` + per-kernel durations ----------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step.run()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        step.run(events=evs[i])
+    barrier()
+    t_wall1 = time.perf_counter()
+    total_ms = evs[0][0].elapsed_time(evs[-1][2])
+    k1_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    k2_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    losses = step.losses.cpu().numpy()
+
+    # ---- e2e: public API, host inputs every step -------------------------------------------------------
+    def e2e_step():
+        step.load_annotations(images, anns)           # pack ragged GT (Python dicts) + pinned -> device
+        step.load_predictions(cls_host, reg_host)     # head outputs pinned -> device
+        step.run()
+        return step.losses.cpu()                      # D2H of [focal, smooth_l1, normaliser]; synchronises
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    h2d = gt_bytes + cls_host.numel() * 4 + reg_host.numel() * 4
+    sampler.stop_flag = True
+
+    times = torch.tensor([total_ms, e2e_ms, k1_ms, k2_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, k1_ms, k2_ms = [float(x) for x in times.cpu()]
+
+    # ---- inference path (extra object) -----------------------------------------------------------------
+    inference = None
+    if not args.no_inference:
+        inference = bench_inference(rn, torch, device, rank, world, args)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        k2_bytes = (12 * C + 56) * N * B              # 68 B/anchor at C=1
+        k1_bytes = 4 * (5 + C + 1) * N * B            # 28 B/anchor at C=1
+        achieved = k2_bytes / (k2_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * B * args.steps / (total_ms * 1e-3), "unit": "pages/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 matching + f32 targets/losses", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pages_per_gpu": B, "anchors_per_page": N, "classes": C,
+                       "l2": "working set per step ~%d MB (> 126 MB L2), no explicit flush" % ((k1_bytes + k2_bytes) // (1 << 20)),
+                       "cuda_graphs": True},
+            "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "pages/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 12, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"kernel": "k_loss_c1 (K2 fused focal + smooth-L1 fwd+bwd)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": k2_bytes,
+                         "us_per_launch": k2_ms * 1e3},
+            "kernels": {"K1_anchor_targets": {"us": k1_ms * 1e3, "algorithmic_bytes": k1_bytes,
+                                              "GBps": k1_bytes / (k1_ms * 1e-3) / 1e9},
+                        "K2_losses": {"us": k2_ms * 1e3, "algorithmic_bytes": k2_bytes, "GBps": achieved}},
+            "losses": {"focal": float(losses[0]), "smooth_l1": float(losses[1]), "normalizer": float(losses[2])},
+            "clocks": sampler.summary(t_wall0, t_wall1),
+        }
+        if inference is not None:
+            line["inference"] = inference
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_leg()
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_inference(rn, torch, device, rank, world, args):
+    """BASELINE configs[2]: 64 pages/GPU, score > 0.05, NMS 0.5, 300 detections, fused head."""
+    import torch.distributed as dist
+    cfg, B = 3, synthetic.CONFIGS[3]['batch']
+    anchors = np.asarray(rn.anchors_for_shape(HW + (3,)))
+    N = anchors.shape[0]
+    _, anns = synthetic.training_batch(cfg, batch=B, first_page=rank * B)
+    cls_np, reg_np = synthetic.inference_predictions(cfg, B, anchors, anns, classes=1, first_page=rank * B)
+    cls_host, reg_host = torch.from_numpy(cls_np).pin_memory(), torch.from_numpy(reg_np).pin_memory()
+    cls_d, reg_d = cls_host.to(device), reg_host.to(device)
+    shape = (B,) + HW + (3,)
+    out = {}
+    for tag, topk in (("reference_semantics", 0), ("pre_nms_top_k_1000", 1000)):
+        head = rn.DetectionHead(pre_nms_top_k=topk)
+        for _ in range(3):
+            head([shape, reg_d, cls_d])
+        steps = max(5, min(args.steps, 50))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            res = head([shape, reg_d, cls_d])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        # e2e: host head outputs in, detections out
+        e0.record()
+        for _ in range(steps):
+            r = head([shape, reg_host.to(device, non_blocking=True), cls_host.to(device, non_blocking=True)])
+            host = [t.cpu() for t in r]
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e2e = e0.elapsed_time(e1) / steps
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = [float(x) for x in t.cpu()]
+        ndet = int((res[1] >= 0).sum().item())
+        out[tag] = {"pages_per_s": world * B / (ms * 1e-3), "ms_per_batch": ms,
+                    "e2e_pages_per_s": world * B / (ms_e2e * 1e-3), "detections_per_page": ndet / B}
+    out["workload"] = "configs[2]: %d pages/GPU of 800x1333, 1 class, thr 0.05, NMS 0.5, 300 detections" % B
+    out["candidates_per_page"] = float((cls_np > 0.05).sum()) / B
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-inference", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,189 @@
+/*
+ * rn_b200.h -- C-ABI of librn_b200.so: the B200 (sm_100a) implementation of RetinaNet's
+ * anchor + detection-head path.
+ *
+ * The reference (jabhinav/RetinaNet-for-Table-Detection) is pure Python and has no FFI; the
+ * functions below are what its Python call sites bind instead of numpy / TensorFlow ops.  Each
+ * entry point cites the reference interface it replaces (file:line, relative to the reference
+ * tree).  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - every `*_dev` / tensor pointer is caller-owned DEVICE memory (e.g. a torch allocation);
+ *     the library never allocates device memory and never synchronises the stream;
+ *   - small tables marked "host" are read synchronously during the call;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - all tensors are dense, row-major, float32 unless stated; row counts are 64-bit;
+ *   - return value: RN_OK (0) or a negative RN_ERR_* code; rn_last_error() gives the message of
+ *     the calling thread's last failure.  Nothing throws.  Re-entrant per (stream, workspace).
+ */
+#ifndef RN_B200_H
+#define RN_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RN_OK             0
+#define RN_ERR_BAD_ARG   -1   /* null pointer, non-positive size, unsupported parameter      */
+#define RN_ERR_CUDA      -2   /* launch / runtime failure (cudaGetLastError)                 */
+#define RN_ERR_WORKSPACE -3   /* workspace smaller than rn_*_workspace_bytes() reports       */
+
+#define RN_MAX_LEVELS 8       /* pyramid levels per anchor table                              */
+
+#define RN_BCE_TF2    0       /* K.binary_crossentropy, tf.keras 2.x / Keras 2.3 form         */
+#define RN_BCE_LOGITS 1       /* standalone Keras <= 2.2 form (via logits)                    */
+
+int         rn_version(void);
+const char* rn_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  anchor generation + IoU/argmax matching + labels + regression targets, one launch per batch.
+ * Replaces: anchors_for_shape (model/anchors.py:169-204) + compute_overlap (model/utils.py:180-211)
+ *           + compute_gt_annotations (model/anchors.py:96-117) + bbox_transform (:282-313)
+ *           + the per-image loop of anchor_targets_bbox (:68-90).
+ *
+ * Anchors are either generated in-kernel from the level table (anchors_dev == NULL; 0 bytes read)
+ * or read from an explicit (N,4) float64 array (anchors_dev != NULL; API fidelity:
+ * anchor_targets_bbox takes `anchors` as an argument).
+ *
+ *   base_anchors_dev  (num_levels, anchors_per_cell, 4) float64: generate_anchors() per level
+ *   level_hw          host, (num_levels, 2) int: feature-map (H_l, W_l)      [guess_shapes]
+ *   level_stride      host, (num_levels) int
+ *   num_anchors       N; must equal sum_l H_l*W_l*anchors_per_cell when anchors are generated
+ *   gt_boxes_dev      (B, Gmax, 4) float64 x1,y1,x2,y2;  gt_labels_dev (B, Gmax) int32 in [0, C];
+ *   gt_count_dev      (B) int32, number of valid GT rows per page (0 allowed)
+ *   img_hw_dev        (B, 2) int32: each page's own (H, W) for the border-ignore rule
+ *                     (model/anchors.py:85-90); NULL disables the rule
+ *   neg_overlap/pos_overlap   compared in float32 (max_iou > neg  -> ignore unless >= pos)
+ * Outputs
+ *   regression_out    (B, N, 5)   float32: 4 targets + state (-1 ignore / 0 bg / 1 fg)
+ *   labels_out        (B, N, C+1) float32: one-hot + state
+ *   argmax_out        (B, N) int32 or NULL: index of the best-overlapping GT (first max)
+ *   npos_out          (B) int32 or NULL: number of state==1 anchors per page
+ *   npos_total_out    1 float or NULL: the same count summed over the batch -- directly usable as
+ *                     `npos_dev` of the loss kernels (integer-valued, so the float sum is exact)
+ */
+int rn_anchor_targets(const double* base_anchors_dev, const int* level_hw, const int* level_stride,
+                      int num_levels, int anchors_per_cell,
+                      const double* anchors_dev, long long num_anchors,
+                      const double* gt_boxes_dev, const int* gt_labels_dev, const int* gt_count_dev,
+                      const int* img_hw_dev, int B, int Gmax, int C,
+                      float neg_overlap, float pos_overlap,
+                      float* regression_out, float* labels_out, int* argmax_out, int* npos_out,
+                      float* npos_total_out, void* stream);
+
+/* anchors_for_shape (model/anchors.py:169-204) on the device: (N,4) float64. */
+int rn_anchors_f64(const double* base_anchors_dev, const int* level_hw, const int* level_stride,
+                   int num_levels, int anchors_per_cell, double* anchors_out, void* stream);
+
+/* compute_overlap (model/utils.py:180-211): (M,4) x (G,4) float64 -> (M,G) float32 IoU. */
+int rn_compute_overlap(const double* boxes1_dev, long long M, const double* boxes2_dev, int G,
+                       float* iou_out, void* stream);
+
+/* bbox_transform (model/anchors.py:282-313), row-wise: anchors (N,4) and gt_boxes (N,4) float64 ->
+ * ((gt - a) / {w,h} - mean) / std as (N,4) float64.  mean4 / std4: host double[4]. */
+int rn_bbox_transform(const double* anchors_dev, const double* gt_boxes_dev, long long N,
+                      const double* mean4, const double* std4, double* out_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  losses, forward + backward in one pass.
+ * Replaces: _focal (model/losses.py:13-44) and _smooth_l1 (:58-90) and their TF autodiff backward.
+ *
+ *   R rows = B*N anchors.  npos_dev: device float holding the positive-anchor COUNT to normalise
+ *   with (e.g. the all-reduced global count); NULL = count state==1 over these R rows first.
+ *   The normaliser is max(1, count).  grad_* may be NULL (forward only).
+ *   losses are written as device floats.  workspace: rn_loss_workspace_bytes().
+ */
+size_t rn_loss_workspace_bytes(void);
+
+int rn_count_positive(const float* y_true, long long R, int row_width, float* npos_out_dev,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+int rn_focal_fwd_bwd(const float* y_true_cls /*(R,C+1)*/, const float* y_pred /*(R,C)*/,
+                     long long R, int C, float alpha, float gamma, int bce_mode,
+                     const float* npos_dev, float* loss_out_dev, float* grad_out /*(R,C)*/,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+int rn_smooth_l1_fwd_bwd(const float* y_true_reg /*(R,5)*/, const float* y_pred /*(R,4)*/,
+                         long long R, float sigma,
+                         const float* npos_dev, float* loss_out_dev, float* grad_out /*(R,4)*/,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* both losses in ONE launch; losses_out_dev[0]=focal, [1]=smooth_l1, [2]=normaliser used. */
+int rn_loss_fwd_bwd(const float* y_true_cls, const float* cls_pred, const float* y_true_reg,
+                    const float* reg_pred, long long R, int C,
+                    float alpha, float gamma, int bce_mode, float sigma,
+                    const float* npos_dev, float* losses_out_dev,
+                    float* grad_cls /*(R,C)*/, float* grad_reg /*(R,4)*/,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Detection head, layer by layer.
+ */
+/* Anchors layer (model/layers.py:42-53 + TF shift model/utils.py:51-80), all levels concatenated
+ * (model/defineModel.py:283-293): float32 anchors (B, N, 4).  base_anchors_f32_dev:
+ * (num_levels, anchors_per_cell, 4) float32 (generate_anchors cast to floatx, layers.py:34). */
+int rn_anchors_f32(const float* base_anchors_f32_dev, const int* level_hw, const int* level_stride,
+                   int num_levels, int anchors_per_cell, int B, float* anchors_out, void* stream);
+
+/* RegressBoxes / bbox_transform_inv (model/layers.py:136-138, model/utils.py:84-112).
+ * mean/std: host float[4]. */
+int rn_regress_boxes(const float* boxes, const float* deltas, long long R,
+                     const float* mean4, const float* std4, float* out, void* stream);
+
+/* ClipBoxes (model/layers.py:157-171): x to [0,width], y to [0,height]. */
+int rn_clip_boxes(const float* boxes, long long R, float width, float height, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3+K4+K5  FilterDetections (model/layers.py:177-264, 298-332): score threshold -> per-class
+ * sort (score desc, anchor asc) -> greedy NMS (strict >) -> cross-class top-k -> pad with -1.
+ *
+ * Two front ends share the sort/NMS/merge back end:
+ *   rn_filter_detections         boxes (B,N,4) already decoded+clipped  [layer-by-layer API]
+ *   rn_decode_filter_detections  fused K3: anchors generated in-kernel (float32, as the Anchors
+ *                                layer does), decode (RegressBoxes) + clip (ClipBoxes) + threshold
+ *                                in one pass over regression (B,N,4) / classification (B,N,C).
+ *   class_specific, nms          flags as in the reference; nms_threshold / score_threshold float32
+ *   max_detections               <= 1024
+ *   pre_nms_top_k                0 = off (reference behaviour).  >0: visit only the k best
+ *                                candidates per (page,class) -- an extension, NOT in the reference.
+ *   cand_cap                     capacity of each (page,class) candidate slab; N = always exact.
+ *                                Overflow is reported in status_out (see below), never silent.
+ * Outputs (padded with -1): out_boxes (B,M,4) f32, out_scores (B,M) f32, out_labels (B,M) i32,
+ *   out_indices (B,M) i32 or NULL (anchor index of each detection; used to gather `other`),
+ *   status_out_dev (B) i32 or NULL: 0 ok, 1 = a slab overflowed for this page (results invalid).
+ */
+size_t rn_filter_workspace_bytes(int B, long long N, int C, int class_specific,
+                                 long long cand_cap, int max_detections);
+
+int rn_filter_detections(const float* boxes, const float* classification,
+                         int B, long long N, int C, int class_specific, int nms,
+                         float score_threshold, float nms_threshold, int max_detections,
+                         int pre_nms_top_k, long long cand_cap,
+                         float* out_boxes, float* out_scores, int* out_labels, int* out_indices,
+                         int* status_out_dev, void* workspace, size_t workspace_bytes, void* stream);
+
+int rn_decode_filter_detections(const float* base_anchors_f32_dev, const int* level_hw,
+                                const int* level_stride, int num_levels, int anchors_per_cell,
+                                const float* regression, const float* classification,
+                                int B, long long N, int C,
+                                const float* mean4, const float* std4, float clip_width, float clip_height,
+                                int class_specific, int nms,
+                                float score_threshold, float nms_threshold, int max_detections,
+                                int pre_nms_top_k, long long cand_cap,
+                                float* out_boxes, float* out_scores, int* out_labels, int* out_indices,
+                                int* status_out_dev, void* workspace, size_t workspace_bytes, void* stream);
+
+/* tf.image.non_max_suppression (call site model/layers.py:211) for one box set:
+ * out_indices (max_output) i32 in selection order, padded with -1; out_count_dev: 1 int32. */
+size_t rn_nms_workspace_bytes(long long K, int max_output);
+int rn_nms(const float* boxes /*(K,4)*/, const float* scores /*(K)*/, long long K,
+           int max_output, float iou_threshold, int* out_indices, int* out_count_dev,
+           void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RN_B200_H */

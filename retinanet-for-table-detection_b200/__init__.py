@@ -1,0 +1,24 @@
+"""retinanet-for-table-detection_b200 -- B200 (sm_100a) implementation of RetinaNet's anchor and
+detection-head path, drop-in for the functions and layers of the reference's ``model/`` package
+(jabhinav/RetinaNet-for-Table-Detection):
+
+    from retinanet_b200 import anchors, utils, losses, layers       # <- from model import ...
+
+``anchors``  anchors_for_shape, anchor_targets_bbox, compute_gt_annotations, bbox_transform, ...  (K1)
+``utils``    compute_overlap, bbox_transform_inv, shift
+``losses``   focal, smooth_l1 (+ fused detection_losses)                                           (K2)
+``layers``   Anchors, RegressBoxes, ClipBoxes, FilterDetections, filter_detections, DetectionHead  (K3-K5)
+
+All arithmetic runs in hand-written CUDA kernels behind the C-ABI of ``include/rn_b200.h``
+(``librn_b200.so``, built by ``build.py``); there is no CPU fallback.
+"""
+from . import _lib  # noqa: F401
+from . import anchors, distributed, layers, losses, pipeline, utils  # noqa: F401
+from .anchors import (AnchorParameters, AnchorParameters_default, anchor_targets_bbox,  # noqa: F401
+                      anchors_for_shape, bbox_transform, compute_gt_annotations, generate_anchors, guess_shapes)
+from .layers import (Anchors, ClipBoxes, DetectionHead, FilterDetections, RegressBoxes,  # noqa: F401
+                     custom_objects, filter_detections)
+from .losses import detection_loss, detection_losses, focal, smooth_l1  # noqa: F401
+from .utils import bbox_transform_inv, compute_overlap  # noqa: F401
+
+__version__ = "0.1.0"

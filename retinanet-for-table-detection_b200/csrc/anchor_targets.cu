@@ -1,0 +1,335 @@
+// K1: fused anchor generation + IoU / first-max argmax matching + labels + regression targets.
+//
+// One launch covers the whole batch: grid = (anchor tiles, pages).  A CTA owns 256 consecutive
+// anchors of one page; the page's GT tables are staged in shared memory in chunks, after culling
+// the ones that cannot intersect the tile's bounding box (warp-shuffle min/max reductions), in GT
+// order so the reference's "first maximum wins" tie rule is preserved.  Outputs are staged in
+// shared memory and written with 128-bit coalesced stores.
+//
+// Precision pipeline (must match numpy bit for bit, see oracle/anchors_np.py):
+//   anchors fp64 (base + centre, one rounding)  ->  IoU fp64  ->  rounded to fp32  ->
+//   strict-greater argmax on fp32  ->  fp32 threshold compares  ->  bbox_transform fp64 -> fp32.
+// The file is compiled with -fmad=false so no multiply-add is contracted.
+#include "rn_common.cuh"
+
+namespace {
+
+constexpr int K1_THREADS = 256;
+constexpr int K1_WARPS = K1_THREADS / 32;
+
+struct K1Params {
+    RnLevels lv;
+    const double* base;      // (L, A, 4)
+    const double* anchors;   // (N, 4) or nullptr
+    int N;
+    const double* gt;        // (B, Gmax, 4)
+    const int* gt_labels;    // (B, Gmax)
+    const int* gt_count;     // (B)
+    const int* img_hw;       // (B, 2) or nullptr
+    int Gmax, C;
+    float neg, pos;
+    float* reg;              // (B, N, 5)
+    float* lab;              // (B, N, C+1)
+    int* argmax;             // (B, N) or nullptr
+    int* npos;               // (B) or nullptr
+    float* npos_total;       // 1 float or nullptr
+    int vec_ok;
+};
+
+// cooperative store of `len` floats starting at element `start` of `base`; 128-bit where aligned
+template <typename Gen>
+__device__ __forceinline__ void store_range(float* base, long long start, int len, bool vec_ok, Gen gen) {
+    float* p = base + start;
+    int head = vec_ok ? (int)((4 - (start & 3)) & 3) : len;
+    if (head > len) head = len;
+    for (int i = threadIdx.x; i < head; i += K1_THREADS) p[i] = gen(i);
+    const int nvec = (len - head) >> 2;
+    for (int v = threadIdx.x; v < nvec; v += K1_THREADS) {
+        const int i = head + 4 * v;
+        rn_stg_stream4(p + i, make_float4(gen(i), gen(i + 1), gen(i + 2), gen(i + 3)));
+    }
+    for (int i = head + 4 * nvec + threadIdx.x; i < len; i += K1_THREADS) p[i] = gen(i);
+}
+
+__device__ __forceinline__ void make_anchor(const RnLevels& lv, const double* base, int n,
+                                            double& x1, double& y1, double& x2, double& y2) {
+    int level, cx, cy, a;
+    rn_locate(lv, n, level, cx, cy, a);
+    const double* b = base + ((size_t)level * lv.anchors_per_cell + a) * 4;
+    const double sx = ((double)cx + 0.5) * (double)lv.stride[level];   // exact in fp64
+    const double sy = ((double)cy + 0.5) * (double)lv.stride[level];
+    x1 = __ldg(b + 0) + sx;
+    y1 = __ldg(b + 1) + sy;
+    x2 = __ldg(b + 2) + sx;
+    y2 = __ldg(b + 3) + sy;
+}
+
+template <bool EXPLICIT>
+__global__ void __launch_bounds__(K1_THREADS) k_anchor_targets(const K1Params p) {
+    __shared__ double s_gx1[K1_THREADS], s_gy1[K1_THREADS], s_gx2[K1_THREADS], s_gy2[K1_THREADS], s_ga[K1_THREADS];
+    __shared__ int s_gidx[K1_THREADS];
+    __shared__ double s_red[K1_WARPS][4];
+    __shared__ int s_wcount[K1_WARPS];
+    __shared__ float s_reg[K1_THREADS * 5];
+    __shared__ float s_state[K1_THREADS];
+    __shared__ int s_hot[K1_THREADS];
+    __shared__ int s_npos;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int n0 = blockIdx.x * K1_THREADS;
+    const int cnt = min(K1_THREADS, p.N - n0);
+    const int n = n0 + tid;
+    const bool valid = tid < cnt;
+    int G = p.gt_count[b];
+    G = max(0, min(G, p.Gmax));
+
+    // ---- this thread's anchor ---------------------------------------------------------------
+    double ax1 = 0, ay1 = 0, ax2 = 0, ay2 = 0;
+    if (valid) {
+        if (EXPLICIT) {
+            const double2* ap = reinterpret_cast<const double2*>(p.anchors + (size_t)n * 4);
+            const double2 lo = __ldg(ap), hi = __ldg(ap + 1);
+            ax1 = lo.x; ay1 = lo.y; ax2 = hi.x; ay2 = hi.y;
+        } else {
+            make_anchor(p.lv, p.base, n, ax1, ay1, ax2, ay2);
+        }
+    }
+    const double aw = ax2 - ax1, ah = ay2 - ay1;
+    const double area_a = aw * ah;
+
+    // ---- tile bounding box (warp shuffles, then across warps through smem) -------------------
+    {
+        const double inf = __longlong_as_double(0x7ff0000000000000ll);
+        double mnx = rn_warp_min(valid ? ax1 : inf), mny = rn_warp_min(valid ? ay1 : inf);
+        double mxx = rn_warp_max(valid ? ax2 : -inf), mxy = rn_warp_max(valid ? ay2 : -inf);
+        if (lane == 0) { s_red[warp][0] = mnx; s_red[warp][1] = mny; s_red[warp][2] = mxx; s_red[warp][3] = mxy; }
+        if (tid == 0) s_npos = 0;
+    }
+    __syncthreads();
+    double tx1 = s_red[0][0], ty1 = s_red[0][1], tx2 = s_red[0][2], ty2 = s_red[0][3];
+#pragma unroll
+    for (int w = 1; w < K1_WARPS; ++w) {
+        tx1 = fmin(tx1, s_red[w][0]); ty1 = fmin(ty1, s_red[w][1]);
+        tx2 = fmax(tx2, s_red[w][2]); ty2 = fmax(ty2, s_red[w][3]);
+    }
+
+    // ---- IoU / argmax over the GT tables that can touch this tile ----------------------------
+    float best = 0.0f;     // an all-zero IoU row has argmax 0 (numpy first-max)
+    int arg = 0;
+    const double* gtb = p.gt + (size_t)b * p.Gmax * 4;
+    for (int g0 = 0; g0 < G; g0 += K1_THREADS) {
+        const int j = g0 + tid;
+        bool keep = false;
+        double gx1 = 0, gy1 = 0, gx2 = 0, gy2 = 0;
+        if (j < G) {
+            gx1 = __ldg(gtb + 4 * j); gy1 = __ldg(gtb + 4 * j + 1);
+            gx2 = __ldg(gtb + 4 * j + 2); gy2 = __ldg(gtb + 4 * j + 3);
+            // a GT that does not reach into the tile box has zero intersection with every anchor in it
+            keep = (gx2 > tx1) && (gx1 < tx2) && (gy2 > ty1) && (gy1 < ty2);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        __syncthreads();                       // previous chunk fully consumed
+        if (lane == 0) s_wcount[warp] = __popc(bal);
+        __syncthreads();
+        int off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < K1_WARPS; ++w) { const int c = s_wcount[w]; if (w < warp) off += c; total += c; }
+        if (keep) {
+            const int pos = off + __popc(bal & ((1u << lane) - 1u));   // stable: GT order kept
+            s_gx1[pos] = gx1; s_gy1[pos] = gy1; s_gx2[pos] = gx2; s_gy2[pos] = gy2;
+            s_ga[pos] = (gx2 - gx1) * (gy2 - gy1);
+            s_gidx[pos] = j;
+        }
+        __syncthreads();
+        if (valid) {
+            for (int m = 0; m < total; ++m) {
+                const double iw = fmin(ax2, s_gx2[m]) - fmax(ax1, s_gx1[m]);
+                const double ih = fmin(ay2, s_gy2[m]) - fmax(ay1, s_gy1[m]);
+                if (iw > 0.0 && ih > 0.0) {
+                    const double inter = iw * ih;
+                    const double uni = area_a + s_ga[m] - inter;
+                    const float iou = (float)(inter / uni);      // fp64 divide, then round to fp32
+                    if (iou > best) { best = iou; arg = s_gidx[m]; }
+                }
+            }
+        }
+    }
+
+    // ---- state, one-hot class, regression targets, border rule ------------------------------
+    float state = 0.0f;
+    int hot = -1;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    if (valid) {
+        if (G > 0) {
+            const bool is_pos = best >= p.pos;
+            const bool is_ign = (best > p.neg) && !is_pos;
+            state = is_pos ? 1.0f : (is_ign ? -1.0f : 0.0f);
+            if (is_pos) hot = __ldg(p.gt_labels + (size_t)b * p.Gmax + arg);
+            const double* g = gtb + 4 * (size_t)arg;
+            t0 = (float)(((__ldg(g + 0) - ax1) / aw) / 0.2);
+            t1 = (float)(((__ldg(g + 1) - ay1) / ah) / 0.2);
+            t2 = (float)(((__ldg(g + 2) - ax2) / aw) / 0.2);
+            t3 = (float)(((__ldg(g + 3) - ay2) / ah) / 0.2);
+        }
+        if (p.img_hw) {
+            const double ccx = (ax1 + ax2) / 2.0, ccy = (ay1 + ay2) / 2.0;
+            if (ccx >= (double)p.img_hw[2 * b + 1] || ccy >= (double)p.img_hw[2 * b]) state = -1.0f;
+        }
+        s_reg[tid * 5 + 0] = t0; s_reg[tid * 5 + 1] = t1; s_reg[tid * 5 + 2] = t2; s_reg[tid * 5 + 3] = t3;
+        s_reg[tid * 5 + 4] = state;
+        s_state[tid] = state;
+        s_hot[tid] = hot;
+        if (p.argmax) p.argmax[(size_t)b * p.N + n] = arg;
+    }
+    if (p.npos || p.npos_total) {
+        const unsigned pb = __ballot_sync(0xffffffffu, valid && state == 1.0f);
+        if (lane == 0 && pb) atomicAdd(&s_npos, __popc(pb));
+    }
+    __syncthreads();
+    if (tid == 0 && s_npos) {
+        if (p.npos) atomicAdd(p.npos + b, s_npos);
+        if (p.npos_total) atomicAdd(p.npos_total, (float)s_npos);   // integer-valued: exact, order-independent
+    }
+
+    // ---- coalesced write-out ------------------------------------------------------------------
+    const long long row0 = (long long)b * p.N + n0;
+    store_range(p.reg, row0 * 5, cnt * 5, p.vec_ok != 0, [&](int i) { return s_reg[i]; });
+    const int CW = p.C + 1;
+    if (p.C == 1) {
+        if (valid) {
+            float2 v = make_float2(hot == 0 ? 1.0f : 0.0f, state);
+            reinterpret_cast<float2*>(p.lab)[row0 + tid] = v;
+        }
+    } else {
+        store_range(p.lab, row0 * CW, cnt * CW, p.vec_ok != 0, [&](int i) {
+            const int r = i / CW, c = i - r * CW;
+            return c == p.C ? s_state[r] : (c == s_hot[r] ? 1.0f : 0.0f);
+        });
+    }
+}
+
+__global__ void k_anchors_f64(const RnLevels lv, const double* base, int N, double* out) {
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        double x1, y1, x2, y2;
+        make_anchor(lv, base, n, x1, y1, x2, y2);
+        double2* o = reinterpret_cast<double2*>(out + (size_t)n * 4);
+        o[0] = make_double2(x1, y1);
+        o[1] = make_double2(x2, y2);
+    }
+}
+
+// compute_overlap: one thread per (box1, box2) pair, box2 fastest (row-major (M,G) output)
+__global__ void k_compute_overlap(const double* b1, long long M, const double* b2, int G, float* out) {
+    const long long total = M * (long long)G;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / G;
+        const int j = (int)(e - i * G);
+        const double ax1 = b1[4 * i], ay1 = b1[4 * i + 1], ax2 = b1[4 * i + 2], ay2 = b1[4 * i + 3];
+        const double gx1 = b2[4 * j], gy1 = b2[4 * j + 1], gx2 = b2[4 * j + 2], gy2 = b2[4 * j + 3];
+        const double iw = fmax(0.0, fmin(ax2, gx2) - fmax(ax1, gx1));
+        const double ih = fmax(0.0, fmin(ay2, gy2) - fmax(ay1, gy1));
+        const double inter = iw * ih;
+        const double uni = (ax2 - ax1) * (ay2 - ay1) + (gx2 - gx1) * (gy2 - gy1) - inter;
+        out[e] = (float)(inter / uni);
+    }
+}
+
+struct Norm4d { double mean[4]; double std[4]; };
+
+__global__ void k_bbox_transform(const double* anchors, const double* gt, long long N, const Norm4d nm, double* out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const double ax1 = anchors[4 * i], ay1 = anchors[4 * i + 1], ax2 = anchors[4 * i + 2], ay2 = anchors[4 * i + 3];
+        const double aw = ax2 - ax1, ah = ay2 - ay1;
+        out[4 * i + 0] = ((gt[4 * i + 0] - ax1) / aw - nm.mean[0]) / nm.std[0];
+        out[4 * i + 1] = ((gt[4 * i + 1] - ay1) / ah - nm.mean[1]) / nm.std[1];
+        out[4 * i + 2] = ((gt[4 * i + 2] - ax2) / aw - nm.mean[2]) / nm.std[2];
+        out[4 * i + 3] = ((gt[4 * i + 3] - ay2) / ah - nm.mean[3]) / nm.std[3];
+    }
+}
+
+}  // namespace
+
+extern "C" int rn_bbox_transform(const double* anchors_dev, const double* gt_boxes_dev, long long N,
+                                 const double* mean4, const double* std4, double* out_dev, void* stream) {
+    RN_REQUIRE(N >= 0, "negative size");
+    if (N == 0) return RN_OK;
+    RN_REQUIRE(anchors_dev && gt_boxes_dev && mean4 && std4 && out_dev, "NULL pointer");
+    Norm4d nm;
+    for (int i = 0; i < 4; ++i) { nm.mean[i] = mean4[i]; nm.std[i] = std4[i]; }
+    const int blocks = (int)min((N + 255) / 256, (long long)RN_NUM_SMS * 8);
+    k_bbox_transform<<<blocks, 256, 0, (cudaStream_t)stream>>>(anchors_dev, gt_boxes_dev, N, nm, out_dev);
+    return rn_check_launch("rn_bbox_transform");
+}
+
+extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* level_hw, const int* level_stride,
+                                 int num_levels, int anchors_per_cell,
+                                 const double* anchors_dev, long long num_anchors,
+                                 const double* gt_boxes_dev, const int* gt_labels_dev, const int* gt_count_dev,
+                                 const int* img_hw_dev, int B, int Gmax, int C,
+                                 float neg_overlap, float pos_overlap,
+                                 float* regression_out, float* labels_out, int* argmax_out, int* npos_out,
+                                 float* npos_total_out, void* stream) {
+    RN_REQUIRE(B >= 1 && B <= 65535, "B must be in [1, 65535] (got %d)", B);
+    RN_REQUIRE(C >= 1, "C must be >= 1");
+    RN_REQUIRE(Gmax >= 0, "Gmax must be >= 0");
+    RN_REQUIRE(num_anchors >= 1 && num_anchors < (1ll << 31), "num_anchors out of range");
+    RN_REQUIRE(gt_count_dev && regression_out && labels_out, "NULL output / gt_count pointer");
+    RN_REQUIRE(Gmax == 0 || (gt_boxes_dev && gt_labels_dev), "NULL GT pointer with Gmax > 0");
+    K1Params p;
+    if (anchors_dev == nullptr) {
+        RN_REQUIRE(base_anchors_dev, "base_anchors_dev is NULL and no explicit anchors given");
+        int rc = rn_make_levels(&p.lv, level_hw, level_stride, num_levels, anchors_per_cell);
+        if (rc) return rc;
+        RN_REQUIRE(p.lv.start[num_levels] == num_anchors, "num_anchors (%lld) does not match the level table (%d)",
+                   num_anchors, p.lv.start[num_levels]);
+    } else {
+        RN_REQUIRE(rn_aligned16(anchors_dev), "anchors_dev must be 16-byte aligned");
+        p.lv.num_levels = 0;
+    }
+    p.base = base_anchors_dev; p.anchors = anchors_dev; p.N = (int)num_anchors;
+    p.gt = gt_boxes_dev; p.gt_labels = gt_labels_dev; p.gt_count = gt_count_dev; p.img_hw = img_hw_dev;
+    p.Gmax = Gmax; p.C = C; p.neg = neg_overlap; p.pos = pos_overlap;
+    p.reg = regression_out; p.lab = labels_out; p.argmax = argmax_out; p.npos = npos_out;
+    p.npos_total = npos_total_out;
+    p.vec_ok = rn_aligned16(regression_out) && rn_aligned16(labels_out);
+    RN_REQUIRE((reinterpret_cast<uintptr_t>(labels_out) & 7u) == 0, "labels_out must be 8-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (npos_out) {
+        cudaError_t e = cudaMemsetAsync(npos_out, 0, sizeof(int) * (size_t)B, s);
+        if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset npos: %s", cudaGetErrorString(e));
+    }
+    if (npos_total_out) {
+        cudaError_t e = cudaMemsetAsync(npos_total_out, 0, sizeof(float), s);
+        if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset npos_total: %s", cudaGetErrorString(e));
+    }
+    dim3 grid((unsigned)((num_anchors + K1_THREADS - 1) / K1_THREADS), (unsigned)B);
+    if (anchors_dev) k_anchor_targets<true><<<grid, K1_THREADS, 0, s>>>(p);
+    else k_anchor_targets<false><<<grid, K1_THREADS, 0, s>>>(p);
+    return rn_check_launch("rn_anchor_targets");
+}
+
+extern "C" int rn_anchors_f64(const double* base_anchors_dev, const int* level_hw, const int* level_stride,
+                              int num_levels, int anchors_per_cell, double* anchors_out, void* stream) {
+    RN_REQUIRE(base_anchors_dev && anchors_out, "NULL pointer");
+    RN_REQUIRE(rn_aligned16(anchors_out), "anchors_out must be 16-byte aligned");
+    RnLevels lv;
+    int rc = rn_make_levels(&lv, level_hw, level_stride, num_levels, anchors_per_cell);
+    if (rc) return rc;
+    const int N = lv.start[num_levels];
+    if (N == 0) return RN_OK;
+    const int blocks = min((N + 255) / 256, RN_NUM_SMS * 8);
+    k_anchors_f64<<<blocks, 256, 0, (cudaStream_t)stream>>>(lv, base_anchors_dev, N, anchors_out);
+    return rn_check_launch("rn_anchors_f64");
+}
+
+extern "C" int rn_compute_overlap(const double* boxes1_dev, long long M, const double* boxes2_dev, int G,
+                                  float* iou_out, void* stream) {
+    RN_REQUIRE(M >= 0 && G >= 0, "negative size");
+    if (M == 0 || G == 0) return RN_OK;
+    RN_REQUIRE(boxes1_dev && boxes2_dev && iou_out, "NULL pointer");
+    const long long total = M * (long long)G;
+    const int blocks = (int)min((total + 255) / 256, (long long)RN_NUM_SMS * 16);
+    k_compute_overlap<<<blocks, 256, 0, (cudaStream_t)stream>>>(boxes1_dev, M, boxes2_dev, G, iou_out);
+    return rn_check_launch("rn_compute_overlap");
+}

@@ -1,0 +1,667 @@
+// K3 + K4 + K5: FilterDetections (reference model/layers.py:177-264, :298-332) for a whole batch,
+// no host synchronisation anywhere.
+//
+//   K3  k_threshold_compact   one pass over classification (B,N,C): score > thr (strict, fp32);
+//                             survivors are decoded (RegressBoxes + ClipBoxes fused, anchors generated
+//                             in-kernel in fp32 like the Anchors layer) or gathered from a dense box
+//                             tensor, and appended to the (page,class) candidate slab with
+//                             warp-aggregated atomics.  The 16-byte regression row of an anchor is only
+//                             fetched when that anchor survives the threshold.
+//   K4  block radix top-k     inside k_segment_nms: 8-bit MSD radix select over the slab's 64-bit keys
+//                             (score bits | ~anchor index) picks the next <= 2048 best candidates, a
+//                             shared-memory bitonic network orders them (score desc, anchor asc).
+//   K5  bitmask NMS           same kernel: candidates are visited 256 at a time; each is tested against
+//                             the boxes selected so far, survivors get a 256x256 suppression bit-matrix
+//                             built with __ballot_sync, one warp resolves the greedy order by scanning
+//                             set bits only.  Stops at max_detections (TF's max_output_size early stop).
+//   k_merge_topk              per page: class-major concatenation + tf.nn.top_k (ties -> earlier
+//                             position) done as a C-way merge of the per-class lists; pad with -1.
+//
+// Semantics restated from tf.image.non_max_suppression / tf.nn.top_k: see oracle/layers_np.py.
+// Compiled with -fmad=false: IoU and decode are evaluated in the reference's fp32 operation order.
+#include "rn_common.cuh"
+
+namespace {
+
+constexpr int K3_THREADS = 256;
+constexpr int NMS_THREADS = 512;
+constexpr int NMS_WARPS = NMS_THREADS / 32;
+constexpr int NMS_CHUNK = 2048;    // candidates ordered per radix-select round
+constexpr int NMS_BATCH = 256;     // candidates resolved per bit-matrix
+constexpr int NMS_WORDS = NMS_BATCH / 32;
+constexpr int MAX_DET_LIMIT = 1024;
+
+struct Norm4 { float mean[4]; float std[4]; };
+
+// order-preserving map float -> uint32 (larger float -> larger uint)
+__device__ __forceinline__ unsigned f2ord(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ unsigned long long make_key(float score, unsigned idx) {
+    return ((unsigned long long)f2ord(score) << 32) | (unsigned long long)(0xffffffffu - idx);
+}
+__device__ __forceinline__ unsigned key_idx(unsigned long long k) { return 0xffffffffu - (unsigned)(k & 0xffffffffu); }
+__device__ __forceinline__ float key_score(unsigned long long k) { return ord2f((unsigned)(k >> 32)); }
+
+struct Slabs {
+    int* counts;                 // (S)
+    unsigned long long* keys;    // (S, cap)
+    float4* boxes;               // (S, cap)   [compact mode]   or the caller's (K) boxes [direct mode]
+    int* labels;                 // (S, cap)   only for class-agnostic filtering
+    long long cap;
+};
+
+struct K3Params {
+    const float* cls;      // (B, N, C)
+    const float* boxes;    // (B, N, 4) dense, or nullptr when decoding
+    const float* reg;      // (B, N, 4) regression (decode mode)
+    const float* base32;   // (L, A, 4) float32 base anchors (decode mode)
+    RnLevels lv;
+    Norm4 nm;
+    float clipW, clipH;
+    int B, N, C;
+    int class_specific;
+    float thr;
+    Slabs sl;
+};
+
+template <bool DECODE>
+__device__ __forceinline__ float4 candidate_box(const K3Params& p, int b, int n) {
+    if (!DECODE) return __ldg(reinterpret_cast<const float4*>(p.boxes) + (size_t)b * p.N + n);
+    int level, cx, cy, a;
+    rn_locate(p.lv, n, level, cx, cy, a);
+    const float* bs = p.base32 + ((size_t)level * p.lv.anchors_per_cell + a) * 4;
+    const float sx = ((float)cx + 0.5f) * (float)p.lv.stride[level];
+    const float sy = ((float)cy + 0.5f) * (float)p.lv.stride[level];
+    const float ax1 = __ldg(bs) + sx, ay1 = __ldg(bs + 1) + sy, ax2 = __ldg(bs + 2) + sx, ay2 = __ldg(bs + 3) + sy;
+    const float4 d = __ldg(reinterpret_cast<const float4*>(p.reg) + (size_t)b * p.N + n);
+    const float w = ax2 - ax1, h = ay2 - ay1;
+    float4 o;
+    o.x = ax1 + (d.x * p.nm.std[0] + p.nm.mean[0]) * w;
+    o.y = ay1 + (d.y * p.nm.std[1] + p.nm.mean[1]) * h;
+    o.z = ax2 + (d.z * p.nm.std[2] + p.nm.mean[2]) * w;
+    o.w = ay2 + (d.w * p.nm.std[3] + p.nm.mean[3]) * h;
+    o.x = fminf(fmaxf(o.x, 0.0f), p.clipW);
+    o.y = fminf(fmaxf(o.y, 0.0f), p.clipH);
+    o.z = fminf(fmaxf(o.z, 0.0f), p.clipW);
+    o.w = fminf(fmaxf(o.w, 0.0f), p.clipH);
+    return o;
+}
+
+// append (key, box[, label]) to slab `seg`; one atomic per group of lanes that share the segment
+template <bool DECODE>
+__device__ __forceinline__ void emit(const K3Params& p, bool is_cand, int seg, int b, int n, float score, int label) {
+    const unsigned cand = __ballot_sync(0xffffffffu, is_cand);
+    if (!is_cand) return;
+    const unsigned peers = __match_any_sync(cand, seg);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(p.sl.counts + seg, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const long long slot = base + __popc(peers & ((1u << lane) - 1u));
+    if (slot < p.sl.cap) {
+        const size_t at = (size_t)seg * p.sl.cap + slot;
+        p.sl.keys[at] = make_key(score, (unsigned)n);
+        p.sl.boxes[at] = candidate_box<DECODE>(p, b, n);
+        if (p.sl.labels) p.sl.labels[at] = label;
+    }
+}
+
+template <bool DECODE>
+__global__ void __launch_bounds__(K3_THREADS) k_threshold_compact(const K3Params p) {
+    if (p.class_specific) {
+        // flat over (b, n, c); 4 consecutive elements per thread, 128-bit loads
+        const long long total = (long long)p.B * p.N * p.C;
+        const long long groups = (total + 3) >> 2;
+        const long long iters = (groups + (long long)gridDim.x * K3_THREADS - 1) / ((long long)gridDim.x * K3_THREADS);
+        for (long long it = 0; it < iters; ++it) {              // uniform trip count: emit() uses full-warp ballots
+            const long long q = (it * gridDim.x + blockIdx.x) * (long long)K3_THREADS + threadIdx.x;
+            const long long e0 = q << 2;
+            float sv[4] = {0.f, 0.f, 0.f, 0.f};
+            int cnt = 0;
+            if (q < groups) {
+                cnt = (int)min(4ll, total - e0);
+                if (cnt == 4) { const float4 v = rn_ldg_stream4(p.cls + e0); sv[0] = v.x; sv[1] = v.y; sv[2] = v.z; sv[3] = v.w; }
+                else for (int k = 0; k < cnt; ++k) sv[k] = __ldg(p.cls + e0 + k);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool is_cand = (k < cnt) && (sv[k] > p.thr);
+                int seg = 0, b = 0, n = 0, c = 0;
+                if (is_cand) {
+                    const long long e = e0 + k;
+                    const long long row = e / p.C;
+                    c = (int)(e - row * p.C);
+                    b = (int)(row / p.N);
+                    n = (int)(row - (long long)b * p.N);
+                    seg = b * p.C + c;
+                }
+                emit<DECODE>(p, is_cand, seg, b, n, sv[k], c);
+            }
+        }
+    } else {
+        // class-agnostic: score = max over classes, label = first argmax (model/layers.py:234-235)
+        const long long total = (long long)p.B * p.N;
+        const long long iters = (total + (long long)gridDim.x * K3_THREADS - 1) / ((long long)gridDim.x * K3_THREADS);
+        for (long long it = 0; it < iters; ++it) {
+            const long long row = (it * gridDim.x + blockIdx.x) * (long long)K3_THREADS + threadIdx.x;
+            bool is_cand = false;
+            float best = 0.f;
+            int label = 0, b = 0, n = 0;
+            if (row < total) {
+                const float* s = p.cls + row * p.C;
+                best = __ldg(s);
+                for (int c = 1; c < p.C; ++c) { const float v = __ldg(s + c); if (v > best) { best = v; label = c; } }
+                b = (int)(row / p.N);
+                n = (int)(row - (long long)b * p.N);
+                is_cand = best > p.thr;
+            }
+            emit<DECODE>(p, is_cand, b, b, n, best, label);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 + K5
+// ------------------------------------------------------------------------------------------------
+struct NmsParams {
+    Slabs sl;
+    int S;                 // segments
+    int segs_per_page;     // C (class specific) or 1
+    int direct_boxes;      // 1: sl.boxes is the caller's box array indexed by anchor idx (rn_nms)
+    int nms;
+    float iou_thr;
+    int max_det;
+    int pre_nms_top_k;
+    // per-segment results
+    int* kept_count;               // (S)
+    unsigned long long* kept_key;  // (S, max_det)
+    float4* kept_box;              // (S, max_det)
+    int* kept_label;               // (S, max_det)
+    int* status;                   // (pages) or nullptr
+};
+
+// TF non_max_suppression_op.cc IOU on corner-normalised boxes with precomputed areas
+__device__ __forceinline__ bool iou_exceeds(const float4 a, const float aa, const float4 b, const float ab, const float thr) {
+    float iou = 0.0f;
+    if (aa > 0.0f && ab > 0.0f) {
+        const float iw = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.0f);
+        const float ih = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.0f);
+        const float inter = iw * ih;
+        iou = inter / (aa + ab - inter);
+    }
+    return iou > thr;
+}
+
+__global__ void __launch_bounds__(NMS_THREADS) k_segment_nms(const NmsParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // dynamic: selected boxes (normalised corners) + areas, sized by max_det
+    float4* s_selbox = reinterpret_cast<float4*>(smem_raw);
+    float* s_selarea = reinterpret_cast<float*>(s_selbox + p.max_det);
+
+    __shared__ unsigned long long s_key[NMS_CHUNK];
+    __shared__ unsigned s_slot[NMS_CHUNK];
+    __shared__ float4 s_cbox[NMS_BATCH];      // corner-normalised
+    __shared__ float4 s_craw[NMS_BATCH];      // as stored
+    __shared__ float s_carea[NMS_BATCH];
+    __shared__ int s_alive[NMS_BATCH];
+    __shared__ unsigned s_mask[NMS_BATCH * NMS_WORDS];
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_want, s_loaded, s_nsel;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int seg = blockIdx.x;
+    const int total = p.sl.counts[seg];
+    const int cnt = (int)min((long long)total, p.sl.cap);
+    if (total > cnt && p.status && tid == 0) p.status[seg / p.segs_per_page] = 1;
+    const int limit = p.pre_nms_top_k > 0 ? min(cnt, p.pre_nms_top_k) : cnt;
+    const unsigned long long* keys = p.sl.keys + (size_t)seg * p.sl.cap;
+    const float4* boxes = p.direct_boxes ? p.sl.boxes : p.sl.boxes + (size_t)seg * p.sl.cap;
+    const int* labels = p.sl.labels ? p.sl.labels + (size_t)seg * p.sl.cap : nullptr;
+    const int seg_label = seg % p.segs_per_page;
+
+    unsigned long long upper = ~0ull;   // keys >= upper have been visited
+    int visited = 0, nsel = 0;
+    if (tid == 0) s_nsel = 0;
+    __syncthreads();
+
+    while (visited < limit && nsel < p.max_det) {
+        const int take = min(NMS_CHUNK, limit - visited);
+        // ---------------- K4: radix select the `take` largest unvisited keys --------------------
+        unsigned long long thr_key = 0ull;
+        if (cnt - visited > take) {
+            if (tid == 0) { s_prefix = 0ull; s_want = take; }
+            unsigned long long mask = 0ull;
+            for (int shift = 56; shift >= 0; shift -= 8) {
+                if (tid < 256) s_hist[tid] = 0u;
+                __syncthreads();
+                const unsigned long long prefix = s_prefix;
+                for (int i = tid; i < cnt; i += NMS_THREADS) {
+                    const unsigned long long k = __ldcg(keys + i);
+                    if (k < upper && (k & mask) == prefix) atomicAdd(&s_hist[(unsigned)(k >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    // suffix sums over the 256 bins, 8 bins per lane, highest digit first
+                    unsigned local[8], run = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) { local[t] = s_hist[255 - (lane * 8 + t)]; run += local[t]; }
+                    unsigned incl = run;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                    unsigned before = incl - run;          // keys in strictly higher digit groups of earlier lanes
+                    const unsigned want = (unsigned)s_want;
+                    int digit = -1; unsigned rem = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        if (digit < 0 && before + local[t] >= want && before < want) { digit = 255 - (lane * 8 + t); rem = want - before; }
+                        before += local[t];
+                    }
+                    if (digit >= 0) { s_prefix = prefix | ((unsigned long long)digit << shift); s_want = (int)rem; }
+                }
+                mask |= 255ull << shift;
+                __syncthreads();
+            }
+            thr_key = s_prefix;          // exactly `take` unvisited keys are >= thr_key
+        }
+        // ---------------- gather the chunk into shared memory ----------------------------------------
+        if (tid == 0) s_loaded = 0;
+        __syncthreads();
+        for (int i = tid; i < cnt; i += NMS_THREADS) {
+            const unsigned long long k = __ldcg(keys + i);
+            if (k < upper && k >= thr_key) {
+                const int at = atomicAdd(&s_loaded, 1);
+                if (at < NMS_CHUNK) { s_key[at] = k; s_slot[at] = (unsigned)i; }
+            }
+        }
+        __syncthreads();
+        const int loaded = min(s_loaded, NMS_CHUNK);
+        int n2 = 32;
+        while (n2 < loaded) n2 <<= 1;
+        for (int i = loaded + tid; i < n2; i += NMS_THREADS) { s_key[i] = 0ull; s_slot[i] = 0u; }
+        __syncthreads();
+        // ---------------- bitonic network, descending (keys are unique) ----------------------------
+        for (int k = 2; k <= n2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < n2; i += NMS_THREADS) {
+                    const int x = i ^ j;
+                    if (x > i) {
+                        const unsigned long long a = s_key[i], b = s_key[x];
+                        const bool desc = ((i & k) == 0);
+                        if (desc ? (a < b) : (a > b)) {
+                            s_key[i] = b; s_key[x] = a;
+                            const unsigned t = s_slot[i]; s_slot[i] = s_slot[x]; s_slot[x] = t;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        const int chunk_n = min(loaded, take);
+        // ---------------- K5: greedy NMS over the ordered chunk, 256 candidates per round --------------
+        for (int s0 = 0; s0 < chunk_n && nsel < p.max_det; s0 += NMS_BATCH) {
+            const int bn = min(NMS_BATCH, chunk_n - s0);
+            if (tid < NMS_BATCH) {
+                int alive = 0;
+                if (tid < bn) {
+                    const unsigned slot = s_slot[s0 + tid];
+                    const float4 r = p.direct_boxes ? __ldg(boxes + key_idx(s_key[s0 + tid])) : __ldcg(boxes + slot);
+                    float4 c;
+                    c.x = fminf(r.x, r.z); c.y = fminf(r.y, r.w); c.z = fmaxf(r.x, r.z); c.w = fmaxf(r.y, r.w);
+                    s_craw[tid] = r; s_cbox[tid] = c;
+                    s_carea[tid] = (c.z - c.x) * (c.w - c.y);
+                    alive = 1;
+                }
+                s_alive[tid] = alive;
+            }
+            __syncthreads();
+            if (p.nms) {
+                // (a) against everything selected so far: 2 threads per candidate split the list
+                {
+                    const int c = tid & (NMS_BATCH - 1), part = tid >> 8;
+                    if (c < bn) {
+                        const float4 cb = s_cbox[c];
+                        const float ca = s_carea[c];
+                        bool dead = false;
+                        for (int s = part; s < nsel && !dead; s += NMS_THREADS / NMS_BATCH)
+                            dead = iou_exceeds(cb, ca, s_selbox[s], s_selarea[s], p.iou_thr);
+                        if (dead) s_alive[c] = 0;
+                    }
+                }
+                __syncthreads();
+                // (b) suppression bit-matrix among the survivors (upper triangle), one ballot per word
+                for (int i = warp; i < bn; i += NMS_WARPS) {
+                    if (!s_alive[i]) continue;
+                    const float4 bi = s_cbox[i];
+                    const float ai = s_carea[i];
+                    for (int w = i >> 5; w < NMS_WORDS; ++w) {
+                        const int j = w * 32 + lane;
+                        const bool hit = (j > i) && (j < bn) && s_alive[j] && iou_exceeds(bi, ai, s_cbox[j], s_carea[j], p.iou_thr);
+                        const unsigned word = __ballot_sync(0xffffffffu, hit);
+                        if (lane == 0) s_mask[i * NMS_WORDS + w] = word;
+                    }
+                }
+                __syncthreads();
+            }
+            // (c) one warp walks the surviving bits in order
+            if (warp == 0) {
+                unsigned mine = 0u;
+#pragma unroll
+                for (int w = 0; w < NMS_WORDS; ++w) {
+                    const unsigned word = __ballot_sync(0xffffffffu, s_alive[w * 32 + lane] != 0);
+                    if (lane == w) mine = word;
+                }
+                int ns = nsel;
+                while (ns < p.max_det) {
+                    const unsigned has = __ballot_sync(0xffffffffu, mine != 0u) & ((1u << NMS_WORDS) - 1u);
+                    if (!has) break;
+                    const int w0 = __ffs(has) - 1;
+                    const unsigned word = __shfl_sync(0xffffffffu, mine, w0);
+                    const int bit = __ffs(word) - 1;
+                    const int i = w0 * 32 + bit;
+                    if (lane == 0) {
+                        s_selbox[ns] = s_cbox[i];
+                        s_selarea[ns] = s_carea[i];
+                        const size_t at = (size_t)seg * p.max_det + ns;
+                        const unsigned long long k = s_key[s0 + i];
+                        p.kept_key[at] = k;
+                        p.kept_box[at] = s_craw[i];
+                        p.kept_label[at] = labels ? labels[s_slot[s0 + i]] : seg_label;
+                    }
+                    ++ns;
+                    if (lane == w0) mine &= ~(1u << bit);
+                    if (p.nms && lane < NMS_WORDS && lane >= w0) mine &= ~s_mask[i * NMS_WORDS + lane];
+                }
+                if (lane == 0) s_nsel = ns;
+            }
+            __syncthreads();
+            nsel = s_nsel;
+        }
+        visited += take;
+        upper = (loaded > 0) ? s_key[chunk_n - 1] : 0ull;
+        __syncthreads();
+    }
+    if (tid == 0) p.kept_count[seg] = nsel;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per page: merge the per-class kept lists (each already ordered) into the global top max_det
+// ------------------------------------------------------------------------------------------------
+struct MergeParams {
+    int pages, segs_per_page, max_det;
+    const int* kept_count;
+    const unsigned long long* kept_key;
+    const float4* kept_box;
+    const int* kept_label;
+    float* out_boxes;   // (pages, max_det, 4)
+    float* out_scores;  // (pages, max_det)
+    int* out_labels;    // (pages, max_det)
+    int* out_indices;   // (pages, max_det) or nullptr
+    int* out_count;     // (pages) or nullptr
+};
+
+__global__ void __launch_bounds__(256) k_merge_topk(const MergeParams p) {
+    extern __shared__ int s_head[];                 // (segs_per_page)
+    __shared__ unsigned long long s_best[8];
+    __shared__ int s_bestc[8];
+    __shared__ int s_win;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = p.segs_per_page, M = p.max_det;
+    for (int c = tid; c < C; c += 256) s_head[c] = 0;
+    __syncthreads();
+    int produced = 0;
+    if (C == 1) {
+        const int n = min(p.kept_count[b], M);
+        for (int m = tid; m < n; m += 256) {
+            const size_t at = (size_t)b * M + m;
+            const unsigned long long k = p.kept_key[at];
+            reinterpret_cast<float4*>(p.out_boxes)[at] = p.kept_box[at];
+            p.out_scores[at] = key_score(k);
+            p.out_labels[at] = p.kept_label[at];
+            if (p.out_indices) p.out_indices[at] = (int)key_idx(k);
+        }
+        produced = n;
+    } else {
+        for (int m = 0; m < M; ++m) {
+            // every thread proposes the best head among its classes: (score desc, class asc)
+            unsigned long long best = 0ull; int bc = -1;
+            for (int c = tid; c < C; c += 256) {
+                const int h = s_head[c];
+                if (h < p.kept_count[b * C + c]) {
+                    const unsigned long long k = p.kept_key[((size_t)b * C + c) * M + h];
+                    const unsigned long long cand = (k & 0xffffffff00000000ull) | (unsigned long long)(0xffffffffu - (unsigned)c);
+                    if (cand > best) { best = cand; bc = c; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+                if (ob > best) { best = ob; bc = oc; }
+            }
+            if (lane == 0) { s_best[warp] = best; s_bestc[warp] = bc; }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long bb = 0ull; int cc = -1;
+                for (int w = 0; w < 8; ++w) if (s_best[w] > bb) { bb = s_best[w]; cc = s_bestc[w]; }
+                s_win = cc;
+                if (cc >= 0) {
+                    const int h = s_head[cc]++;
+                    const size_t src = ((size_t)b * C + cc) * M + h;
+                    const size_t at = (size_t)b * M + m;
+                    const unsigned long long k = p.kept_key[src];
+                    reinterpret_cast<float4*>(p.out_boxes)[at] = p.kept_box[src];
+                    p.out_scores[at] = key_score(k);
+                    p.out_labels[at] = p.kept_label[src];
+                    if (p.out_indices) p.out_indices[at] = (int)key_idx(k);
+                }
+            }
+            __syncthreads();
+            if (s_win < 0) break;
+            ++produced;
+        }
+    }
+    for (int m = produced + tid; m < M; m += 256) {
+        const size_t at = (size_t)b * M + m;
+        reinterpret_cast<float4*>(p.out_boxes)[at] = make_float4(-1.f, -1.f, -1.f, -1.f);
+        p.out_scores[at] = -1.0f;
+        p.out_labels[at] = -1;
+        if (p.out_indices) p.out_indices[at] = -1;
+    }
+    if (p.out_count && tid == 0) p.out_count[b] = produced;
+}
+
+__global__ void k_keys_from_scores(const float* scores, long long K, unsigned long long* keys, int* count) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < K; i += (long long)gridDim.x * blockDim.x)
+        keys[i] = make_key(scores[i], (unsigned)i);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *count = (int)K;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace carving (256-byte aligned sections)
+// ------------------------------------------------------------------------------------------------
+struct FilterWs {
+    int* counts; int* kept_count; int* status;
+    unsigned long long* keys; float4* boxes; int* labels;
+    unsigned long long* kept_key; float4* kept_box; int* kept_label;
+    size_t bytes;
+};
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+FilterWs carve(void* ws, int B, int S, long long cap, int max_det, bool agnostic) {
+    FilterWs w;
+    size_t off = 0;
+    char* base = reinterpret_cast<char*>(ws);
+    auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align256(bytes); return p; };
+    w.counts = reinterpret_cast<int*>(take(sizeof(int) * S));
+    w.kept_count = reinterpret_cast<int*>(take(sizeof(int) * S));
+    w.status = reinterpret_cast<int*>(take(sizeof(int) * B));
+    w.keys = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * (size_t)S * cap));
+    w.boxes = reinterpret_cast<float4*>(take(sizeof(float4) * (size_t)S * cap));
+    w.labels = agnostic ? reinterpret_cast<int*>(take(sizeof(int) * (size_t)S * cap)) : nullptr;
+    w.kept_key = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * (size_t)S * max_det));
+    w.kept_box = reinterpret_cast<float4*>(take(sizeof(float4) * (size_t)S * max_det));
+    w.kept_label = reinterpret_cast<int*>(take(sizeof(int) * (size_t)S * max_det));
+    w.bytes = off;
+    return w;
+}
+
+size_t nms_dynamic_smem(int max_det) { return (size_t)max_det * (sizeof(float4) + sizeof(float)); }
+
+int run_back_end(const FilterWs& w, int B, int S, int segs_per_page, long long cap, int direct_boxes, const float4* direct,
+                 int nms, float nms_thr, int max_det, int pre_nms_top_k,
+                 float* out_boxes, float* out_scores, int* out_labels, int* out_indices, int* out_count,
+                 int* status, cudaStream_t s) {
+    NmsParams np;
+    np.sl.counts = w.counts; np.sl.keys = w.keys; np.sl.boxes = direct_boxes ? const_cast<float4*>(direct) : w.boxes;
+    np.sl.labels = w.labels; np.sl.cap = cap;
+    np.S = S; np.segs_per_page = segs_per_page; np.direct_boxes = direct_boxes; np.nms = nms; np.iou_thr = nms_thr;
+    np.max_det = max_det; np.pre_nms_top_k = pre_nms_top_k;
+    np.kept_count = w.kept_count; np.kept_key = w.kept_key; np.kept_box = w.kept_box; np.kept_label = w.kept_label;
+    np.status = status;
+    const size_t dyn = nms_dynamic_smem(max_det);
+    // static (~43 KB) + dynamic shared memory exceeds the 48 KB default: opt in (227 KB per CTA on sm_100a)
+    cudaError_t ae = cudaFuncSetAttribute(k_segment_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_dynamic_smem(MAX_DET_LIMIT));
+    if (ae != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
+    k_segment_nms<<<S, NMS_THREADS, dyn, s>>>(np);
+    int rc = rn_check_launch("k_segment_nms");
+    if (rc) return rc;
+    MergeParams mp;
+    mp.pages = B; mp.segs_per_page = segs_per_page; mp.max_det = max_det;
+    mp.kept_count = w.kept_count; mp.kept_key = w.kept_key; mp.kept_box = w.kept_box; mp.kept_label = w.kept_label;
+    mp.out_boxes = out_boxes; mp.out_scores = out_scores; mp.out_labels = out_labels; mp.out_indices = out_indices;
+    mp.out_count = out_count;
+    k_merge_topk<<<B, 256, sizeof(int) * (size_t)segs_per_page, s>>>(mp);
+    return rn_check_launch("k_merge_topk");
+}
+
+int filter_common(K3Params kp, bool decode, int nms, float nms_thr, int max_det, int pre_nms_top_k, long long cand_cap,
+                  float* out_boxes, float* out_scores, int* out_labels, int* out_indices, int* status_out,
+                  void* workspace, size_t workspace_bytes, cudaStream_t s) {
+    const int B = kp.B, C = kp.C;
+    RN_REQUIRE(B >= 1 && kp.N >= 1 && C >= 1, "bad shape");
+    RN_REQUIRE(max_det >= 1 && max_det <= MAX_DET_LIMIT, "max_detections must be in [1, %d]", MAX_DET_LIMIT);
+    RN_REQUIRE(cand_cap >= 1, "cand_cap must be >= 1");
+    RN_REQUIRE(out_boxes && out_scores && out_labels && workspace, "NULL pointer");
+    RN_REQUIRE(rn_aligned16(out_boxes) && rn_aligned16(workspace), "out_boxes / workspace must be 16-byte aligned");
+    RN_REQUIRE(rn_aligned16(kp.cls), "classification must be 16-byte aligned");
+    RN_REQUIRE(pre_nms_top_k >= 0, "pre_nms_top_k must be >= 0");
+    if (cand_cap > kp.N) cand_cap = kp.N;
+    const int spp = kp.class_specific ? C : 1;
+    const long long S64 = (long long)B * spp;
+    RN_REQUIRE(S64 < (1ll << 30), "too many (page, class) segments");
+    const int S = (int)S64;
+    FilterWs w = carve(workspace, B, S, cand_cap, max_det, !kp.class_specific);
+    if (workspace_bytes < w.bytes) return rn_fail(RN_ERR_WORKSPACE, "filter workspace too small: %zu < %zu", workspace_bytes, w.bytes);
+    // counts, kept_count, status are contiguous at the front of the workspace
+    cudaError_t e = cudaMemsetAsync(w.counts, 0, (size_t)((char*)w.keys - (char*)w.counts), s);
+    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+    if (status_out) {
+        e = cudaMemsetAsync(status_out, 0, sizeof(int) * (size_t)B, s);
+        if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+    }
+    kp.sl.counts = w.counts; kp.sl.keys = w.keys; kp.sl.boxes = w.boxes; kp.sl.labels = w.labels; kp.sl.cap = cand_cap;
+    const long long units = kp.class_specific ? ((long long)B * kp.N * C + 3) / 4 : (long long)B * kp.N;
+    long long blocks = (units + K3_THREADS - 1) / K3_THREADS;
+    if (blocks > (long long)RN_NUM_SMS * 8) blocks = (long long)RN_NUM_SMS * 8;
+    if (decode) k_threshold_compact<true><<<(int)blocks, K3_THREADS, 0, s>>>(kp);
+    else k_threshold_compact<false><<<(int)blocks, K3_THREADS, 0, s>>>(kp);
+    int rc = rn_check_launch("k_threshold_compact");
+    if (rc) return rc;
+    return run_back_end(w, B, S, spp, cand_cap, 0, nullptr, nms, nms_thr, max_det, pre_nms_top_k,
+                        out_boxes, out_scores, out_labels, out_indices, nullptr,
+                        status_out ? status_out : w.status, s);
+}
+
+}  // namespace
+
+extern "C" size_t rn_filter_workspace_bytes(int B, long long N, int C, int class_specific, long long cand_cap, int max_detections) {
+    if (B < 1 || N < 1 || C < 1 || max_detections < 1) return 0;
+    if (cand_cap < 1 || cand_cap > N) cand_cap = N;
+    const long long S = (long long)B * (class_specific ? C : 1);
+    return carve(nullptr, B, (int)S, cand_cap, max_detections, !class_specific).bytes;
+}
+
+extern "C" int rn_filter_detections(const float* boxes, const float* classification,
+                                    int B, long long N, int C, int class_specific, int nms,
+                                    float score_threshold, float nms_threshold, int max_detections,
+                                    int pre_nms_top_k, long long cand_cap,
+                                    float* out_boxes, float* out_scores, int* out_labels, int* out_indices,
+                                    int* status_out_dev, void* workspace, size_t workspace_bytes, void* stream) {
+    RN_REQUIRE(boxes && classification, "NULL input");
+    RN_REQUIRE(rn_aligned16(boxes), "boxes must be 16-byte aligned");
+    RN_REQUIRE(N < (1ll << 31), "N too large");
+    K3Params kp = {};
+    kp.cls = classification; kp.boxes = boxes; kp.B = B; kp.N = (int)N; kp.C = C;
+    kp.class_specific = class_specific ? 1 : 0; kp.thr = score_threshold;
+    return filter_common(kp, false, nms ? 1 : 0, nms_threshold, max_detections, pre_nms_top_k, cand_cap,
+                         out_boxes, out_scores, out_labels, out_indices, status_out_dev,
+                         workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int rn_decode_filter_detections(const float* base_anchors_f32_dev, const int* level_hw,
+                                           const int* level_stride, int num_levels, int anchors_per_cell,
+                                           const float* regression, const float* classification,
+                                           int B, long long N, int C,
+                                           const float* mean4, const float* std4, float clip_width, float clip_height,
+                                           int class_specific, int nms,
+                                           float score_threshold, float nms_threshold, int max_detections,
+                                           int pre_nms_top_k, long long cand_cap,
+                                           float* out_boxes, float* out_scores, int* out_labels, int* out_indices,
+                                           int* status_out_dev, void* workspace, size_t workspace_bytes, void* stream) {
+    RN_REQUIRE(base_anchors_f32_dev && regression && classification && mean4 && std4, "NULL input");
+    RN_REQUIRE(rn_aligned16(regression), "regression must be 16-byte aligned");
+    K3Params kp = {};
+    int rc = rn_make_levels(&kp.lv, level_hw, level_stride, num_levels, anchors_per_cell);
+    if (rc) return rc;
+    RN_REQUIRE(kp.lv.start[num_levels] == N, "N (%lld) does not match the level table (%d)", N, kp.lv.start[num_levels]);
+    kp.cls = classification; kp.reg = regression; kp.base32 = base_anchors_f32_dev;
+    for (int i = 0; i < 4; ++i) { kp.nm.mean[i] = mean4[i]; kp.nm.std[i] = std4[i]; }
+    kp.clipW = clip_width; kp.clipH = clip_height;
+    kp.B = B; kp.N = (int)N; kp.C = C; kp.class_specific = class_specific ? 1 : 0; kp.thr = score_threshold;
+    return filter_common(kp, true, nms ? 1 : 0, nms_threshold, max_detections, pre_nms_top_k, cand_cap,
+                         out_boxes, out_scores, out_labels, out_indices, status_out_dev,
+                         workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" size_t rn_nms_workspace_bytes(long long K, int max_output) {
+    if (K < 1 || max_output < 1) return 256;
+    FilterWs w = carve(nullptr, 1, 1, K, max_output, false);
+    // + scratch outputs of the merge stage (boxes, scores, labels)
+    return w.bytes + align256(sizeof(float4) * (size_t)max_output) + 2 * align256(sizeof(float) * (size_t)max_output);
+}
+
+extern "C" int rn_nms(const float* boxes, const float* scores, long long K, int max_output, float iou_threshold,
+                      int* out_indices, int* out_count_dev, void* workspace, size_t workspace_bytes, void* stream) {
+    RN_REQUIRE(out_indices && out_count_dev && workspace, "NULL pointer");
+    RN_REQUIRE(K >= 0 && K < (1ll << 31), "K out of range");
+    RN_REQUIRE(max_output >= 1 && max_output <= MAX_DET_LIMIT, "max_output must be in [1, %d]", MAX_DET_LIMIT);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (workspace_bytes < rn_nms_workspace_bytes(K, max_output)) return rn_fail(RN_ERR_WORKSPACE, "nms workspace too small");
+    RN_REQUIRE(rn_aligned16(workspace), "workspace must be 16-byte aligned");
+    const long long cap = K < 1 ? 1 : K;
+    FilterWs w = carve(workspace, 1, 1, cap, max_output, false);
+    char* tail = reinterpret_cast<char*>(workspace) + w.bytes;
+    float* sc_boxes = reinterpret_cast<float*>(tail); tail += align256(sizeof(float4) * (size_t)max_output);
+    float* sc_scores = reinterpret_cast<float*>(tail); tail += align256(sizeof(float) * (size_t)max_output);
+    int* sc_labels = reinterpret_cast<int*>(tail);
+    cudaError_t e = cudaMemsetAsync(w.counts, 0, (size_t)((char*)w.keys - (char*)w.counts), s);
+    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+    if (K > 0) {
+        RN_REQUIRE(boxes && scores, "NULL input");
+        RN_REQUIRE(rn_aligned16(boxes), "boxes must be 16-byte aligned");
+        const int blocks = (int)min((K + 255) / 256, (long long)RN_NUM_SMS * 4);
+        k_keys_from_scores<<<blocks, 256, 0, s>>>(scores, K, w.keys, w.counts);
+        int rc = rn_check_launch("k_keys_from_scores");
+        if (rc) return rc;
+    }
+    return run_back_end(w, 1, 1, 1, cap, 1, reinterpret_cast<const float4*>(boxes), 1, iou_threshold, max_output, 0,
+                        sc_boxes, sc_scores, sc_labels, out_indices, out_count_dev, w.status, s);
+}

@@ -1,0 +1,112 @@
+// Shared helpers for librn_b200 (sm_100a).  Internal header; the public C-ABI is include/rn_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/rn_b200.h"
+
+#define RN_NUM_SMS 148   // B200: 2 dies x 74 SMs; grids of streaming kernels are sized in multiples of this
+
+// ---------------------------------------------------------------------------------------------
+// error reporting (thread-local message, negative return codes; nothing throws)
+// ---------------------------------------------------------------------------------------------
+char* rn_error_buffer();
+
+static inline int rn_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(rn_error_buffer(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define RN_REQUIRE(cond, ...) do { if (!(cond)) return rn_fail(RN_ERR_BAD_ARG, __VA_ARGS__); } while (0)
+
+static inline int rn_check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return RN_OK;
+}
+
+static inline bool rn_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---------------------------------------------------------------------------------------------
+// pyramid level table, passed to kernels by value
+// ---------------------------------------------------------------------------------------------
+struct RnLevels {
+    int num_levels;
+    int anchors_per_cell;
+    int h[RN_MAX_LEVELS];
+    int w[RN_MAX_LEVELS];
+    int stride[RN_MAX_LEVELS];
+    int start[RN_MAX_LEVELS + 1];   // first anchor index of each level; start[num_levels] = N
+};
+
+static inline int rn_make_levels(RnLevels* t, const int* level_hw, const int* level_stride,
+                                 int num_levels, int anchors_per_cell) {
+    RN_REQUIRE(level_hw && level_stride, "level table is NULL");
+    RN_REQUIRE(num_levels >= 1 && num_levels <= RN_MAX_LEVELS, "num_levels must be in [1, %d]", RN_MAX_LEVELS);
+    RN_REQUIRE(anchors_per_cell >= 1 && anchors_per_cell <= 64, "anchors_per_cell must be in [1, 64]");
+    t->num_levels = num_levels;
+    t->anchors_per_cell = anchors_per_cell;
+    long long n = 0;
+    for (int l = 0; l < RN_MAX_LEVELS; ++l) { t->h[l] = 0; t->w[l] = 0; t->stride[l] = 1; t->start[l] = 0; }
+    for (int l = 0; l < num_levels; ++l) {
+        RN_REQUIRE(level_hw[2 * l] >= 0 && level_hw[2 * l + 1] >= 0 && level_stride[l] > 0, "bad level %d", l);
+        t->h[l] = level_hw[2 * l];
+        t->w[l] = level_hw[2 * l + 1];
+        t->stride[l] = level_stride[l];
+        t->start[l] = (int)n;
+        n += (long long)t->h[l] * t->w[l] * anchors_per_cell;
+        RN_REQUIRE(n < (1ll << 31), "too many anchors per page");
+    }
+    for (int l = num_levels; l <= RN_MAX_LEVELS; ++l) t->start[l] = (int)n;
+    return RN_OK;
+}
+
+// anchor index -> (level, cell x, cell y, anchor-in-cell).  Order: level-major, then y, x, a
+// (reference model/anchors.py:195-202, :232-236).
+__device__ __forceinline__ void rn_locate(const RnLevels& t, int n, int& level, int& cx, int& cy, int& a) {
+    level = 0;
+#pragma unroll
+    for (int l = 1; l < RN_MAX_LEVELS; ++l)
+        if (l < t.num_levels && n >= t.start[l]) level = l;
+    int r = n - t.start[level];
+    int cell = r / t.anchors_per_cell;
+    a = r - cell * t.anchors_per_cell;
+    cy = cell / t.w[level];
+    cx = cell - cy * t.w[level];
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp / block reductions
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T rn_warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double rn_warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double rn_warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// streaming (evict-first) 128-bit global accesses: the big tensors on this path are touched once
+__device__ __forceinline__ float4 rn_ldg_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void rn_stg_stream4(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}

@@ -1,0 +1,170 @@
+"""Drop-in for the reference's ``model/losses.py``: ``focal(alpha, gamma)`` and ``smooth_l1(sigma)``
+return functors ``f(y_true, y_pred) -> scalar`` (``RetinaNet.py:125-131``, ``defineModel.py:22-23``).
+
+The functors are differentiable w.r.t. ``y_pred``: a ``torch.autograd.Function`` whose forward launches
+kernel K2 (``csrc/losses.cu``), which produces the loss *and* the gradient in the same pass; backward
+only scales the stored gradient by the incoming one.  :func:`detection_losses` runs both losses in a
+single launch (the fused path the benchmark measures).
+
+Extra keyword ``normalizer`` (not in the reference): a device float tensor holding the positive-anchor
+COUNT to normalise with -- the per-page counts K1 returns, summed and, on several GPUs, all-reduced
+(``distributed.global_positive_count``).  Without it the count is taken from ``y_true`` on the device
+first, exactly as the reference does (``model/losses.py:40-42``, ``:88-89``).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+BCE_MODES = {"tf2": _lib.RN_BCE_TF2, "logits": _lib.RN_BCE_LOGITS}
+
+
+def _prep(y_true, y_pred, last_true, last_pred):
+    """Accept numpy or torch, return contiguous float32 CUDA tensors + whether inputs were numpy."""
+    _lib.require_cuda()
+    as_numpy = not isinstance(y_pred, torch.Tensor)
+    if isinstance(y_pred, torch.Tensor) and y_pred.is_cuda:
+        device = y_pred.device
+    else:
+        device = torch.device("cuda", torch.cuda.current_device())
+    yt = torch.as_tensor(y_true).to(device=device, dtype=torch.float32).contiguous()
+    yp = torch.as_tensor(y_pred).to(device=device, dtype=torch.float32)
+    if not yp.is_contiguous():
+        yp = yp.contiguous()
+    if yt.shape[-1] != last_true(yp) or yt.shape[:-1] != yp.shape[:-1]:
+        raise ValueError("y_true %s does not match y_pred %s" % (tuple(yt.shape), tuple(yp.shape)))
+    if last_pred is not None and yp.shape[-1] != last_pred:
+        raise ValueError("y_pred last dimension must be %d" % last_pred)
+    return yt, yp, device, as_numpy
+
+
+def _norm_tensor(normalizer, device):
+    if normalizer is None:
+        return None
+    if isinstance(normalizer, torch.Tensor):
+        n = normalizer.to(device=device, dtype=torch.float32).reshape(-1)
+        return n.sum().reshape(1) if n.numel() != 1 else n.contiguous()
+    return torch.tensor([float(normalizer)], dtype=torch.float32, device=device)
+
+
+class _FocalFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_pred, y_true, npos, alpha, gamma, bce):
+        device = y_pred.device
+        R = y_pred.numel() // y_pred.shape[-1]
+        C = y_pred.shape[-1]
+        need_grad = ctx.needs_input_grad[0]
+        loss = torch.empty((), dtype=torch.float32, device=device)
+        grad = torch.empty_like(y_pred) if need_grad else None
+        ws, ws_bytes = _lib.loss_workspace(device)
+        _lib.check(_lib.load().rn_focal_fwd_bwd(_lib.ptr(y_true), _lib.ptr(y_pred), R, C, alpha, gamma, bce,
+                                                _lib.ptr(npos), _lib.ptr(loss), _lib.ptr(grad),
+                                                _lib.ptr(ws), ws_bytes, _lib.stream_ptr(device)), "rn_focal_fwd_bwd")
+        ctx.grad = grad
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        return (ctx.grad * g if ctx.grad is not None else None), None, None, None, None, None
+
+
+class _SmoothL1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_pred, y_true, npos, sigma):
+        device = y_pred.device
+        R = y_pred.numel() // 4
+        need_grad = ctx.needs_input_grad[0]
+        loss = torch.empty((), dtype=torch.float32, device=device)
+        grad = torch.empty_like(y_pred) if need_grad else None
+        ws, ws_bytes = _lib.loss_workspace(device)
+        _lib.check(_lib.load().rn_smooth_l1_fwd_bwd(_lib.ptr(y_true), _lib.ptr(y_pred), R, sigma,
+                                                    _lib.ptr(npos), _lib.ptr(loss), _lib.ptr(grad),
+                                                    _lib.ptr(ws), ws_bytes, _lib.stream_ptr(device)),
+                   "rn_smooth_l1_fwd_bwd")
+        ctx.grad = grad
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        return (ctx.grad * g if ctx.grad is not None else None), None, None, None
+
+
+def focal(alpha=0.25, gamma=2.0, bce="tf2"):
+    """model/losses.py:5-46.  ``bce`` selects the restated ``K.binary_crossentropy`` form ("tf2":
+    clip + epsilon inside the logs; "logits": standalone Keras <= 2.2) -- see DESIGN.md."""
+    if bce not in BCE_MODES:
+        raise ValueError("bce must be one of %s" % sorted(BCE_MODES))
+
+    def _focal(y_true, y_pred, normalizer=None):
+        """y_true (B,N,C+1) [labels..., anchor state], y_pred (B,N,C) probabilities -> scalar."""
+        yt, yp, device, as_numpy = _prep(y_true, y_pred, lambda p: p.shape[-1] + 1, None)
+        out = _FocalFn.apply(yp, yt, _norm_tensor(normalizer, device), float(alpha), float(gamma), BCE_MODES[bce])
+        return np.float32(out.item()) if as_numpy else out
+
+    return _focal
+
+
+def smooth_l1(sigma=3.0):
+    """model/losses.py:49-91."""
+
+    def _smooth_l1(y_true, y_pred, normalizer=None):
+        """y_true (B,N,5) [4 targets, anchor state], y_pred (B,N,4) -> scalar."""
+        yt, yp, device, as_numpy = _prep(y_true, y_pred, lambda p: 5, 4)
+        out = _SmoothL1Fn.apply(yp, yt, _norm_tensor(normalizer, device), float(sigma))
+        return np.float32(out.item()) if as_numpy else out
+
+    return _smooth_l1
+
+
+def detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None,
+                     alpha=0.25, gamma=2.0, sigma=3.0, bce="tf2", want_grads=True, out=None, workspace=None):
+    """Both losses, forward + backward, in ONE launch of K2 (``rn_loss_fwd_bwd``).
+
+    All tensors are float32 CUDA: ``y_true_reg`` (B,N,5), ``y_true_cls`` (B,N,C+1) in the order
+    ``anchor_targets_bbox`` returns them; ``reg_pred`` (B,N,4), ``cls_pred`` (B,N,C).
+    Returns ``(losses, grad_cls, grad_reg)`` where ``losses`` is a 3-float device tensor
+    ``[focal, smooth_l1, normaliser]`` and the gradients are d(loss)/d(pred) of the respective loss."""
+    device = cls_pred.device
+    C = cls_pred.shape[-1]
+    R = cls_pred.numel() // C
+    if out is None:
+        losses = torch.empty(3, dtype=torch.float32, device=device)
+        grad_cls = torch.empty_like(cls_pred) if want_grads else None
+        grad_reg = torch.empty_like(reg_pred) if want_grads else None
+    else:
+        losses, grad_cls, grad_reg = out
+    if workspace is None:
+        ws, ws_bytes = _lib.loss_workspace(device)
+    else:
+        ws, ws_bytes = workspace, workspace.numel()       # caller-owned, zero-filled uint8 tensor
+    npos = _norm_tensor(normalizer, device)
+    _lib.check(_lib.load().rn_loss_fwd_bwd(_lib.ptr(y_true_cls), _lib.ptr(cls_pred), _lib.ptr(y_true_reg),
+                                           _lib.ptr(reg_pred), R, C, float(alpha), float(gamma), BCE_MODES[bce],
+                                           float(sigma), _lib.ptr(npos),
+                                           _lib.ptr(losses), _lib.ptr(grad_cls), _lib.ptr(grad_reg),
+                                           _lib.ptr(ws), ws_bytes, _lib.stream_ptr(device)), "rn_loss_fwd_bwd")
+    return losses, grad_cls, grad_reg
+
+
+class _DetectionLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cls_pred, reg_pred, y_true_cls, y_true_reg, npos, alpha, gamma, sigma, bce):
+        want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        losses, gc, gr = detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, npos, alpha, gamma, sigma,
+                                          bce, want_grads=want)
+        ctx.gc, ctx.gr = gc, gr
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g_focal, g_sl1):
+        gc = ctx.gc * g_focal if ctx.gc is not None else None
+        gr = ctx.gr * g_sl1 if ctx.gr is not None else None
+        return gc, gr, None, None, None, None, None, None, None
+
+
+def detection_loss(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None,
+                   alpha=0.25, gamma=2.0, sigma=3.0, bce="tf2"):
+    """Autograd-aware fused version: returns ``(focal_loss, smooth_l1_loss)`` scalars."""
+    return _DetectionLossFn.apply(cls_pred.contiguous(), reg_pred.contiguous(), y_true_cls.contiguous(),
+                                  y_true_reg.contiguous(), _norm_tensor(normalizer, cls_pred.device),
+                                  float(alpha), float(gamma), float(sigma), bce)

@@ -1,0 +1,129 @@
+"""The training-target step as one replayable unit: K1 (targets) -> normaliser -> K2 (losses fwd+bwd).
+
+``TargetLossStep`` owns static device buffers for one batch shape and, at world size 1, captures the two
+kernel launches into a CUDA graph so a step costs one ``cudaGraphLaunch`` instead of several Python-side
+launches (the kernels are ~tens of microseconds; launch overhead would otherwise dominate).  With several
+ranks the positive count is all-reduced between K1 and K2 (``distributed.global_positive_count``), the
+two halves being captured separately.
+
+This is host plumbing around the C-ABI; it adds no arithmetic of its own.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from . import anchors as _anchors
+from . import distributed as _dist
+from . import losses as _losses
+
+
+class TargetLossStep(object):
+    def __init__(self, image_shape, batch, gmax, num_classes, anchor_params=None, pyramid_levels=None,
+                 negative_overlap=0.4, positive_overlap=0.5, alpha=0.25, gamma=2.0, sigma=3.0, bce="tf2",
+                 use_graph=True, device=None):
+        _lib.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.spec = _anchors.make_spec(image_shape, pyramid_levels, anchor_params, None)
+        self.B, self.G, self.C, self.N = int(batch), max(1, int(gmax)), int(num_classes), self.spec.num_anchors
+        self.neg, self.pos = negative_overlap, positive_overlap
+        self.loss_kw = dict(alpha=alpha, gamma=gamma, sigma=sigma, bce=bce)
+        d, B, G, N, C = self.device, self.B, self.G, self.N, self.C
+        # one staging block: boxes f64 | labels i32 | counts i32 | img_hw i32  (same layout as upload_annotations)
+        self.nb, self.nl, self.nc, self.ni = B * G * 32, B * G * 4, B * 4, B * 8
+        total = self.nb + self.nl + self.nc + self.ni
+        self.gt_host = torch.zeros(total, dtype=torch.uint8, pin_memory=True)
+        self.gt_dev = torch.zeros(total, dtype=torch.uint8, device=d)
+        o = 0
+        self.d_boxes = self.gt_dev[o:o + self.nb].view(torch.float64).view(B, G, 4); o += self.nb
+        self.d_labels = self.gt_dev[o:o + self.nl].view(torch.int32).view(B, G); o += self.nl
+        self.d_counts = self.gt_dev[o:o + self.nc].view(torch.int32); o += self.nc
+        self.d_hw = self.gt_dev[o:o + self.ni].view(torch.int32).view(B, 2)
+        self.cls_pred = torch.zeros((B, N, C), dtype=torch.float32, device=d)
+        self.reg_pred = torch.zeros((B, N, 4), dtype=torch.float32, device=d)
+        self.y_reg = torch.empty((B, N, 5), dtype=torch.float32, device=d)
+        self.y_cls = torch.empty((B, N, C + 1), dtype=torch.float32, device=d)
+        self.npos_total = torch.zeros(1, dtype=torch.float32, device=d)
+        self.npos = None
+        self.losses = torch.zeros(3, dtype=torch.float32, device=d)
+        self.grad_cls = torch.empty_like(self.cls_pred)
+        self.grad_reg = torch.empty_like(self.reg_pred)
+        self.loss_ws = torch.zeros(int(_lib.load().rn_loss_workspace_bytes()), dtype=torch.uint8, device=d)
+        self.use_graph = use_graph
+        self._graphs = None
+        self.kernel_launches_per_step = 2      # K1 + K2 (memsets and NCCL are not ours)
+
+    # ---- inputs ---------------------------------------------------------------------------------
+    def load_annotations(self, image_group, annotations_group):
+        """Pack the ragged GT list (reference format) and copy it to the static device block (async)."""
+        boxes, labels, counts, img_hw = _anchors.pack_annotations(image_group, annotations_group, self.C)
+        B, G = labels.shape
+        if B != self.B or G > self.G:
+            raise ValueError("batch of %d pages / %d GT does not fit this step (%d pages, %d GT)" % (B, G, self.B, self.G))
+        hv = self.gt_host.numpy()
+        hb = hv[:self.nb].view(np.float64).reshape(self.B, self.G, 4)
+        hl = hv[self.nb:self.nb + self.nl].view(np.int32).reshape(self.B, self.G)
+        hb[:, :G] = boxes
+        hl[:, :G] = labels
+        hv[self.nb + self.nl:self.nb + self.nl + self.nc].view(np.int32)[:] = counts
+        hv[self.nb + self.nl + self.nc:].view(np.int32).reshape(self.B, 2)[:] = img_hw
+        self.gt_dev.copy_(self.gt_host, non_blocking=True)
+        return self.gt_host.numel()
+
+    def load_predictions(self, cls_pred, reg_pred):
+        """Head outputs (host pinned or device tensors) into the static buffers (async)."""
+        self.cls_pred.copy_(cls_pred, non_blocking=True)
+        self.reg_pred.copy_(reg_pred, non_blocking=True)
+
+    # ---- the two halves ----------------------------------------------------------------------------
+    def _targets(self):
+        _, _, self.npos, _ = _anchors.anchor_targets_device(self.spec, self.d_boxes, self.d_labels, self.d_counts,
+                                                            self.d_hw, self.C, self.neg, self.pos,
+                                                            out=(self.y_reg, self.y_cls), npos_total=self.npos_total)
+
+    def _losses(self):
+        _losses.detection_losses(self.y_reg, self.y_cls, self.reg_pred, self.cls_pred, normalizer=self.npos_total,
+                                 out=(self.losses, self.grad_cls, self.grad_reg), workspace=self.loss_ws,
+                                 **self.loss_kw)
+
+    def _capture(self, fn):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+
+    def _build_graphs(self):
+        # warm up on a side stream (allocations, lazy module loading) before capture
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self._targets()
+            self._losses()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        self._graphs = (self._capture(self._targets), self._capture(self._losses))
+
+    def run(self, events=None):
+        """One step on the current stream.  Results: ``losses`` [focal, smooth_l1, normaliser],
+        ``grad_cls``, ``grad_reg``, ``y_reg``, ``y_cls`` (static tensors, overwritten every step).
+        ``events``: optional 3 CUDA events recorded before K1, between K1 and K2 (after the all-reduce
+        when there are several ranks) and after K2 -- used by the benchmark's roofline accounting."""
+        rank, world = _dist.world()
+        if self.use_graph and self._graphs is None:
+            self._build_graphs()
+        if events is not None:
+            events[0].record()
+        if self.use_graph:
+            self._graphs[0].replay()
+        else:
+            self._targets()
+        if world > 1:
+            torch.distributed.all_reduce(self.npos_total)
+        if events is not None:
+            events[1].record()
+        if self.use_graph:
+            self._graphs[1].replay()
+        else:
+            self._losses()
+        if events is not None:
+            events[2].record()
+        return self.losses

@@ -1,0 +1,122 @@
+"""Seeded synthetic pages for the tests, the golden-vector generator and ``bench.py``.
+
+Distributions follow SURVEY.md §8(d): only page *shapes* matter (no pixels are touched by the
+path), GT tables are wide boxes, training predictions sit at the prior (p ~ 0.01), inference
+predictions are a low-score background plus clusters of high-score anchors planted around each
+GT table.  Seeds: ``1234 + 1000*config + page_index`` with ``np.random.RandomState``.
+
+This module is pure numpy host code; it never touches the oracle or the CUDA library.
+"""
+import numpy as np
+
+# (H, W), max GT per page, classes, pages per batch  -- BASELINE.json "configs"
+CONFIGS = {
+    1: dict(hw=(800, 1333), gmax=3, classes=1, batch=1),
+    2: dict(hw=(800, 1333), gmax=20, classes=1, batch=16),
+    3: dict(hw=(800, 1333), gmax=20, classes=1, batch=64),
+    4: dict(hw=(1600, 2400), gmax=20, classes=1, batch=4),
+    5: dict(hw=(800, 1333), gmax=100, classes=80, batch=16),
+}
+
+
+class PageShape(object):
+    """Stand-in for an image array: the path only ever reads ``.shape``
+    (reference ``model/anchors.py:85-87``)."""
+
+    def __init__(self, shape):
+        self.shape = tuple(int(s) for s in shape)
+
+
+def page_seed(config, page_index):
+    return 1234 + 1000 * int(config) + int(page_index)
+
+
+def level_shapes(hw, levels=(3, 4, 5, 6, 7)):
+    return [((hw[0] + 2 ** l - 1) // 2 ** l, (hw[1] + 2 ** l - 1) // 2 ** l) for l in levels]
+
+
+def num_anchors(hw, levels=(3, 4, 5, 6, 7), per_cell=9):
+    return int(sum(h * w for h, w in level_shapes(hw, levels)) * per_cell)
+
+
+def gt_for_page(config, page_index, hw=None, gmax=None, classes=None, anchors=None):
+    """One page's annotations ``{'bboxes': (G,4) f64, 'labels': (G,) f64}``."""
+    cfg = CONFIGS[config]
+    H, W = hw or cfg['hw']
+    gmax = gmax or cfg['gmax']
+    classes = classes or cfg['classes']
+    rs = np.random.RandomState(page_seed(config, page_index))
+    G = int(rs.randint(1, gmax + 1))
+    scale = 800.0 / 1700.0                      # resize factor applied by the data generator
+    H0, W0 = H / scale, W / scale
+    w = rs.uniform(0.2 * W0, 0.9 * W0, G)
+    h = rs.uniform(0.05 * H0, 0.5 * H0, G)
+    x1 = rs.uniform(0, 1, G) * (W0 - w)
+    y1 = rs.uniform(0, 1, G) * (H0 - h)
+    boxes = np.stack([x1, y1, x1 + w, y1 + h], axis=1) * scale
+    labels = rs.randint(0, classes, G).astype(np.float64)
+    if anchors is not None and rs.uniform() < 0.05:
+        # adversarial: snap one GT onto the top half of an anchor (IoU ~ exactly 0.5) and
+        # duplicate it so that two GT boxes tie
+        a = anchors[int(rs.randint(0, anchors.shape[0]))]
+        snapped = np.array([a[0], a[1], a[2], a[1] + (a[3] - a[1]) / 2])
+        boxes = np.concatenate([boxes, snapped[None], snapped[None]], axis=0)
+        labels = np.concatenate([labels, [0.0, float(classes - 1)]])
+    return {'bboxes': boxes, 'labels': labels}
+
+
+def training_batch(config, batch=None, hw=None, mixed_widths=False, anchors=None, first_page=0):
+    """``(image_group, annotations_group)`` for the training-target path."""
+    cfg = CONFIGS[config]
+    batch = batch or cfg['batch']
+    H, W = hw or cfg['hw']
+    images, anns = [], []
+    for i in range(batch):
+        pw = W if (not mixed_widths or i % 2 == 0) else int(round(W * 0.8))
+        images.append(PageShape((H, pw, 3)))
+        anns.append(gt_for_page(config, first_page + i, hw=(H, pw), anchors=anchors))
+    return images, anns
+
+
+def training_predictions(config, batch, n_anchors, classes=None, first_page=0):
+    """Head outputs at initialisation: ``cls = sigmoid(N(-4.595, 1))`` (prior 0.01,
+    reference ``model/defineModel.py:78``), ``reg ~ N(0, 1)``; float32."""
+    classes = classes or CONFIGS[config]['classes']
+    rs = np.random.RandomState(page_seed(config, first_page) + 500)
+    logits = rs.normal(-4.595, 1.0, (batch, n_anchors, classes))
+    cls = (1.0 / (1.0 + np.exp(-logits))).astype(np.float32)
+    reg = rs.normal(0.0, 1.0, (batch, n_anchors, 4)).astype(np.float32)
+    return cls, reg
+
+
+def _iou_f64(a, g):
+    iw = np.maximum(0, np.minimum(a[:, 2], g[2]) - np.maximum(a[:, 0], g[0]))
+    ih = np.maximum(0, np.minimum(a[:, 3], g[3]) - np.maximum(a[:, 1], g[1]))
+    inter = iw * ih
+    return inter / ((a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1]) + (g[2] - g[0]) * (g[3] - g[1]) - inter)
+
+
+def inference_predictions(config, batch, anchors, annotations_group, classes=None, first_page=0,
+                          planted_per_gt=200):
+    """Head outputs of a trained model, synthetic: background ``cls = sigmoid(N(-6, 1.5))``
+    (~2 % of anchors above 0.05), ``reg ~ N(0, 0.5)``; around each GT table ``planted_per_gt``
+    overlapping anchors get scores U(0.3, 0.99) and regressions that decode close to the table."""
+    classes = classes or CONFIGS[config]['classes']
+    n = anchors.shape[0]
+    rs = np.random.RandomState(page_seed(config, first_page) + 700)
+    cls = (1.0 / (1.0 + np.exp(-rs.normal(-6.0, 1.5, (batch, n, classes))))).astype(np.float32)
+    reg = rs.normal(0.0, 0.5, (batch, n, 4)).astype(np.float32)
+    aw = anchors[:, 2] - anchors[:, 0]
+    ah = anchors[:, 3] - anchors[:, 1]
+    for b in range(batch):
+        ann = annotations_group[b]
+        for g, lab in zip(ann['bboxes'], ann['labels']):
+            near = np.nonzero(_iou_f64(anchors, g) > 0.3)[0]
+            if near.size == 0:
+                continue
+            pick = rs.choice(near, size=min(planted_per_gt, near.size), replace=False)
+            cls[b, pick, int(lab)] = rs.uniform(0.3, 0.99, pick.size).astype(np.float32)
+            t = np.stack([(g[0] - anchors[pick, 0]) / aw[pick], (g[1] - anchors[pick, 1]) / ah[pick],
+                          (g[2] - anchors[pick, 2]) / aw[pick], (g[3] - anchors[pick, 3]) / ah[pick]], axis=1) / 0.2
+            reg[b, pick] = (t + rs.normal(0, 0.15, t.shape)).astype(np.float32)
+    return cls, reg

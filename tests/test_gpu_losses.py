@@ -1,0 +1,134 @@
+"""GPU parity, K2: fused focal / smooth-L1 forward+backward vs the numpy oracle (fp32 restatement of
+model/losses.py).  Tolerance: north_star's 1e-5 relative for losses; gradients 1e-5 relative with a
+1e-7 absolute floor (values are ~1e-3/n_pos)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import losses_np as OL
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def make_case(seed, B, N, C, p_ignore=0.1, p_pos=0.1, logit_mu=-2.0):
+    rs = np.random.RandomState(seed)
+    state = rs.choice([-1, 0, 1], (B, N), p=[p_ignore, 1 - p_ignore - p_pos, p_pos]).astype(np.float32)
+    y_cls = np.zeros((B, N, C + 1), np.float32)
+    y_cls[:, :, -1] = state
+    hot = rs.randint(0, C, (B, N))
+    bb, nn = np.nonzero(state == 1)
+    y_cls[bb, nn, hot[bb, nn]] = 1
+    p = (1 / (1 + np.exp(-rs.normal(logit_mu, 2, (B, N, C))))).astype(np.float32)
+    y_reg = np.concatenate([rs.normal(0, 1, (B, N, 4)).astype(np.float32), state[:, :, None]], axis=2)
+    r = (y_reg[:, :, :4] + rs.normal(0, 0.2, (B, N, 4))).astype(np.float32)
+    return y_cls, p, y_reg, r
+
+
+def close(got, want, rtol=RTOL, atol=0.0):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return np.all(np.abs(got - want) <= atol + rtol * np.abs(want))
+
+
+@pytest.mark.parametrize("C", [1, 3, 80])
+@pytest.mark.parametrize("bce", ["tf2", "logits"])
+def test_focal_vs_oracle(rn, C, bce):
+    y_cls, p, _, _ = make_case(10 + C, 2, 3001, C)
+    p[0, 0, 0], p[0, 1, 0], p[0, 2, C - 1], p[0, 3, 0] = 0.0, 1.0, 1e-8, 1 - 1e-8
+    want_l, want_g = OL.focal(bce=bce)(y_cls, p, return_grad=True)
+    yp = torch.tensor(p, device="cuda", requires_grad=True)
+    loss = rn.focal(bce=bce)(torch.tensor(y_cls, device="cuda"), yp)
+    loss.backward()
+    assert close(loss.item(), want_l)
+    assert close(yp.grad.cpu().numpy(), want_g, atol=1e-7 * float(np.abs(want_g).max()))
+    # ignored anchors get exactly zero gradient
+    assert not yp.grad.cpu().numpy()[y_cls[:, :, -1] == -1].any()
+
+
+def test_smooth_l1_vs_oracle(rn):
+    _, _, y_reg, r = make_case(20, 3, 2500, 1)
+    r[0, 5] = y_reg[0, 5, :4]
+    y_reg[0, 5, 4] = 1
+    want_l, want_g = OL.smooth_l1()(y_reg, r, return_grad=True)
+    yp = torch.tensor(r, device="cuda", requires_grad=True)
+    loss = rn.smooth_l1()(torch.tensor(y_reg, device="cuda"), yp)
+    (2.0 * loss).backward()                      # upstream gradient is applied in backward
+    assert close(loss.item(), want_l)
+    assert close(yp.grad.cpu().numpy(), 2.0 * want_g, atol=1e-9)
+    assert not yp.grad.cpu().numpy()[y_reg[:, :, 4] != 1].any()
+    for sigma in (1.0, 2.5):
+        wl = OL.smooth_l1(sigma)(y_reg, r)
+        assert close(rn.smooth_l1(sigma)(y_reg, r), wl)        # numpy in -> numpy scalar out
+
+
+def test_golden_tf_half(rn, golden_tf):
+    g = golden_tf
+    for mode in ("tf2", "logits"):
+        yp = torch.tensor(g['loss_p'], device="cuda", requires_grad=True)
+        l = rn.focal(bce=mode)(torch.tensor(g['loss_y_cls'], device="cuda"), yp)
+        l.backward()
+        assert close(l.item(), g['focal_%s_loss' % mode])
+        assert close(yp.grad.cpu().numpy(), g['focal_%s_grad' % mode], atol=1e-7 * float(np.abs(g['focal_%s_grad' % mode]).max()))
+    yp = torch.tensor(g['loss_r'], device="cuda", requires_grad=True)
+    l = rn.smooth_l1()(torch.tensor(g['loss_y_reg'], device="cuda"), yp)
+    l.backward()
+    assert close(l.item(), g['sl1_loss']) and close(yp.grad.cpu().numpy(), g['sl1_grad'], atol=1e-9)
+
+
+@pytest.mark.parametrize("C", [1, 5])
+def test_fused_equals_separate_and_normalizer(rn, C):
+    y_cls, p, y_reg, r = make_case(30 + C, 2, 4099, C)
+    t = lambda a: torch.tensor(a, device="cuda")
+    losses, gc, gr = rn.detection_losses(t(y_reg), t(y_cls), t(r), t(p))
+    wf, wgf = OL.focal()(y_cls, p, return_grad=True)
+    ws, wgs = OL.smooth_l1()(y_reg, r, return_grad=True)
+    npos = float((y_cls[:, :, -1] == 1).sum())
+    l = losses.cpu().numpy()
+    assert close(l[0], wf) and close(l[1], ws) and l[2] == max(1.0, npos)
+    assert close(gc.cpu().numpy(), wgf, atol=1e-7 * float(np.abs(wgf).max())) and close(gr.cpu().numpy(), wgs, atol=1e-9)
+    # explicit (global) normaliser: a device tensor of per-page counts, e.g. the K1 by-product all-reduced
+    counts = torch.tensor([1000, 500], dtype=torch.int32, device="cuda")
+    losses2, gc2, _ = rn.detection_losses(t(y_reg), t(y_cls), t(r), t(p), normalizer=counts)
+    wf2, wgf2 = OL.focal()(y_cls, p, return_grad=True, normalizer=1500.0)
+    assert close(losses2.cpu().numpy()[0], wf2) and close(gc2.cpu().numpy(), wgf2, atol=1e-7 * float(np.abs(wgf2).max()))
+    # autograd wrapper
+    cp, rp = t(p).requires_grad_(), t(r).requires_grad_()
+    lf, ls = rn.detection_loss(t(y_reg), t(y_cls), rp, cp)
+    (lf + ls).backward()
+    assert close(cp.grad.cpu().numpy(), wgf, atol=1e-7 * float(np.abs(wgf).max())) and close(rp.grad.cpu().numpy(), wgs, atol=1e-9)
+
+
+def test_no_positive_and_nan_in_ignored_rows(rn):
+    """Normaliser is max(1, 0) = 1 with no positives; NaN predictions in ignored / non-positive rows do
+    not leak (TF gathers those rows away before any arithmetic)."""
+    y_cls, p, y_reg, r = make_case(40, 1, 1000, 1, p_pos=0.0)
+    ign = y_cls[0, :, -1] == -1
+    p[0, ign, 0] = np.nan
+    r[0, :, :] = np.nan
+    t = lambda a: torch.tensor(a, device="cuda")
+    losses, gc, gr = rn.detection_losses(t(y_reg), t(y_cls), t(r), t(p))
+    l = losses.cpu().numpy()
+    pm = np.where(ign[None, :, None], np.float32(0.5), p)
+    assert l[2] == 1.0 and l[1] == 0.0 and close(l[0], OL.focal()(y_cls, pm))
+    assert np.isfinite(gc.cpu().numpy()).all() and not gr.cpu().numpy().any()
+
+
+def test_full_size_properties(rn):
+    """Config-2 size (16 x 200,700 anchors): the loss is a sum over pages -> compare the full-batch result
+    with per-page launches sharing the same normaliser (linearity), and with the oracle on one page."""
+    B, N = 16, 200700
+    y_cls, p, y_reg, r = make_case(50, B, N, 1, p_ignore=0.01, p_pos=0.002, logit_mu=-4.6)
+    t = lambda a: torch.tensor(a, device="cuda")
+    Y_reg, Y_cls, R, P = t(y_reg), t(y_cls), t(r), t(p)
+    losses, gc, gr = rn.detection_losses(Y_reg, Y_cls, R, P)
+    total = losses.cpu().numpy()
+    norm = torch.tensor([total[2]], device="cuda")
+    acc = np.zeros(2)
+    for b in range(B):
+        lb, gcb, grb = rn.detection_losses(Y_reg[b:b + 1], Y_cls[b:b + 1], R[b:b + 1], P[b:b + 1], normalizer=norm)
+        acc += lb.cpu().numpy()[:2].astype(np.float64)
+        assert torch.equal(gcb[0], gc[b]) and torch.equal(grb[0], gr[b])
+    assert close(total[:2], acc, rtol=1e-5)
+    wl, wg = OL.focal()(y_cls[:1], p[:1], return_grad=True, normalizer=float(total[2]))
+    assert close(gc[0].cpu().numpy(), wg[0], atol=1e-7 * float(np.abs(wg).max()))

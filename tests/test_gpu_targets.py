@@ -1,0 +1,167 @@
+"""GPU parity, K1: CUDA path (through the C-ABI) vs the numpy oracle and the golden fixtures generated
+from the reference's own code.  Bar: BIT-EXACT (labels, states, argmax indices AND the float32 regression
+targets -- the fp64 pipeline is reproduced operation by operation)."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+import synthetic
+from oracle import anchors_np as O
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and a.dtype == b.dtype and a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("shape", [(800, 1333, 3), (1600, 2400, 3), (67, 93, 3), (1, 1, 3), (511, 513, 3)])
+def test_anchors_for_shape_bit_exact(rn, shape):
+    got = rn.anchors_for_shape(shape)
+    want = O.anchors_for_shape(shape)
+    assert got.dtype == np.float64 and same(np.asarray(got), want)
+
+
+def test_anchors_golden(rn, golden_numpy):
+    g = golden_numpy
+    a = np.asarray(rn.anchors_for_shape((800, 1333, 3)))
+    assert list(a.shape) == list(g['a800_shape']) and sha(a) == str(g['a800_sha'])
+    assert same(a[g['a800_rows_idx']], g['a800_rows'])
+    assert sha(np.asarray(rn.anchors_for_shape((1600, 2400, 3)))) == str(g['a1600_sha'])
+    custom = rn.AnchorParameters([24, 48, 100, 200, 400], [8, 16, 32, 64, 128],
+                                 np.array([0.3, 1, 2.5], np.float32), np.array([1, 1.3], np.float32))
+    assert same(np.asarray(rn.anchors_for_shape((70, 90, 3), anchor_params=custom)), g['custom_anchors'])
+    for size in (32, 64, 128, 256, 512):
+        assert same(rn.generate_anchors(size), g['base_%d' % size])
+
+
+def test_shift_and_shapes(rn):
+    base = O.generate_anchors(64)
+    assert same(rn.anchors.shift((5, 7), 16, base), O.shift((5, 7), 16, base))
+    got = rn.guess_shapes((800, 1333, 3), [3, 4, 5, 6, 7])
+    assert [tuple(int(v) for v in s) for s in got] == [(100, 167), (50, 84), (25, 42), (13, 21), (7, 11)]
+
+
+def test_compute_overlap_bit_exact(rn, golden_numpy):
+    g = golden_numpy
+    got = rn.compute_overlap(g['small_anchors'], g['overlap_gt'])
+    assert got.dtype == np.float32 and same(got, g['overlap_small'])
+    rs = np.random.RandomState(3)
+    a = O.anchors_for_shape((200, 300, 3))
+    gt = np.stack([rs.uniform(0, 150, 33), rs.uniform(0, 100, 33), rs.uniform(150, 300, 33), rs.uniform(100, 200, 33)], 1)
+    assert same(rn.compute_overlap(a, gt), O.compute_overlap(a, gt))
+    assert rn.compute_overlap(a, np.zeros((0, 4))).shape == (a.shape[0], 0)
+
+
+def test_small_batch_golden_full(rn, golden_numpy):
+    g = golden_numpy
+    anchors = rn.anchors_for_shape((67, 93, 3))
+    imgs = [synthetic.PageShape(s) for s in g['small_shapes']]
+    anns = [{'bboxes': g['small_gt_%d' % i], 'labels': g['small_gl_%d' % i]} for i in range(3)]
+    reg, lab, npos = rn.anchor_targets_bbox(anchors, imgs, anns, 3, return_npos=True)
+    assert same(reg, g['small_reg']) and same(lab, g['small_lab'])
+    assert list(npos) == [int((g['small_lab'][b, :, -1] == 1).sum()) for b in range(3)]
+    # explicit-anchor path (plain ndarray, no generation spec) gives the same bits
+    reg2, lab2 = rn.anchor_targets_bbox(np.array(anchors), imgs, anns, 3)
+    assert same(reg2, reg) and same(lab2, lab)
+
+
+def test_survey_pages_golden(rn, golden_numpy):
+    g = golden_numpy
+    anchors = rn.anchors_for_shape((800, 1333, 3))
+    page3 = {'bboxes': np.array([[100, 100, 600, 400], [50, 500, 700, 760], [800, 100, 1300, 300]], dtype=np.float64),
+             'labels': np.zeros(3)}
+    reg, lab = rn.anchor_targets_bbox(anchors, [synthetic.PageShape((800, 1333, 3))], [page3], 1)
+    st = lab[0, :, -1]
+    assert (st == 1).sum() == 66 and (st == -1).sum() == 943
+    assert np.array_equal(np.nonzero(st == 1)[0], g['page3_pos']) and np.array_equal(np.nonzero(st == -1)[0], g['page3_ign'])
+    assert sha(reg) == str(g['page3_reg_sha']) and sha(lab) == str(g['page3_lab_sha'])
+    pos, ign, amax = rn.compute_gt_annotations(anchors, page3['bboxes'])
+    assert amax.dtype == np.int64 and sha(amax.astype(np.int32)) == str(g['page3_argmax_sha'])
+    empty = {'bboxes': np.zeros((0, 4)), 'labels': np.zeros((0,))}
+    reg, lab = rn.anchor_targets_bbox(anchors, [synthetic.PageShape((800, 1333, 3))], [empty], 1)
+    assert (lab[0, :, -1] == -1).sum() == 792 and not reg[0, :, :4].any()
+    assert sha(reg) == str(g['empty_reg_sha']) and sha(lab) == str(g['empty_lab_sha'])
+
+
+@pytest.mark.parametrize("name", ["exact", "dup", "f32tie", "degenerate"])
+def test_tie_cases_golden(rn, golden_numpy, name):
+    """Threshold / tie semantics: IoU == 0.5 positive, IoU == 0.4 background, equal maxima
+    (also equal only after fp32 rounding) -> lowest GT index, zero-area GT."""
+    g = golden_numpy
+    anc, gt, gl = g['tie_%s_anchors' % name], g['tie_%s_gt' % name], g['tie_%s_gl' % name]
+    reg, lab = rn.anchor_targets_bbox(anc, [synthetic.PageShape((2000, 2000, 3))], [{'bboxes': gt, 'labels': gl}], 3)
+    assert same(reg, g['tie_%s_reg' % name]) and same(lab, g['tie_%s_lab' % name])
+    _, _, amax = rn.compute_gt_annotations(anc, gt)
+    assert np.array_equal(amax, g['tie_%s_argmax' % name])
+
+
+@pytest.mark.parametrize("cfg,batch,mixed", [(1, 1, False), (2, 3, True), (5, 1, False), (4, 1, False)])
+def test_synthetic_configs_golden_and_oracle(rn, golden_numpy, cfg, batch, mixed):
+    g = golden_numpy
+    c = synthetic.CONFIGS[cfg]
+    anchors = rn.anchors_for_shape(c['hw'] + (3,))
+    imgs, anns = synthetic.training_batch(cfg, batch=batch, mixed_widths=mixed, anchors=np.asarray(anchors))
+    reg, lab, npos = rn.anchor_targets_bbox(anchors, imgs, anns, c['classes'], return_npos=True)
+    assert sha(reg) == str(g['cfg%d_reg_sha' % cfg]) and sha(lab) == str(g['cfg%d_lab_sha' % cfg])
+    assert list(npos) == list(g['cfg%d_npos' % cfg])
+    assert same(reg[0, g['cfg%d_pos0' % cfg]], g['cfg%d_reg_pos0' % cfg])
+    if cfg in (1, 2):
+        oreg, olab = O.anchor_targets_bbox(np.asarray(anchors), imgs, anns, c['classes'])
+        assert same(reg, oreg) and same(lab, olab)
+
+
+def test_full_size_batch_vs_oracle_and_properties(rn):
+    """Config 2 at full size (16 pages, <= 20 GT): equality with the oracle on 4 pages and the
+    size-independent properties on all: state in {-1,0,1}, one-hot only on positives (or overridden
+    positives), npos == count(state == 1), device output == host output."""
+    c = synthetic.CONFIGS[2]
+    anchors = rn.anchors_for_shape(c['hw'] + (3,))
+    imgs, anns = synthetic.training_batch(2, anchors=np.asarray(anchors))
+    reg_t, lab_t, npos_t = rn.anchor_targets_bbox(anchors, imgs, anns, 1, output="torch", return_npos=True)
+    reg, lab = rn.anchor_targets_bbox(anchors, imgs, anns, 1)
+    assert same(reg_t.cpu().numpy(), reg) and same(lab_t.cpu().numpy(), lab)
+    st = lab[:, :, -1]
+    assert set(np.unique(st)) <= {-1.0, 0.0, 1.0} and same(st, reg[:, :, -1])
+    assert np.array_equal(npos_t.cpu().numpy(), (st == 1).sum(axis=1))
+    assert not lab[:, :, 0][(st == 0)].any()
+    oreg, olab = O.anchor_targets_bbox(np.asarray(anchors), imgs[:4], anns[:4], 1)
+    assert same(reg[:4], oreg) and same(lab[:4], olab)
+
+
+def test_many_gt_chunks_and_large_labels(rn):
+    """More GT boxes than one shared-memory chunk (256) and C = 7: exercises chunked culling + generic label rows."""
+    rs = np.random.RandomState(5)
+    anchors = rn.anchors_for_shape((300, 400, 3))
+    G = 700
+    x1 = rs.uniform(0, 350, G); y1 = rs.uniform(0, 250, G)
+    gt = np.stack([x1, y1, x1 + rs.uniform(5, 120, G), y1 + rs.uniform(5, 120, G)], 1)
+    ann = {'bboxes': gt, 'labels': rs.randint(0, 7, G).astype(np.float64)}
+    img = synthetic.PageShape((300, 390, 3))
+    reg, lab = rn.anchor_targets_bbox(anchors, [img], [ann], 7)
+    oreg, olab = O.anchor_targets_bbox(np.asarray(anchors), [img], [ann], 7)
+    assert same(reg, oreg) and same(lab, olab)
+
+
+def test_bbox_transform_and_errors(rn):
+    rs = np.random.RandomState(9)
+    a = O.anchors_for_shape((64, 64, 3))
+    g = a + rs.normal(0, 3, a.shape)
+    assert same(rn.bbox_transform(a, g), O.bbox_transform(a, g))
+    assert same(rn.bbox_transform(a, g, mean=[0.1, 0, 0, 0], std=(0.1, 0.1, 0.2, 0.2)),
+                O.bbox_transform(a, g, mean=[0.1, 0, 0, 0], std=(0.1, 0.1, 0.2, 0.2)))
+    with pytest.raises(ValueError):
+        rn.bbox_transform(a, g, mean=0.0)
+    with pytest.raises(ValueError):
+        rn.bbox_transform(a, g, std="x")
+    with pytest.raises(AssertionError):
+        rn.anchor_targets_bbox(a, [synthetic.PageShape((64, 64, 3))], [], 1)
+    with pytest.raises(AssertionError):
+        rn.anchor_targets_bbox(a, [synthetic.PageShape((64, 64, 3))], [{'bboxes': np.zeros((0, 4))}], 1)
