@@ -10,6 +10,14 @@
 //   anchors fp64 (base + centre, one rounding)  ->  IoU fp64  ->  rounded to fp32  ->
 //   strict-greater argmax on fp32  ->  fp32 threshold compares  ->  bbox_transform fp64 -> fp32.
 // The file is compiled with -fmad=false so no multiply-add is contracted.
+//
+// fp64 divisions are the expensive part (B200 issues fp64 at half rate and a correctly rounded divide is
+// ~20 instructions).  Every quotient on this path is only ever consumed after rounding to fp32, so each is
+// first computed with a fast reciprocal (hardware approximation + 2 Newton steps, relative error < 2^-45)
+// and accepted when its fp32 rounding cannot depend on that error: the 29 mantissa bits dropped by the
+// fp64->fp32 conversion must be further than 2^16 fp64-ulps from the rounding midpoint.  Otherwise
+// (probability ~2.4e-4 per value) the exact IEEE expression of the reference is evaluated.  The result is
+// bit-identical to always dividing.
 #include "rn_common.cuh"
 
 namespace {
@@ -64,11 +72,39 @@ __device__ __forceinline__ void make_anchor(const RnLevels& lv, const double* ba
     y2 = __ldg(b + 3) + sy;
 }
 
+// reciprocal with relative error < 2^-45 for positive normal x (garbage in -> rejected by the check below)
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));     // ~20 good bits
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);                                          // ~40
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);                                       // ~52
+}
+
+// v approximates (to < 2^-45 relative) a value that the reference rounds to fp32: true when the fp32
+// rounding of v is guaranteed to equal the fp32 rounding of the exact value
+__device__ __forceinline__ bool f32_rounding_safe(double v) {
+    const long long b = __double_as_longlong(v);
+    const int e = (int)((b >> 52) & 0x7ff);                    // biased exponent; fp32 normals need >= 897
+    const int dist = abs((int)(b & 0x1fffffff) - (1 << 28));   // 29 dropped bits vs the rounding midpoint
+    return (e >= 900) && (e <= 1140) && (dist > (1 << 16));
+}
+
+// one regression target: ((g - a) / len) / 0.2 rounded to fp32 (model/anchors.py:300-311)
+__device__ __forceinline__ float reg_target(double g, double a, double len, double rlen) {
+    const double d = g - a;
+    if (d == 0.0) return (float)((d / len) / 0.2);            // exact zero (sign kept); no fast path needed
+    const double approx = (d * rlen) * 5.0;
+    if (f32_rounding_safe(approx)) return (float)approx;
+    return (float)((d / len) / 0.2);
+}
+
 template <bool EXPLICIT>
 __global__ void __launch_bounds__(K1_THREADS) k_anchor_targets(const K1Params p) {
     __shared__ double s_gx1[K1_THREADS], s_gy1[K1_THREADS], s_gx2[K1_THREADS], s_gy2[K1_THREADS], s_ga[K1_THREADS];
     __shared__ int s_gidx[K1_THREADS];
-    __shared__ double s_red[K1_WARPS][4];
+    __shared__ float s_red[K1_WARPS][4];
     __shared__ int s_wcount[K1_WARPS];
     __shared__ float s_reg[K1_THREADS * 5];
     __shared__ float s_state[K1_THREADS];
@@ -98,21 +134,22 @@ __global__ void __launch_bounds__(K1_THREADS) k_anchor_targets(const K1Params p)
     const double aw = ax2 - ax1, ah = ay2 - ay1;
     const double area_a = aw * ah;
 
-    // ---- tile bounding box (warp shuffles, then across warps through smem) -------------------
+    // ---- tile bounding box: fp32 with outward rounding (conservative), warp shuffles then smem ----
     {
-        const double inf = __longlong_as_double(0x7ff0000000000000ll);
-        double mnx = rn_warp_min(valid ? ax1 : inf), mny = rn_warp_min(valid ? ay1 : inf);
-        double mxx = rn_warp_max(valid ? ax2 : -inf), mxy = rn_warp_max(valid ? ay2 : -inf);
+        const float inf = __int_as_float(0x7f800000);
+        const float mnx = rn_warp_min(valid ? __double2float_rd(ax1) : inf), mny = rn_warp_min(valid ? __double2float_rd(ay1) : inf);
+        const float mxx = rn_warp_max(valid ? __double2float_ru(ax2) : -inf), mxy = rn_warp_max(valid ? __double2float_ru(ay2) : -inf);
         if (lane == 0) { s_red[warp][0] = mnx; s_red[warp][1] = mny; s_red[warp][2] = mxx; s_red[warp][3] = mxy; }
         if (tid == 0) s_npos = 0;
     }
     __syncthreads();
-    double tx1 = s_red[0][0], ty1 = s_red[0][1], tx2 = s_red[0][2], ty2 = s_red[0][3];
+    float fx1 = s_red[0][0], fy1 = s_red[0][1], fx2 = s_red[0][2], fy2 = s_red[0][3];
 #pragma unroll
     for (int w = 1; w < K1_WARPS; ++w) {
-        tx1 = fmin(tx1, s_red[w][0]); ty1 = fmin(ty1, s_red[w][1]);
-        tx2 = fmax(tx2, s_red[w][2]); ty2 = fmax(ty2, s_red[w][3]);
+        fx1 = fminf(fx1, s_red[w][0]); fy1 = fminf(fy1, s_red[w][1]);
+        fx2 = fmaxf(fx2, s_red[w][2]); fy2 = fmaxf(fy2, s_red[w][3]);
     }
+    const double tx1 = (double)fx1, ty1 = (double)fy1, tx2 = (double)fx2, ty2 = (double)fy2;
 
     // ---- IoU / argmax over the GT tables that can touch this tile ----------------------------
     float best = 0.0f;     // an all-zero IoU row has argmax 0 (numpy first-max)
@@ -149,7 +186,8 @@ __global__ void __launch_bounds__(K1_THREADS) k_anchor_targets(const K1Params p)
                 if (iw > 0.0 && ih > 0.0) {
                     const double inter = iw * ih;
                     const double uni = area_a + s_ga[m] - inter;
-                    const float iou = (float)(inter / uni);      // fp64 divide, then round to fp32
+                    const double q = inter * rcp_fast(uni);
+                    const float iou = f32_rounding_safe(q) ? (float)q : (float)(inter / uni);   // == (float)(inter / uni)
                     if (iou > best) { best = iou; arg = s_gidx[m]; }
                 }
             }
@@ -167,10 +205,11 @@ __global__ void __launch_bounds__(K1_THREADS) k_anchor_targets(const K1Params p)
             state = is_pos ? 1.0f : (is_ign ? -1.0f : 0.0f);
             if (is_pos) hot = __ldg(p.gt_labels + (size_t)b * p.Gmax + arg);
             const double* g = gtb + 4 * (size_t)arg;
-            t0 = (float)(((__ldg(g + 0) - ax1) / aw) / 0.2);
-            t1 = (float)(((__ldg(g + 1) - ay1) / ah) / 0.2);
-            t2 = (float)(((__ldg(g + 2) - ax2) / aw) / 0.2);
-            t3 = (float)(((__ldg(g + 3) - ay2) / ah) / 0.2);
+            const double rw = rcp_fast(aw), rh = rcp_fast(ah);
+            t0 = reg_target(__ldg(g + 0), ax1, aw, rw);
+            t1 = reg_target(__ldg(g + 1), ay1, ah, rh);
+            t2 = reg_target(__ldg(g + 2), ax2, aw, rw);
+            t3 = reg_target(__ldg(g + 3), ay2, ah, rh);
         }
         if (p.img_hw) {
             const double ccx = (ax1 + ax2) / 2.0, ccy = (ay1 + ay2) / 2.0;

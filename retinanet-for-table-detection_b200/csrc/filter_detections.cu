@@ -24,7 +24,7 @@
 namespace {
 
 constexpr int K3_THREADS = 256;
-constexpr int NMS_THREADS = 512;
+constexpr int NMS_THREADS = 1024;
 constexpr int NMS_WARPS = NMS_THREADS / 32;
 constexpr int NMS_CHUNK = 2048;    // candidates ordered per radix-select round
 constexpr int NMS_BATCH = 256;     // candidates resolved per bit-matrix
@@ -66,6 +66,8 @@ struct K3Params {
     int B, N, C;
     int class_specific;
     float thr;
+    float inv_c;           // 1 / C for rn_div
+    int vec_ok;            // page rows of `cls` are 16-byte aligned
     Slabs sl;
 };
 
@@ -92,18 +94,10 @@ __device__ __forceinline__ float4 candidate_box(const K3Params& p, int b, int n)
     return o;
 }
 
-// append (key, box[, label]) to slab `seg`; one atomic per group of lanes that share the segment
+// write one candidate into slot `slot` of slab `seg` (dropped when the slab is full; the count keeps
+// growing so the overflow is detected by k_segment_nms)
 template <bool DECODE>
-__device__ __forceinline__ void emit(const K3Params& p, bool is_cand, int seg, int b, int n, float score, int label) {
-    const unsigned cand = __ballot_sync(0xffffffffu, is_cand);
-    if (!is_cand) return;
-    const unsigned peers = __match_any_sync(cand, seg);
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(peers) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(p.sl.counts + seg, __popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    const long long slot = base + __popc(peers & ((1u << lane) - 1u));
+__device__ __forceinline__ void put(const K3Params& p, int seg, long long slot, int b, int n, float score, int label) {
     if (slot < p.sl.cap) {
         const size_t at = (size_t)seg * p.sl.cap + slot;
         p.sl.keys[at] = make_key(score, (unsigned)n);
@@ -112,57 +106,68 @@ __device__ __forceinline__ void emit(const K3Params& p, bool is_cand, int seg, i
     }
 }
 
+// grid = (tiles of a page, pages): no division is needed to find the page, and when C == 1 every lane of
+// a warp feeds the same slab, so a warp needs ONE atomic: per-thread candidate counts are prefix-summed
+// with shuffles and the warp's total reserves a contiguous slot range.
 template <bool DECODE>
 __global__ void __launch_bounds__(K3_THREADS) k_threshold_compact(const K3Params p) {
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
     if (p.class_specific) {
-        // flat over (b, n, c); 4 consecutive elements per thread, 128-bit loads
-        const long long total = (long long)p.B * p.N * p.C;
-        const long long groups = (total + 3) >> 2;
-        const long long iters = (groups + (long long)gridDim.x * K3_THREADS - 1) / ((long long)gridDim.x * K3_THREADS);
-        for (long long it = 0; it < iters; ++it) {              // uniform trip count: emit() uses full-warp ballots
-            const long long q = (it * gridDim.x + blockIdx.x) * (long long)K3_THREADS + threadIdx.x;
-            const long long e0 = q << 2;
-            float sv[4] = {0.f, 0.f, 0.f, 0.f};
-            int cnt = 0;
-            if (q < groups) {
-                cnt = (int)min(4ll, total - e0);
-                if (cnt == 4) { const float4 v = rn_ldg_stream4(p.cls + e0); sv[0] = v.x; sv[1] = v.y; sv[2] = v.z; sv[3] = v.w; }
-                else for (int k = 0; k < cnt; ++k) sv[k] = __ldg(p.cls + e0 + k);
-            }
+        // 4 consecutive elements of the page's (N, C) score matrix per thread
+        const int total = p.N * p.C;                             // < 2^31 (checked on the host)
+        const int e0 = (blockIdx.x * K3_THREADS + threadIdx.x) * 4;
+        const float* src = p.cls + (size_t)b * total;
+        float sv[4] = {0.f, 0.f, 0.f, 0.f};
+        const int cnt = max(0, min(4, total - e0));
+        if (cnt == 4 && p.vec_ok) { const float4 v = rn_ldg_stream4(src + e0); sv[0] = v.x; sv[1] = v.y; sv[2] = v.z; sv[3] = v.w; }
+        else for (int k = 0; k < cnt; ++k) sv[k] = __ldg(src + e0 + k);
+        unsigned m = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (k < cnt && sv[k] > p.thr) m |= 1u << k;
+        if (p.C == 1) {
+            const int mine = __popc(m);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+            if (warp_total == 0) return;
+            int base = 0;
+            if (lane == 31) base = atomicAdd(p.sl.counts + b, warp_total);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            long long slot = base + (incl - mine);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (m & (1u << k)) put<DECODE>(p, b, slot++, b, e0 + k, sv[k], 0);
+        } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const bool is_cand = (k < cnt) && (sv[k] > p.thr);
-                int seg = 0, b = 0, n = 0, c = 0;
-                if (is_cand) {
-                    const long long e = e0 + k;
-                    const long long row = e / p.C;
-                    c = (int)(e - row * p.C);
-                    b = (int)(row / p.N);
-                    n = (int)(row - (long long)b * p.N);
-                    seg = b * p.C + c;
+                if (m & (1u << k)) {
+                    const int e = e0 + k;
+                    const int n = rn_div(e, p.C, p.inv_c);
+                    const int c = e - n * p.C;
+                    const int seg = b * p.C + c;
+                    put<DECODE>(p, seg, atomicAdd(p.sl.counts + seg, 1), b, n, sv[k], c);
                 }
-                emit<DECODE>(p, is_cand, seg, b, n, sv[k], c);
             }
         }
     } else {
         // class-agnostic: score = max over classes, label = first argmax (model/layers.py:234-235)
-        const long long total = (long long)p.B * p.N;
-        const long long iters = (total + (long long)gridDim.x * K3_THREADS - 1) / ((long long)gridDim.x * K3_THREADS);
-        for (long long it = 0; it < iters; ++it) {
-            const long long row = (it * gridDim.x + blockIdx.x) * (long long)K3_THREADS + threadIdx.x;
-            bool is_cand = false;
-            float best = 0.f;
-            int label = 0, b = 0, n = 0;
-            if (row < total) {
-                const float* s = p.cls + row * p.C;
-                best = __ldg(s);
-                for (int c = 1; c < p.C; ++c) { const float v = __ldg(s + c); if (v > best) { best = v; label = c; } }
-                b = (int)(row / p.N);
-                n = (int)(row - (long long)b * p.N);
-                is_cand = best > p.thr;
-            }
-            emit<DECODE>(p, is_cand, b, b, n, best, label);
+        const int n = blockIdx.x * K3_THREADS + threadIdx.x;
+        bool is_cand = false;
+        float best = 0.f;
+        int label = 0;
+        if (n < p.N) {
+            const float* s = p.cls + ((size_t)b * p.N + n) * p.C;
+            best = __ldg(s);
+            for (int c = 1; c < p.C; ++c) { const float v = __ldg(s + c); if (v > best) { best = v; label = c; } }
+            is_cand = best > p.thr;
         }
+        const unsigned bal = __ballot_sync(0xffffffffu, is_cand);
+        if (bal == 0) return;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(p.sl.counts + b, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (is_cand) put<DECODE>(p, b, base + __popc(bal & ((1u << lane) - 1u)), b, n, best, label);
     }
 }
 
@@ -187,15 +192,28 @@ struct NmsParams {
 };
 
 // TF non_max_suppression_op.cc IOU on corner-normalised boxes with precomputed areas
+// Exact fast rejects first (they never change the outcome): a non-positive area or an empty intersection
+// gives IoU 0; and since IoU <= min(area)/max(area), boxes whose areas differ by more than the threshold
+// allows (0.1 % safety margin over fp32 rounding) cannot exceed it.  Only the remaining pairs pay the divide.
 __device__ __forceinline__ bool iou_exceeds(const float4 a, const float aa, const float4 b, const float ab, const float thr) {
-    float iou = 0.0f;
-    if (aa > 0.0f && ab > 0.0f) {
-        const float iw = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.0f);
-        const float ih = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.0f);
-        const float inter = iw * ih;
-        iou = inter / (aa + ab - inter);
+    if (thr < 0.0f) {                       // degenerate threshold: fall back to the plain formula
+        float iou = 0.0f;
+        if (aa > 0.0f && ab > 0.0f) {
+            const float iw = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.0f);
+            const float ih = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.0f);
+            const float inter = iw * ih;
+            iou = inter / (aa + ab - inter);
+        }
+        return iou > thr;
     }
-    return iou > thr;
+    if (!(aa > 0.0f && ab > 0.0f)) return false;
+    if (fminf(aa, ab) < thr * fmaxf(aa, ab) * 0.999f) return false;
+    const float iw = fminf(a.z, b.z) - fmaxf(a.x, b.x);
+    if (!(iw > 0.0f)) return false;
+    const float ih = fminf(a.w, b.w) - fmaxf(a.y, b.y);
+    if (!(ih > 0.0f)) return false;
+    const float inter = iw * ih;
+    return inter / (aa + ab - inter) > thr;
 }
 
 __global__ void __launch_bounds__(NMS_THREADS) k_segment_nms(const NmsParams p) {
@@ -568,11 +586,14 @@ int filter_common(K3Params kp, bool decode, int nms, float nms_thr, int max_det,
         if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
     }
     kp.sl.counts = w.counts; kp.sl.keys = w.keys; kp.sl.boxes = w.boxes; kp.sl.labels = w.labels; kp.sl.cap = cand_cap;
-    const long long units = kp.class_specific ? ((long long)B * kp.N * C + 3) / 4 : (long long)B * kp.N;
-    long long blocks = (units + K3_THREADS - 1) / K3_THREADS;
-    if (blocks > (long long)RN_NUM_SMS * 8) blocks = (long long)RN_NUM_SMS * 8;
-    if (decode) k_threshold_compact<true><<<(int)blocks, K3_THREADS, 0, s>>>(kp);
-    else k_threshold_compact<false><<<(int)blocks, K3_THREADS, 0, s>>>(kp);
+    RN_REQUIRE((long long)kp.N * C < (1ll << 31) - 4096, "N * C too large for one page");
+    RN_REQUIRE(B <= 65535, "B must be <= 65535");
+    kp.inv_c = 1.0f / (float)C;
+    kp.vec_ok = (((long long)kp.N * C) % 4 == 0) ? 1 : 0;
+    const long long units = kp.class_specific ? ((long long)kp.N * C + 3) / 4 : (long long)kp.N;
+    const dim3 grid((unsigned)((units + K3_THREADS - 1) / K3_THREADS), (unsigned)B);
+    if (decode) k_threshold_compact<true><<<grid, K3_THREADS, 0, s>>>(kp);
+    else k_threshold_compact<false><<<grid, K3_THREADS, 0, s>>>(kp);
     int rc = rn_check_launch("k_threshold_compact");
     if (rc) return rc;
     return run_back_end(w, B, S, spp, cand_cap, 0, nullptr, nms, nms_thr, max_det, pre_nms_top_k,

@@ -41,6 +41,8 @@ struct RnLevels {
     int w[RN_MAX_LEVELS];
     int stride[RN_MAX_LEVELS];
     int start[RN_MAX_LEVELS + 1];   // first anchor index of each level; start[num_levels] = N
+    float inv_w[RN_MAX_LEVELS];     // 1 / w[l], for the float-assisted exact integer division below
+    float inv_a;                    // 1 / anchors_per_cell
 };
 
 static inline int rn_make_levels(RnLevels* t, const int* level_hw, const int* level_stride,
@@ -51,18 +53,31 @@ static inline int rn_make_levels(RnLevels* t, const int* level_hw, const int* le
     t->num_levels = num_levels;
     t->anchors_per_cell = anchors_per_cell;
     long long n = 0;
-    for (int l = 0; l < RN_MAX_LEVELS; ++l) { t->h[l] = 0; t->w[l] = 0; t->stride[l] = 1; t->start[l] = 0; }
+    for (int l = 0; l < RN_MAX_LEVELS; ++l) { t->h[l] = 0; t->w[l] = 0; t->stride[l] = 1; t->start[l] = 0; t->inv_w[l] = 1.0f; }
+    t->inv_a = 1.0f / (float)anchors_per_cell;
     for (int l = 0; l < num_levels; ++l) {
         RN_REQUIRE(level_hw[2 * l] >= 0 && level_hw[2 * l + 1] >= 0 && level_stride[l] > 0, "bad level %d", l);
         t->h[l] = level_hw[2 * l];
         t->w[l] = level_hw[2 * l + 1];
         t->stride[l] = level_stride[l];
+        t->inv_w[l] = t->w[l] > 0 ? 1.0f / (float)t->w[l] : 1.0f;
         t->start[l] = (int)n;
         n += (long long)t->h[l] * t->w[l] * anchors_per_cell;
         RN_REQUIRE(n < (1ll << 31), "too many anchors per page");
     }
     for (int l = num_levels; l <= RN_MAX_LEVELS; ++l) t->start[l] = (int)n;
     return RN_OK;
+}
+
+// exact r / d for 0 <= r, d > 0: float estimate (inv = 1/d) + one correction step; the estimate is within
+// +-1 of the quotient while r < 2^24, a hardware integer division is used beyond that
+__device__ __forceinline__ int rn_div(int r, int d, float inv) {
+    if (r >= (1 << 24)) return r / d;
+    int q = (int)((float)r * inv);
+    const int rem = r - q * d;
+    if (rem < 0) --q;
+    else if (rem >= d) ++q;
+    return q;
 }
 
 // anchor index -> (level, cell x, cell y, anchor-in-cell).  Order: level-major, then y, x, a
@@ -72,10 +87,10 @@ __device__ __forceinline__ void rn_locate(const RnLevels& t, int n, int& level, 
 #pragma unroll
     for (int l = 1; l < RN_MAX_LEVELS; ++l)
         if (l < t.num_levels && n >= t.start[l]) level = l;
-    int r = n - t.start[level];
-    int cell = r / t.anchors_per_cell;
+    const int r = n - t.start[level];
+    const int cell = rn_div(r, t.anchors_per_cell, t.inv_a);
     a = r - cell * t.anchors_per_cell;
-    cy = cell / t.w[level];
+    cy = rn_div(cell, t.w[level], t.inv_w[level]);
     cx = cell - cy * t.w[level];
 }
 
@@ -88,14 +103,14 @@ __device__ __forceinline__ T rn_warp_sum(T v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ __forceinline__ double rn_warp_min(double v) {
+__device__ __forceinline__ float rn_warp_min(float v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ double rn_warp_max(double v) {
+__device__ __forceinline__ float rn_warp_max(float v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
 

@@ -145,6 +145,8 @@ class ClipBoxes(_Layer):
 def _gather_other(other, indices, max_detections):
     """``other`` tensors follow the selected anchors (model/layers.py:247,255): gather + pad with -1."""
     outs = []
+    if not other:
+        return outs
     valid = indices >= 0
     safe = indices.clamp(min=0).long()
     for o in other:
