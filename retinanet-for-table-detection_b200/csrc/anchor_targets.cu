@@ -42,21 +42,35 @@ struct K1Params {
     int* npos;               // (B) or nullptr
     float* npos_total;       // 1 float or nullptr
     int vec_ok;
+    double max_coord;        // upper bound of any anchor-centre coordinate (for the reciprocal table, see wrapper)
 };
 
 // cooperative store of `len` floats starting at element `start` of `base`; 128-bit where aligned
-template <int THREADS, typename Gen>
-__device__ __forceinline__ void store_range(float* base, long long start, int len, bool vec_ok, Gen gen) {
+template <typename Gen>
+__device__ __forceinline__ void store_range(float* base, long long start, int len, bool vec_ok, int nthreads, Gen gen) {
     float* p = base + start;
     int head = vec_ok ? (int)((4 - (start & 3)) & 3) : len;
     if (head > len) head = len;
-    for (int i = threadIdx.x; i < head; i += THREADS) p[i] = gen(i);
+#pragma unroll 1
+    for (int i = threadIdx.x; i < head; i += nthreads) p[i] = gen(i);
     const int nvec = (len - head) >> 2;
-    for (int v = threadIdx.x; v < nvec; v += THREADS) {
+#pragma unroll 1
+    for (int v = threadIdx.x; v < nvec; v += nthreads) {
         const int i = head + 4 * v;
         rn_stg_stream4(p + i, make_float4(gen(i), gen(i + 1), gen(i + 2), gen(i + 3)));
     }
-    for (int i = head + 4 * nvec + threadIdx.x; i < len; i += THREADS) p[i] = gen(i);
+#pragma unroll 1
+    for (int i = head + 4 * nvec + threadIdx.x; i < len; i += nthreads) p[i] = gen(i);
+}
+
+// labels rows of C+1 floats (one-hot + state) for `cnt` anchors starting at row `row0`, any C
+__device__ __noinline__ void store_labels_generic(float* lab, long long row0, int cnt, int C, bool vec_ok, int nthreads,
+                                                  const float* s_state, const int* s_hot) {
+    const int CW = C + 1;
+    store_range(lab, row0 * CW, cnt * CW, vec_ok, nthreads, [&](int i) {
+        const int r = i / CW, c = i - r * CW;
+        return c == C ? s_state[r] : (c == s_hot[r] ? 1.0f : 0.0f);
+    });
 }
 
 __device__ __forceinline__ void make_anchor(const RnLevels& lv, const double* base, int n,
@@ -91,13 +105,26 @@ __device__ __forceinline__ bool f32_rounding_safe(double v) {
     return (e >= 900) && (e <= 1140) && (dist > (1 << 16));
 }
 
+// The exact IEEE expressions of the reference.  Rarely executed and deliberately NOT inlined: a correctly
+// rounded fp64 divide is ~100 SASS lines per site, and inlining it at every use made the kernels larger
+// than the instruction cache (ncu: 40 % of stall samples were "no instruction").
+__device__ __noinline__ float reg_target_exact(double d, double len) { return (float)((d / len) / 0.2); }
+__device__ __noinline__ float iou_exact(double inter, double uni) { return (float)(inter / uni); }
+
+// same with the reciprocal pre-multiplied by 5 (r5 ~ 5/len to < 2^-40 relative)
+__device__ __forceinline__ float reg_target5(double g, double a, double len, double r5) {
+    const double d = g - a;
+    const double approx = d * r5;
+    if (d != 0.0 && f32_rounding_safe(approx)) return (float)approx;
+    return reg_target_exact(d, len);
+}
+
 // one regression target: ((g - a) / len) / 0.2 rounded to fp32 (model/anchors.py:300-311)
 __device__ __forceinline__ float reg_target(double g, double a, double len, double rlen) {
     const double d = g - a;
-    if (d == 0.0) return (float)((d / len) / 0.2);            // exact zero (sign kept); no fast path needed
     const double approx = (d * rlen) * 5.0;
-    if (f32_rounding_safe(approx)) return (float)approx;
-    return (float)((d / len) / 0.2);
+    if (d != 0.0 && f32_rounding_safe(approx)) return (float)approx;
+    return reg_target_exact(d, len);                          // also the exact (signed) zero
 }
 
 template <bool EXPLICIT>
@@ -187,7 +214,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_anchor_targets(const K1Params p)
                     const double inter = iw * ih;
                     const double uni = area_a + s_ga[m] - inter;
                     const double q = inter * rcp_fast(uni);
-                    const float iou = f32_rounding_safe(q) ? (float)q : (float)(inter / uni);   // == (float)(inter / uni)
+                    const float iou = f32_rounding_safe(q) ? (float)q : iou_exact(inter, uni);   // == (float)(inter / uni)
                     if (iou > best) { best = iou; arg = s_gidx[m]; }
                 }
             }
@@ -233,229 +260,188 @@ __global__ void __launch_bounds__(K1_THREADS) k_anchor_targets(const K1Params p)
 
     // ---- coalesced write-out ------------------------------------------------------------------
     const long long row0 = (long long)b * p.N + n0;
-    store_range<K1_THREADS>(p.reg, row0 * 5, cnt * 5, p.vec_ok != 0, [&](int i) { return s_reg[i]; });
-    const int CW = p.C + 1;
+    store_range(p.reg, row0 * 5, cnt * 5, p.vec_ok != 0, K1_THREADS, [&](int i) { return s_reg[i]; });
     if (p.C == 1) {
         if (valid) {
             float2 v = make_float2(hot == 0 ? 1.0f : 0.0f, state);
             reinterpret_cast<float2*>(p.lab)[row0 + tid] = v;
         }
     } else {
-        store_range<K1_THREADS>(p.lab, row0 * CW, cnt * CW, p.vec_ok != 0, [&](int i) {
-            const int r = i / CW, c = i - r * CW;
-            return c == p.C ? s_state[r] : (c == s_hot[r] ? 1.0f : 0.0f);
-        });
+        store_labels_generic(p.lab, row0, cnt, p.C, p.vec_ok != 0, K1_THREADS, s_state, s_hot);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1, generated anchors, A anchors per cell known at compile time: one thread per CELL.
+// K1 for generated anchors: a WARP owns 32 consecutive cells and ONE anchor type.
 //
-// The A anchors of a cell share their centre, so everything that only depends on the cell is done once
-// per A anchors: locating the cell, the border rule pre-test, and -- the big one -- the GT overlap tests:
-// a GT is first tested against the cell's hull (exactly min/max over the A anchors, because rounding is
-// monotonic: RN(min_a(b) + s) = min_a RN(b + s)); only GT tables that touch the hull are then tested
-// against the individual anchors.  Arithmetic per anchor is identical to k_anchor_targets.
+// thread (warp w, lane) -> cell = c0 + (w / A) * 32 + lane, anchor-in-cell a = w % A.  Every lane of a warp
+// therefore uses the same base box (and the same 5/width, 5/height table entry), consecutive lanes are
+// consecutive cells of a feature-map row, and the warp's bounding box is tight: the page's GT tables are
+// staged once per CTA (unculled, in GT order) and each warp culls them against its own box with one
+// ballot per 32 tables, then walks the surviving bits in order -- warp-uniform control flow, the exact
+// per-anchor test only for tables that can actually touch the warp.  Arithmetic per anchor is identical
+// to k_anchor_targets; results are staged in shared memory in the reference's anchor order
+// (cell-major, anchor-minor) and written with 128-bit stores.
 // ------------------------------------------------------------------------------------------------
-constexpr int KC_THREADS = 128;
-constexpr int KC_WARPS = KC_THREADS / 32;
-constexpr int KC_CHUNK = 64;          // GT tables staged per round (one 64-bit hit mask per cell)
+constexpr int KW_MAX_ANCHORS = 768;   // anchors per CTA: 32 cells * (cell groups) * A
+constexpr int KW_MAX_THREADS = 768;
+constexpr int KW_CHUNK = 256;         // GT tables staged per round
 
-template <int A>
-__global__ void __launch_bounds__(KC_THREADS) k_anchor_targets_cells(const K1Params p) {
-    __shared__ double s_base[RN_MAX_LEVELS * A * 4];
-    __shared__ double s_hull[RN_MAX_LEVELS][4];
-    __shared__ double s_gx1[KC_CHUNK], s_gy1[KC_CHUNK], s_gx2[KC_CHUNK], s_gy2[KC_CHUNK], s_ga[KC_CHUNK];
-    __shared__ int s_gidx[KC_CHUNK];
-    __shared__ float s_red[KC_WARPS][4];
-    __shared__ int s_wcount[2];
-    __shared__ float s_reg[KC_THREADS * A * 5];
-    __shared__ float s_state[KC_THREADS * A];
-    __shared__ int s_hot[KC_THREADS * A];
+__global__ void __launch_bounds__(KW_MAX_THREADS) k_anchor_targets_warpcells(const K1Params p, const int groups) {
+    __shared__ double s_base[RN_MAX_LEVELS * 32 * 4];      // A <= 24 here
+    __shared__ double s_r5[RN_MAX_LEVELS * 32 * 2];        // ~5/width, ~5/height per (level, a)
+    __shared__ double s_gx1[KW_CHUNK], s_gy1[KW_CHUNK], s_gx2[KW_CHUNK], s_gy2[KW_CHUNK], s_ga[KW_CHUNK];
+    __shared__ float s_reg[KW_MAX_ANCHORS * 5];
+    __shared__ float s_state[KW_MAX_ANCHORS];
+    __shared__ int s_hot[KW_MAX_ANCHORS];
     __shared__ int s_npos;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = blockDim.x;
+    const int A = p.lv.anchors_per_cell, L = p.lv.num_levels;
     const int b = blockIdx.y;
-    const int L = p.lv.num_levels;
-    for (int i = tid; i < L * A * 4; i += KC_THREADS) s_base[i] = __ldg(p.base + i);
+    for (int i = tid; i < L * A * 4; i += nthreads) s_base[i] = __ldg(p.base + i);
     if (tid == 0) s_npos = 0;
     __syncthreads();
-    if (tid < L) {
-        double x1 = s_base[tid * A * 4], y1 = s_base[tid * A * 4 + 1], x2 = s_base[tid * A * 4 + 2], y2 = s_base[tid * A * 4 + 3];
-        for (int a = 1; a < A; ++a) {
-            const double* q = s_base + (tid * A + a) * 4;
-            x1 = fmin(x1, q[0]); y1 = fmin(y1, q[1]); x2 = fmax(x2, q[2]); y2 = fmax(y2, q[3]);
-        }
-        s_hull[tid][0] = x1; s_hull[tid][1] = y1; s_hull[tid][2] = x2; s_hull[tid][3] = y2;
+    for (int i = tid; i < L * A; i += nthreads) {
+        // 5/width, 5/height of the base box stand in for the anchor's own (they differ by rounding only)
+        // when that difference is far inside the fast path's tolerance; 0 = compute per anchor
+        const double w = s_base[4 * i + 2] - s_base[4 * i], h = s_base[4 * i + 3] - s_base[4 * i + 1];
+        const bool ok = (w > 0.0) && (h > 0.0) && (p.max_coord < 4096.0 * fmin(w, h));
+        s_r5[2 * i] = ok ? 5.0 * rcp_fast(w) : 0.0;
+        s_r5[2 * i + 1] = ok ? 5.0 * rcp_fast(h) : 0.0;
     }
-    __syncthreads();
 
     const int cells_total = p.N / A;
-    const int c0 = blockIdx.x * KC_THREADS;
-    const int ncell = min(KC_THREADS, cells_total - c0);
-    const bool valid = tid < ncell;
-    const int gc = c0 + tid;
+    const int cells_per_cta = 32 * groups;
+    const int c0 = blockIdx.x * cells_per_cta;
+    const int ncell = min(cells_per_cta, cells_total - c0);
+    const int grp = warp / A, a = warp - grp * A;          // warp-uniform
+    const int lc = grp * 32 + lane;                        // cell within the CTA
+    const bool valid = lc < ncell;
+    const int gc = c0 + lc;
     int G = p.gt_count[b];
     G = max(0, min(G, p.Gmax));
 
-    // ---- this thread's cell -----------------------------------------------------------------------
+    // ---- this thread's anchor ------------------------------------------------------------------------
     int level = 0;
-    double sx = 0, sy = 0, hx1 = 0, hy1 = 0, hx2 = 0, hy2 = 0;
+    double ax1 = 0, ay1 = 0, ax2 = 0, ay2 = 0;
     if (valid) {
 #pragma unroll
         for (int l = 1; l < RN_MAX_LEVELS; ++l)
             if (l < L && gc * A >= p.lv.start[l]) level = l;
-        const int r = gc - p.lv.start[level] / A;
+        const int r = gc - rn_div(p.lv.start[level], A, p.lv.inv_a);
         const int cy = rn_div(r, p.lv.w[level], p.lv.inv_w[level]);
         const int cx = r - cy * p.lv.w[level];
-        sx = ((double)cx + 0.5) * (double)p.lv.stride[level];
-        sy = ((double)cy + 0.5) * (double)p.lv.stride[level];
-        hx1 = s_hull[level][0] + sx; hy1 = s_hull[level][1] + sy;
-        hx2 = s_hull[level][2] + sx; hy2 = s_hull[level][3] + sy;
+        const double sx = ((double)cx + 0.5) * (double)p.lv.stride[level];
+        const double sy = ((double)cy + 0.5) * (double)p.lv.stride[level];
+        const double* bs = s_base + (level * A + a) * 4;
+        ax1 = bs[0] + sx; ay1 = bs[1] + sy; ax2 = bs[2] + sx; ay2 = bs[3] + sy;
     }
-    const double* bs = s_base + level * A * 4;
+    const double aw = ax2 - ax1, ah = ay2 - ay1;
+    const double area_a = aw * ah;
+    const bool matchable = valid && (aw > 0.0) && (ah > 0.0);
 
-    // ---- tile bounding box (fp32, rounded outwards) ---------------------------------------------------
-    {
-        const float inf = __int_as_float(0x7f800000);
-        const float mnx = rn_warp_min(valid ? __double2float_rd(hx1) : inf), mny = rn_warp_min(valid ? __double2float_rd(hy1) : inf);
-        const float mxx = rn_warp_max(valid ? __double2float_ru(hx2) : -inf), mxy = rn_warp_max(valid ? __double2float_ru(hy2) : -inf);
-        if (lane == 0) { s_red[warp][0] = mnx; s_red[warp][1] = mny; s_red[warp][2] = mxx; s_red[warp][3] = mxy; }
-    }
-    __syncthreads();
-    float fx1 = s_red[0][0], fy1 = s_red[0][1], fx2 = s_red[0][2], fy2 = s_red[0][3];
-#pragma unroll
-    for (int w = 1; w < KC_WARPS; ++w) {
-        fx1 = fminf(fx1, s_red[w][0]); fy1 = fminf(fy1, s_red[w][1]);
-        fx2 = fmaxf(fx2, s_red[w][2]); fy2 = fmaxf(fy2, s_red[w][3]);
-    }
-    const double tx1 = (double)fx1, ty1 = (double)fy1, tx2 = (double)fx2, ty2 = (double)fy2;
+    // ---- warp bounding box (fp32, rounded outwards) ---------------------------------------------------
+    const float inf = __int_as_float(0x7f800000);
+    const double wx1 = (double)rn_warp_min(valid ? __double2float_rd(ax1) : inf);
+    const double wy1 = (double)rn_warp_min(valid ? __double2float_rd(ay1) : inf);
+    const double wx2 = (double)rn_warp_max(valid ? __double2float_ru(ax2) : -inf);
+    const double wy2 = (double)rn_warp_max(valid ? __double2float_ru(ay2) : -inf);
 
     // ---- matching -------------------------------------------------------------------------------------
-    float best[A];
-    int arg[A];
-#pragma unroll
-    for (int a = 0; a < A; ++a) { best[a] = 0.0f; arg[a] = 0; }
+    float best = 0.0f;     // an all-zero IoU row has argmax 0 (numpy first-max)
+    int arg = 0;
     const double* gtb = p.gt + (size_t)b * p.Gmax * 4;
-    for (int g0 = 0; g0 < G; g0 += KC_CHUNK) {
-        const int j = g0 + tid;
-        bool keep = false;
-        double gx1 = 0, gy1 = 0, gx2 = 0, gy2 = 0;
-        if (tid < KC_CHUNK && j < G) {
-            gx1 = __ldg(gtb + 4 * j); gy1 = __ldg(gtb + 4 * j + 1);
-            gx2 = __ldg(gtb + 4 * j + 2); gy2 = __ldg(gtb + 4 * j + 3);
-            // empty GT boxes and GT boxes outside the tile have zero intersection with every anchor here
-            keep = (gx2 > gx1) && (gy2 > gy1) && (gx2 > tx1) && (gx1 < tx2) && (gy2 > ty1) && (gy1 < ty2);
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        __syncthreads();                                   // previous chunk fully consumed
-        if (lane == 0 && warp < 2) s_wcount[warp] = __popc(bal);
-        __syncthreads();
-        const int total = s_wcount[0] + s_wcount[1];
-        if (keep) {
-            const int pos = (warp == 1 ? s_wcount[0] : 0) + __popc(bal & ((1u << lane) - 1u));   // GT order kept
-            s_gx1[pos] = gx1; s_gy1[pos] = gy1; s_gx2[pos] = gx2; s_gy2[pos] = gy2;
-            s_ga[pos] = (gx2 - gx1) * (gy2 - gy1);
-            s_gidx[pos] = j;
+    for (int g0 = 0; g0 < G; g0 += KW_CHUNK) {
+        const int chunk = min(KW_CHUNK, G - g0);
+        __syncthreads();                                   // previous chunk consumed (and s_r5 complete)
+        for (int j = tid; j < chunk; j += nthreads) {
+            const double gx1 = __ldg(gtb + 4 * (g0 + j)), gy1 = __ldg(gtb + 4 * (g0 + j) + 1);
+            const double gx2 = __ldg(gtb + 4 * (g0 + j) + 2), gy2 = __ldg(gtb + 4 * (g0 + j) + 3);
+            s_gx1[j] = gx1; s_gy1[j] = gy1; s_gx2[j] = gx2; s_gy2[j] = gy2;
+            s_ga[j] = (gx2 - gx1) * (gy2 - gy1);
         }
         __syncthreads();
-        if (!valid || total == 0) continue;
-        unsigned long long hits = 0ull;
-        for (int m = 0; m < total; ++m)
-            if (s_gx2[m] > hx1 && s_gx1[m] < hx2 && s_gy2[m] > hy1 && s_gy1[m] < hy2) hits |= 1ull << m;
-        if (hits == 0ull) continue;
-#pragma unroll
-        for (int a = 0; a < A; ++a) {
-            const double ax1 = bs[a * 4] + sx, ay1 = bs[a * 4 + 1] + sy, ax2 = bs[a * 4 + 2] + sx, ay2 = bs[a * 4 + 3] + sy;
-            if (!(ax2 > ax1 && ay2 > ay1)) continue;
-            const double area_a = (ax2 - ax1) * (ay2 - ay1);
-            unsigned long long mm = hits;
-            while (mm) {
-                const int m = __ffsll((long long)mm) - 1;
-                mm &= mm - 1ull;
+        for (int q0 = 0; q0 < chunk; q0 += 32) {
+            const int j = q0 + lane;
+            bool touch = false;
+            if (j < chunk) {
+                const double gx1 = s_gx1[j], gy1 = s_gy1[j], gx2 = s_gx2[j], gy2 = s_gy2[j];
+                // empty tables and tables outside the warp's box have zero intersection with all 32 anchors
+                touch = (gx2 > gx1) && (gy2 > gy1) && (gx2 > wx1) && (gx1 < wx2) && (gy2 > wy1) && (gy1 < wy2);
+            }
+            unsigned live = __ballot_sync(0xffffffffu, touch);
+            while (live) {                                 // warp-uniform, ascending GT order
+                const int m = q0 + __ffs(live) - 1;
+                live &= live - 1u;
                 const double g1 = s_gx1[m], g2 = s_gx2[m], g3 = s_gy1[m], g4 = s_gy2[m];
-                if (g2 > ax1 && g1 < ax2 && g4 > ay1 && g3 < ay2) {
+                if (matchable && g2 > ax1 && g1 < ax2 && g4 > ay1 && g3 < ay2) {
                     const double iw = fmin(ax2, g2) - fmax(ax1, g1);
                     const double ih = fmin(ay2, g4) - fmax(ay1, g3);
                     const double inter = iw * ih;
                     const double uni = area_a + s_ga[m] - inter;
                     const double q = inter * rcp_fast(uni);
-                    const float iou = f32_rounding_safe(q) ? (float)q : (float)(inter / uni);
-                    if (iou > best[a]) { best[a] = iou; arg[a] = s_gidx[m]; }
+                    const float iou = f32_rounding_safe(q) ? (float)q : iou_exact(inter, uni);
+                    if (iou > best) { best = iou; arg = g0 + m; }
                 }
             }
         }
     }
+    if (G == 0) __syncthreads();                           // s_r5 complete
 
     // ---- state, one-hot class, regression targets, border rule ------------------------------------------
-    int my_pos = 0;
+    float state = 0.0f;
     if (valid) {
-        // border rule (model/anchors.py:85-90) compares the anchor CENTRE, which is the cell centre up to an
-        // ulp: decide per cell when the centre is at least one pixel away from the page edge
-        int border = 0;                                    // 0 inside, 1 outside, 2 evaluate per anchor
+        int hot = -1;
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+        if (G > 0) {
+            const bool is_pos = best >= p.pos;
+            const bool is_ign = (best > p.neg) && !is_pos;
+            state = is_pos ? 1.0f : (is_ign ? -1.0f : 0.0f);
+            if (is_pos) hot = __ldg(p.gt_labels + (size_t)b * p.Gmax + arg);
+            const double* g = gtb + 4 * (size_t)arg;
+            double rw = s_r5[2 * (level * A + a)], rh = s_r5[2 * (level * A + a) + 1];
+            if (rw == 0.0) { rw = 5.0 * rcp_fast(aw); rh = 5.0 * rcp_fast(ah); }
+            t0 = reg_target5(__ldg(g + 0), ax1, aw, rw);
+            t1 = reg_target5(__ldg(g + 1), ay1, ah, rh);
+            t2 = reg_target5(__ldg(g + 2), ax2, aw, rw);
+            t3 = reg_target5(__ldg(g + 3), ay2, ah, rh);
+        }
         if (p.img_hw) {
-            const double W = (double)p.img_hw[2 * b + 1], H = (double)p.img_hw[2 * b];
-            if (sx >= W + 1.0 || sy >= H + 1.0) border = 1;
-            else if (sx > W - 1.0 || sy > H - 1.0) border = 2;
+            const double ccx = (ax1 + ax2) / 2.0, ccy = (ay1 + ay2) / 2.0;
+            if (ccx >= (double)p.img_hw[2 * b + 1] || ccy >= (double)p.img_hw[2 * b]) state = -1.0f;
         }
-#pragma unroll
-        for (int a = 0; a < A; ++a) {
-            const double ax1 = bs[a * 4] + sx, ay1 = bs[a * 4 + 1] + sy, ax2 = bs[a * 4 + 2] + sx, ay2 = bs[a * 4 + 3] + sy;
-            float state = 0.0f, t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-            int hot = -1;
-            if (G > 0) {
-                const bool is_pos = best[a] >= p.pos;
-                const bool is_ign = (best[a] > p.neg) && !is_pos;
-                state = is_pos ? 1.0f : (is_ign ? -1.0f : 0.0f);
-                if (is_pos) hot = __ldg(p.gt_labels + (size_t)b * p.Gmax + arg[a]);
-                const double* g = gtb + 4 * (size_t)arg[a];
-                const double aw = ax2 - ax1, ah = ay2 - ay1;
-                const double rw = rcp_fast(aw), rh = rcp_fast(ah);
-                t0 = reg_target(__ldg(g + 0), ax1, aw, rw);
-                t1 = reg_target(__ldg(g + 1), ay1, ah, rh);
-                t2 = reg_target(__ldg(g + 2), ax2, aw, rw);
-                t3 = reg_target(__ldg(g + 3), ay2, ah, rh);
-            }
-            if (border == 1) state = -1.0f;
-            else if (border == 2) {
-                const double ccx = (ax1 + ax2) / 2.0, ccy = (ay1 + ay2) / 2.0;
-                if (ccx >= (double)p.img_hw[2 * b + 1] || ccy >= (double)p.img_hw[2 * b]) state = -1.0f;
-            }
-            const int k = tid * A + a;
-            s_reg[k * 5 + 0] = t0; s_reg[k * 5 + 1] = t1; s_reg[k * 5 + 2] = t2; s_reg[k * 5 + 3] = t3; s_reg[k * 5 + 4] = state;
-            s_state[k] = state;
-            s_hot[k] = hot;
-            my_pos += (state == 1.0f);
-            if (p.argmax) p.argmax[(size_t)b * p.N + (size_t)gc * A + a] = arg[a];
-        }
+        const int k = lc * A + a;                           // the reference's order inside the CTA's range
+        s_reg[k * 5 + 0] = t0; s_reg[k * 5 + 1] = t1; s_reg[k * 5 + 2] = t2; s_reg[k * 5 + 3] = t3; s_reg[k * 5 + 4] = state;
+        s_state[k] = state;
+        s_hot[k] = hot;
+        if (p.argmax) p.argmax[(size_t)b * p.N + (size_t)gc * A + a] = arg;
     }
     if (p.npos || p.npos_total) {
-        my_pos = rn_warp_sum(my_pos);
-        if (lane == 0 && my_pos) atomicAdd(&s_npos, my_pos);
+        const unsigned pb = __ballot_sync(0xffffffffu, valid && state == 1.0f);
+        if (lane == 0 && pb) atomicAdd(&s_npos, __popc(pb));
     }
     __syncthreads();
     if (tid == 0 && s_npos) {
         if (p.npos) atomicAdd(p.npos + b, s_npos);
-        if (p.npos_total) atomicAdd(p.npos_total, (float)s_npos);
+        if (p.npos_total) atomicAdd(p.npos_total, (float)s_npos);   // integer-valued: exact, order-independent
     }
 
-    // ---- coalesced write-out: the CTA's anchors are contiguous -----------------------------------------------
+    // ---- coalesced write-out: the CTA's anchors are contiguous ------------------------------------------
     const long long row0 = (long long)b * p.N + (long long)c0 * A;
     const int cnt = ncell * A;
-    store_range<KC_THREADS>(p.reg, row0 * 5, cnt * 5, p.vec_ok != 0, [&](int i) { return s_reg[i]; });
-    const int CW = p.C + 1;
+    store_range(p.reg, row0 * 5, cnt * 5, p.vec_ok != 0, nthreads, [&](int i) { return s_reg[i]; });
     if (p.C == 1) {
-        store_range<KC_THREADS>(p.lab, row0 * 2, cnt * 2, p.vec_ok != 0, [&](int i) {
+        store_range(p.lab, row0 * 2, cnt * 2, p.vec_ok != 0, nthreads, [&](int i) {
             const int r = i >> 1;
             return (i & 1) ? s_state[r] : (s_hot[r] == 0 ? 1.0f : 0.0f);
         });
     } else {
-        store_range<KC_THREADS>(p.lab, row0 * CW, cnt * CW, p.vec_ok != 0, [&](int i) {
-            const int r = i / CW, c = i - r * CW;
-            return c == p.C ? s_state[r] : (c == s_hot[r] ? 1.0f : 0.0f);
-        });
+        store_labels_generic(p.lab, row0, cnt, p.C, p.vec_ok != 0, nthreads, s_state, s_hot);
     }
 }
+
 
 __global__ void k_anchors_f64(const RnLevels lv, const double* base, int N, double* out) {
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
@@ -554,11 +540,23 @@ extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* leve
     dim3 grid((unsigned)((num_anchors + K1_THREADS - 1) / K1_THREADS), (unsigned)B);
     if (anchors_dev) {
         k_anchor_targets<true><<<grid, K1_THREADS, 0, s>>>(p);
-    } else if (anchors_per_cell == 9) {
-        // the default RetinaNet layout (3 ratios x 3 scales): one thread per cell
-        const long long cells = num_anchors / 9;
-        dim3 cgrid((unsigned)((cells + KC_THREADS - 1) / KC_THREADS), (unsigned)B);
-        k_anchor_targets_cells<9><<<cgrid, KC_THREADS, 0, s>>>(p);
+    } else if (anchors_per_cell <= 24) {
+        // warp = 32 cells x one anchor type; `groups` cell groups per CTA so that a CTA has ~256-320 threads
+        const int A = anchors_per_cell;
+        const int groups = A >= 8 ? 1 : 8 / A;
+        const long long cells = num_anchors / A;
+        // The regression fast path takes 5/width from a per-(level, anchor type) table.  The true width of a
+        // generated anchor, RN(b2+s) - RN(b0+s), deviates from b2-b0 by at most ~2 ulp(max coordinate) =
+        // 2^-51 max_coord; the fast path tolerates 2^-36 relative, so the kernel uses the table only where
+        // max_coord / min(width, height) < 2^12 (relative deviation < 2^-39) and a per-anchor reciprocal else.
+        double max_coord = 1.0;
+        for (int l = 0; l < num_levels; ++l) {
+            const double ext = (double)level_stride[l] * (double)((level_hw[2 * l] > level_hw[2 * l + 1] ? level_hw[2 * l] : level_hw[2 * l + 1]) + 1);
+            if (ext > max_coord) max_coord = ext;
+        }
+        p.max_coord = max_coord;
+        dim3 cgrid((unsigned)((cells + 32 * groups - 1) / (32 * groups)), (unsigned)B);
+        k_anchor_targets_warpcells<<<cgrid, 32 * groups * A, 0, s>>>(p, groups);
     } else {
         k_anchor_targets<false><<<grid, K1_THREADS, 0, s>>>(p);
     }
