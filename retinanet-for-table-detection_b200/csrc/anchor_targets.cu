@@ -272,90 +272,88 @@ __global__ void __launch_bounds__(K1_THREADS) k_anchor_targets(const K1Params p)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1 for generated anchors: a WARP owns 32 consecutive cells and ONE anchor type.
+// K1 for generated anchors: a CTA owns a 32-cell x KT_ROWS-row tile of one feature map, a WARP one anchor
+// type of that tile, a THREAD one (anchor type, column) and walks the tile's rows.
 //
-// thread (warp w, lane) -> cell = c0 + (w / A) * 32 + lane, anchor-in-cell a = w % A.  Every lane of a warp
-// therefore uses the same base box (and the same 5/width, 5/height table entry), consecutive lanes are
-// consecutive cells of a feature-map row, and the warp's bounding box is tight: the page's GT tables are
-// staged once per CTA (unculled, in GT order) and each warp culls them against its own box with one
-// ballot per 32 tables, then walks the surviving bits in order -- warp-uniform control flow, the exact
-// per-anchor test only for tables that can actually touch the warp.  Arithmetic per anchor is identical
-// to k_anchor_targets; results are staged in shared memory in the reference's anchor order
-// (cell-major, anchor-minor) and written with 128-bit stores.
+// Everything that depends only on the column is computed once per KT_ROWS anchors (x extent, 5/width, the
+// x half of every GT overlap test and the intersection width); everything that depends only on the warp is
+// warp-uniform (base box, row geometry, the warp's exact bounding box -> one ballot culls 32 GT tables, and
+// the surviving tables are walked with warp-uniform control flow).  The per-anchor arithmetic is the one of
+// k_anchor_targets, operation for operation.  Results are staged in shared memory in the reference's
+// anchor order (cell-major, anchor-minor; each tile row is one contiguous range) and written with 128-bit
+// stores.
 // ------------------------------------------------------------------------------------------------
-constexpr int KW_MAX_ANCHORS = 768;   // anchors per CTA: 32 cells * (cell groups) * A
-constexpr int KW_MAX_THREADS = 768;
-constexpr int KW_CHUNK = 256;         // GT tables staged per round
+constexpr int KT_ROWS = 4;
+constexpr int KT_MAX_A = 24;
+constexpr int KT_CHUNK = 256;          // GT tables staged per round
 
-__global__ void __launch_bounds__(KW_MAX_THREADS) k_anchor_targets_warpcells(const K1Params p, const int groups) {
-    __shared__ double s_base[RN_MAX_LEVELS * 32 * 4];      // A <= 24 here
-    __shared__ double s_r5[RN_MAX_LEVELS * 32 * 2];        // ~5/width, ~5/height per (level, a)
-    __shared__ double s_gx1[KW_CHUNK], s_gy1[KW_CHUNK], s_gx2[KW_CHUNK], s_gy2[KW_CHUNK], s_ga[KW_CHUNK];
-    __shared__ float s_reg[KW_MAX_ANCHORS * 5];
-    __shared__ float s_state[KW_MAX_ANCHORS];
-    __shared__ int s_hot[KW_MAX_ANCHORS];
+struct K1Tiles {
+    int tile_start[RN_MAX_LEVELS + 1];  // first tile of each level
+    int tiles_x[RN_MAX_LEVELS];
+    float inv_tiles_x[RN_MAX_LEVELS];
+};
+
+__global__ void __launch_bounds__(32 * KT_MAX_A) k_anchor_targets_tiles(const K1Params p, const K1Tiles tl) {
+    extern __shared__ __align__(16) float s_dyn[];
+    __shared__ double s_gx1[KT_CHUNK], s_gy1[KT_CHUNK], s_gx2[KT_CHUNK], s_gy2[KT_CHUNK], s_ga[KT_CHUNK];
     __shared__ int s_npos;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nthreads = blockDim.x;
+    const int tid = threadIdx.x, lane = tid & 31, a = tid >> 5;
     const int A = p.lv.anchors_per_cell, L = p.lv.num_levels;
+    const int nthreads = 32 * A;
     const int b = blockIdx.y;
-    for (int i = tid; i < L * A * 4; i += nthreads) s_base[i] = __ldg(p.base + i);
+    float* s_reg = s_dyn;                                   // [KT_ROWS][32][A][5]
+    float* s_state = s_reg + KT_ROWS * 32 * A * 5;          // [KT_ROWS][32][A]
+    int* s_hot = reinterpret_cast<int*>(s_state + KT_ROWS * 32 * A);
     if (tid == 0) s_npos = 0;
-    __syncthreads();
-    for (int i = tid; i < L * A; i += nthreads) {
-        // 5/width, 5/height of the base box stand in for the anchor's own (they differ by rounding only)
-        // when that difference is far inside the fast path's tolerance; 0 = compute per anchor
-        const double w = s_base[4 * i + 2] - s_base[4 * i], h = s_base[4 * i + 3] - s_base[4 * i + 1];
-        const bool ok = (w > 0.0) && (h > 0.0) && (p.max_coord < 4096.0 * fmin(w, h));
-        s_r5[2 * i] = ok ? 5.0 * rcp_fast(w) : 0.0;
-        s_r5[2 * i + 1] = ok ? 5.0 * rcp_fast(h) : 0.0;
-    }
 
-    const int cells_total = p.N / A;
-    const int cells_per_cta = 32 * groups;
-    const int c0 = blockIdx.x * cells_per_cta;
-    const int ncell = min(cells_per_cta, cells_total - c0);
-    const int grp = warp / A, a = warp - grp * A;          // warp-uniform
-    const int lc = grp * 32 + lane;                        // cell within the CTA
-    const bool valid = lc < ncell;
-    const int gc = c0 + lc;
+    // ---- tile -> (level, tile x, tile y): block-uniform -------------------------------------------------
+    int level = 0;
+    for (int l = 1; l < L; ++l)
+        if ((int)blockIdx.x >= tl.tile_start[l]) level = l;
+    const int t = blockIdx.x - tl.tile_start[level];
+    const int ty = rn_div(t, tl.tiles_x[level], tl.inv_tiles_x[level]);
+    const int tx = t - ty * tl.tiles_x[level];
+    const int W = p.lv.w[level], H = p.lv.h[level];
+    const double stride = (double)p.lv.stride[level];
+    const int cx0 = tx * 32, cy0 = ty * KT_ROWS;
+    const int ncols = min(32, W - cx0), nrows = min(KT_ROWS, H - cy0);
+    const bool valid_x = lane < ncols;
     int G = p.gt_count[b];
     G = max(0, min(G, p.Gmax));
 
-    // ---- this thread's anchor ------------------------------------------------------------------------
-    int level = 0;
-    double ax1 = 0, ay1 = 0, ax2 = 0, ay2 = 0;
-    if (valid) {
+    // ---- geometry: base box (warp-uniform), column extent (per thread), row extents (warp-uniform) -----
+    const double* bs = p.base + ((size_t)level * A + a) * 4;
+    const double b0 = __ldg(bs), b1 = __ldg(bs + 1), b2 = __ldg(bs + 2), b3 = __ldg(bs + 3);
+    const double sx = ((double)(cx0 + lane) + 0.5) * stride;
+    const double ax1 = b0 + sx, ax2 = b2 + sx;
+    const double aw = ax2 - ax1;
+    double ay1[KT_ROWS], ay2[KT_ROWS], ah[KT_ROWS];
 #pragma unroll
-        for (int l = 1; l < RN_MAX_LEVELS; ++l)
-            if (l < L && gc * A >= p.lv.start[l]) level = l;
-        const int r = gc - rn_div(p.lv.start[level], A, p.lv.inv_a);
-        const int cy = rn_div(r, p.lv.w[level], p.lv.inv_w[level]);
-        const int cx = r - cy * p.lv.w[level];
-        const double sx = ((double)cx + 0.5) * (double)p.lv.stride[level];
-        const double sy = ((double)cy + 0.5) * (double)p.lv.stride[level];
-        const double* bs = s_base + (level * A + a) * 4;
-        ax1 = bs[0] + sx; ay1 = bs[1] + sy; ax2 = bs[2] + sx; ay2 = bs[3] + sy;
+    for (int r = 0; r < KT_ROWS; ++r) {
+        const double sy = ((double)(cy0 + r) + 0.5) * stride;
+        ay1[r] = b1 + sy; ay2[r] = b3 + sy;
+        ah[r] = ay2[r] - ay1[r];
     }
-    const double aw = ax2 - ax1, ah = ay2 - ay1;
-    const double area_a = aw * ah;
-    const bool matchable = valid && (aw > 0.0) && (ah > 0.0);
-
-    // ---- warp bounding box (fp32, rounded outwards) ---------------------------------------------------
-    const float inf = __int_as_float(0x7f800000);
-    const double wx1 = (double)rn_warp_min(valid ? __double2float_rd(ax1) : inf);
-    const double wy1 = (double)rn_warp_min(valid ? __double2float_rd(ay1) : inf);
-    const double wx2 = (double)rn_warp_max(valid ? __double2float_ru(ax2) : -inf);
-    const double wy2 = (double)rn_warp_max(valid ? __double2float_ru(ay2) : -inf);
+    // 5/width, 5/height for the regression fast path: the base box's stand in for the anchor's own (they
+    // differ by rounding only) when that is far inside the fast path's tolerance (see the wrapper)
+    const bool table_ok = (b2 > b0) && (b3 > b1) && (p.max_coord < 4096.0 * fmin(b2 - b0, b3 - b1));
+    const double r5w = 5.0 * rcp_fast(table_ok ? b2 - b0 : aw);
+    const double r5h_tab = table_ok ? 5.0 * rcp_fast(b3 - b1) : 0.0;
+    const bool match_x = valid_x && (aw > 0.0);
+    // exact bounding box of the warp's anchors (first / last valid column, first / last valid row)
+    const double wx1 = b0 + ((double)cx0 + 0.5) * stride, wx2 = b2 + ((double)(cx0 + ncols - 1) + 0.5) * stride;
+    const double wy1 = ay1[0], wy2 = b3 + ((double)(cy0 + nrows - 1) + 0.5) * stride;
 
     // ---- matching -------------------------------------------------------------------------------------
-    float best = 0.0f;     // an all-zero IoU row has argmax 0 (numpy first-max)
-    int arg = 0;
+    float best[KT_ROWS];
+    int arg[KT_ROWS];
+#pragma unroll
+    for (int r = 0; r < KT_ROWS; ++r) { best[r] = 0.0f; arg[r] = 0; }   // all-zero IoU row -> argmax 0
     const double* gtb = p.gt + (size_t)b * p.Gmax * 4;
-    for (int g0 = 0; g0 < G; g0 += KW_CHUNK) {
-        const int chunk = min(KW_CHUNK, G - g0);
-        __syncthreads();                                   // previous chunk consumed (and s_r5 complete)
+    for (int g0 = 0; g0 < G; g0 += KT_CHUNK) {
+        const int chunk = min(KT_CHUNK, G - g0);
+        __syncthreads();                                   // previous chunk consumed
         for (int j = tid; j < chunk; j += nthreads) {
             const double gx1 = __ldg(gtb + 4 * (g0 + j)), gy1 = __ldg(gtb + 4 * (g0 + j) + 1);
             const double gx2 = __ldg(gtb + 4 * (g0 + j) + 2), gy2 = __ldg(gtb + 4 * (g0 + j) + 3);
@@ -368,59 +366,73 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) k_anchor_targets_warpcells(con
             bool touch = false;
             if (j < chunk) {
                 const double gx1 = s_gx1[j], gy1 = s_gy1[j], gx2 = s_gx2[j], gy2 = s_gy2[j];
-                // empty tables and tables outside the warp's box have zero intersection with all 32 anchors
+                // empty tables and tables outside the warp's box have zero intersection with all its anchors
                 touch = (gx2 > gx1) && (gy2 > gy1) && (gx2 > wx1) && (gx1 < wx2) && (gy2 > wy1) && (gy1 < wy2);
             }
             unsigned live = __ballot_sync(0xffffffffu, touch);
             while (live) {                                 // warp-uniform, ascending GT order
                 const int m = q0 + __ffs(live) - 1;
                 live &= live - 1u;
-                const double g1 = s_gx1[m], g2 = s_gx2[m], g3 = s_gy1[m], g4 = s_gy2[m];
-                if (matchable && g2 > ax1 && g1 < ax2 && g4 > ay1 && g3 < ay2) {
+                const double g1 = s_gx1[m], g2 = s_gx2[m];
+                if (match_x && g2 > ax1 && g1 < ax2) {
                     const double iw = fmin(ax2, g2) - fmax(ax1, g1);
-                    const double ih = fmin(ay2, g4) - fmax(ay1, g3);
-                    const double inter = iw * ih;
-                    const double uni = area_a + s_ga[m] - inter;
-                    const double q = inter * rcp_fast(uni);
-                    const float iou = f32_rounding_safe(q) ? (float)q : iou_exact(inter, uni);
-                    if (iou > best) { best = iou; arg = g0 + m; }
+                    const double g3 = s_gy1[m], g4 = s_gy2[m], ga = s_ga[m];
+#pragma unroll
+                    for (int r = 0; r < KT_ROWS; ++r) {
+                        if (r < nrows && g4 > ay1[r] && g3 < ay2[r] && ah[r] > 0.0) {
+                            const double ih = fmin(ay2[r], g4) - fmax(ay1[r], g3);
+                            const double inter = iw * ih;
+                            const double uni = aw * ah[r] + ga - inter;
+                            const double q = inter * rcp_fast(uni);
+                            const float iou = f32_rounding_safe(q) ? (float)q : iou_exact(inter, uni);
+                            if (iou > best[r]) { best[r] = iou; arg[r] = g0 + m; }
+                        }
+                    }
                 }
             }
         }
     }
-    if (G == 0) __syncthreads();                           // s_r5 complete
 
     // ---- state, one-hot class, regression targets, border rule ------------------------------------------
-    float state = 0.0f;
-    if (valid) {
-        int hot = -1;
-        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-        if (G > 0) {
-            const bool is_pos = best >= p.pos;
-            const bool is_ign = (best > p.neg) && !is_pos;
-            state = is_pos ? 1.0f : (is_ign ? -1.0f : 0.0f);
-            if (is_pos) hot = __ldg(p.gt_labels + (size_t)b * p.Gmax + arg);
-            const double* g = gtb + 4 * (size_t)arg;
-            double rw = s_r5[2 * (level * A + a)], rh = s_r5[2 * (level * A + a) + 1];
-            if (rw == 0.0) { rw = 5.0 * rcp_fast(aw); rh = 5.0 * rcp_fast(ah); }
-            t0 = reg_target5(__ldg(g + 0), ax1, aw, rw);
-            t1 = reg_target5(__ldg(g + 1), ay1, ah, rh);
-            t2 = reg_target5(__ldg(g + 2), ax2, aw, rw);
-            t3 = reg_target5(__ldg(g + 3), ay2, ah, rh);
-        }
+    int my_pos = 0;
+    if (valid_x) {
+        bool out_x = false;
+        double img_h = 0.0;
         if (p.img_hw) {
-            const double ccx = (ax1 + ax2) / 2.0, ccy = (ay1 + ay2) / 2.0;
-            if (ccx >= (double)p.img_hw[2 * b + 1] || ccy >= (double)p.img_hw[2 * b]) state = -1.0f;
+            out_x = ((ax1 + ax2) / 2.0) >= (double)p.img_hw[2 * b + 1];
+            img_h = (double)p.img_hw[2 * b];
         }
-        const int k = lc * A + a;                           // the reference's order inside the CTA's range
-        s_reg[k * 5 + 0] = t0; s_reg[k * 5 + 1] = t1; s_reg[k * 5 + 2] = t2; s_reg[k * 5 + 3] = t3; s_reg[k * 5 + 4] = state;
-        s_state[k] = state;
-        s_hot[k] = hot;
-        if (p.argmax) p.argmax[(size_t)b * p.N + (size_t)gc * A + a] = arg;
+#pragma unroll
+        for (int r = 0; r < KT_ROWS; ++r) {
+            if (r < nrows) {
+                float state = 0.0f, t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+                int hot = -1;
+                if (G > 0) {
+                    const bool is_pos = best[r] >= p.pos;
+                    const bool is_ign = (best[r] > p.neg) && !is_pos;
+                    state = is_pos ? 1.0f : (is_ign ? -1.0f : 0.0f);
+                    if (is_pos) hot = __ldg(p.gt_labels + (size_t)b * p.Gmax + arg[r]);
+                    const double* g = gtb + 4 * (size_t)arg[r];
+                    const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(ah[r]);
+                    t0 = reg_target5(__ldg(g + 0), ax1, aw, r5w);
+                    t1 = reg_target5(__ldg(g + 1), ay1[r], ah[r], r5h);
+                    t2 = reg_target5(__ldg(g + 2), ax2, aw, r5w);
+                    t3 = reg_target5(__ldg(g + 3), ay2[r], ah[r], r5h);
+                }
+                if (p.img_hw && (out_x || ((ay1[r] + ay2[r]) / 2.0) >= img_h)) state = -1.0f;
+                const int k = (r * 32 + lane) * A + a;      // reference order within the tile row
+                s_reg[k * 5 + 0] = t0; s_reg[k * 5 + 1] = t1; s_reg[k * 5 + 2] = t2; s_reg[k * 5 + 3] = t3; s_reg[k * 5 + 4] = state;
+                s_state[k] = state;
+                s_hot[k] = hot;
+                my_pos += (state == 1.0f);
+                if (p.argmax)
+                    p.argmax[(size_t)b * p.N + p.lv.start[level] + ((size_t)(cy0 + r) * W + cx0 + lane) * A + a] = arg[r];
+            }
+        }
     }
     if (p.npos || p.npos_total) {
-        const unsigned pb = __ballot_sync(0xffffffffu, valid && state == 1.0f);
-        if (lane == 0 && pb) atomicAdd(&s_npos, __popc(pb));
+        my_pos = rn_warp_sum(my_pos);
+        if (lane == 0 && my_pos) atomicAdd(&s_npos, my_pos);
     }
     __syncthreads();
     if (tid == 0 && s_npos) {
@@ -428,17 +440,22 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) k_anchor_targets_warpcells(con
         if (p.npos_total) atomicAdd(p.npos_total, (float)s_npos);   // integer-valued: exact, order-independent
     }
 
-    // ---- coalesced write-out: the CTA's anchors are contiguous ------------------------------------------
-    const long long row0 = (long long)b * p.N + (long long)c0 * A;
-    const int cnt = ncell * A;
-    store_range(p.reg, row0 * 5, cnt * 5, p.vec_ok != 0, nthreads, [&](int i) { return s_reg[i]; });
-    if (p.C == 1) {
-        store_range(p.lab, row0 * 2, cnt * 2, p.vec_ok != 0, nthreads, [&](int i) {
-            const int r = i >> 1;
-            return (i & 1) ? s_state[r] : (s_hot[r] == 0 ? 1.0f : 0.0f);
-        });
-    } else {
-        store_labels_generic(p.lab, row0, cnt, p.C, p.vec_ok != 0, nthreads, s_state, s_hot);
+    // ---- write-out: each tile row is one contiguous anchor range ----------------------------------------
+    const int cnt = ncols * A;
+    for (int r = 0; r < nrows; ++r) {
+        const long long row0 = (long long)b * p.N + p.lv.start[level] + ((long long)(cy0 + r) * W + cx0) * A;
+        const float* sr = s_reg + r * 32 * A * 5;
+        const float* ss = s_state + r * 32 * A;
+        const int* sh = s_hot + r * 32 * A;
+        store_range(p.reg, row0 * 5, cnt * 5, p.vec_ok != 0, nthreads, [&](int i) { return sr[i]; });
+        if (p.C == 1) {
+            store_range(p.lab, row0 * 2, cnt * 2, p.vec_ok != 0, nthreads, [&](int i) {
+                const int q = i >> 1;
+                return (i & 1) ? ss[q] : (sh[q] == 0 ? 1.0f : 0.0f);
+            });
+        } else {
+            store_labels_generic(p.lab, row0, cnt, p.C, p.vec_ok != 0, nthreads, ss, sh);
+        }
     }
 }
 
@@ -540,23 +557,32 @@ extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* leve
     dim3 grid((unsigned)((num_anchors + K1_THREADS - 1) / K1_THREADS), (unsigned)B);
     if (anchors_dev) {
         k_anchor_targets<true><<<grid, K1_THREADS, 0, s>>>(p);
-    } else if (anchors_per_cell <= 24) {
-        // warp = 32 cells x one anchor type; `groups` cell groups per CTA so that a CTA has ~256-320 threads
+    } else if (anchors_per_cell <= KT_MAX_A) {
         const int A = anchors_per_cell;
-        const int groups = A >= 8 ? 1 : 8 / A;
-        const long long cells = num_anchors / A;
-        // The regression fast path takes 5/width from a per-(level, anchor type) table.  The true width of a
-        // generated anchor, RN(b2+s) - RN(b0+s), deviates from b2-b0 by at most ~2 ulp(max coordinate) =
-        // 2^-51 max_coord; the fast path tolerates 2^-36 relative, so the kernel uses the table only where
+        // The regression fast path takes 5/width from the base box.  The true width of a generated anchor,
+        // RN(b2+s) - RN(b0+s), deviates from b2-b0 by at most ~2 ulp(max coordinate) = 2^-51 max_coord; the
+        // fast path tolerates 2^-36 relative, so the kernel uses the base box only where
         // max_coord / min(width, height) < 2^12 (relative deviation < 2^-39) and a per-anchor reciprocal else.
         double max_coord = 1.0;
+        K1Tiles tl;
+        int tiles = 0;
+        for (int l = 0; l < RN_MAX_LEVELS; ++l) { tl.tile_start[l] = 0; tl.tiles_x[l] = 1; tl.inv_tiles_x[l] = 1.0f; }
         for (int l = 0; l < num_levels; ++l) {
-            const double ext = (double)level_stride[l] * (double)((level_hw[2 * l] > level_hw[2 * l + 1] ? level_hw[2 * l] : level_hw[2 * l + 1]) + 1);
+            const int h = level_hw[2 * l], w = level_hw[2 * l + 1];
+            const double ext = (double)level_stride[l] * (double)((h > w ? h : w) + 1);
             if (ext > max_coord) max_coord = ext;
+            tl.tile_start[l] = tiles;
+            tl.tiles_x[l] = (w + 31) / 32 > 0 ? (w + 31) / 32 : 1;
+            tl.inv_tiles_x[l] = 1.0f / (float)tl.tiles_x[l];
+            tiles += ((w + 31) / 32) * ((h + KT_ROWS - 1) / KT_ROWS);
         }
+        for (int l = num_levels; l <= RN_MAX_LEVELS; ++l) tl.tile_start[l] = tiles;
         p.max_coord = max_coord;
-        dim3 cgrid((unsigned)((cells + 32 * groups - 1) / (32 * groups)), (unsigned)B);
-        k_anchor_targets_warpcells<<<cgrid, 32 * groups * A, 0, s>>>(p, groups);
+        const size_t dyn = (size_t)KT_ROWS * 32 * A * 7 * sizeof(float);
+        cudaError_t ae = cudaFuncSetAttribute(k_anchor_targets_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)((size_t)KT_ROWS * 32 * KT_MAX_A * 7 * sizeof(float)));
+        if (ae != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
+        if (tiles > 0) k_anchor_targets_tiles<<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);
     } else {
         k_anchor_targets<false><<<grid, K1_THREADS, 0, s>>>(p);
     }
