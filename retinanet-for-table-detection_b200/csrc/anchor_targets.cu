@@ -19,6 +19,7 @@
 // (probability ~2.4e-4 per value) the exact IEEE expression of the reference is evaluated.  The result is
 // bit-identical to always dividing.
 #include "rn_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -99,11 +100,17 @@ __device__ __forceinline__ double rcp_fast(double x) {
 // v approximates (to < 2^-45 relative) a value that the reference rounds to fp32: true when the fp32
 // rounding of v is guaranteed to equal the fp32 rounding of the exact value
 __device__ __forceinline__ bool f32_rounding_safe(double v) {
-    const long long b = __double_as_longlong(v);
-    const int e = (int)((b >> 52) & 0x7ff);                    // biased exponent; fp32 normals need >= 897
-    const int dist = abs((int)(b & 0x1fffffff) - (1 << 28));   // 29 dropped bits vs the rounding midpoint
-    return (e >= 900) && (e <= 1140) && (dist > (1 << 16));
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    // biased exponent in [900, 1140] (fp32 normals need >= 897): one unsigned range compare
+    const bool exp_ok = ((hi & 0x7ff00000u) - (900u << 20)) <= (240u << 20);
+    // the 29 bits dropped by fp64 -> fp32 must be further than 2^16 from the rounding midpoint 2^28
+    const bool far = (((lo & 0x1fffffffu) - ((1u << 28) - (1u << 16))) > (1u << 17));
+    return exp_ok && far;
 }
+
+// min / max of ordered (non-NaN) doubles without the NaN fix-up of fmin / fmax
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
 
 // The exact IEEE expressions of the reference.  Rarely executed and deliberately NOT inlined: a correctly
 // rounded fp64 divide is ~100 SASS lines per site, and inlining it at every use made the kernels larger
@@ -293,9 +300,13 @@ struct K1Tiles {
     float inv_tiles_x[RN_MAX_LEVELS];
 };
 
-__global__ void __launch_bounds__(32 * KT_MAX_A) k_anchor_targets_tiles(const K1Params p, const K1Tiles tl) {
+// MAXA bounds the block size (32 * A threads) so that the register budget can be set per instantiation:
+// <9, 4> is the RetinaNet default (288 threads, >= 4 CTAs per SM), <KT_MAX_A, 1> covers the rest
+template <int MAXA, int MINB>
+__global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const K1Params p, const K1Tiles tl) {
     extern __shared__ __align__(16) float s_dyn[];
     __shared__ double s_gx1[KT_CHUNK], s_gy1[KT_CHUNK], s_gx2[KT_CHUNK], s_gy2[KT_CHUNK], s_ga[KT_CHUNK];
+    __shared__ double s_row[KT_MAX_A][KT_ROWS][3];          // per (anchor type, tile row): y1, y2, height
     __shared__ int s_npos;
 
     const int tid = threadIdx.x, lane = tid & 31, a = tid >> 5;
@@ -328,13 +339,14 @@ __global__ void __launch_bounds__(32 * KT_MAX_A) k_anchor_targets_tiles(const K1
     const double sx = ((double)(cx0 + lane) + 0.5) * stride;
     const double ax1 = b0 + sx, ax2 = b2 + sx;
     const double aw = ax2 - ax1;
-    double ay1[KT_ROWS], ay2[KT_ROWS], ah[KT_ROWS];
-#pragma unroll
-    for (int r = 0; r < KT_ROWS; ++r) {
-        const double sy = ((double)(cy0 + r) + 0.5) * stride;
-        ay1[r] = b1 + sy; ay2[r] = b3 + sy;
-        ah[r] = ay2[r] - ay1[r];
+    // row geometry is the same for the whole warp: keep it in shared memory, not in 24 registers per thread
+    if (lane < KT_ROWS) {
+        const double sy = ((double)(cy0 + lane) + 0.5) * stride;
+        const double y1 = b1 + sy, y2 = b3 + sy;
+        s_row[a][lane][0] = y1; s_row[a][lane][1] = y2; s_row[a][lane][2] = y2 - y1;
     }
+    __syncwarp();
+    const double (*row)[3] = s_row[a];
     // 5/width, 5/height for the regression fast path: the base box's stand in for the anchor's own (they
     // differ by rounding only) when that is far inside the fast path's tolerance (see the wrapper)
     const bool table_ok = (b2 > b0) && (b3 > b1) && (p.max_coord < 4096.0 * fmin(b2 - b0, b3 - b1));
@@ -343,7 +355,7 @@ __global__ void __launch_bounds__(32 * KT_MAX_A) k_anchor_targets_tiles(const K1
     const bool match_x = valid_x && (aw > 0.0);
     // exact bounding box of the warp's anchors (first / last valid column, first / last valid row)
     const double wx1 = b0 + ((double)cx0 + 0.5) * stride, wx2 = b2 + ((double)(cx0 + ncols - 1) + 0.5) * stride;
-    const double wy1 = ay1[0], wy2 = b3 + ((double)(cy0 + nrows - 1) + 0.5) * stride;
+    const double wy1 = b1 + ((double)cy0 + 0.5) * stride, wy2 = b3 + ((double)(cy0 + nrows - 1) + 0.5) * stride;
 
     // ---- matching -------------------------------------------------------------------------------------
     float best[KT_ROWS];
@@ -375,14 +387,15 @@ __global__ void __launch_bounds__(32 * KT_MAX_A) k_anchor_targets_tiles(const K1
                 live &= live - 1u;
                 const double g1 = s_gx1[m], g2 = s_gx2[m];
                 if (match_x && g2 > ax1 && g1 < ax2) {
-                    const double iw = fmin(ax2, g2) - fmax(ax1, g1);
+                    const double iw = dmin(ax2, g2) - dmax(ax1, g1);
                     const double g3 = s_gy1[m], g4 = s_gy2[m], ga = s_ga[m];
 #pragma unroll
                     for (int r = 0; r < KT_ROWS; ++r) {
-                        if (r < nrows && g4 > ay1[r] && g3 < ay2[r] && ah[r] > 0.0) {
-                            const double ih = fmin(ay2[r], g4) - fmax(ay1[r], g3);
+                        const double y1 = row[r][0], y2 = row[r][1], hh = row[r][2];
+                        if (r < nrows && g4 > y1 && g3 < y2 && hh > 0.0) {
+                            const double ih = dmin(y2, g4) - dmax(y1, g3);
                             const double inter = iw * ih;
-                            const double uni = aw * ah[r] + ga - inter;
+                            const double uni = aw * hh + ga - inter;
                             const double q = inter * rcp_fast(uni);
                             const float iou = f32_rounding_safe(q) ? (float)q : iou_exact(inter, uni);
                             if (iou > best[r]) { best[r] = iou; arg[r] = g0 + m; }
@@ -405,6 +418,7 @@ __global__ void __launch_bounds__(32 * KT_MAX_A) k_anchor_targets_tiles(const K1
 #pragma unroll
         for (int r = 0; r < KT_ROWS; ++r) {
             if (r < nrows) {
+                const double y1 = row[r][0], y2 = row[r][1], hh = row[r][2];
                 float state = 0.0f, t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
                 int hot = -1;
                 if (G > 0) {
@@ -413,13 +427,13 @@ __global__ void __launch_bounds__(32 * KT_MAX_A) k_anchor_targets_tiles(const K1
                     state = is_pos ? 1.0f : (is_ign ? -1.0f : 0.0f);
                     if (is_pos) hot = __ldg(p.gt_labels + (size_t)b * p.Gmax + arg[r]);
                     const double* g = gtb + 4 * (size_t)arg[r];
-                    const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(ah[r]);
+                    const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(hh);
                     t0 = reg_target5(__ldg(g + 0), ax1, aw, r5w);
-                    t1 = reg_target5(__ldg(g + 1), ay1[r], ah[r], r5h);
+                    t1 = reg_target5(__ldg(g + 1), y1, hh, r5h);
                     t2 = reg_target5(__ldg(g + 2), ax2, aw, r5w);
-                    t3 = reg_target5(__ldg(g + 3), ay2[r], ah[r], r5h);
+                    t3 = reg_target5(__ldg(g + 3), y2, hh, r5h);
                 }
-                if (p.img_hw && (out_x || ((ay1[r] + ay2[r]) / 2.0) >= img_h)) state = -1.0f;
+                if (p.img_hw && (out_x || ((y1 + y2) / 2.0) >= img_h)) state = -1.0f;
                 const int k = (r * 32 + lane) * A + a;      // reference order within the tile row
                 s_reg[k * 5 + 0] = t0; s_reg[k * 5 + 1] = t1; s_reg[k * 5 + 2] = t2; s_reg[k * 5 + 3] = t3; s_reg[k * 5 + 4] = state;
                 s_state[k] = state;
@@ -440,25 +454,54 @@ __global__ void __launch_bounds__(32 * KT_MAX_A) k_anchor_targets_tiles(const K1
         if (p.npos_total) atomicAdd(p.npos_total, (float)s_npos);   // integer-valued: exact, order-independent
     }
 
-    // ---- write-out: each tile row is one contiguous anchor range ----------------------------------------
+    // ---- write-out: each tile row is one contiguous anchor range; ONE loop over 16-byte units of all rows ---
+    // unit 0 of a row = the (<= 3) floats before the first 16-byte boundary, then whole float4s, the last unit
+    // being a partial tail -- so rows with any alignment (e.g. N = 719,523) still use 128-bit stores
     const int cnt = ncols * A;
-    for (int r = 0; r < nrows; ++r) {
-        const long long row0 = (long long)b * p.N + p.lv.start[level] + ((long long)(cy0 + r) * W + cx0) * A;
-        const float* sr = s_reg + r * 32 * A * 5;
-        const float* ss = s_state + r * 32 * A;
-        const int* sh = s_hot + r * 32 * A;
-        store_range(p.reg, row0 * 5, cnt * 5, p.vec_ok != 0, nthreads, [&](int i) { return sr[i]; });
-        if (p.C == 1) {
-            store_range(p.lab, row0 * 2, cnt * 2, p.vec_ok != 0, nthreads, [&](int i) {
-                const int q = i >> 1;
-                return (i & 1) ? ss[q] : (sh[q] == 0 ? 1.0f : 0.0f);
-            });
-        } else {
-            store_labels_generic(p.lab, row0, cnt, p.C, p.vec_ok != 0, nthreads, ss, sh);
+    const long long tile_row0 = (long long)b * p.N + p.lv.start[level] + ((long long)cy0 * W + cx0) * A;
+    {
+        const int len = cnt * 5, upr = (len >> 2) + 2;      // units per row (upper bound)
+        const float inv_upr = 1.0f / (float)upr;
+        for (int u = tid; u < nrows * upr; u += nthreads) {
+            const int r = rn_div(u, upr, inv_upr), v = u - r * upr;
+            const long long start = (tile_row0 + (long long)r * W * A) * 5;
+            const float* sr = s_reg + r * 32 * A * 5;
+            float* dst = p.reg + start;
+            const int head = p.vec_ok ? (int)((4 - (start & 3)) & 3) : 0;
+            if (v == 0) {
+                for (int i = 0; i < head && i < len; ++i) dst[i] = sr[i];
+            } else {
+                const int i = head + 4 * (v - 1);
+                if (p.vec_ok && i + 4 <= len) rn_stg_stream4(dst + i, make_float4(sr[i], sr[i + 1], sr[i + 2], sr[i + 3]));
+                else for (int k = i; k < len && k < i + 4; ++k) dst[k] = sr[k];
+            }
         }
     }
+    if (p.C == 1) {
+        const int len = cnt * 2, upr = (len >> 2) + 2;
+        const float inv_upr = 1.0f / (float)upr;
+        for (int u = tid; u < nrows * upr; u += nthreads) {
+            const int r = rn_div(u, upr, inv_upr), v = u - r * upr;
+            const long long start = (tile_row0 + (long long)r * W * A) * 2;
+            const float* ss = s_state + r * 32 * A;
+            const int* sh = s_hot + r * 32 * A;
+            float* dst = p.lab + start;
+            const int head = p.vec_ok ? (int)((4 - (start & 3)) & 3) : 0;     // 0 or 2 (rows are 8-byte aligned)
+            auto gen = [&](int i) { const int q = i >> 1; return (i & 1) ? ss[q] : (sh[q] == 0 ? 1.0f : 0.0f); };
+            if (v == 0) {
+                for (int i = 0; i < head && i < len; ++i) dst[i] = gen(i);
+            } else {
+                const int i = head + 4 * (v - 1);
+                if (p.vec_ok && i + 4 <= len) rn_stg_stream4(dst + i, make_float4(gen(i), gen(i + 1), gen(i + 2), gen(i + 3)));
+                else for (int k = i; k < len && k < i + 4; ++k) dst[k] = gen(k);
+            }
+        }
+    } else {
+        for (int r = 0; r < nrows; ++r)
+            store_labels_generic(p.lab, tile_row0 + (long long)r * W * A, cnt, p.C, p.vec_ok != 0, nthreads,
+                                 s_state + r * 32 * A, s_hot + r * 32 * A);
+    }
 }
-
 
 __global__ void k_anchors_f64(const RnLevels lv, const double* base, int N, double* out) {
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
@@ -579,10 +622,17 @@ extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* leve
         for (int l = num_levels; l <= RN_MAX_LEVELS; ++l) tl.tile_start[l] = tiles;
         p.max_coord = max_coord;
         const size_t dyn = (size_t)KT_ROWS * 32 * A * 7 * sizeof(float);
-        cudaError_t ae = cudaFuncSetAttribute(k_anchor_targets_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)((size_t)KT_ROWS * 32 * KT_MAX_A * 7 * sizeof(float)));
-        if (ae != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
-        if (tiles > 0) k_anchor_targets_tiles<<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);
+        if (tiles > 0 && A <= 9) {
+            static const int minb = getenv("RN_K1_MINB") ? atoi(getenv("RN_K1_MINB")) : 4;   // tuning knob
+            if (minb >= 4) k_anchor_targets_tiles<9, 4><<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);
+            else if (minb == 3) k_anchor_targets_tiles<9, 3><<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);
+            else k_anchor_targets_tiles<9, 2><<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);
+        } else if (tiles > 0) {
+            cudaError_t ae = cudaFuncSetAttribute(k_anchor_targets_tiles<KT_MAX_A, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)((size_t)KT_ROWS * 32 * KT_MAX_A * 7 * sizeof(float)));
+            if (ae != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
+            k_anchor_targets_tiles<KT_MAX_A, 1><<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);
+        }
     } else {
         k_anchor_targets<false><<<grid, K1_THREADS, 0, s>>>(p);
     }
