@@ -1,0 +1,29 @@
+"""Per-phase clock64 breakdown of k_segment_nms (RN_NMS_TIMING=1) at the benchmark's inference sizes."""
+import os
+import sys
+
+os.environ["RN_NMS_TIMING"] = "1"
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import retinanet_b200 as rn  # noqa: E402
+import synthetic  # noqa: E402
+
+HW, B = (800, 1333), 64
+anchors = np.asarray(rn.anchors_for_shape(HW + (3,)))
+_, anns = synthetic.training_batch(3, batch=B)
+cls, reg = synthetic.inference_predictions(3, B, anchors, anns, classes=1)
+cls_d, reg_d = torch.from_numpy(cls).cuda(), torch.from_numpy(reg).cuda()
+names = ["radix select", "gather", "bitonic sort", "batch load", "(a) vs selected", "(b) bit-matrix", "(c) resolve"]
+for topk in (0, 1000):
+    head = rn.DetectionHead(pre_nms_top_k=topk)
+    for _ in range(3):
+        head([(B,) + HW + (3,), reg_d, cls_d])
+    torch.cuda.synchronize()
+    ws = [v for k, v in rn._lib._scratch.items() if k[0] == "filter"][0]
+    t = ws[:64].view(torch.int64).cpu().numpy().astype(np.float64)
+    print("pre_nms_top_k=%d: ticks per segment (thread 0): total %.0f" % (topk, t.sum() / B))
+    for n, v in zip(names, t):
+        print("   %-16s %8.0f  %5.1f%%" % (n, v / B, 100 * v / t.sum()))

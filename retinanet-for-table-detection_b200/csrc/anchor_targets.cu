@@ -301,7 +301,7 @@ struct K1Tiles {
 };
 
 // MAXA bounds the block size (32 * A threads) so that the register budget can be set per instantiation:
-// <9, 4> is the RetinaNet default (288 threads, >= 4 CTAs per SM), <KT_MAX_A, 1> covers the rest
+// <9, 3> is the RetinaNet default (288 threads, >= 3 CTAs per SM), <KT_MAX_A, 1> covers the rest
 template <int MAXA, int MINB>
 __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const K1Params p, const K1Tiles tl) {
     extern __shared__ __align__(16) float s_dyn[];
@@ -623,7 +623,7 @@ extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* leve
         p.max_coord = max_coord;
         const size_t dyn = (size_t)KT_ROWS * 32 * A * 7 * sizeof(float);
         if (tiles > 0 && A <= 9) {
-            static const int minb = getenv("RN_K1_MINB") ? atoi(getenv("RN_K1_MINB")) : 4;   // tuning knob
+            static const int minb = getenv("RN_K1_MINB") ? atoi(getenv("RN_K1_MINB")) : 3;   // tuning knob (measured: 3 CTAs/SM, 75 registers, is fastest)
             if (minb >= 4) k_anchor_targets_tiles<9, 4><<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);
             else if (minb == 3) k_anchor_targets_tiles<9, 3><<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);
             else k_anchor_targets_tiles<9, 2><<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);

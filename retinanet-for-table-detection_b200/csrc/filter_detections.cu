@@ -20,6 +20,7 @@
 // Semantics restated from tf.image.non_max_suppression / tf.nn.top_k: see oracle/layers_np.py.
 // Compiled with -fmad=false: IoU and decode are evaluated in the reference's fp32 operation order.
 #include "rn_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -94,80 +95,94 @@ __device__ __forceinline__ float4 candidate_box(const K3Params& p, int b, int n)
     return o;
 }
 
-// write one candidate into slot `slot` of slab `seg` (dropped when the slab is full; the count keeps
-// growing so the overflow is detected by k_segment_nms)
-template <bool DECODE>
-__device__ __forceinline__ void put(const K3Params& p, int seg, long long slot, int b, int n, float score, int label) {
-    if (slot < p.sl.cap) {
-        const size_t at = (size_t)seg * p.sl.cap + slot;
-        p.sl.keys[at] = make_key(score, (unsigned)n);
-        p.sl.boxes[at] = candidate_box<DECODE>(p, b, n);
-        if (p.sl.labels) p.sl.labels[at] = label;
-    }
-}
+// grid = (tiles of a page, pages).  Two phases per CTA so that the sparse candidates (~2.5 % of the scores)
+// never make whole warps walk the divergent decode path:
+//   1. every thread streams K3_VEC float4 groups of scores (all loads issued up front) and pushes the
+//      survivors of `score > thr` into a shared-memory list (shared-memory atomics);
+//   2. the list is consumed densely, one candidate per thread: slot reservation (ONE global atomic per CTA
+//      when all candidates feed the same slab, i.e. C == 1 or class-agnostic; one per candidate otherwise),
+//      box decode, key/box store.
+constexpr int K3_VEC = 4;                                   // float4 groups per thread
+constexpr int K3_TILE = K3_THREADS * K3_VEC * 4;            // scores per CTA (class-specific path)
 
-// grid = (tiles of a page, pages): no division is needed to find the page, and when C == 1 every lane of
-// a warp feeds the same slab, so a warp needs ONE atomic: per-thread candidate counts are prefix-summed
-// with shuffles and the warp's total reserves a contiguous slot range.
 template <bool DECODE>
 __global__ void __launch_bounds__(K3_THREADS) k_threshold_compact(const K3Params p) {
-    const int b = blockIdx.y;
-    const int lane = threadIdx.x & 31;
+    __shared__ int s_elem[K3_TILE];
+    __shared__ float s_score[K3_TILE];
+    __shared__ int s_label[K3_THREADS * K3_VEC];            // class-agnostic path only
+    __shared__ int s_count, s_base;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    const bool one_slab = (p.C == 1) || !p.class_specific;
     if (p.class_specific) {
-        // 4 consecutive elements of the page's (N, C) score matrix per thread
-        const int total = p.N * p.C;                             // < 2^31 (checked on the host)
-        const int e0 = (blockIdx.x * K3_THREADS + threadIdx.x) * 4;
+        const int total = p.N * p.C;                        // scores of this page, < 2^31 (checked on the host)
         const float* src = p.cls + (size_t)b * total;
-        float sv[4] = {0.f, 0.f, 0.f, 0.f};
-        const int cnt = max(0, min(4, total - e0));
-        if (cnt == 4 && p.vec_ok) { const float4 v = rn_ldg_stream4(src + e0); sv[0] = v.x; sv[1] = v.y; sv[2] = v.z; sv[3] = v.w; }
-        else for (int k = 0; k < cnt; ++k) sv[k] = __ldg(src + e0 + k);
-        unsigned m = 0;
+        const int tile0 = blockIdx.x * K3_TILE;
+        float sv[K3_VEC][4];
+        int cnt[K3_VEC];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) if (k < cnt && sv[k] > p.thr) m |= 1u << k;
-        if (p.C == 1) {
-            const int mine = __popc(m);
-            int incl = mine;
+        for (int g = 0; g < K3_VEC; ++g) {
+            const int e0 = tile0 + (g * K3_THREADS + tid) * 4;
+            cnt[g] = max(0, min(4, total - e0));
+            sv[g][0] = sv[g][1] = sv[g][2] = sv[g][3] = 0.f;
+            if (cnt[g] == 4 && p.vec_ok) { const float4 v = rn_ldg_stream4(src + e0); sv[g][0] = v.x; sv[g][1] = v.y; sv[g][2] = v.z; sv[g][3] = v.w; }
+            else for (int k = 0; k < cnt[g]; ++k) sv[g][k] = __ldg(src + e0 + k);
+        }
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
-            if (warp_total == 0) return;
-            int base = 0;
-            if (lane == 31) base = atomicAdd(p.sl.counts + b, warp_total);
-            base = __shfl_sync(0xffffffffu, base, 31);
-            long long slot = base + (incl - mine);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (m & (1u << k)) put<DECODE>(p, b, slot++, b, e0 + k, sv[k], 0);
-        } else {
+        for (int g = 0; g < K3_VEC; ++g) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (m & (1u << k)) {
-                    const int e = e0 + k;
-                    const int n = rn_div(e, p.C, p.inv_c);
-                    const int c = e - n * p.C;
-                    const int seg = b * p.C + c;
-                    put<DECODE>(p, seg, atomicAdd(p.sl.counts + seg, 1), b, n, sv[k], c);
+                if (k < cnt[g] && sv[g][k] > p.thr) {
+                    const int at = atomicAdd(&s_count, 1);
+                    s_elem[at] = tile0 + (g * K3_THREADS + tid) * 4 + k;
+                    s_score[at] = sv[g][k];
                 }
             }
         }
     } else {
         // class-agnostic: score = max over classes, label = first argmax (model/layers.py:234-235)
-        const int n = blockIdx.x * K3_THREADS + threadIdx.x;
-        bool is_cand = false;
-        float best = 0.f;
-        int label = 0;
-        if (n < p.N) {
-            const float* s = p.cls + ((size_t)b * p.N + n) * p.C;
-            best = __ldg(s);
-            for (int c = 1; c < p.C; ++c) { const float v = __ldg(s + c); if (v > best) { best = v; label = c; } }
-            is_cand = best > p.thr;
+#pragma unroll
+        for (int g = 0; g < K3_VEC; ++g) {
+            const int n = blockIdx.x * (K3_THREADS * K3_VEC) + g * K3_THREADS + tid;
+            if (n < p.N) {
+                const float* s = p.cls + ((size_t)b * p.N + n) * p.C;
+                float best = __ldg(s);
+                int label = 0;
+                for (int c = 1; c < p.C; ++c) { const float v = __ldg(s + c); if (v > best) { best = v; label = c; } }
+                if (best > p.thr) {
+                    const int at = atomicAdd(&s_count, 1);
+                    s_elem[at] = n; s_score[at] = best; s_label[at] = label;
+                }
+            }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, is_cand);
-        if (bal == 0) return;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(p.sl.counts + b, __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (is_cand) put<DECODE>(p, b, base + __popc(bal & ((1u << lane) - 1u)), b, n, best, label);
+    }
+    __syncthreads();
+    const int found = s_count;
+    if (found == 0) return;
+    if (one_slab) {
+        if (tid == 0) s_base = atomicAdd(p.sl.counts + b, found);
+        __syncthreads();
+    }
+    for (int i = tid; i < found; i += K3_THREADS) {
+        const int e = s_elem[i];
+        int n = e, c = 0, seg = b;
+        long long slot;
+        if (one_slab) {
+            slot = (long long)s_base + i;
+            if (!p.class_specific) c = s_label[i];
+        } else {
+            n = rn_div(e, p.C, p.inv_c);
+            c = e - n * p.C;
+            seg = b * p.C + c;
+            slot = atomicAdd(p.sl.counts + seg, 1);
+        }
+        if (slot < p.sl.cap) {                              // dropped when the slab is full; the count keeps
+            const size_t at = (size_t)seg * p.sl.cap + slot;    // growing so k_segment_nms reports the overflow
+            p.sl.keys[at] = make_key(s_score[i], (unsigned)n);
+            p.sl.boxes[at] = candidate_box<DECODE>(p, b, n);
+            if (p.sl.labels) p.sl.labels[at] = c;
+        }
     }
 }
 
@@ -189,6 +204,7 @@ struct NmsParams {
     float4* kept_box;              // (S, max_det)
     int* kept_label;               // (S, max_det)
     int* status;                   // (pages) or nullptr
+    unsigned long long* timing;    // 8 phase counters (clock64 ticks of thread 0, summed over CTAs) or nullptr
 };
 
 // TF non_max_suppression_op.cc IOU on corner-normalised boxes with precomputed areas
@@ -244,6 +260,9 @@ __global__ void __launch_bounds__(NMS_THREADS) k_segment_nms(const NmsParams p) 
     const int* labels = p.sl.labels ? p.sl.labels + (size_t)seg * p.sl.cap : nullptr;
     const int seg_label = seg % p.segs_per_page;
 
+    // optional phase timing (RN_NMS_TIMING=1): thread 0 accumulates clock64() deltas per phase
+    long long t_mark = p.timing ? clock64() : 0;
+#define RN_PHASE(k) do { if (p.timing && tid == 0) { const long long now = clock64(); atomicAdd(p.timing + (k), (unsigned long long)(now - t_mark)); t_mark = now; } } while (0)
     unsigned long long upper = ~0ull;   // keys >= upper have been visited
     int visited = 0, nsel = 0;
     if (tid == 0) s_nsel = 0;
@@ -288,6 +307,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_segment_nms(const NmsParams p) 
             }
             thr_key = s_prefix;          // exactly `take` unvisited keys are >= thr_key
         }
+        RN_PHASE(0);
         // ---------------- gather the chunk into shared memory ----------------------------------------
         if (tid == 0) s_loaded = 0;
         __syncthreads();
@@ -304,6 +324,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_segment_nms(const NmsParams p) 
         while (n2 < loaded) n2 <<= 1;
         for (int i = loaded + tid; i < n2; i += NMS_THREADS) { s_key[i] = 0ull; s_slot[i] = 0u; }
         __syncthreads();
+        RN_PHASE(1);
         // ---------------- bitonic network, descending (keys are unique) ----------------------------
         for (int k = 2; k <= n2; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
@@ -322,6 +343,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_segment_nms(const NmsParams p) 
             }
         }
         const int chunk_n = min(loaded, take);
+        RN_PHASE(2);
         // ---------------- K5: greedy NMS over the ordered chunk, 256 candidates per round --------------
         for (int s0 = 0; s0 < chunk_n && nsel < p.max_det; s0 += NMS_BATCH) {
             const int bn = min(NMS_BATCH, chunk_n - s0);
@@ -340,6 +362,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_segment_nms(const NmsParams p) 
             }
             __syncthreads();
             if (p.nms) {
+                RN_PHASE(3);
                 // (a) against everything selected so far: 2 threads per candidate split the list
                 {
                     const int c = tid & (NMS_BATCH - 1), part = tid >> 8;
@@ -353,6 +376,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_segment_nms(const NmsParams p) 
                     }
                 }
                 __syncthreads();
+                RN_PHASE(4);
                 // (b) suppression bit-matrix among the survivors (upper triangle), one ballot per word
                 for (int i = warp; i < bn; i += NMS_WARPS) {
                     if (!s_alive[i]) continue;
@@ -367,6 +391,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_segment_nms(const NmsParams p) 
                 }
                 __syncthreads();
             }
+            RN_PHASE(5);
             // (c) one warp walks the surviving bits in order
             if (warp == 0) {
                 unsigned mine = 0u;
@@ -400,12 +425,14 @@ __global__ void __launch_bounds__(NMS_THREADS) k_segment_nms(const NmsParams p) 
             }
             __syncthreads();
             nsel = s_nsel;
+            RN_PHASE(6);
         }
         visited += take;
         upper = (loaded > 0) ? s_key[chunk_n - 1] : 0ull;
         __syncthreads();
     }
     if (tid == 0) p.kept_count[seg] = nsel;
+#undef RN_PHASE
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -505,6 +532,7 @@ __global__ void k_keys_from_scores(const float* scores, long long K, unsigned lo
 // workspace carving (256-byte aligned sections)
 // ------------------------------------------------------------------------------------------------
 struct FilterWs {
+    unsigned long long* timing;
     int* counts; int* kept_count; int* status;
     unsigned long long* keys; float4* boxes; int* labels;
     unsigned long long* kept_key; float4* kept_box; int* kept_label;
@@ -518,6 +546,7 @@ FilterWs carve(void* ws, int B, int S, long long cap, int max_det, bool agnostic
     size_t off = 0;
     char* base = reinterpret_cast<char*>(ws);
     auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align256(bytes); return p; };
+    w.timing = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * 8));   // first 64 bytes
     w.counts = reinterpret_cast<int*>(take(sizeof(int) * S));
     w.kept_count = reinterpret_cast<int*>(take(sizeof(int) * S));
     w.status = reinterpret_cast<int*>(take(sizeof(int) * B));
@@ -544,6 +573,8 @@ int run_back_end(const FilterWs& w, int B, int S, int segs_per_page, long long c
     np.max_det = max_det; np.pre_nms_top_k = pre_nms_top_k;
     np.kept_count = w.kept_count; np.kept_key = w.kept_key; np.kept_box = w.kept_box; np.kept_label = w.kept_label;
     np.status = status;
+    static const bool timing_on = getenv("RN_NMS_TIMING") != nullptr;
+    np.timing = timing_on ? w.timing : nullptr;
     const size_t dyn = nms_dynamic_smem(max_det);
     // static (~43 KB) + dynamic shared memory exceeds the 48 KB default: opt in (227 KB per CTA on sm_100a)
     cudaError_t ae = cudaFuncSetAttribute(k_segment_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_dynamic_smem(MAX_DET_LIMIT));
@@ -579,7 +610,7 @@ int filter_common(K3Params kp, bool decode, int nms, float nms_thr, int max_det,
     FilterWs w = carve(workspace, B, S, cand_cap, max_det, !kp.class_specific);
     if (workspace_bytes < w.bytes) return rn_fail(RN_ERR_WORKSPACE, "filter workspace too small: %zu < %zu", workspace_bytes, w.bytes);
     // counts, kept_count, status are contiguous at the front of the workspace
-    cudaError_t e = cudaMemsetAsync(w.counts, 0, (size_t)((char*)w.keys - (char*)w.counts), s);
+    cudaError_t e = cudaMemsetAsync(w.timing, 0, (size_t)((char*)w.keys - (char*)w.timing), s);
     if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
     if (status_out) {
         e = cudaMemsetAsync(status_out, 0, sizeof(int) * (size_t)B, s);
@@ -590,8 +621,9 @@ int filter_common(K3Params kp, bool decode, int nms, float nms_thr, int max_det,
     RN_REQUIRE(B <= 65535, "B must be <= 65535");
     kp.inv_c = 1.0f / (float)C;
     kp.vec_ok = (((long long)kp.N * C) % 4 == 0) ? 1 : 0;
-    const long long units = kp.class_specific ? ((long long)kp.N * C + 3) / 4 : (long long)kp.N;
-    const dim3 grid((unsigned)((units + K3_THREADS - 1) / K3_THREADS), (unsigned)B);
+    const long long tiles = kp.class_specific ? ((long long)kp.N * C + K3_TILE - 1) / K3_TILE
+                                              : ((long long)kp.N + K3_THREADS * K3_VEC - 1) / (K3_THREADS * K3_VEC);
+    const dim3 grid((unsigned)tiles, (unsigned)B);
     if (decode) k_threshold_compact<true><<<grid, K3_THREADS, 0, s>>>(kp);
     else k_threshold_compact<false><<<grid, K3_THREADS, 0, s>>>(kp);
     int rc = rn_check_launch("k_threshold_compact");
@@ -673,7 +705,7 @@ extern "C" int rn_nms(const float* boxes, const float* scores, long long K, int 
     float* sc_boxes = reinterpret_cast<float*>(tail); tail += align256(sizeof(float4) * (size_t)max_output);
     float* sc_scores = reinterpret_cast<float*>(tail); tail += align256(sizeof(float) * (size_t)max_output);
     int* sc_labels = reinterpret_cast<int*>(tail);
-    cudaError_t e = cudaMemsetAsync(w.counts, 0, (size_t)((char*)w.keys - (char*)w.counts), s);
+    cudaError_t e = cudaMemsetAsync(w.timing, 0, (size_t)((char*)w.keys - (char*)w.timing), s);
     if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
     if (K > 0) {
         RN_REQUIRE(boxes && scores, "NULL input");
