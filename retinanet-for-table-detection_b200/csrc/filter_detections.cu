@@ -232,7 +232,78 @@ __device__ __forceinline__ bool iou_exceeds(const float4 a, const float aa, cons
     return inter / (aa + ab - inter) > thr;
 }
 
-__global__ void __launch_bounds__(NMS_THREADS) k_segment_nms(const NmsParams p) {
+
+// Descending bitonic sort of n (power of two, 128 <= n <= NMS_CHUNK) (key, slot) pairs in shared memory.
+// Each of the first n/4 threads keeps 4 consecutive elements in registers: compare-exchange distances 1-2
+// are thread-local, 4-64 are warp shuffles, only distances >= 128 go through shared memory -- 10 block-wide
+// exchange steps for n = 2048 instead of 66.  Keys are unique (zero padding excepted, which never swaps).
+// Must be called by all threads of the CTA.
+__device__ __forceinline__ void ce_keep(unsigned long long& a, unsigned& av, unsigned long long b, unsigned bv, bool take_max) {
+    const bool sw = take_max ? (b > a) : (b < a);
+    if (sw) { a = b; av = bv; }
+}
+
+__device__ void sort_chunk_desc(unsigned long long* s_key, unsigned* s_slot, const int n, const int tid) {
+    const bool act = tid < (n >> 2);                 // warp-uniform: n/4 is a multiple of 32
+    const int i0 = tid * 4;
+    unsigned long long k4[4] = {0ull, 0ull, 0ull, 0ull};
+    unsigned v4[4] = {0u, 0u, 0u, 0u};
+    if (act) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { k4[e] = s_key[i0 + e]; v4[e] = s_slot[i0 + e]; }
+    }
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 128) {
+                if (act) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { s_key[i0 + e] = k4[e]; s_slot[i0 + e] = v4[e]; }
+                }
+                __syncthreads();
+                if (act) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = i0 + e, x = i ^ j;
+                        ce_keep(k4[e], v4[e], s_key[x], s_slot[x], ((i & j) == 0) == ((i & k) == 0));
+                    }
+                }
+                __syncthreads();
+            } else if (j >= 4) {
+                if (act) {
+                    const int lm = j >> 2;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = i0 + e;
+                        const unsigned long long b = __shfl_xor_sync(0xffffffffu, k4[e], lm);
+                        const unsigned bv = __shfl_xor_sync(0xffffffffu, v4[e], lm);
+                        ce_keep(k4[e], v4[e], b, bv, ((i & j) == 0) == ((i & k) == 0));
+                    }
+                }
+            } else if (act) {
+                const bool desc = ((i0 & k) == 0);     // k >= 2j; for k >= 4 all 4 elements share the direction
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int x = e ^ j;
+                    if (x > e) {
+                        const bool d = (k >= 4) ? desc : (((i0 + e) & k) == 0);
+                        const bool sw = d ? (k4[e] < k4[x]) : (k4[e] > k4[x]);
+                        if (sw) {
+                            const unsigned long long tk = k4[e]; k4[e] = k4[x]; k4[x] = tk;
+                            const unsigned tv = v4[e]; v4[e] = v4[x]; v4[x] = tv;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (act) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { s_key[i0 + e] = k4[e]; s_slot[i0 + e] = v4[e]; }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // dynamic: selected boxes (normalised corners) + areas, sized by max_det
     float4* s_selbox = reinterpret_cast<float4*>(smem_raw);
@@ -245,6 +316,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_segment_nms(const NmsParams p) 
     __shared__ float s_carea[NMS_BATCH];
     __shared__ int s_alive[NMS_BATCH];
     __shared__ unsigned s_mask[NMS_BATCH * NMS_WORDS];
+    __shared__ unsigned short s_pick[NMS_BATCH];
     __shared__ unsigned s_hist[256];
     __shared__ unsigned long long s_prefix;
     __shared__ int s_want, s_loaded, s_nsel;
@@ -320,28 +392,13 @@ __global__ void __launch_bounds__(NMS_THREADS) k_segment_nms(const NmsParams p) 
         }
         __syncthreads();
         const int loaded = min(s_loaded, NMS_CHUNK);
-        int n2 = 32;
+        int n2 = 128;
         while (n2 < loaded) n2 <<= 1;
         for (int i = loaded + tid; i < n2; i += NMS_THREADS) { s_key[i] = 0ull; s_slot[i] = 0u; }
         __syncthreads();
         RN_PHASE(1);
         // ---------------- bitonic network, descending (keys are unique) ----------------------------
-        for (int k = 2; k <= n2; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < n2; i += NMS_THREADS) {
-                    const int x = i ^ j;
-                    if (x > i) {
-                        const unsigned long long a = s_key[i], b = s_key[x];
-                        const bool desc = ((i & k) == 0);
-                        if (desc ? (a < b) : (a > b)) {
-                            s_key[i] = b; s_key[x] = a;
-                            const unsigned t = s_slot[i]; s_slot[i] = s_slot[x]; s_slot[x] = t;
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-        }
+        sort_chunk_desc(s_key, s_slot, n2, tid);
         const int chunk_n = min(loaded, take);
         RN_PHASE(2);
         // ---------------- K5: greedy NMS over the ordered chunk, 256 candidates per round --------------
@@ -378,14 +435,24 @@ __global__ void __launch_bounds__(NMS_THREADS) k_segment_nms(const NmsParams p) 
                 __syncthreads();
                 RN_PHASE(4);
                 // (b) suppression bit-matrix among the survivors (upper triangle), one ballot per word
+                unsigned aw[NMS_WORDS];                     // alive columns, 32 per word (warp-uniform)
+#pragma unroll
+                for (int w = 0; w < NMS_WORDS; ++w) aw[w] = __ballot_sync(0xffffffffu, s_alive[w * 32 + lane] != 0);
                 for (int i = warp; i < bn; i += NMS_WARPS) {
                     if (!s_alive[i]) continue;
                     const float4 bi = s_cbox[i];
                     const float ai = s_carea[i];
-                    for (int w = i >> 5; w < NMS_WORDS; ++w) {
-                        const int j = w * 32 + lane;
-                        const bool hit = (j > i) && (j < bn) && s_alive[j] && iou_exceeds(bi, ai, s_cbox[j], s_carea[j], p.iou_thr);
-                        const unsigned word = __ballot_sync(0xffffffffu, hit);
+                    const int w_first = i >> 5;
+#pragma unroll
+                    for (int w = 0; w < NMS_WORDS; ++w) {      // unrolled: the 8 words are independent
+                        if (w < w_first) continue;
+                        unsigned word = 0u;
+                        if (aw[w]) {
+                            const int j = w * 32 + lane;
+                            const bool hit = (j > i) && ((aw[w] >> lane) & 1u) &&
+                                             iou_exceeds(bi, ai, s_cbox[j], s_carea[j], p.iou_thr);
+                            word = __ballot_sync(0xffffffffu, hit);
+                        }
                         if (lane == 0) s_mask[i * NMS_WORDS + w] = word;
                     }
                 }
@@ -408,20 +475,23 @@ __global__ void __launch_bounds__(NMS_THREADS) k_segment_nms(const NmsParams p) 
                     const unsigned word = __shfl_sync(0xffffffffu, mine, w0);
                     const int bit = __ffs(word) - 1;
                     const int i = w0 * 32 + bit;
-                    if (lane == 0) {
-                        s_selbox[ns] = s_cbox[i];
-                        s_selarea[ns] = s_carea[i];
-                        const size_t at = (size_t)seg * p.max_det + ns;
-                        const unsigned long long k = s_key[s0 + i];
-                        p.kept_key[at] = k;
-                        p.kept_box[at] = s_craw[i];
-                        p.kept_label[at] = labels ? labels[s_slot[s0 + i]] : seg_label;
-                    }
+                    if (lane == 0) s_pick[ns - nsel] = (unsigned short)i;
                     ++ns;
                     if (lane == w0) mine &= ~(1u << bit);
                     if (p.nms && lane < NMS_WORDS && lane >= w0) mine &= ~s_mask[i * NMS_WORDS + lane];
                 }
                 if (lane == 0) s_nsel = ns;
+            }
+            __syncthreads();
+            // the picked candidates join the selected list / the kept arrays, one thread each
+            for (int t = tid; t < s_nsel - nsel; t += NMS_THREADS) {
+                const int i = s_pick[t], ns = nsel + t;
+                s_selbox[ns] = s_cbox[i];
+                s_selarea[ns] = s_carea[i];
+                const size_t at = (size_t)seg * p.max_det + ns;
+                p.kept_key[at] = s_key[s0 + i];
+                p.kept_box[at] = s_craw[i];
+                p.kept_label[at] = labels ? labels[s_slot[s0 + i]] : seg_label;
             }
             __syncthreads();
             nsel = s_nsel;
