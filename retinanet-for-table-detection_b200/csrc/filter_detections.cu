@@ -243,6 +243,15 @@ __device__ __forceinline__ void ce_keep(unsigned long long& a, unsigned& av, uns
     if (sw) { a = b; av = bv; }
 }
 
+// (lo, hi) pair inside a thread: descending -> larger key first
+__device__ __forceinline__ void ce_local(unsigned long long& a, unsigned& av, unsigned long long& b, unsigned& bv, bool desc) {
+    const bool sw = desc ? (a < b) : (a > b);
+    if (sw) {
+        const unsigned long long tk = a; a = b; b = tk;
+        const unsigned tv = av; av = bv; bv = tv;
+    }
+}
+
 __device__ void sort_chunk_desc(unsigned long long* s_key, unsigned* s_slot, const int n, const int tid) {
     const bool act = tid < (n >> 2);                 // warp-uniform: n/4 is a multiple of 32
     const int i0 = tid * 4;
@@ -280,18 +289,15 @@ __device__ void sort_chunk_desc(unsigned long long* s_key, unsigned* s_slot, con
                     }
                 }
             } else if (act) {
-                const bool desc = ((i0 & k) == 0);     // k >= 2j; for k >= 4 all 4 elements share the direction
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int x = e ^ j;
-                    if (x > e) {
-                        const bool d = (k >= 4) ? desc : (((i0 + e) & k) == 0);
-                        const bool sw = d ? (k4[e] < k4[x]) : (k4[e] > k4[x]);
-                        if (sw) {
-                            const unsigned long long tk = k4[e]; k4[e] = k4[x]; k4[x] = tk;
-                            const unsigned tv = v4[e]; v4[e] = v4[x]; v4[x] = tv;
-                        }
-                    }
+                // thread-local exchanges, written out so that k4 / v4 stay in registers (no dynamic indexing)
+                if (j == 2) {
+                    const bool d = ((i0 & k) == 0);                      // k >= 4: one direction per thread
+                    ce_local(k4[0], v4[0], k4[2], v4[2], d);
+                    ce_local(k4[1], v4[1], k4[3], v4[3], d);
+                } else {
+                    const bool d01 = ((i0 & k) == 0), d23 = (((i0 + 2) & k) == 0);   // differ only when k == 2
+                    ce_local(k4[0], v4[0], k4[1], v4[1], d01);
+                    ce_local(k4[2], v4[2], k4[3], v4[3], d23);
                 }
             }
         }
@@ -338,6 +344,17 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     unsigned long long upper = ~0ull;   // keys >= upper have been visited
     int visited = 0, nsel = 0;
     if (tid == 0) s_nsel = 0;
+    // The slab's keys are read ONCE into registers (8 per thread) when the slab has <= 8192 candidates -- the
+    // radix-select passes and the gathers of every round then run out of registers; larger slabs stream the
+    // keys from global memory (L2) in every pass.
+    constexpr int KPT = 8;
+    const bool in_regs = cnt <= KPT * NMS_THREADS;
+    unsigned long long rk[KPT];
+#pragma unroll
+    for (int t = 0; t < KPT; ++t) {
+        const int i = t * NMS_THREADS + tid;
+        rk[t] = (in_regs && i < cnt) ? __ldcg(keys + i) : 0ull;      // 0 never matches (real keys are > 0)
+    }
     __syncthreads();
 
     while (visited < limit && nsel < p.max_det) {
@@ -351,9 +368,17 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                 if (tid < 256) s_hist[tid] = 0u;
                 __syncthreads();
                 const unsigned long long prefix = s_prefix;
-                for (int i = tid; i < cnt; i += NMS_THREADS) {
-                    const unsigned long long k = __ldcg(keys + i);
-                    if (k < upper && (k & mask) == prefix) atomicAdd(&s_hist[(unsigned)(k >> shift) & 255u], 1u);
+                if (in_regs) {
+#pragma unroll
+                    for (int t = 0; t < KPT; ++t) {
+                        const unsigned long long k = rk[t];
+                        if (k != 0ull && k < upper && (k & mask) == prefix) atomicAdd(&s_hist[(unsigned)(k >> shift) & 255u], 1u);
+                    }
+                } else {
+                    for (int i = tid; i < cnt; i += NMS_THREADS) {
+                        const unsigned long long k = __ldcg(keys + i);
+                        if (k < upper && (k & mask) == prefix) atomicAdd(&s_hist[(unsigned)(k >> shift) & 255u], 1u);
+                    }
                 }
                 __syncthreads();
                 if (warp == 0) {
@@ -383,11 +408,22 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
         // ---------------- gather the chunk into shared memory ----------------------------------------
         if (tid == 0) s_loaded = 0;
         __syncthreads();
-        for (int i = tid; i < cnt; i += NMS_THREADS) {
-            const unsigned long long k = __ldcg(keys + i);
-            if (k < upper && k >= thr_key) {
-                const int at = atomicAdd(&s_loaded, 1);
-                if (at < NMS_CHUNK) { s_key[at] = k; s_slot[at] = (unsigned)i; }
+        if (in_regs) {
+#pragma unroll
+            for (int t = 0; t < KPT; ++t) {
+                const unsigned long long k = rk[t];
+                if (k != 0ull && k < upper && k >= thr_key) {
+                    const int at = atomicAdd(&s_loaded, 1);
+                    if (at < NMS_CHUNK) { s_key[at] = k; s_slot[at] = (unsigned)(t * NMS_THREADS + tid); }
+                }
+            }
+        } else {
+            for (int i = tid; i < cnt; i += NMS_THREADS) {
+                const unsigned long long k = __ldcg(keys + i);
+                if (k < upper && k >= thr_key) {
+                    const int at = atomicAdd(&s_loaded, 1);
+                    if (at < NMS_CHUNK) { s_key[at] = k; s_slot[at] = (unsigned)i; }
+                }
             }
         }
         __syncthreads();
