@@ -111,13 +111,18 @@ int rn_smooth_l1_fwd_bwd(const float* y_true_reg /*(R,5)*/, const float* y_pred 
                          const float* npos_dev, float* loss_out_dev, float* grad_out /*(R,4)*/,
                          void* workspace, size_t workspace_bytes, void* stream);
 
-/* both losses in ONE launch; losses_out_dev[0]=focal, [1]=smooth_l1, [2]=normaliser used. */
+/* both losses in ONE launch; losses_out_dev[0]=focal, [1]=smooth_l1, [2]=normaliser used.
+ * flags: RN_LOSS_SHARED_STATE = the smooth-L1 part takes the anchor state from y_true_cls's last column
+ * instead of y_true_reg's.  anchor_targets_bbox writes the same state into both (model/anchors.py:73-77,
+ * 89-90), so for targets that come from rn_anchor_targets the result is identical while 20 B/anchor of
+ * reads disappear; leave 0 for arbitrary y_true tensors. */
+#define RN_LOSS_SHARED_STATE 1
 int rn_loss_fwd_bwd(const float* y_true_cls, const float* cls_pred, const float* y_true_reg,
                     const float* reg_pred, long long R, int C,
                     float alpha, float gamma, int bce_mode, float sigma,
                     const float* npos_dev, float* losses_out_dev,
                     float* grad_cls /*(R,C)*/, float* grad_reg /*(R,4)*/,
-                    void* workspace, size_t workspace_bytes, void* stream);
+                    int flags, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Detection head, layer by layer.

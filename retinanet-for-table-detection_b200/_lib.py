@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "librn_b200.so")
 
 RN_BCE_TF2 = 0
 RN_BCE_LOGITS = 1
+RN_LOSS_SHARED_STATE = 1
 
 
 class RnError(RuntimeError):
@@ -40,7 +41,7 @@ SIGNATURES = {
     "rn_focal_fwd_bwd": (c_int, [_P, _P, c_longlong, c_int, c_float, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "rn_smooth_l1_fwd_bwd": (c_int, [_P, _P, c_longlong, c_float, _P, _P, _P, _P, c_size_t, _P]),
     "rn_loss_fwd_bwd": (c_int, [_P, _P, _P, _P, c_longlong, c_int, c_float, c_float, c_int, c_float,
-                                _P, _P, _P, _P, _P, c_size_t, _P]),
+                                _P, _P, _P, _P, c_int, _P, c_size_t, _P]),
     "rn_anchors_f32": (c_int, [_P, _HI, _HI, c_int, c_int, c_int, _P, _P]),
     "rn_regress_boxes": (c_int, [_P, _P, c_longlong, _HF, _HF, _P, _P]),
     "rn_clip_boxes": (c_int, [_P, c_longlong, c_float, c_float, _P, _P]),

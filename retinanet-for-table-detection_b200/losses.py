@@ -117,13 +117,18 @@ def smooth_l1(sigma=3.0):
 
 
 def detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None,
-                     alpha=0.25, gamma=2.0, sigma=3.0, bce="tf2", want_grads=True, out=None, workspace=None):
+                     alpha=0.25, gamma=2.0, sigma=3.0, bce="tf2", want_grads=True, out=None, workspace=None,
+                     shared_state=False):
     """Both losses, forward + backward, in ONE launch of K2 (``rn_loss_fwd_bwd``).
 
     All tensors are float32 CUDA: ``y_true_reg`` (B,N,5), ``y_true_cls`` (B,N,C+1) in the order
     ``anchor_targets_bbox`` returns them; ``reg_pred`` (B,N,4), ``cls_pred`` (B,N,C).
     Returns ``(losses, grad_cls, grad_reg)`` where ``losses`` is a 3-float device tensor
-    ``[focal, smooth_l1, normaliser]`` and the gradients are d(loss)/d(pred) of the respective loss."""
+    ``[focal, smooth_l1, normaliser]`` and the gradients are d(loss)/d(pred) of the respective loss.
+
+    ``shared_state=True``: the smooth-L1 part reads the anchor state from ``y_true_cls[..., -1]`` instead of
+    ``y_true_reg[..., -1]``.  ``anchor_targets_bbox`` always writes the same state into both, so for its
+    outputs the result is identical and 20 B/anchor of reads disappear; keep ``False`` for foreign tensors."""
     device = cls_pred.device
     C = cls_pred.shape[-1]
     R = cls_pred.numel() // C
@@ -142,6 +147,7 @@ def detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None
                                            _lib.ptr(reg_pred), R, C, float(alpha), float(gamma), BCE_MODES[bce],
                                            float(sigma), _lib.ptr(npos),
                                            _lib.ptr(losses), _lib.ptr(grad_cls), _lib.ptr(grad_reg),
+                                           _lib.RN_LOSS_SHARED_STATE if shared_state else 0,
                                            _lib.ptr(ws), ws_bytes, _lib.stream_ptr(device)), "rn_loss_fwd_bwd")
     return losses, grad_cls, grad_reg
 

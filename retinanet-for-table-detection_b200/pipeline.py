@@ -20,13 +20,14 @@ from . import losses as _losses
 class TargetLossStep(object):
     def __init__(self, image_shape, batch, gmax, num_classes, anchor_params=None, pyramid_levels=None,
                  negative_overlap=0.4, positive_overlap=0.5, alpha=0.25, gamma=2.0, sigma=3.0, bce="tf2",
-                 use_graph=True, device=None):
+                 use_graph=True, device=None, shared_state=True):
         _lib.require_cuda()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.spec = _anchors.make_spec(image_shape, pyramid_levels, anchor_params, None)
         self.B, self.G, self.C, self.N = int(batch), max(1, int(gmax)), int(num_classes), self.spec.num_anchors
         self.neg, self.pos = negative_overlap, positive_overlap
-        self.loss_kw = dict(alpha=alpha, gamma=gamma, sigma=sigma, bce=bce)
+        # both target tensors come from K1 in the same step, so their state columns are identical
+        self.loss_kw = dict(alpha=alpha, gamma=gamma, sigma=sigma, bce=bce, shared_state=shared_state)
         d, B, G, N, C = self.device, self.B, self.G, self.N, self.C
         # one staging block: boxes f64 | labels i32 | counts i32 | img_hw i32  (same layout as upload_annotations)
         self.nb, self.nl, self.nc, self.ni = B * G * 32, B * G * 4, B * 4, B * 8

@@ -99,6 +99,29 @@ def test_fused_equals_separate_and_normalizer(rn, C):
     assert close(cp.grad.cpu().numpy(), wgf, atol=1e-7 * float(np.abs(wgf).max())) and close(rp.grad.cpu().numpy(), wgs, atol=1e-9)
 
 
+def test_shared_state_flag_is_identical_for_k1_targets(rn):
+    """RN_LOSS_SHARED_STATE: smooth-L1 reads the state from the label rows.  For targets produced by K1 the two
+    state columns are the same, so losses and gradients must be bit-identical to the default mode."""
+    import synthetic
+    hw = (256, 320)
+    anchors = rn.anchors_for_shape(hw + (3,))
+    imgs = [synthetic.PageShape(hw + (3,)), synthetic.PageShape((256, 300, 3))]
+    anns = [synthetic.gt_for_page(2, i, hw=hw, gmax=6) for i in range(2)]
+    y_reg, y_cls, npos = rn.anchor_targets_bbox(anchors, imgs, anns, 1, output="torch", return_npos=True)
+    assert torch.equal(y_reg[..., -1], y_cls[..., -1])
+    cls, reg = synthetic.training_predictions(2, 2, anchors.shape[0], classes=1)
+    t = lambda a: torch.tensor(a, device="cuda")
+    a = rn.detection_losses(y_reg, y_cls, t(reg), t(cls), normalizer=npos)
+    b = rn.detection_losses(y_reg, y_cls, t(reg), t(cls), normalizer=npos, shared_state=True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    step = rn.pipeline.TargetLossStep(hw + (3,), 2, 8, 1)
+    step.load_annotations(imgs, anns)
+    step.load_predictions(t(cls), t(reg))
+    step.run()
+    assert torch.equal(step.losses, a[0]) and torch.equal(step.grad_cls, a[1]) and torch.equal(step.grad_reg, a[2])
+    assert torch.equal(step.y_reg, y_reg) and torch.equal(step.y_cls, y_cls)
+
+
 def test_no_positive_and_nan_in_ignored_rows(rn):
     """Normaliser is max(1, 0) = 1 with no positives; NaN predictions in ignored / non-positive rows do
     not leak (TF gathers those rows away before any arithmetic)."""
