@@ -1,0 +1,28 @@
+#!/bin/bash
+# GPU-box capture recipe (run under gpurun from the repo root):
+#   gpurun --timeout 1500 -- 'bash profiles/capture.sh r1f'
+# 1. parity tests  2. the default bench line  3. ncu launch list of the same bench command
+# 4. one `ncu --set full` capture of the four hot kernels (profiles/run_kernels.py, no CUDA graphs).
+# Every ncu run follows a plain run of the same command that exited 0.
+set -u
+TAG=${1:-r1}
+OUT=gpurun_out
+mkdir -p $OUT
+python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1
+echo "pytest_exit=$?" | tee -a $OUT/pytest_$TAG.log
+tail -3 $OUT/pytest_$TAG.log
+python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
+echo "bench_exit=$?"
+cat $OUT/bench_$TAG.json
+BCMD="python bench.py --steps 3 --warmup 3 --no-cpu"
+$BCMD > $OUT/plain_bench_$TAG.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+    --log-file $OUT/launches_$TAG.csv $BCMD > $OUT/ncu_launch_$TAG.log 2>&1
+echo "launchlist_exit=$?"
+KCMD="python profiles/run_kernels.py 2"
+$KCMD > $OUT/plain_kernels_$TAG.log 2>&1 &&
+ncu --set full --clock-control none --import-source on \
+    -k regex:'k_anchor_targets|k_loss|k_threshold_compact|k_segment_nms' -c 8 \
+    -o $OUT/prof_$TAG -f $KCMD > $OUT/ncu_full_$TAG.log 2>&1
+echo "ncufull_exit=$?"
+tail -5 $OUT/ncu_full_$TAG.log
