@@ -39,6 +39,17 @@ METRIC = "pages/sec (anchor targets + focal/smooth-L1 fwd+bwd) @800x1333"
 WORKLOAD = "configs[1]: training-target path, 16 pages/GPU of 800x1333, 1 class, <=20 GT, 200700 anchors/page"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
+    capture of this workload (profiles/ncu_traffic.json, written by hand from profiles/*_ncu_full.md)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh).get(kernel, {}).get("bytes_per_launch")
+    except Exception:
+        return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -139,7 +150,7 @@ def cpu_baseline_leg(budget_s=20.0):
     try:
         pool.run(range(min(pool.cores, PAGES_PER_GPU)))                 # warm-up (imports, anchors)
         pages, elapsed, reps = 0, 0.0, 0
-        while elapsed < budget_s / 2 and reps < 4:
+        while elapsed < budget_s * 0.75 and reps < 400:
             elapsed += pool.run(range(PAGES_PER_GPU))
             pages += PAGES_PER_GPU
             reps += 1
@@ -288,7 +299,7 @@ def run_ours(args):
             "gpu_launches": 2 * args.steps,
             "roofline": {"kernel": "k_loss_c1 (K2 fused focal + smooth-L1 fwd+bwd)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": k2_bytes,
+                         "traffic": ncu_traffic("k_loss_c1"), "peak_source": peak_src, "bytes_per_launch": k2_bytes,
                          "bytes_per_anchor": k2_bytes / (N * B), "us_per_launch": k2_ms * 1e3,
                          "achieved_survey_bytes": k2_bytes_survey / (k2_ms * 1e-3) / 1e9},
             "kernels": {"K1_anchor_targets": {"us": k1_ms * 1e3, "algorithmic_bytes": k1_bytes,
