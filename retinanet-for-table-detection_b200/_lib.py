@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librn_b200.so")
+LIB_PATH = os.environ.get("RN_B200_LIB") or os.path.join(_HERE, "librn_b200.so")   # env: A/B builds for profiles/ sweeps
 
 RN_BCE_TF2 = 0
 RN_BCE_LOGITS = 1

@@ -57,5 +57,20 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines):
+    """A/B builds for the tuning sweeps under profiles/: librn_b200.<name>.so compiled with extra -D flags;
+    select it at run time with RN_B200_LIB=<path> (see _lib.py)."""
+    out = os.path.join(HERE, "librn_b200.%s.so" % name)
+    cmd = [os.environ.get("NVCC", "nvcc")] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out] + _sources()
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed (%s):\n%s" % (" ".join(cmd), proc.stdout))
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
