@@ -122,7 +122,7 @@ __device__ __noinline__ float iou_exact(double inter, double uni) { return (floa
 __device__ __forceinline__ float reg_target5(double g, double a, double len, double r5) {
     const double d = g - a;
     const double approx = d * r5;
-    if (d != 0.0 && f32_rounding_safe(approx)) return (float)approx;
+    if (f32_rounding_safe(approx)) return (float)approx;     // d == 0 gives exponent 0 -> exact path (signed zero)
     return reg_target_exact(d, len);
 }
 
@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
     float* s_reg = s_dyn;                                   // [KT_ROWS][32][A][5]
     float* s_state = s_reg + KT_ROWS * 32 * A * 5;          // [KT_ROWS][32][A]
     int* s_hot = reinterpret_cast<int*>(s_state + KT_ROWS * 32 * A);
+    double* s_ih = reinterpret_cast<double*>(s_hot + KT_ROWS * 32 * A);   // [A][KT_ROWS][32], 8-byte aligned: 7 * 128 * A floats precede it
     if (tid == 0) s_npos = 0;
 
     // ---- tile -> (level, tile x, tile y): block-uniform -------------------------------------------------
@@ -355,13 +356,17 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
     const bool match_x = valid_x && (aw > 0.0);
     // exact bounding box of the warp's anchors (first / last valid column, first / last valid row)
     const double wx1 = b0 + ((double)cx0 + 0.5) * stride, wx2 = b2 + ((double)(cx0 + ncols - 1) + 0.5) * stride;
-    const double wy1 = b1 + ((double)cy0 + 0.5) * stride, wy2 = b3 + ((double)(cy0 + nrows - 1) + 0.5) * stride;
 
     // ---- matching -------------------------------------------------------------------------------------
+    // The y half of every (anchor, table) overlap depends only on (anchor type, tile row, table): it is the
+    // same for all 32 lanes of the warp.  So for each group of 32 tables lane j computes the intersection
+    // heights of table j with the warp's KT_ROWS rows once (s_ih) plus a row mask; the per-thread loop then
+    // only does the x half once per table and one multiply / divide / compare per overlapping row.
     float best[KT_ROWS];
     int arg[KT_ROWS];
 #pragma unroll
     for (int r = 0; r < KT_ROWS; ++r) { best[r] = 0.0f; arg[r] = 0; }   // all-zero IoU row -> argmax 0
+    double* ihw = s_ih + (size_t)a * (KT_ROWS * 32);       // this warp's [KT_ROWS][32] intersection heights
     const double* gtb = p.gt + (size_t)b * p.Gmax * 4;
     for (int g0 = 0; g0 < G; g0 += KT_CHUNK) {
         const int chunk = min(KT_CHUNK, G - g0);
@@ -375,27 +380,34 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
         __syncthreads();
         for (int q0 = 0; q0 < chunk; q0 += 32) {
             const int j = q0 + lane;
-            bool touch = false;
+            unsigned rows_hit = 0u;
             if (j < chunk) {
                 const double gx1 = s_gx1[j], gy1 = s_gy1[j], gx2 = s_gx2[j], gy2 = s_gy2[j];
-                // empty tables and tables outside the warp's box have zero intersection with all its anchors
-                touch = (gx2 > gx1) && (gy2 > gy1) && (gx2 > wx1) && (gx1 < wx2) && (gy2 > wy1) && (gy1 < wy2);
-            }
-            unsigned live = __ballot_sync(0xffffffffu, touch);
-            while (live) {                                 // warp-uniform, ascending GT order
-                const int m = q0 + __ffs(live) - 1;
-                live &= live - 1u;
-                const double g1 = s_gx1[m], g2 = s_gx2[m];
-                if (match_x && g2 > ax1 && g1 < ax2) {
-                    const double iw = dmin(ax2, g2) - dmax(ax1, g1);
-                    const double g3 = s_gy1[m], g4 = s_gy2[m], ga = s_ga[m];
+                // empty tables and tables outside the warp's x range have zero intersection with all its anchors
+                if ((gx2 > gx1) && (gy2 > gy1) && (gx2 > wx1) && (gx1 < wx2)) {
 #pragma unroll
                     for (int r = 0; r < KT_ROWS; ++r) {
                         const double y1 = row[r][0], y2 = row[r][1], hh = row[r][2];
-                        if (r < nrows && g4 > y1 && g3 < y2 && hh > 0.0) {
-                            const double ih = dmin(y2, g4) - dmax(y1, g3);
-                            const double inter = iw * ih;
-                            const double uni = aw * hh + ga - inter;
+                        ihw[r * 32 + lane] = dmin(y2, gy2) - dmax(y1, gy1);
+                        if (r < nrows && gy2 > y1 && gy1 < y2 && hh > 0.0) rows_hit |= 1u << r;
+                    }
+                }
+            }
+            unsigned live = __ballot_sync(0xffffffffu, rows_hit != 0u);   // also orders the s_ih writes
+            while (live) {                                 // warp-uniform, ascending GT order
+                const int ml = __ffs(live) - 1;
+                live &= live - 1u;
+                const int m = q0 + ml;
+                const unsigned rmask = __shfl_sync(0xffffffffu, rows_hit, ml);
+                const double g1 = s_gx1[m], g2 = s_gx2[m];
+                if (match_x && g2 > ax1 && g1 < ax2) {
+                    const double iw = dmin(ax2, g2) - dmax(ax1, g1);
+                    const double ga = s_ga[m];
+#pragma unroll
+                    for (int r = 0; r < KT_ROWS; ++r) {
+                        if (rmask & (1u << r)) {
+                            const double inter = iw * ihw[r * 32 + ml];
+                            const double uni = aw * row[r][2] + ga - inter;
                             const double q = inter * rcp_fast(uni);
                             const float iou = f32_rounding_safe(q) ? (float)q : iou_exact(inter, uni);
                             if (iou > best[r]) { best[r] = iou; arg[r] = g0 + m; }
@@ -403,6 +415,7 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                     }
                 }
             }
+            __syncwarp();                                  // s_ih is rewritten by the next group
         }
     }
 
@@ -415,11 +428,13 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
             out_x = ((ax1 + ax2) / 2.0) >= (double)p.img_hw[2 * b + 1];
             img_h = (double)p.img_hw[2 * b];
         }
+        int prev = -1;                                      // the x targets depend on the column and the table only
+        float t0 = 0.f, t2 = 0.f;
 #pragma unroll
         for (int r = 0; r < KT_ROWS; ++r) {
             if (r < nrows) {
                 const double y1 = row[r][0], y2 = row[r][1], hh = row[r][2];
-                float state = 0.0f, t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+                float state = 0.0f, t1 = 0.f, t3 = 0.f;
                 int hot = -1;
                 if (G > 0) {
                     const bool is_pos = best[r] >= p.pos;
@@ -428,9 +443,12 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                     if (is_pos) hot = __ldg(p.gt_labels + (size_t)b * p.Gmax + arg[r]);
                     const double* g = gtb + 4 * (size_t)arg[r];
                     const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(hh);
-                    t0 = reg_target5(__ldg(g + 0), ax1, aw, r5w);
+                    if (arg[r] != prev) {
+                        prev = arg[r];
+                        t0 = reg_target5(__ldg(g + 0), ax1, aw, r5w);
+                        t2 = reg_target5(__ldg(g + 2), ax2, aw, r5w);
+                    }
                     t1 = reg_target5(__ldg(g + 1), y1, hh, r5h);
-                    t2 = reg_target5(__ldg(g + 2), ax2, aw, r5w);
                     t3 = reg_target5(__ldg(g + 3), y2, hh, r5h);
                 }
                 if (p.img_hw && (out_x || ((y1 + y2) / 2.0) >= img_h)) state = -1.0f;
@@ -621,16 +639,25 @@ extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* leve
         }
         for (int l = num_levels; l <= RN_MAX_LEVELS; ++l) tl.tile_start[l] = tiles;
         p.max_coord = max_coord;
-        const size_t dyn = (size_t)KT_ROWS * 32 * A * 7 * sizeof(float);
+        const size_t dyn = (size_t)KT_ROWS * 32 * A * (7 * sizeof(float) + sizeof(double));
+        // static + dynamic shared memory exceeds the 48 KB default: opt in once per instantiation
+        static bool attr_done = false;
+        if (!attr_done) {
+            const int big = (int)((size_t)KT_ROWS * 32 * KT_MAX_A * (7 * sizeof(float) + sizeof(double)));
+            const int small = (int)((size_t)KT_ROWS * 32 * 9 * (7 * sizeof(float) + sizeof(double)));
+            cudaError_t ae = cudaFuncSetAttribute(k_anchor_targets_tiles<KT_MAX_A, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+            if (ae != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
+            attr_done = true;
+        }
         if (tiles > 0 && A <= 9) {
-            static const int minb = getenv("RN_K1_MINB") ? atoi(getenv("RN_K1_MINB")) : 3;   // tuning knob (measured: 3 CTAs/SM, 75 registers, is fastest)
+            static const int minb = getenv("RN_K1_MINB") ? atoi(getenv("RN_K1_MINB")) : 3;   // tuning knob (measured: 3 CTAs/SM is fastest)
             if (minb >= 4) k_anchor_targets_tiles<9, 4><<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);
             else if (minb == 3) k_anchor_targets_tiles<9, 3><<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);
             else k_anchor_targets_tiles<9, 2><<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);
         } else if (tiles > 0) {
-            cudaError_t ae = cudaFuncSetAttribute(k_anchor_targets_tiles<KT_MAX_A, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  (int)((size_t)KT_ROWS * 32 * KT_MAX_A * 7 * sizeof(float)));
-            if (ae != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
             k_anchor_targets_tiles<KT_MAX_A, 1><<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);
         }
     } else {
