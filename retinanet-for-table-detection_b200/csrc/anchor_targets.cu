@@ -15,8 +15,9 @@
 // ~20 instructions).  Every quotient on this path is only ever consumed after rounding to fp32, so each is
 // first computed with a fast reciprocal (hardware approximation + 2 Newton steps, relative error < 2^-45)
 // and accepted when its fp32 rounding cannot depend on that error: the 29 mantissa bits dropped by the
-// fp64->fp32 conversion must be further than 2^16 fp64-ulps from the rounding midpoint.  Otherwise
-// (probability ~2.4e-4 per value) the exact IEEE expression of the reference is evaluated.  The result is
+// fp64->fp32 conversion must be further than 2^17 fp64-ulps (2^-35 relative; the error budget, including the
+// base-box width substitution of the regression path, is 2^-37) from the rounding midpoint.  Otherwise
+// (probability ~5e-4 per value) the exact IEEE expression of the reference is evaluated.  The result is
 // bit-identical to always dividing.
 #include "rn_common.cuh"
 #include <stdlib.h>
@@ -87,24 +88,24 @@ __device__ __forceinline__ void make_anchor(const RnLevels& lv, const double* ba
     y2 = __ldg(b + 3) + sy;
 }
 
-// reciprocal with relative error < 2^-45 for positive normal x (garbage in -> rejected by the check below)
+// reciprocal with relative error < 2^-39 for positive normal x (garbage in -> rejected by the check below).
+// rcp.approx.ftz.f64 has the upper 20 mantissa bits right (|1 - x r0| <= 2^-20); one Newton step squares that:
+// x r1 = 1 - e^2, e^2 <= 2^-40, plus two fp64 roundings.  f32_rounding_safe() tolerates 2^-36.
 __device__ __forceinline__ double rcp_fast(double x) {
     double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));     // ~20 good bits
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);                                          // ~40
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);                                       // ~52
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    return fma(r, e, r);
 }
 
-// v approximates (to < 2^-45 relative) a value that the reference rounds to fp32: true when the fp32
+// v approximates (to < 2^-38 relative) a value that the reference rounds to fp32: true when the fp32
 // rounding of v is guaranteed to equal the fp32 rounding of the exact value
 __device__ __forceinline__ bool f32_rounding_safe(double v) {
     const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
     // biased exponent in [900, 1140] (fp32 normals need >= 897): one unsigned range compare
     const bool exp_ok = ((hi & 0x7ff00000u) - (900u << 20)) <= (240u << 20);
-    // the 29 bits dropped by fp64 -> fp32 must be further than 2^16 from the rounding midpoint 2^28
-    const bool far = (((lo & 0x1fffffffu) - ((1u << 28) - (1u << 16))) > (1u << 17));
+    // the 29 bits dropped by fp64 -> fp32 must be further than 2^17 from the rounding midpoint 2^28
+    const bool far = (((lo & 0x1fffffffu) - ((1u << 28) - (1u << 17))) > (1u << 18));
     return exp_ok && far;
 }
 
@@ -290,9 +291,14 @@ __global__ void __launch_bounds__(K1_THREADS) k_anchor_targets(const K1Params p)
 // anchor order (cell-major, anchor-minor; each tile row is one contiguous range) and written with 128-bit
 // stores.
 // ------------------------------------------------------------------------------------------------
-constexpr int KT_ROWS = 4;
+constexpr int KT_ROWS = 4;             // the write-out's row decode assumes 4
 constexpr int KT_MAX_A = 24;
 constexpr int KT_CHUNK = 256;          // GT tables staged per round
+
+// dynamic shared memory of k_anchor_targets_tiles: staged regression rows, staged label rows, intersection heights
+static size_t kt_dyn_smem(int A) {
+    return (size_t)KT_ROWS * ((32 * A * 5 + 4) + (32 * A * 2 + 4)) * sizeof(float) + (size_t)A * KT_ROWS * 32 * sizeof(double);
+}
 
 struct K1Tiles {
     int tile_start[RN_MAX_LEVELS + 1];  // first tile of each level
@@ -306,6 +312,7 @@ template <int MAXA, int MINB>
 __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const K1Params p, const K1Tiles tl) {
     extern __shared__ __align__(16) float s_dyn[];
     __shared__ double s_gx1[KT_CHUNK], s_gy1[KT_CHUNK], s_gx2[KT_CHUNK], s_gy2[KT_CHUNK], s_ga[KT_CHUNK];
+    __shared__ int s_glab[KT_CHUNK];
     __shared__ double s_row[KT_MAX_A][KT_ROWS][3];          // per (anchor type, tile row): y1, y2, height
     __shared__ int s_npos;
 
@@ -313,21 +320,30 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
     const int A = p.lv.anchors_per_cell, L = p.lv.num_levels;
     const int nthreads = 32 * A;
     const int b = blockIdx.y;
-    float* s_reg = s_dyn;                                   // [KT_ROWS][32][A][5]
-    float* s_state = s_reg + KT_ROWS * 32 * A * 5;          // [KT_ROWS][32][A]
-    int* s_hot = reinterpret_cast<int*>(s_state + KT_ROWS * 32 * A);
-    double* s_ih = reinterpret_cast<double*>(s_hot + KT_ROWS * 32 * A);   // [A][KT_ROWS][32], 8-byte aligned: 7 * 128 * A floats precede it
+    // staging rows are shifted by the destination's misalignment (start & 3 floats) so that 16-byte units of
+    // shared memory map to 16-byte units of global memory: the write-out is LDS.128 + STG.128 per unit
+    const int reg_stride = 32 * A * 5 + 4, lab_stride = 32 * A * 2 + 4;     // floats per staged tile row (multiples of 4)
+    float* s_reg = s_dyn;                                   // [KT_ROWS][reg_stride]
+    float* s_lab = s_reg + KT_ROWS * reg_stride;            // C == 1: [KT_ROWS][lab_stride] {one-hot, state} pairs
+    float* s_state = s_lab;                                 // C  > 1: [KT_ROWS][32][A] states, then the hot classes
+    int* s_hot = reinterpret_cast<int*>(s_lab + KT_ROWS * 32 * A);
+    double* s_ih = reinterpret_cast<double*>(s_lab + KT_ROWS * lab_stride);   // [A][KT_ROWS][32]; 8-byte aligned
     if (tid == 0) s_npos = 0;
 
     // ---- tile -> (level, tile x, tile y): block-uniform -------------------------------------------------
-    int level = 0;
-    for (int l = 1; l < L; ++l)
-        if ((int)blockIdx.x >= tl.tile_start[l]) level = l;
-    const int t = blockIdx.x - tl.tile_start[level];
-    const int ty = rn_div(t, tl.tiles_x[level], tl.inv_tiles_x[level]);
-    const int tx = t - ty * tl.tiles_x[level];
-    const int W = p.lv.w[level], H = p.lv.h[level];
-    const double stride = (double)p.lv.stride[level];
+    // (static indices only: dynamic indexing of by-value kernel parameters would force a local-memory copy)
+    int level = 0, tstart = 0, tiles_x = tl.tiles_x[0], W = p.lv.w[0], H = p.lv.h[0], istride = p.lv.stride[0], lstart = p.lv.start[0];
+    float inv_tiles_x = tl.inv_tiles_x[0];
+#pragma unroll
+    for (int l = 1; l < RN_MAX_LEVELS; ++l)
+        if (l < L && (int)blockIdx.x >= tl.tile_start[l]) {
+            level = l; tstart = tl.tile_start[l]; tiles_x = tl.tiles_x[l]; inv_tiles_x = tl.inv_tiles_x[l];
+            W = p.lv.w[l]; H = p.lv.h[l]; istride = p.lv.stride[l]; lstart = p.lv.start[l];
+        }
+    const int t = blockIdx.x - tstart;
+    const int ty = rn_div(t, tiles_x, inv_tiles_x);
+    const int tx = t - ty * tiles_x;
+    const double stride = (double)istride;
     const int cx0 = tx * 32, cy0 = ty * KT_ROWS;
     const int ncols = min(32, W - cx0), nrows = min(KT_ROWS, H - cy0);
     const bool valid_x = lane < ncols;
@@ -348,11 +364,6 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
     }
     __syncwarp();
     const double (*row)[3] = s_row[a];
-    // 5/width, 5/height for the regression fast path: the base box's stand in for the anchor's own (they
-    // differ by rounding only) when that is far inside the fast path's tolerance (see the wrapper)
-    const bool table_ok = (b2 > b0) && (b3 > b1) && (p.max_coord < 4096.0 * fmin(b2 - b0, b3 - b1));
-    const double r5w = 5.0 * rcp_fast(table_ok ? b2 - b0 : aw);
-    const double r5h_tab = table_ok ? 5.0 * rcp_fast(b3 - b1) : 0.0;
     const bool match_x = valid_x && (aw > 0.0);
     // exact bounding box of the warp's anchors (first / last valid column, first / last valid row)
     const double wx1 = b0 + ((double)cx0 + 0.5) * stride, wx2 = b2 + ((double)(cx0 + ncols - 1) + 0.5) * stride;
@@ -376,6 +387,7 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
             const double gx2 = __ldg(gtb + 4 * (g0 + j) + 2), gy2 = __ldg(gtb + 4 * (g0 + j) + 3);
             s_gx1[j] = gx1; s_gy1[j] = gy1; s_gx2[j] = gx2; s_gy2[j] = gy2;
             s_ga[j] = (gx2 - gx1) * (gy2 - gy1);
+            s_glab[j] = __ldg(p.gt_labels + (size_t)b * p.Gmax + g0 + j);
         }
         __syncthreads();
         for (int q0 = 0; q0 < chunk; q0 += 32) {
@@ -403,14 +415,29 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                 if (match_x && g2 > ax1 && g1 < ax2) {
                     const double iw = dmin(ax2, g2) - dmax(ax1, g1);
                     const double ga = s_ga[m];
+                    if (rmask == (1u << KT_ROWS) - 1u) {
+                        // every row of the tile overlaps (the common case inside a table): no per-row branches, so
+                        // pairs of reciprocal chains (MUFU -> DFMA -> DFMA -> DMUL) overlap each other
 #pragma unroll
-                    for (int r = 0; r < KT_ROWS; ++r) {
-                        if (rmask & (1u << r)) {
-                            const double inter = iw * ihw[r * 32 + ml];
-                            const double uni = aw * row[r][2] + ga - inter;
-                            const double q = inter * rcp_fast(uni);
-                            const float iou = f32_rounding_safe(q) ? (float)q : iou_exact(inter, uni);
-                            if (iou > best[r]) { best[r] = iou; arg[r] = g0 + m; }
+                        for (int r = 0; r < KT_ROWS; r += 2) {          // two rows at a time: ILP without spilling
+                            const double i0 = iw * ihw[r * 32 + ml], i1 = iw * ihw[(r + 1) * 32 + ml];
+                            const double u0 = aw * row[r][2] + ga - i0, u1 = aw * row[r + 1][2] + ga - i1;
+                            const double q0v = i0 * rcp_fast(u0), q1v = i1 * rcp_fast(u1);
+                            const float iou0 = f32_rounding_safe(q0v) ? (float)q0v : iou_exact(i0, u0);
+                            const float iou1 = f32_rounding_safe(q1v) ? (float)q1v : iou_exact(i1, u1);
+                            if (iou0 > best[r]) { best[r] = iou0; arg[r] = g0 + m; }
+                            if (iou1 > best[r + 1]) { best[r + 1] = iou1; arg[r + 1] = g0 + m; }
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < KT_ROWS; ++r) {
+                            if (rmask & (1u << r)) {
+                                const double inter = iw * ihw[r * 32 + ml];
+                                const double uni = aw * row[r][2] + ga - inter;
+                                const double q = inter * rcp_fast(uni);
+                                const float iou = f32_rounding_safe(q) ? (float)q : iou_exact(inter, uni);
+                                if (iou > best[r]) { best[r] = iou; arg[r] = g0 + m; }
+                            }
                         }
                     }
                 }
@@ -421,6 +448,18 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
 
     // ---- state, one-hot class, regression targets, border rule ------------------------------------------
     int my_pos = 0;
+    // misalignment (in anchors, mod 4) of the tile's first anchor and of one feature-map row; unsigned wrap-around
+    // keeps the low two bits right.  Row r is staged shifted by ((al0 + r * alw) * 5) & 3 = (al0 + r * alw) & 3 floats
+    // (regression) and ((al0 + r * alw) * 2) & 3 floats (labels).
+    const unsigned al0 = ((unsigned)b * (unsigned)p.N + (unsigned)lstart + ((unsigned)cy0 * (unsigned)W + (unsigned)cx0) * (unsigned)A) & 3u;
+    const unsigned alw = ((unsigned)W * (unsigned)A) & 3u;
+    const bool gt_staged = G <= KT_CHUNK;                   // the (only) chunk is still in shared memory
+    // 5/width, 5/height for the regression fast path: the base box's stand in for the anchor's own (they
+    // differ by rounding only) when that is far inside the fast path's tolerance (see the wrapper)
+    const double bw = __ldg(bs + 2) - __ldg(bs), bh = __ldg(bs + 3) - __ldg(bs + 1);     // re-read: not kept live across the matching loop
+    const bool table_ok = (bw > 0.0) && (bh > 0.0) && (p.max_coord < 4096.0 * fmin(bw, bh));
+    const double r5w = 5.0 * rcp_fast(table_ok ? bw : aw);
+    const double r5h_tab = table_ok ? 5.0 * rcp_fast(bh) : 0.0;
     if (valid_x) {
         bool out_x = false;
         double img_h = 0.0;
@@ -437,28 +476,43 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                 float state = 0.0f, t1 = 0.f, t3 = 0.f;
                 int hot = -1;
                 if (G > 0) {
+                    const int m = arg[r];
                     const bool is_pos = best[r] >= p.pos;
                     const bool is_ign = (best[r] > p.neg) && !is_pos;
                     state = is_pos ? 1.0f : (is_ign ? -1.0f : 0.0f);
-                    if (is_pos) hot = __ldg(p.gt_labels + (size_t)b * p.Gmax + arg[r]);
-                    const double* g = gtb + 4 * (size_t)arg[r];
-                    const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(hh);
-                    if (arg[r] != prev) {
-                        prev = arg[r];
-                        t0 = reg_target5(__ldg(g + 0), ax1, aw, r5w);
-                        t2 = reg_target5(__ldg(g + 2), ax2, aw, r5w);
+                    double gx1, gy1, gx2, gy2;
+                    if (gt_staged) {
+                        gx1 = s_gx1[m]; gy1 = s_gy1[m]; gx2 = s_gx2[m]; gy2 = s_gy2[m];
+                        if (is_pos) hot = s_glab[m];
+                    } else {
+                        const double* g = gtb + 4 * (size_t)m;
+                        gx1 = __ldg(g); gy1 = __ldg(g + 1); gx2 = __ldg(g + 2); gy2 = __ldg(g + 3);
+                        if (is_pos) hot = __ldg(p.gt_labels + (size_t)b * p.Gmax + m);
                     }
-                    t1 = reg_target5(__ldg(g + 1), y1, hh, r5h);
-                    t3 = reg_target5(__ldg(g + 3), y2, hh, r5h);
+                    const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(hh);
+                    if (m != prev) {
+                        prev = m;
+                        t0 = reg_target5(gx1, ax1, aw, r5w);
+                        t2 = reg_target5(gx2, ax2, aw, r5w);
+                    }
+                    t1 = reg_target5(gy1, y1, hh, r5h);
+                    t3 = reg_target5(gy2, y2, hh, r5h);
                 }
                 if (p.img_hw && (out_x || ((y1 + y2) / 2.0) >= img_h)) state = -1.0f;
-                const int k = (r * 32 + lane) * A + a;      // reference order within the tile row
-                s_reg[k * 5 + 0] = t0; s_reg[k * 5 + 1] = t1; s_reg[k * 5 + 2] = t2; s_reg[k * 5 + 3] = t3; s_reg[k * 5 + 4] = state;
-                s_state[k] = state;
-                s_hot[k] = hot;
+                const int k = lane * A + a;                 // reference order within the tile row
+                const unsigned al = al0 + r * alw;          // first anchor of the staged row, mod 4 in the low bits
+                float* sr = s_reg + r * reg_stride + (int)(al & 3u) + k * 5;
+                sr[0] = t0; sr[1] = t1; sr[2] = t2; sr[3] = t3; sr[4] = state;
+                if (p.C == 1) {
+                    float* sl = s_lab + r * lab_stride + (int)((al & 1u) * 2u) + k * 2;
+                    sl[0] = hot == 0 ? 1.0f : 0.0f; sl[1] = state;
+                } else {
+                    s_state[r * 32 * A + k] = state;
+                    s_hot[r * 32 * A + k] = hot;
+                }
                 my_pos += (state == 1.0f);
                 if (p.argmax)
-                    p.argmax[(size_t)b * p.N + p.lv.start[level] + ((size_t)(cy0 + r) * W + cx0 + lane) * A + a] = arg[r];
+                    p.argmax[(size_t)b * p.N + lstart + ((size_t)(cy0 + r) * W + cx0 + lane) * A + a] = arg[r];
             }
         }
     }
@@ -472,46 +526,40 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
         if (p.npos_total) atomicAdd(p.npos_total, (float)s_npos);   // integer-valued: exact, order-independent
     }
 
-    // ---- write-out: each tile row is one contiguous anchor range; ONE loop over 16-byte units of all rows ---
-    // unit 0 of a row = the (<= 3) floats before the first 16-byte boundary, then whole float4s, the last unit
-    // being a partial tail -- so rows with any alignment (e.g. N = 719,523) still use 128-bit stores
     const int cnt = ncols * A;
-    const long long tile_row0 = (long long)b * p.N + p.lv.start[level] + ((long long)cy0 * W + cx0) * A;
+    const long long tile_row0 = (long long)b * p.N + lstart + ((long long)cy0 * W + cx0) * A;
+    // ---- write-out: each tile row is one contiguous anchor range; ONE loop over the 16-byte units of all rows.
+    // Unit v of a row covers staged floats [4v, 4v+4) = global floats [start - shift + 4v, ...): whole units are
+    // one LDS.128 + one STG.128, the (<= 2) partial units at the ends of a row are written float by float.
     {
-        const int len = cnt * 5, upr = (len >> 2) + 2;      // units per row (upper bound)
-        const float inv_upr = 1.0f / (float)upr;
+        const int len = cnt * 5, upr = (len + 3) / 4 + 1;   // units per row (upper bound incl. the shift)
         for (int u = tid; u < nrows * upr; u += nthreads) {
-            const int r = rn_div(u, upr, inv_upr), v = u - r * upr;
+            const int r = (u >= upr) + (u >= 2 * upr) + (u >= 3 * upr), v = u - r * upr;      // KT_ROWS == 4
             const long long start = (tile_row0 + (long long)r * W * A) * 5;
-            const float* sr = s_reg + r * 32 * A * 5;
-            float* dst = p.reg + start;
-            const int head = p.vec_ok ? (int)((4 - (start & 3)) & 3) : 0;
-            if (v == 0) {
-                for (int i = 0; i < head && i < len; ++i) dst[i] = sr[i];
+            const int shift = p.vec_ok ? (int)(start & 3) : 0;
+            const float* sr = s_reg + r * reg_stride + (p.vec_ok ? 0 : (int)(start & 3));
+            float* dst = p.reg + (start - shift);
+            const int i = 4 * v;
+            if (p.vec_ok && i >= shift && i + 4 <= shift + len) {
+                rn_stg_stream4(dst + i, *reinterpret_cast<const float4*>(sr + i));
             } else {
-                const int i = head + 4 * (v - 1);
-                if (p.vec_ok && i + 4 <= len) rn_stg_stream4(dst + i, make_float4(sr[i], sr[i + 1], sr[i + 2], sr[i + 3]));
-                else for (int k = i; k < len && k < i + 4; ++k) dst[k] = sr[k];
+                for (int k = max(i, shift); k < min(i + 4, shift + len); ++k) dst[k] = sr[k];
             }
         }
     }
     if (p.C == 1) {
-        const int len = cnt * 2, upr = (len >> 2) + 2;
-        const float inv_upr = 1.0f / (float)upr;
+        const int len = cnt * 2, upr = (len + 3) / 4 + 1;
         for (int u = tid; u < nrows * upr; u += nthreads) {
-            const int r = rn_div(u, upr, inv_upr), v = u - r * upr;
+            const int r = (u >= upr) + (u >= 2 * upr) + (u >= 3 * upr), v = u - r * upr;
             const long long start = (tile_row0 + (long long)r * W * A) * 2;
-            const float* ss = s_state + r * 32 * A;
-            const int* sh = s_hot + r * 32 * A;
-            float* dst = p.lab + start;
-            const int head = p.vec_ok ? (int)((4 - (start & 3)) & 3) : 0;     // 0 or 2 (rows are 8-byte aligned)
-            auto gen = [&](int i) { const int q = i >> 1; return (i & 1) ? ss[q] : (sh[q] == 0 ? 1.0f : 0.0f); };
-            if (v == 0) {
-                for (int i = 0; i < head && i < len; ++i) dst[i] = gen(i);
+            const int shift = p.vec_ok ? (int)(start & 3) : 0;                    // 0 or 2
+            const float* sl = s_lab + r * lab_stride + (p.vec_ok ? 0 : (int)(start & 3));
+            float* dst = p.lab + (start - shift);
+            const int i = 4 * v;
+            if (p.vec_ok && i >= shift && i + 4 <= shift + len) {
+                rn_stg_stream4(dst + i, *reinterpret_cast<const float4*>(sl + i));
             } else {
-                const int i = head + 4 * (v - 1);
-                if (p.vec_ok && i + 4 <= len) rn_stg_stream4(dst + i, make_float4(gen(i), gen(i + 1), gen(i + 2), gen(i + 3)));
-                else for (int k = i; k < len && k < i + 4; ++k) dst[k] = gen(k);
+                for (int k = max(i, shift); k < min(i + 4, shift + len); ++k) dst[k] = sl[k];
             }
         }
     } else {
@@ -639,12 +687,11 @@ extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* leve
         }
         for (int l = num_levels; l <= RN_MAX_LEVELS; ++l) tl.tile_start[l] = tiles;
         p.max_coord = max_coord;
-        const size_t dyn = (size_t)KT_ROWS * 32 * A * (7 * sizeof(float) + sizeof(double));
+        const size_t dyn = kt_dyn_smem(A);
         // static + dynamic shared memory exceeds the 48 KB default: opt in once per instantiation
         static bool attr_done = false;
         if (!attr_done) {
-            const int big = (int)((size_t)KT_ROWS * 32 * KT_MAX_A * (7 * sizeof(float) + sizeof(double)));
-            const int small = (int)((size_t)KT_ROWS * 32 * 9 * (7 * sizeof(float) + sizeof(double)));
+            const int big = (int)kt_dyn_smem(KT_MAX_A), small = (int)kt_dyn_smem(9);
             cudaError_t ae = cudaFuncSetAttribute(k_anchor_targets_tiles<KT_MAX_A, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
             if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
             if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
