@@ -52,6 +52,11 @@ class TargetLossStep(object):
         self.use_graph = use_graph
         self._graphs = None
         self.kernel_launches_per_step = 2      # K1 + K2 (memsets and NCCL are not ours)
+        # run_from_host(): copy stream, per-chunk events, per-chunk loss rows
+        self._copy_stream = None
+        self._chunk_losses = None
+        self._chunk_events = None
+        self._losses_host = None
 
     # ---- inputs ---------------------------------------------------------------------------------
     def load_annotations(self, image_group, annotations_group):
@@ -102,6 +107,57 @@ class TargetLossStep(object):
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         self._graphs = (self._capture(self._targets), self._capture(self._losses))
+
+    # ---- host inputs, copies overlapped with the kernels -----------------------------------------------
+    def run_from_host(self, image_group, annotations_group, cls_host, reg_host, chunks=4):
+        """One step whose inputs live in (pinned) HOST memory: the head outputs are copied page-chunk by
+        page-chunk on a copy stream while K1 runs on the compute stream (K1 needs only the GT block), and K2
+        is launched per chunk as soon as that chunk's predictions have landed.  Every K2 launch uses the
+        batch-global normaliser, so per-chunk losses add up to the batch loss (the loss is a sum over anchors)
+        and the gradients are identical to a single launch.  Returns the three floats
+        ``[focal, smooth_l1, normaliser]`` on the host (one D2H copy of ``chunks`` x 12 bytes); the device tensor
+        ``losses`` of :meth:`run` is not touched."""
+        rank, world = _dist.world()
+        dev = self.device
+        chunks = max(1, min(int(chunks), self.B))
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        if self._chunk_losses is None or self._chunk_losses.shape[0] != chunks:
+            self._chunk_losses = torch.zeros((chunks, 3), dtype=torch.float32, device=dev)
+            self._losses_host = torch.zeros((chunks, 3), dtype=torch.float32).pin_memory()
+            self._chunk_events = [torch.cuda.Event() for _ in range(chunks)]
+        if self.use_graph and self._graphs is None:
+            self._build_graphs()
+        compute = torch.cuda.current_stream(dev)
+        self._copy_stream.wait_stream(compute)              # the previous step's K2 has consumed the buffers
+        # the 64 MB of head outputs go first: the PCIe link is the bottleneck of this step, so it starts before
+        # the (Python) GT packing, which then runs on the CPU while the copies are in flight
+        bounds = [(self.B * i) // chunks for i in range(chunks + 1)]
+        with torch.cuda.stream(self._copy_stream):
+            for i in range(chunks):
+                lo, hi = bounds[i], bounds[i + 1]
+                self.cls_pred[lo:hi].copy_(cls_host[lo:hi], non_blocking=True)
+                self.reg_pred[lo:hi].copy_(reg_host[lo:hi], non_blocking=True)
+                self._chunk_events[i].record(self._copy_stream)
+        self.load_annotations(image_group, annotations_group)
+        if self.use_graph:
+            self._graphs[0].replay()
+        else:
+            self._targets()
+        if world > 1:
+            torch.distributed.all_reduce(self.npos_total)
+        for i in range(chunks):
+            lo, hi = bounds[i], bounds[i + 1]
+            compute.wait_event(self._chunk_events[i])
+            _losses.detection_losses(self.y_reg[lo:hi], self.y_cls[lo:hi], self.reg_pred[lo:hi], self.cls_pred[lo:hi],
+                                     normalizer=self.npos_total,
+                                     out=(self._chunk_losses[i], self.grad_cls[lo:hi], self.grad_reg[lo:hi]),
+                                     workspace=self.loss_ws, **self.loss_kw)
+        self._losses_host.copy_(self._chunk_losses, non_blocking=True)
+        compute.synchronize()
+        out = self._losses_host.sum(dim=0)
+        out[2] = self._losses_host[0, 2]                    # the normaliser is the same in every row
+        return out
 
     def run(self, events=None):
         """One step on the current stream.  Results: ``losses`` [focal, smooth_l1, normaliser],

@@ -1,0 +1,41 @@
+"""GPU: TargetLossStep -- the graph-replayed resident step and the overlapped host-input step give the same
+targets, gradients (bit for bit) and losses (the per-chunk loss sums are added on the host: 1e-6 relative)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 4])
+def test_run_from_host_matches_resident_run(rn, chunks):
+    import synthetic
+    from oracle import anchors_np as OA
+    from oracle import losses_np as OL
+    hw, B = (256, 320), 5
+    anchors = rn.anchors_for_shape(hw + (3,))
+    N = anchors.shape[0]
+    imgs = [synthetic.PageShape(hw + (3,)) for _ in range(B)]
+    anns = [synthetic.gt_for_page(2, i, hw=hw, gmax=6) for i in range(B)]
+    cls, reg = synthetic.training_predictions(2, B, N, classes=1)
+    cls_h, reg_h = torch.from_numpy(cls).pin_memory(), torch.from_numpy(reg).pin_memory()
+
+    step = rn.pipeline.TargetLossStep(hw + (3,), B, 8, 1)
+    step.load_annotations(imgs, anns)
+    step.load_predictions(cls_h, reg_h)
+    want = step.run().cpu().numpy().copy()
+    gc, gr = step.grad_cls.clone(), step.grad_reg.clone()
+    yr, yc = step.y_reg.clone(), step.y_cls.clone()
+
+    step2 = rn.pipeline.TargetLossStep(hw + (3,), B, 8, 1)
+    for _ in range(2):                                   # twice: buffers are reused across steps
+        got = step2.run_from_host(imgs, anns, cls_h, reg_h, chunks=chunks).numpy()
+    assert torch.equal(step2.y_reg, yr) and torch.equal(step2.y_cls, yc)
+    assert torch.equal(step2.grad_cls, gc) and torch.equal(step2.grad_reg, gr)
+    assert got[2] == want[2] and np.allclose(got[:2], want[:2], rtol=1e-6, atol=0)
+
+    # and both agree with the oracle
+    oreg, olab = OA.anchor_targets_bbox(OA.anchors_for_shape(hw + (3,)), imgs, anns, 1)
+    assert yr.cpu().numpy().tobytes() == oreg.tobytes() and yc.cpu().numpy().tobytes() == olab.tobytes()
+    wf, ws = OL.focal()(olab, cls), OL.smooth_l1()(oreg, reg)
+    assert abs(got[0] - wf) <= 1e-5 * abs(wf) and abs(got[1] - ws) <= 1e-5 * abs(ws)
