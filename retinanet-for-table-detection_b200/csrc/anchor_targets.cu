@@ -469,6 +469,7 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
         }
         int prev = -1;                                      // the x targets depend on the column and the table only
         float t0 = 0.f, t2 = 0.f;
+        double gy1 = 0.0, gy2 = 0.0;
 #pragma unroll
         for (int r = 0; r < KT_ROWS; ++r) {
             if (r < nrows) {
@@ -480,21 +481,20 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                     const bool is_pos = best[r] >= p.pos;
                     const bool is_ign = (best[r] > p.neg) && !is_pos;
                     state = is_pos ? 1.0f : (is_ign ? -1.0f : 0.0f);
-                    double gx1, gy1, gx2, gy2;
-                    if (gt_staged) {
-                        gx1 = s_gx1[m]; gy1 = s_gy1[m]; gx2 = s_gx2[m]; gy2 = s_gy2[m];
-                        if (is_pos) hot = s_glab[m];
-                    } else {
-                        const double* g = gtb + 4 * (size_t)m;
-                        gx1 = __ldg(g); gy1 = __ldg(g + 1); gx2 = __ldg(g + 2); gy2 = __ldg(g + 3);
-                        if (is_pos) hot = __ldg(p.gt_labels + (size_t)b * p.Gmax + m);
-                    }
-                    const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(hh);
-                    if (m != prev) {
+                    if (m != prev) {                        // coordinates and x targets change with the table only
                         prev = m;
+                        double gx1, gx2;
+                        if (gt_staged) {
+                            gx1 = s_gx1[m]; gy1 = s_gy1[m]; gx2 = s_gx2[m]; gy2 = s_gy2[m];
+                        } else {
+                            const double* g = gtb + 4 * (size_t)m;
+                            gx1 = __ldg(g); gy1 = __ldg(g + 1); gx2 = __ldg(g + 2); gy2 = __ldg(g + 3);
+                        }
                         t0 = reg_target5(gx1, ax1, aw, r5w);
                         t2 = reg_target5(gx2, ax2, aw, r5w);
                     }
+                    if (is_pos) hot = gt_staged ? s_glab[m] : __ldg(p.gt_labels + (size_t)b * p.Gmax + m);
+                    const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(hh);
                     t1 = reg_target5(gy1, y1, hh, r5h);
                     t3 = reg_target5(gy2, y2, hh, r5h);
                 }
