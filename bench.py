@@ -235,6 +235,16 @@ def run_ours(args):
     # ---- resident: `value` + per-kernel durations ----------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         step.run()
+    exchange = "none (1 rank)"
+    if world > 1:
+        # the normaliser K2 used must be the all-reduced positive count, whichever way it was exchanged
+        check = step.npos_total.clone()
+        if step.peer is None:
+            check = check * 0 + step.losses[2]            # npos_total already holds the all-reduced count
+        else:
+            dist.all_reduce(check)
+        assert float(check) == float(step.losses[2]) or float(check) < 1.0, (float(check), float(step.losses[2]))
+        exchange = "NVLink peer mailbox (rn_peer_publish + K2 prologue)" if step.peer is not None else "NCCL all_reduce"
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
@@ -293,7 +303,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64 matching + f32 targets/losses", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pages_per_gpu": B, "anchors_per_page": N, "classes": C,
                        "l2": "working set per step ~%d MB (> 126 MB L2), no explicit flush" % ((k1_bytes + k2_bytes) // (1 << 20)),
-                       "cuda_graphs": True},
+                       "cuda_graphs": True, "count_exchange": exchange},
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "pages/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 12 * E2E_CHUNKS, "ms_per_step": e2e_ms / args.steps,
                     "h2d_GBps": h2d / (e2e_ms / args.steps * 1e-3) / 1e9,

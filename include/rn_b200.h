@@ -117,6 +117,8 @@ int rn_smooth_l1_fwd_bwd(const float* y_true_reg /*(R,5)*/, const float* y_pred 
  * 89-90), so for targets that come from rn_anchor_targets the result is identical while 20 B/anchor of
  * reads disappear; leave 0 for arbitrary y_true tensors. */
 #define RN_LOSS_SHARED_STATE 1
+#define RN_LOSS_NPOS_PEER_BOX 2   /* npos_dev is this rank's peer mailbox (rn_peer_box_create): the normaliser is
+                                    the sum of the counts all ranks published for the current step           */
 int rn_loss_fwd_bwd(const float* y_true_cls, const float* cls_pred, const float* y_true_reg,
                     const float* reg_pred, long long R, int C,
                     float alpha, float gamma, int bce_mode, float sigma,
@@ -187,6 +189,30 @@ size_t rn_nms_workspace_bytes(long long K, int max_output);
 int rn_nms(const float* boxes /*(K,4)*/, const float* scores /*(K)*/, long long K,
            int max_output, float iou_threshold, int* out_indices, int* out_count_dev,
            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * C1  the path's only exchange step: the batch-global positive-anchor count of the two losses
+ *     (model/losses.py:40-44, :88-90; with keras.utils.multi_gpu_model the loss sees the merged
+ *     batch, RetinaNet.py:106-112), exchanged over NVLink peer memory between the ranks of one node.
+ *
+ * Each rank creates one mailbox (device memory owned by the library, the only allocation it makes),
+ * sends the 64-byte CUDA IPC handle to the other ranks (any transport; the Python host uses
+ * torch.distributed.all_gather_object) and opens theirs.  Per step, after K1:
+ *     rn_peer_publish(npos_total_dev, box[rank], boxes, rank, world, stream)
+ * stores {step, count} into slot `rank` of every rank's mailbox (one 8-byte P2P store per peer), and
+ *     rn_loss_fwd_bwd(..., npos_dev = box[rank], ..., flags | RN_LOSS_NPOS_PEER_BOX, ...)
+ * waits (on local memory, inside the kernel) until all `world` counts of the step have arrived and
+ * uses their sum.  No NCCL call, no host synchronisation, CUDA-graph capturable.  All ranks must run
+ * the same sequence of publish / loss steps; a peer that never publishes turns the losses into NaN
+ * after ~2 s instead of hanging the GPU.  world <= 16 (one NVSwitch domain).
+ * ------------------------------------------------------------------------------------------- */
+size_t rn_peer_box_bytes(void);
+int rn_peer_box_create(int world, void** box_out, void* ipc_handle_out64);
+int rn_peer_box_open(const void* ipc_handle64, void** peer_box_out);
+int rn_peer_box_close(void* peer_box);
+int rn_peer_box_destroy(void* box);
+int rn_peer_publish(const float* value_dev, void* local_box, void* const* boxes_of_all_ranks /* host, (world) */,
+                    int rank, int world, void* stream);
 
 #ifdef __cplusplus
 }

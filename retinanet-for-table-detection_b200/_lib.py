@@ -17,6 +17,8 @@ LIB_PATH = os.environ.get("RN_B200_LIB") or os.path.join(_HERE, "librn_b200.so")
 RN_BCE_TF2 = 0
 RN_BCE_LOGITS = 1
 RN_LOSS_SHARED_STATE = 1
+RN_LOSS_NPOS_PEER_BOX = 2
+RN_MAX_WORLD = 16
 
 
 class RnError(RuntimeError):
@@ -53,6 +55,12 @@ SIGNATURES = {
                                             c_int, c_longlong, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "rn_nms_workspace_bytes": (c_size_t, [c_longlong, c_int]),
     "rn_nms": (c_int, [_P, _P, c_longlong, c_int, c_float, _P, _P, _P, c_size_t, _P]),
+    "rn_peer_box_bytes": (c_size_t, []),
+    "rn_peer_box_create": (c_int, [c_int, POINTER(c_void_p), c_void_p]),
+    "rn_peer_box_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "rn_peer_box_close": (c_int, [c_void_p]),
+    "rn_peer_box_destroy": (c_int, [c_void_p]),
+    "rn_peer_publish": (c_int, [_P, c_void_p, POINTER(c_void_p), c_int, c_int, _P]),
 }
 
 _lib = None

@@ -1,0 +1,94 @@
+// Peer mailbox: the one exchange step of the path (the batch-global positive-anchor count, C1 in DESIGN.md) done
+// over NVLink peer memory instead of a NCCL all-reduce.
+//
+// Every rank owns a mailbox in its own HBM, mapped into the other ranks of the node through CUDA IPC.  After K1
+// a one-CTA kernel bumps the rank's step counter and stores {step, count} as ONE 64-bit word into slot `rank` of
+// EVERY rank's mailbox (P2P stores over NVLink / NVSwitch, one per peer).  K2's prologue (csrc/losses.cu) reads
+// its own mailbox -- local memory -- until all `world` slots carry the current step, and adds the counts in rank
+// order (integer-valued floats: exact and identical on every rank).  No NCCL launch, no host round trip, and both
+// kernels stay capturable in CUDA graphs (the step number lives in device memory, not in a kernel argument).
+//
+// Slots are double-buffered by step parity.  Rank r can publish step s+2 only after its K2(s+1) has seen every
+// rank's step s+1, which each rank publishes after its own K2(s) in stream order -- so slot (s & 1) is never
+// overwritten before every rank has consumed step s.  All ranks must run the same sequence of steps.
+#include "rn_common.cuh"
+#include "peer_box.cuh"
+
+namespace {
+
+struct PeerPtrs { RnPeerBox* p[RN_MAX_WORLD]; };
+
+__global__ void k_peer_publish(const float* value, RnPeerBox* local, const PeerPtrs peers, int rank, int world) {
+    __shared__ unsigned long long s_step;
+    if (threadIdx.x == 0) {
+        s_step = local->step + 1ull;
+        local->step = s_step;                       // read by this rank's K2, later in the same stream
+    }
+    __syncthreads();
+    const unsigned long long step = s_step;
+    const unsigned long long word = (step << 32) | (unsigned long long)__float_as_uint(__ldcg(value));
+    if ((int)threadIdx.x < world) {
+        volatile unsigned long long* slot = &peers.p[threadIdx.x]->slots[step & 1ull][rank];
+        *slot = word;                               // one aligned 8-byte store per peer: count and step arrive together
+    }
+}
+
+}  // namespace
+
+extern "C" size_t rn_peer_box_bytes(void) { return sizeof(RnPeerBox); }
+
+extern "C" int rn_peer_box_create(int world, void** box_out, void* ipc_handle_out64) {
+    RN_REQUIRE(world >= 1 && world <= RN_MAX_WORLD, "world must be in [1, %d]", RN_MAX_WORLD);
+    RN_REQUIRE(box_out && ipc_handle_out64, "NULL pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(RnPeerBox));
+    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+    RnPeerBox init = {};
+    init.world = world;
+    e = cudaMemcpy(d, &init, sizeof(init), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(ipc_handle_out64), d);
+    if (e != cudaSuccess) { cudaFree(d); return rn_fail(RN_ERR_CUDA, "peer box setup: %s", cudaGetErrorString(e)); }
+    *box_out = d;
+    return RN_OK;
+}
+
+extern "C" int rn_peer_box_open(const void* ipc_handle64, void** peer_box_out) {
+    RN_REQUIRE(ipc_handle64 && peer_box_out, "NULL pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle64, sizeof(h));
+    void* d = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&d, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+    *peer_box_out = d;
+    return RN_OK;
+}
+
+extern "C" int rn_peer_box_close(void* peer_box) {
+    if (!peer_box) return RN_OK;
+    cudaError_t e = cudaIpcCloseMemHandle(peer_box);
+    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaIpcCloseMemHandle: %s", cudaGetErrorString(e));
+    return RN_OK;
+}
+
+extern "C" int rn_peer_box_destroy(void* box) {
+    if (!box) return RN_OK;
+    cudaError_t e = cudaFree(box);
+    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFree: %s", cudaGetErrorString(e));
+    return RN_OK;
+}
+
+extern "C" int rn_peer_publish(const float* value_dev, void* local_box, void* const* boxes_of_all_ranks, int rank, int world,
+                               void* stream) {
+    RN_REQUIRE(value_dev && local_box && boxes_of_all_ranks, "NULL pointer");
+    RN_REQUIRE(world >= 1 && world <= RN_MAX_WORLD && rank >= 0 && rank < world, "bad rank / world (%d / %d)", rank, world);
+    PeerPtrs pp;
+    for (int r = 0; r < RN_MAX_WORLD; ++r) pp.p[r] = nullptr;
+    for (int r = 0; r < world; ++r) {
+        RN_REQUIRE(boxes_of_all_ranks[r] != nullptr, "box of rank %d is NULL", r);
+        pp.p[r] = reinterpret_cast<RnPeerBox*>(boxes_of_all_ranks[r]);
+    }
+    RN_REQUIRE(boxes_of_all_ranks[rank] == local_box, "boxes_of_all_ranks[rank] must be the local box");
+    k_peer_publish<<<1, 32, 0, (cudaStream_t)stream>>>(value_dev, reinterpret_cast<RnPeerBox*>(local_box), pp, rank, world);
+    return rn_check_launch("rn_peer_publish");
+}

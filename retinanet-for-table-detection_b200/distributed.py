@@ -6,8 +6,13 @@ merged batch, ``RetinaNet.py:106-112``): the per-rank positive counts K1 returns
 ``all_reduce`` before K2 scales its gradients, and the two loss sums are reduced afterwards.  Works with
 any ``torch.distributed`` backend (NCCL over NVLink on the GPU box; gloo in the CPU tests).
 """
+import ctypes
+import os
+
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 
 def world():
@@ -41,3 +46,71 @@ def reduce_losses(losses, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
     return out
+
+
+class PeerCounter(object):
+    """The positive-count exchange over NVLink peer memory (C-ABI ``rn_peer_*``, ``csrc/peer_box.cu``): every
+    rank of the node owns a mailbox, mapped into the others through CUDA IPC; ``publish`` (one tiny kernel after
+    K1) stores this rank's count into every mailbox, and K2 -- called with ``box`` as its normaliser and the
+    ``RN_LOSS_NPOS_PEER_BOX`` flag -- waits in its prologue, on local memory, for all counts of the step and adds
+    them in rank order.  Replaces the NCCL all-reduce between K1 and K2 (one launch + ~10-20 us per step) and
+    keeps the whole step capturable in CUDA graphs.
+
+    ``PeerCounter.create()`` returns ``None`` when there is one rank, when the ranks are not all on one node /
+    GPU peer access is unavailable, or when ``RN_B200_PEER_BOX=0``; callers then fall back to
+    :func:`global_positive_count` (``all_reduce``)."""
+
+    def __init__(self, rank, world, box, peers):
+        self.rank, self.world, self.box, self.peers = rank, world, box, peers
+        self._arr = (ctypes.c_void_p * world)(*peers)
+
+    @classmethod
+    def create(cls, group=None):
+        rank, world = (dist.get_rank(group), dist.get_world_size(group)) if (dist.is_available() and dist.is_initialized()) else (0, 1)
+        if world < 2 or world > _lib.RN_MAX_WORLD or os.environ.get("RN_B200_PEER_BOX", "1") == "0":
+            return None
+        if not torch.cuda.is_available():
+            return None
+        lib = _lib.load()
+        box = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        ok = lib.rn_peer_box_create(world, ctypes.byref(box), handle) == 0
+        infos = [None] * world
+        dist.all_gather_object(infos, (ok, bytes(handle.raw), os.uname().nodename), group=group)
+        usable = all(i[0] for i in infos) and len(set(i[2] for i in infos)) == 1
+        peers = [None] * world
+        if usable:
+            for r in range(world):
+                if r == rank:
+                    peers[r] = box.value
+                    continue
+                ptr = ctypes.c_void_p()
+                hb = ctypes.create_string_buffer(infos[r][1], 64)
+                if lib.rn_peer_box_open(hb, ctypes.byref(ptr)) != 0:
+                    usable = False
+                    break
+                peers[r] = ptr.value
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(usable), group=group)
+        if not all(flags):                                  # every rank must take the same path
+            for r, ptr in enumerate(peers):
+                if ptr is not None and r != rank:
+                    lib.rn_peer_box_close(ctypes.c_void_p(ptr))
+            if ok:
+                lib.rn_peer_box_destroy(box)
+            return None
+        return cls(rank, world, box.value, peers)
+
+    def publish(self, value, device=None):
+        """Enqueue the publication of the 1-float device tensor ``value`` (this rank's positive count)."""
+        _lib.check(_lib.load().rn_peer_publish(_lib.ptr(value), ctypes.c_void_p(self.box), self._arr, self.rank, self.world,
+                                               _lib.stream_ptr(device)), "rn_peer_publish")
+
+    def close(self):
+        lib = _lib.load()
+        for r, ptr in enumerate(self.peers):
+            if ptr is not None and r != self.rank:
+                lib.rn_peer_box_close(ctypes.c_void_p(ptr))
+        if self.box is not None:
+            lib.rn_peer_box_destroy(ctypes.c_void_p(self.box))
+        self.peers, self.box = [], None

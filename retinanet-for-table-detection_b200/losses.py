@@ -11,6 +11,8 @@ COUNT to normalise with -- the per-page counts K1 returns, summed and, on severa
 (``distributed.global_positive_count``).  Without it the count is taken from ``y_true`` on the device
 first, exactly as the reference does (``model/losses.py:40-42``, ``:88-89``).
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -118,7 +120,7 @@ def smooth_l1(sigma=3.0):
 
 def detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None,
                      alpha=0.25, gamma=2.0, sigma=3.0, bce="tf2", want_grads=True, out=None, workspace=None,
-                     shared_state=False):
+                     shared_state=False, peer_box=None):
     """Both losses, forward + backward, in ONE launch of K2 (``rn_loss_fwd_bwd``).
 
     All tensors are float32 CUDA: ``y_true_reg`` (B,N,5), ``y_true_cls`` (B,N,C+1) in the order
@@ -128,7 +130,10 @@ def detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None
 
     ``shared_state=True``: the smooth-L1 part reads the anchor state from ``y_true_cls[..., -1]`` instead of
     ``y_true_reg[..., -1]``.  ``anchor_targets_bbox`` always writes the same state into both, so for its
-    outputs the result is identical and 20 B/anchor of reads disappear; keep ``False`` for foreign tensors."""
+    outputs the result is identical and 20 B/anchor of reads disappear; keep ``False`` for foreign tensors.
+
+    ``peer_box``: a :class:`distributed.PeerCounter` whose ``publish`` was enqueued for this step on every rank;
+    the kernel then takes the sum of the published counts as the normaliser (``normalizer`` is ignored)."""
     device = cls_pred.device
     C = cls_pred.shape[-1]
     R = cls_pred.numel() // C
@@ -142,12 +147,18 @@ def detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None
         ws, ws_bytes = _lib.loss_workspace(device)
     else:
         ws, ws_bytes = workspace, workspace.numel()       # caller-owned, zero-filled uint8 tensor
-    npos = _norm_tensor(normalizer, device)
+    flags = _lib.RN_LOSS_SHARED_STATE if shared_state else 0
+    if peer_box is not None:                              # normaliser = sum of the counts the ranks published
+        npos_ptr = ctypes.c_void_p(peer_box.box)
+        flags |= _lib.RN_LOSS_NPOS_PEER_BOX
+    else:
+        npos = _norm_tensor(normalizer, device)
+        npos_ptr = _lib.ptr(npos)
     _lib.check(_lib.load().rn_loss_fwd_bwd(_lib.ptr(y_true_cls), _lib.ptr(cls_pred), _lib.ptr(y_true_reg),
                                            _lib.ptr(reg_pred), R, C, float(alpha), float(gamma), BCE_MODES[bce],
-                                           float(sigma), _lib.ptr(npos),
+                                           float(sigma), npos_ptr,
                                            _lib.ptr(losses), _lib.ptr(grad_cls), _lib.ptr(grad_reg),
-                                           _lib.RN_LOSS_SHARED_STATE if shared_state else 0,
+                                           flags,
                                            _lib.ptr(ws), ws_bytes, _lib.stream_ptr(device)), "rn_loss_fwd_bwd")
     return losses, grad_cls, grad_reg
 

@@ -20,7 +20,7 @@ from . import losses as _losses
 class TargetLossStep(object):
     def __init__(self, image_shape, batch, gmax, num_classes, anchor_params=None, pyramid_levels=None,
                  negative_overlap=0.4, positive_overlap=0.5, alpha=0.25, gamma=2.0, sigma=3.0, bce="tf2",
-                 use_graph=True, device=None, shared_state=True):
+                 use_graph=True, device=None, shared_state=True, peer_box=True):
         _lib.require_cuda()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.spec = _anchors.make_spec(image_shape, pyramid_levels, anchor_params, None)
@@ -53,6 +53,8 @@ class TargetLossStep(object):
         self._graphs = None
         self.kernel_launches_per_step = 2      # K1 + K2 (memsets and NCCL are not ours)
         # run_from_host(): copy stream, per-chunk events, per-chunk loss rows
+        rank, world = _dist.world()
+        self.peer = _dist.PeerCounter.create() if (world > 1 and peer_box) else None   # NVLink mailbox or None
         self._copy_stream = None
         self._chunk_losses = None
         self._chunk_events = None
@@ -85,11 +87,18 @@ class TargetLossStep(object):
         _, _, self.npos, _ = _anchors.anchor_targets_device(self.spec, self.d_boxes, self.d_labels, self.d_counts,
                                                             self.d_hw, self.C, self.neg, self.pos,
                                                             out=(self.y_reg, self.y_cls), npos_total=self.npos_total)
+        if self.peer is not None:
+            self.peer.publish(self.npos_total, self.device)     # this rank's count -> every rank's mailbox
+
+    def _exchange(self):
+        """Several ranks without the peer mailbox: the count is all-reduced between the two kernels."""
+        if self.peer is None and _dist.world()[1] > 1:
+            torch.distributed.all_reduce(self.npos_total)
 
     def _losses(self):
         _losses.detection_losses(self.y_reg, self.y_cls, self.reg_pred, self.cls_pred, normalizer=self.npos_total,
                                  out=(self.losses, self.grad_cls, self.grad_reg), workspace=self.loss_ws,
-                                 **self.loss_kw)
+                                 peer_box=self.peer, **self.loss_kw)
 
     def _capture(self, fn):
         g = torch.cuda.CUDAGraph()
@@ -144,15 +153,14 @@ class TargetLossStep(object):
             self._graphs[0].replay()
         else:
             self._targets()
-        if world > 1:
-            torch.distributed.all_reduce(self.npos_total)
+        self._exchange()
         for i in range(chunks):
             lo, hi = bounds[i], bounds[i + 1]
             compute.wait_event(self._chunk_events[i])
             _losses.detection_losses(self.y_reg[lo:hi], self.y_cls[lo:hi], self.reg_pred[lo:hi], self.cls_pred[lo:hi],
                                      normalizer=self.npos_total,
                                      out=(self._chunk_losses[i], self.grad_cls[lo:hi], self.grad_reg[lo:hi]),
-                                     workspace=self.loss_ws, **self.loss_kw)
+                                     workspace=self.loss_ws, peer_box=self.peer, **self.loss_kw)
         self._losses_host.copy_(self._chunk_losses, non_blocking=True)
         compute.synchronize()
         out = self._losses_host.sum(dim=0)
@@ -173,8 +181,7 @@ class TargetLossStep(object):
             self._graphs[0].replay()
         else:
             self._targets()
-        if world > 1:
-            torch.distributed.all_reduce(self.npos_total)
+        self._exchange()
         if events is not None:
             events[1].record()
         if self.use_graph:

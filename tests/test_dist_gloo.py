@@ -35,6 +35,7 @@ def _worker(rank, world, port, out_dir):
     rs = np.random.RandomState(0)
     cls = (1 / (1 + np.exp(-rs.normal(-3, 1, (pages, anc.shape[0], 1))))).astype(np.float32)
     reg = rs.normal(0, 1, (pages, anc.shape[0], 4)).astype(np.float32)
+    assert rn.distributed.PeerCounter.create() is None      # no GPU here: the all_reduce fallback is the path under test
     lo, hi = rn.distributed.shard_pages(pages)
     y_reg, y_cls = O.anchor_targets_bbox(anc, imgs[lo:hi], anns[lo:hi], 1)
     npos_local = torch.tensor((y_cls[:, :, -1] == 1).sum(axis=1), dtype=torch.int32)
