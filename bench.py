@@ -357,6 +357,26 @@ def bench_inference(rn, torch, device, rank, world, args):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
+        # two batches in flight on two streams (serving loop): k_segment_nms runs one CTA per (page, class), i.e. 64
+        # of the 148 SMs per batch, so a second independent batch fills the other SMs.  Workspaces are per stream.
+        streams = [torch.cuda.Stream(device) for _ in range(2)]
+        for st in streams:
+            st.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(st):
+                head([shape, reg_d, cls_d])
+        torch.cuda.synchronize()
+        e0.record()
+        for st in streams:
+            st.wait_stream(torch.cuda.current_stream(device))
+        for i in range(2 * steps):
+            with torch.cuda.stream(streams[i % 2]):
+                res2 = head([shape, reg_d, cls_d])
+        for st in streams:
+            torch.cuda.current_stream(device).wait_stream(st)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_2s = e0.elapsed_time(e1) / (2 * steps)
+        assert torch.equal(res2[1], res[1])
         # e2e: host head outputs in, detections out
         e0.record()
         for _ in range(steps):
@@ -365,12 +385,13 @@ def bench_inference(rn, torch, device, rank, world, args):
         e1.record()
         torch.cuda.synchronize()
         ms_e2e = e0.elapsed_time(e1) / steps
-        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
+        t = torch.tensor([ms, ms_e2e, ms_2s], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = [float(x) for x in t.cpu()]
+        ms, ms_e2e, ms_2s = [float(x) for x in t.cpu()]
         ndet = int((res[1] >= 0).sum().item())
         out[tag] = {"pages_per_s": world * B / (ms * 1e-3), "ms_per_batch": ms,
+                    "pages_per_s_two_streams": world * B / (ms_2s * 1e-3),
                     "e2e_pages_per_s": world * B / (ms_e2e * 1e-3), "detections_per_page": ndet / B}
     out["workload"] = "configs[2]: %d pages/GPU of 800x1333, 1 class, thr 0.05, NMS 0.5, 300 detections" % B
     out["candidates_per_page"] = float((cls_np > 0.05).sum()) / B

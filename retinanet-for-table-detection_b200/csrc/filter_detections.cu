@@ -81,7 +81,10 @@ __device__ __forceinline__ float4 candidate_box(const K3Params& p, int b, int n)
     const float sx = ((float)cx + 0.5f) * (float)p.lv.stride[level];
     const float sy = ((float)cy + 0.5f) * (float)p.lv.stride[level];
     const float ax1 = __ldg(bs) + sx, ay1 = __ldg(bs + 1) + sy, ax2 = __ldg(bs + 2) + sx, ay2 = __ldg(bs + 3) + sy;
-    const float4 d = __ldg(reinterpret_cast<const float4*>(p.reg) + (size_t)b * p.N + n);
+    // scattered 16-byte rows (~2.5 % of the anchors): no L1 allocation and the smallest L2 fetch granularity
+    float4 d;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(d.x), "=f"(d.y), "=f"(d.z), "=f"(d.w) : "l"(reinterpret_cast<const float4*>(p.reg) + (size_t)b * p.N + n));
     const float w = ax2 - ax1, h = ay2 - ay1;
     float4 o;
     o.x = ax1 + (d.x * p.nm.std[0] + p.nm.mean[0]) * w;
@@ -108,10 +111,10 @@ constexpr int K3_TILE = K3_THREADS * K3_VEC * 4;            // scores per CTA (c
 template <bool DECODE>
 __global__ void __launch_bounds__(K3_THREADS) k_threshold_compact(const K3Params p) {
     __shared__ int s_elem[K3_TILE];
-    __shared__ float s_score[K3_TILE];
+    __shared__ float s_score[K3_THREADS * K3_VEC];          // class-agnostic path only (score = max over classes)
     __shared__ int s_label[K3_THREADS * K3_VEC];            // class-agnostic path only
     __shared__ int s_count, s_base;
-    const int b = blockIdx.y, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) s_count = 0;
     __syncthreads();
     const bool one_slab = (p.C == 1) || !p.class_specific;
@@ -127,17 +130,33 @@ __global__ void __launch_bounds__(K3_THREADS) k_threshold_compact(const K3Params
             cnt[g] = max(0, min(4, total - e0));
             sv[g][0] = sv[g][1] = sv[g][2] = sv[g][3] = 0.f;
             if (cnt[g] == 4 && p.vec_ok) { const float4 v = rn_ldg_stream4(src + e0); sv[g][0] = v.x; sv[g][1] = v.y; sv[g][2] = v.z; sv[g][3] = v.w; }
-            else for (int k = 0; k < cnt[g]; ++k) sv[g][k] = __ldg(src + e0 + k);
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (k < cnt[g]) sv[g][k] = __ldg(src + e0 + k);   // static indices: sv stays in registers
+            }
         }
+        // survivors of this thread -> warp prefix sum -> ONE shared-memory atomic per warp reserves the list slots
+        unsigned hits = 0u;                                 // bit g*4+k
 #pragma unroll
-        for (int g = 0; g < K3_VEC; ++g) {
+        for (int g = 0; g < K3_VEC; ++g)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (k < cnt[g] && sv[g][k] > p.thr) {
-                    const int at = atomicAdd(&s_count, 1);
-                    s_elem[at] = tile0 + (g * K3_THREADS + tid) * 4 + k;
-                    s_score[at] = sv[g][k];
-                }
+            for (int k = 0; k < 4; ++k)
+                if (k < cnt[g] && sv[g][k] > p.thr) hits |= 1u << (g * 4 + k);
+        const int mine = __popc(hits);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+        int at = 0;
+        if (warp_total) {                                   // warp-uniform
+            if (lane == 31) at = atomicAdd(&s_count, warp_total);
+            at = __shfl_sync(0xffffffffu, at, 31) + incl - mine;
+            // only the element index is staged; the score is re-read (an L2 hit) by the thread that takes the
+            // candidate, together with its regression row
+            while (hits) {
+                const int j = __ffs(hits) - 1;
+                hits &= hits - 1u;
+                s_elem[at++] = tile0 + (((j >> 2) * K3_THREADS + tid) << 2) + (j & 3);
             }
         }
     } else {
@@ -160,28 +179,39 @@ __global__ void __launch_bounds__(K3_THREADS) k_threshold_compact(const K3Params
     __syncthreads();
     const int found = s_count;
     if (found == 0) return;
-    if (one_slab) {
-        if (tid == 0) s_base = atomicAdd(p.sl.counts + b, found);
-        __syncthreads();
-    }
-    for (int i = tid; i < found; i += K3_THREADS) {
-        const int e = s_elem[i];
-        int n = e, c = 0, seg = b;
-        long long slot;
-        if (one_slab) {
-            slot = (long long)s_base + i;
-            if (!p.class_specific) c = s_label[i];
-        } else {
-            n = rn_div(e, p.C, p.inv_c);
-            c = e - n * p.C;
-            seg = b * p.C + c;
-            slot = atomicAdd(p.sl.counts + seg, 1);
+    // slot reservation (one global atomic per CTA when all candidates feed one slab) is issued first and only
+    // waited for after the candidates' boxes have been fetched and decoded: the two round trips overlap
+    if (one_slab && tid == 0) s_base = atomicAdd(p.sl.counts + b, found);
+    for (int i0 = 0; i0 < found; i0 += K3_THREADS) {
+        const int i = i0 + tid;
+        const bool act = i < found;
+        int n = 0, c = 0, seg = b;
+        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+        float score = 0.f;
+        long long slot = 0;
+        if (act) {
+            const int e = s_elem[i];
+            n = e;
+            score = p.class_specific ? __ldg(p.cls + (size_t)b * p.N * p.C + e) : s_score[i];
+            if (one_slab) {
+                if (!p.class_specific) c = s_label[i];
+            } else {
+                n = rn_div(e, p.C, p.inv_c);
+                c = e - n * p.C;
+                seg = b * p.C + c;
+                slot = atomicAdd(p.sl.counts + seg, 1);
+            }
+            box = candidate_box<DECODE>(p, b, n);
         }
-        if (slot < p.sl.cap) {                              // dropped when the slab is full; the count keeps
-            const size_t at = (size_t)seg * p.sl.cap + slot;    // growing so k_segment_nms reports the overflow
-            p.sl.keys[at] = make_key(s_score[i], (unsigned)n);
-            p.sl.boxes[at] = candidate_box<DECODE>(p, b, n);
-            if (p.sl.labels) p.sl.labels[at] = c;
+        if (one_slab && i0 == 0) __syncthreads();           // s_base has arrived
+        if (act) {
+            if (one_slab) slot = (long long)s_base + i;
+            if (slot < p.sl.cap) {                          // dropped when the slab is full; the count keeps
+                const size_t dst = (size_t)seg * p.sl.cap + slot;   // growing so k_segment_nms reports the overflow
+                p.sl.keys[dst] = make_key(score, (unsigned)n);
+                p.sl.boxes[dst] = box;
+                if (p.sl.labels) p.sl.labels[dst] = c;
+            }
         }
     }
 }
