@@ -98,6 +98,11 @@ __device__ __forceinline__ float4 candidate_box(const K3Params& p, int b, int n)
     return o;
 }
 
+// Measured (profiles/k3_probe.py, 64 pages): streaming the 51 MB of scores alone takes 12.5-14.5 us; the 326 k
+// candidates add ~13 us, which is the HBM random-access rate for their scattered 16-byte regression rows
+// (~22 G rows/s), not instruction issue or atomics -- a persistent, warp-autonomous, software-pipelined variant
+// (no block barriers, next chunk's loads in flight during the candidate phase, 4 candidates per lane in flight)
+// streamed faster (12.5 us) but took 34 us with candidates and was not kept.
 // grid = (tiles of a page, pages).  Two phases per CTA so that the sparse candidates (~2.5 % of the scores)
 // never make whole warps walk the divergent decode path:
 //   1. every thread streams K3_VEC float4 groups of scores (all loads issued up front) and pushes the
