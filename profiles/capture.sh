@@ -14,6 +14,12 @@ tail -3 $OUT/pytest_$TAG.log
 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
 echo "bench_exit=$?"
 cat $OUT/bench_$TAG.json
+# launch list of the `value` region only (K1 + K2 per step), then of the whole default bench command
+VCMD="python bench.py --steps 10 --warmup 3 --no-cpu --no-inference --no-e2e"
+$VCMD > $OUT/plain_value_$TAG.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+    --log-file $OUT/launches_value_$TAG.csv $VCMD > $OUT/ncu_launch_value_$TAG.log 2>&1
+echo "launchlist_value_exit=$?"
 BCMD="python bench.py --steps 3 --warmup 3 --no-cpu"
 $BCMD > $OUT/plain_bench_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
