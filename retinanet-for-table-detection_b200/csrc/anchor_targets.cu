@@ -279,6 +279,29 @@ __global__ void __launch_bounds__(K1_THREADS) k_anchor_targets(const K1Params p)
     }
 }
 
+// One staged row -> global memory through the TMA engine.  `dst` and `src` are 16-byte aligned and in phase; floats
+// [lo, hi) of the staged row are valid (lo < 4).  Whole 16-byte chunks go in one bulk copy, the partial chunks at the
+// ends in one 16-byte copy each with a byte mask (sm_100 cp_mask: bit i = byte i of the chunk).
+__device__ __forceinline__ void rn_bulk_store_row(float* dst, const float* src, int lo, int hi) {
+    const unsigned s0 = (unsigned)__cvta_generic_to_shared(src);
+    auto mask_of = [](int a, int b) { return (unsigned short)(((1u << (4 * b)) - 1u) & ~((1u << (4 * a)) - 1u)); };   // floats [a, b) of a chunk
+    const int first_full = lo ? 1 : 0, last_full = hi >> 2;     // chunks [first_full, last_full) are whole
+    if (last_full < first_full || (last_full == 0 && lo)) {     // everything inside chunk 0
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.cp_mask [%0], [%1], 16, %2;"
+                     :: "l"(dst), "r"(s0), "h"(mask_of(lo, hi)) : "memory");
+        return;
+    }
+    if (lo)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.cp_mask [%0], [%1], 16, %2;"
+                     :: "l"(dst), "r"(s0), "h"(mask_of(lo, 4)) : "memory");
+    if (last_full > first_full)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     :: "l"(dst + 4 * first_full), "r"(s0 + 16u * first_full), "r"(16u * (unsigned)(last_full - first_full)) : "memory");
+    if (hi & 3)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.cp_mask [%0], [%1], 16, %2;"
+                     :: "l"(dst + 4 * last_full), "r"(s0 + 16u * last_full), "h"(mask_of(0, hi & 3)) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1 for generated anchors: a CTA owns a 32-cell x KT_ROWS-row tile of one feature map, a WARP one anchor
 // type of that tile, a THREAD one (anchor type, column) and walks the tile's rows.
@@ -520,6 +543,7 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
         my_pos = rn_warp_sum(my_pos);
         if (lane == 0 && my_pos) atomicAdd(&s_npos, my_pos);
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the staged rows are read by the TMA engine below
     __syncthreads();
     if (tid == 0 && s_npos) {
         if (p.npos) atomicAdd(p.npos + b, s_npos);
@@ -528,7 +552,34 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
 
     const int cnt = ncols * A;
     const long long tile_row0 = (long long)b * p.N + lstart + ((long long)cy0 * W + cx0) * A;
-    // ---- write-out: each tile row is one contiguous anchor range; ONE loop over the 16-byte units of all rows.
+    // ---- write-out: each tile row is one contiguous anchor range, staged with the destination's 16-byte phase.
+    if (p.vec_ok) {
+        // TMA bulk stores: ONE thread per (row, tensor) hands its staged row to the copy engine --
+        // cp.async.bulk.global.shared::cta for the 16-byte aligned interior, the sm_100 .cp_mask form (a byte mask
+        // inside one 16-byte chunk) for the partial chunks at the two ends -- instead of every thread looping
+        // over LDS.128 / STG.128 pairs (that loop was ~15 % of the kernel's instructions).
+        const int job = tid;                                // jobs [0, KT_ROWS): regression rows, [KT_ROWS, 2 KT_ROWS): label rows
+        const bool lab_job = job >= KT_ROWS;
+        const int r = lab_job ? job - KT_ROWS : job;
+        if (job < 2 * KT_ROWS && r < nrows && !(lab_job && p.C != 1)) {
+            const int per = lab_job ? 2 : 5;
+            const long long start = (tile_row0 + (long long)r * W * A) * per;
+            const int len = cnt * per, shift = (int)(start & 3);
+            const float* src = lab_job ? s_lab + r * lab_stride : s_reg + r * reg_stride;
+            float* dst = (lab_job ? p.lab : p.reg) + (start - shift);
+            const int end = shift + len;                    // staged floats [shift, end) are valid
+            rn_bulk_store_row(dst, src, shift, end);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the CTA's shared memory may go away after this
+        }
+        if (p.C != 1) {
+            for (int r2 = 0; r2 < nrows; ++r2)
+                store_labels_generic(p.lab, tile_row0 + (long long)r2 * W * A, cnt, p.C, true, nthreads,
+                                     s_state + r2 * 32 * A, s_hot + r2 * 32 * A);
+        }
+        return;
+    }
+    // unaligned output tensors: plain stores
     // Unit v of a row covers staged floats [4v, 4v+4) = global floats [start - shift + 4v, ...): whole units are
     // one LDS.128 + one STG.128, the (<= 2) partial units at the ends of a row are written float by float.
     {
