@@ -191,6 +191,16 @@ int rn_nms(const float* boxes /*(K,4)*/, const float* scores /*(K)*/, long long 
            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * N3  the reference's host post-step on the detections (RetinaNet.py:366-377):
+ *     boxes /= image_scale (fp32 division, per page) and the score cut -- the reference walks the
+ *     score-sorted detections and stops at the first score < 0.6; count_out[b] is that position
+ *     (M when no score is below the cut; padding rows carry score -1).
+ *   boxes (B, M, 4), scores (B, M), image_scale_dev (B) float32; boxes_out may alias boxes.
+ * ------------------------------------------------------------------------------------------- */
+int rn_rescale_cut(const float* boxes, const float* scores, const float* image_scale_dev, int B, int M,
+                   float min_score, float* boxes_out, int* count_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * C1  the path's only exchange step: the batch-global positive-anchor count of the two losses
  *     (model/losses.py:40-44, :88-90; with keras.utils.multi_gpu_model the loss sees the merged
  *     batch, RetinaNet.py:106-112), exchanged over NVLink peer memory between the ranks of one node.

@@ -106,3 +106,28 @@ def load_reference():
     finally:
         _remove_stubs()
     return ref_anchors, ref_utils
+
+
+def load_reference_generator():
+    """The reference's ``csv_generator`` module (``Generator.filter_annotations`` / ``compute_inputs`` /
+    ``compute_targets`` are plain numpy).  ``Shapes`` lives in the archived FasterRCNN tree; ``keras.utils.Sequence``
+    is stubbed as ``object``.  Instances are made with ``Generator.__new__`` (the constructor reads a dataset)."""
+    if not reference_available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    import importlib
+    if "csv_generator" in sys.modules and hasattr(sys.modules["csv_generator"], "Generator"):
+        return sys.modules["csv_generator"]
+    _install_stubs()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    shapes_dir = os.path.join(REFERENCE_ROOT, "FasterRCNN")      # only for `Shapes`; searched last
+    if shapes_dir not in sys.path:
+        sys.path.append(shapes_dir)
+    try:
+        sys.modules["keras"].utils.Sequence = object
+        importlib.import_module("model.utils")
+        importlib.import_module("model.anchors")
+        gen = importlib.import_module("csv_generator")
+    finally:
+        _remove_stubs()
+    return gen

@@ -91,3 +91,45 @@ extern "C" int rn_clip_boxes(const float* boxes, long long R, float width, float
     k_clip_boxes<<<stream_grid(R), 256, 0, (cudaStream_t)stream>>>(boxes, R, width, height, out);
     return rn_check_launch("rn_clip_boxes");
 }
+
+// ------------------------------------------------------------------------------------------------
+// N3  host post-step of the reference (RetinaNet.py:366-377) as an epilogue on the detections:
+//   boxes /= image_scale   (fp32 division by the page's resize scale, as numpy does on the float32 array)
+//   visible = number of leading detections before the first score < min_score (the reference walks the
+//             score-sorted list and breaks there; padding entries have score -1)
+// One CTA per page; detections are at most a few hundred rows.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) k_rescale_cut(const float* boxes, const float* scores, const float* scale, int M,
+                                                     float min_score, float* boxes_out, int* count_out) {
+    __shared__ int s_first;
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) s_first = M;
+    __syncthreads();
+    const float sc = __ldg(scale + b);
+    int first = M;
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        const size_t at = (size_t)b * M + m;
+        float4 v = __ldg(reinterpret_cast<const float4*>(boxes) + at);
+        v.x = __fdiv_rn(v.x, sc); v.y = __fdiv_rn(v.y, sc); v.z = __fdiv_rn(v.z, sc); v.w = __fdiv_rn(v.w, sc);
+        reinterpret_cast<float4*>(boxes_out)[at] = v;
+        if (__ldg(scores + at) < min_score && m < first) first = m;     // NaN < x is false, as in the reference's `if`
+    }
+    if (first < M) atomicMin(&s_first, first);
+    __syncthreads();
+    if (threadIdx.x == 0) count_out[b] = s_first;
+}
+
+}  // namespace
+
+extern "C" int rn_rescale_cut(const float* boxes, const float* scores, const float* image_scale_dev, int B, int M,
+                              float min_score, float* boxes_out, int* count_out, void* stream) {
+    RN_REQUIRE(boxes && scores && image_scale_dev && boxes_out && count_out, "NULL pointer");
+    RN_REQUIRE(B >= 0 && M >= 0, "negative size");
+    if (B == 0) return RN_OK;
+    RN_REQUIRE(B <= 2147483647 && M <= (1 << 24), "size out of range");
+    RN_REQUIRE(rn_aligned16(boxes) && rn_aligned16(boxes_out), "boxes must be 16-byte aligned");
+    k_rescale_cut<<<B, 256, 0, (cudaStream_t)stream>>>(boxes, scores, image_scale_dev, M, min_score, boxes_out, count_out);
+    return rn_check_launch("rn_rescale_cut");
+}
