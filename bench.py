@@ -283,6 +283,32 @@ def run_ours(args):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms, k1_ms, k2_ms = [float(x) for x in times.cpu()]
 
+    # ---- N2 (extra object): K2 fed by the per-level head outputs, sigmoid fused ---------------------------
+    levels = None
+    if not args.no_inference:
+        spec = step.spec
+        rows = [int(h) * int(w) * spec.per_cell for h, w in spec.level_hw]
+        rs = np.random.RandomState(77 + rank)
+        cls_l = [torch.from_numpy(rs.normal(-4.6, 1.0, (B, n, 1)).astype(np.float32)).to(device) for n in rows]
+        reg_l = [torch.from_numpy(rs.normal(0.0, 1.0, (B, n, 4)).astype(np.float32)).to(device) for n in rows]
+        outs = (torch.empty(3, dtype=torch.float32, device=device), [torch.empty_like(c) for c in cls_l], [torch.empty_like(r) for r in reg_l])
+        run_levels = lambda: rn.detection_losses_levels(step.y_reg, step.y_cls, reg_l, cls_l, normalizer=step.npos_total,
+                                                        from_logits=True, out=outs, workspace=step.loss_ws)
+        for _ in range(5):
+            run_levels()
+        torch.cuda.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 50
+        l0.record()
+        for _ in range(reps):
+            run_levels()
+        l1.record()
+        torch.cuda.synchronize()
+        lv_us = l0.elapsed_time(l1) / reps * 1e3
+        levels = {"kernel": "k_loss_c1_levels (per-level logits in, sigmoid fused, per-level gradients out)",
+                  "us_per_launch": lv_us, "level_rows": rows,
+                  "note": "back-to-back launches incl. launch overhead; replaces sigmoid + Concatenate(axis=1) + K2"}
+
     # ---- inference path (extra object) -----------------------------------------------------------------
     inference = None
     if not args.no_inference:
@@ -336,6 +362,9 @@ def run_ours(args):
         }
         if inference is not None:
             line["inference"] = inference
+        if levels is not None:
+            levels["GBps"] = k2_bytes / (levels["us_per_launch"] * 1e-6) / 1e9
+            line["per_level_heads"] = levels
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line))

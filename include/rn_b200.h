@@ -126,6 +126,22 @@ int rn_loss_fwd_bwd(const float* y_true_cls, const float* cls_pred, const float*
                     float* grad_cls /*(R,C)*/, float* grad_reg /*(R,4)*/,
                     int flags, void* workspace, size_t workspace_bytes, void* stream);
 
+/* N2  the same fused losses fed by the heads' PER-LEVEL outputs (model/defineModel.py:119-123, 163-166, 217):
+ * level l contributes cls_levels[l] (B, n_l, 1) and reg_levels[l] (B, n_l, 4); sum_l n_l = N.  No
+ * Concatenate(axis=1) copy is needed, and with RN_LOSS_FROM_LOGITS the classification tensors hold the LOGITS
+ * (the heads' Activation('sigmoid') is fused: p = 1 / (1 + exp(-z))) and grad_cls_levels receive
+ * d loss / d logit.  Targets are the concatenated (B, N, .) tensors rn_anchor_targets writes.
+ * Covers the reference's table-detection configuration: C == 1, gamma == 2, RN_BCE_TF2, RN_LOSS_SHARED_STATE.
+ * The *_levels arguments are HOST arrays of num_levels device pointers; level_rows is a host array (n_l). */
+#define RN_LOSS_FROM_LOGITS 4
+int rn_loss_fwd_bwd_levels(const float* y_true_cls, const float* y_true_reg,
+                           const float* const* cls_levels, const float* const* reg_levels,
+                           const long long* level_rows, int num_levels, int B, int C,
+                           float alpha, float gamma, int bce_mode, float sigma,
+                           const float* npos_dev, float* losses_out_dev,
+                           float* const* grad_cls_levels, float* const* grad_reg_levels,
+                           int flags, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Detection head, layer by layer.
  */

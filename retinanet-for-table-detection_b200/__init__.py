@@ -20,7 +20,7 @@ from .anchors import (AnchorParameters, AnchorParameters_default, anchor_targets
                       anchors_for_shape, bbox_transform, compute_gt_annotations, generate_anchors, guess_shapes)
 from .layers import (Anchors, ClipBoxes, DetectionHead, FilterDetections, RegressBoxes,  # noqa: F401
                      custom_objects, filter_detections)
-from .losses import detection_loss, detection_losses, focal, smooth_l1  # noqa: F401
+from .losses import detection_loss, detection_losses, detection_losses_levels, focal, smooth_l1  # noqa: F401
 from .utils import bbox_transform_inv, compute_overlap  # noqa: F401
 
 __version__ = "0.1.0"

@@ -18,6 +18,7 @@ RN_BCE_TF2 = 0
 RN_BCE_LOGITS = 1
 RN_LOSS_SHARED_STATE = 1
 RN_LOSS_NPOS_PEER_BOX = 2
+RN_LOSS_FROM_LOGITS = 4
 RN_MAX_WORLD = 16
 
 
@@ -44,6 +45,9 @@ SIGNATURES = {
     "rn_smooth_l1_fwd_bwd": (c_int, [_P, _P, c_longlong, c_float, _P, _P, _P, _P, c_size_t, _P]),
     "rn_loss_fwd_bwd": (c_int, [_P, _P, _P, _P, c_longlong, c_int, c_float, c_float, c_int, c_float,
                                 _P, _P, _P, _P, c_int, _P, c_size_t, _P]),
+    "rn_loss_fwd_bwd_levels": (c_int, [_P, _P, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_longlong), c_int, c_int, c_int,
+                                       c_float, c_float, c_int, c_float, _P, _P, POINTER(c_void_p), POINTER(c_void_p),
+                                       c_int, _P, c_size_t, _P]),
     "rn_anchors_f32": (c_int, [_P, _HI, _HI, c_int, c_int, c_int, _P, _P]),
     "rn_regress_boxes": (c_int, [_P, _P, c_longlong, _HF, _HF, _P, _P]),
     "rn_clip_boxes": (c_int, [_P, c_longlong, c_float, c_float, _P, _P]),

@@ -163,6 +163,54 @@ def detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None
     return losses, grad_cls, grad_reg
 
 
+def detection_losses_levels(y_true_reg, y_true_cls, reg_levels, cls_levels, normalizer=None, from_logits=True,
+                            alpha=0.25, gamma=2.0, sigma=3.0, bce="tf2", out=None, workspace=None, peer_box=None):
+    """The fused losses fed by the heads' per-level outputs: ``cls_levels[l]`` is the
+    (B, n_l, 1) classification tensor of pyramid level l -- LOGITS when ``from_logits`` (the heads'
+    ``Activation('sigmoid')``, model/defineModel.py:123, is fused into the kernel), else probabilities -- and
+    ``reg_levels[l]`` the (B, n_l, 4) regression; the ``Concatenate(axis=1)`` of model/defineModel.py:217 never
+    happens.  Targets are the concatenated ``(B, N, .)`` tensors of ``anchor_targets_bbox`` (state shared).
+
+    Returns ``(losses[3], grad_cls_levels, grad_reg_levels)``; the classification gradients are w.r.t. what was
+    passed in (logits or probabilities).  C == 1, gamma == 2, TF2 cross-entropy only (``rn_loss_fwd_bwd_levels``)."""
+    device = y_true_cls.device
+    L = len(cls_levels)
+    if len(reg_levels) != L or L < 1:
+        raise ValueError("cls_levels and reg_levels must have the same, non-zero number of levels")
+    B = int(y_true_cls.shape[0])
+    rows = [int(c.shape[1]) for c in cls_levels]
+    for c, r in zip(cls_levels, reg_levels):
+        if tuple(c.shape) != (B, c.shape[1], 1) or tuple(r.shape) != (B, c.shape[1], 4) or not (c.is_contiguous() and r.is_contiguous()):
+            raise ValueError("level tensors must be contiguous (B, n_l, 1) / (B, n_l, 4); got %s / %s" % (tuple(c.shape), tuple(r.shape)))
+    if sum(rows) != int(y_true_cls.shape[1]) or tuple(y_true_reg.shape) != (B, sum(rows), 5) or int(y_true_cls.shape[2]) != 2:
+        raise ValueError("targets %s / %s do not match the levels (%d anchors, 1 class)"
+                         % (tuple(y_true_reg.shape), tuple(y_true_cls.shape), sum(rows)))
+    if out is None:
+        losses = torch.empty(3, dtype=torch.float32, device=device)
+        g_cls = [torch.empty_like(c) for c in cls_levels]
+        g_reg = [torch.empty_like(r) for r in reg_levels]
+    else:
+        losses, g_cls, g_reg = out
+    if workspace is None:
+        ws, ws_bytes = _lib.loss_workspace(device)
+    else:
+        ws, ws_bytes = workspace, workspace.numel()
+    flags = _lib.RN_LOSS_SHARED_STATE | (_lib.RN_LOSS_FROM_LOGITS if from_logits else 0)
+    if peer_box is not None:
+        npos_ptr = ctypes.c_void_p(peer_box.box)
+        flags |= _lib.RN_LOSS_NPOS_PEER_BOX
+    else:
+        npos = _norm_tensor(normalizer, device)
+        npos_ptr = _lib.ptr(npos)
+    arr = lambda ts: (ctypes.c_void_p * L)(*[t.data_ptr() for t in ts])
+    rows_arr = (ctypes.c_longlong * L)(*rows)
+    _lib.check(_lib.load().rn_loss_fwd_bwd_levels(_lib.ptr(y_true_cls), _lib.ptr(y_true_reg), arr(cls_levels), arr(reg_levels),
+                                                  rows_arr, L, B, 1, float(alpha), float(gamma), BCE_MODES[bce], float(sigma),
+                                                  npos_ptr, _lib.ptr(losses), arr(g_cls), arr(g_reg), flags,
+                                                  _lib.ptr(ws), ws_bytes, _lib.stream_ptr(device)), "rn_loss_fwd_bwd_levels")
+    return losses, g_cls, g_reg
+
+
 class _DetectionLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cls_pred, reg_pred, y_true_cls, y_true_reg, npos, alpha, gamma, sigma, bce):

@@ -184,3 +184,37 @@ def test_full_size_properties(rn):
     assert close(total[:2], acc, rtol=1e-5)
     wl, wg = OL.focal()(y_cls[:1], p[:1], return_grad=True, normalizer=float(total[2]))
     assert close(gc[0].cpu().numpy(), wg[0], atol=1e-7 * float(np.abs(wg).max()))
+
+
+@pytest.mark.parametrize("from_logits", [True, False])
+@pytest.mark.parametrize("rows", [[150, 37, 10, 3, 1], [64, 64], [1], [33, 31, 65, 2]])
+def test_per_level_heads_fused_sigmoid(rn, rows, from_logits):
+    """N2: per-level (B, n_l, 1) logits / (B, n_l, 4) regression straight into the fused losses -- same losses and
+    gradients as sigmoid + Concatenate(axis=1) + the reference losses (oracle), gradients w.r.t. the logits.
+    Level sizes are chosen so that warp chunks (64 rows) cross level and page boundaries at every phase."""
+    B, N = 3, sum(rows)
+    y_cls, p, y_reg, r = make_case(70 + N, B, N, 1, p_ignore=0.05, p_pos=0.05, logit_mu=-3.0)
+    y_reg[:, :, 4] = y_cls[:, :, 1]
+    rs = np.random.RandomState(N)
+    z = rs.normal(-3.0, 2.5, (B, N, 1)).astype(np.float32)
+    z[0, 0, 0], z[0, min(1, N - 1), 0] = 40.0, -40.0                      # saturated sigmoid on both sides
+    prob = (np.float32(1) / (np.float32(1) + np.exp(-z))).astype(np.float32) if from_logits else p
+    want_f, want_gf = OL.focal()(y_cls, prob, return_grad=True)
+    want_s, want_gs = OL.smooth_l1()(y_reg, r, return_grad=True)
+    if from_logits:
+        want_gf = want_gf * (prob * (np.float32(1) - prob))
+    src = z if from_logits else p
+    t = lambda a: torch.tensor(np.ascontiguousarray(a), device="cuda")
+    bounds = np.concatenate([[0], np.cumsum(rows)])
+    cls_l = [t(src[:, bounds[i]:bounds[i + 1]]) for i in range(len(rows))]
+    reg_l = [t(r[:, bounds[i]:bounds[i + 1]]) for i in range(len(rows))]
+    losses, g_cls, g_reg = rn.detection_losses_levels(t(y_reg), t(y_cls), reg_l, cls_l, from_logits=from_logits)
+    l = losses.cpu().numpy()
+    assert close(l[0], want_f) and close(l[1], want_s) and l[2] == max(1.0, float((y_cls[:, :, 1] == 1).sum()))
+    got_gf = np.concatenate([g.cpu().numpy() for g in g_cls], axis=1)
+    got_gs = np.concatenate([g.cpu().numpy() for g in g_reg], axis=1)
+    assert close(got_gf, want_gf, atol=1e-7 * float(np.abs(want_gf).max()))
+    assert close(got_gs, want_gs, atol=1e-9)
+    if not from_logits:                                                   # probabilities in: bit-identical to the concatenated path
+        ref = rn.detection_losses(t(y_reg), t(y_cls), t(r), t(p), shared_state=True)
+        assert torch.equal(torch.cat(g_cls, 1), ref[1]) and torch.equal(torch.cat(g_reg, 1), ref[2])
