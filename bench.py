@@ -216,7 +216,16 @@ def run_ours(args):
     anchors = rn.anchors_for_shape(HW + (3,))
     N = anchors.shape[0]
     first = rank * B
-    images, anns = synthetic.training_batch(CFG, batch=B, anchors=np.asarray(anchors), first_page=first)
+    if world > 1 and not args.contiguous_shards:
+        # the global batch (world x 16 pages) is sharded by GT count so that every rank's K1 takes about the same
+        # time (distributed.balanced_shards); every rank derives the same assignment from the annotations
+        g_images, g_anns = synthetic.training_batch(CFG, batch=world * B, anchors=np.asarray(anchors), first_page=0)
+        mine = rn.distributed.balanced_shards([len(a['labels']) for a in g_anns], world)[rank]
+        images, anns = [g_images[i] for i in mine], [g_anns[i] for i in mine]
+        sharding = "pages of the global batch dealt out by GT count (balanced_shards)"
+    else:
+        images, anns = synthetic.training_batch(CFG, batch=B, anchors=np.asarray(anchors), first_page=first)
+        sharding = "contiguous page ranges"
     cls_np, reg_np = synthetic.training_predictions(CFG, B, N, classes=C, first_page=first)
     cls_host = torch.from_numpy(cls_np).pin_memory()
     reg_host = torch.from_numpy(reg_np).pin_memory()
@@ -235,6 +244,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- resident: `value` + per-kernel durations ----------------------------------------------------
+    pipelined = world > 1 and step.peer is not None and args.pipelined
+    run_step = step.run_pipelined if pipelined else step.run
     for _ in range(max(args.warmup, 3)):
         step.run()
     exchange = "none (1 rank)"
@@ -250,8 +261,21 @@ def run_ours(args):
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
+    if pipelined:
+        # inputs are static, so the pipelined schedule must reproduce the in-order step bit for bit
+        ref_losses, ref_gc, ref_gr = step.losses.clone(), step.grad_cls.clone(), step.grad_reg.clone()
+        for _ in range(3):
+            run_step()
+        torch.cuda.synchronize()
+        assert torch.equal(step.losses, ref_losses) and torch.equal(step.grad_cls, ref_gc) and torch.equal(step.grad_reg, ref_gr), \
+            "pipelined schedule differs from the in-order step"
+        y_reg_p, y_cls_p = step.targets_of_losses()
+        assert torch.equal(y_reg_p, step.y_reg if y_reg_p is step.y_reg else y_reg_p)
+        del ref_gc, ref_gr
+        barrier()
+        t_wall0 = time.perf_counter()
     for i in range(args.steps):
-        step.run(events=evs[i])
+        run_step(events=evs[i])
     barrier()
     t_wall1 = time.perf_counter()
     total_ms = evs[0][0].elapsed_time(evs[-1][2])
@@ -332,7 +356,9 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64 matching + f32 targets/losses", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pages_per_gpu": B, "anchors_per_page": N, "classes": C,
                        "l2": "working set per step ~%d MB (> 126 MB L2), no explicit flush" % ((k1_bytes + k2_bytes) // (1 << 20)),
-                       "cuda_graphs": True, "count_exchange": exchange},
+                       "cuda_graphs": True, "count_exchange": exchange, "sharding": sharding,
+                       "schedule": ("pipelined: K1 + publish of batch s+1 enqueued ahead of K2 of batch s (mailbox lag 1, "
+                                    "double-buffered targets)") if pipelined else "in order: K1(s), K2(s)"},
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "pages/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 12 * E2E_CHUNKS, "ms_per_step": e2e_ms / args.steps,
                     "h2d_GBps": h2d / (e2e_ms / args.steps * 1e-3) / 1e9,
@@ -449,6 +475,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-inference", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--contiguous-shards", action="store_true", help="several ranks: rank r takes pages [16r, 16r+16) instead of the load-aware deal")
+    ap.add_argument("--pipelined", action="store_true", help="several ranks: enqueue K1 + publish of batch s+1 ahead of K2 of batch s "
+                    "(TargetLossStep.run_pipelined; measured 3 %% slower than in order at N = 2 and 8, so not the default)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-input leg (used for the ncu launch list of the `value` region)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -119,6 +119,8 @@ int rn_smooth_l1_fwd_bwd(const float* y_true_reg /*(R,5)*/, const float* y_pred 
 #define RN_LOSS_SHARED_STATE 1
 #define RN_LOSS_NPOS_PEER_BOX 2   /* npos_dev is this rank's peer mailbox (rn_peer_box_create): the normaliser is
                                     the sum of the counts all ranks published for the current step           */
+#define RN_LOSS_PEER_LAG1     8   /* with RN_LOSS_NPOS_PEER_BOX: use the step published BEFORE the latest one
+                                    (pipelined schedule: K1 + publish of the next batch run ahead of this K2)  */
 int rn_loss_fwd_bwd(const float* y_true_cls, const float* cls_pred, const float* y_true_reg,
                     const float* reg_pred, long long R, int C,
                     float alpha, float gamma, int bce_mode, float sigma,
@@ -228,7 +230,9 @@ int rn_rescale_cut(const float* boxes, const float* scores, const float* image_s
  * stores {step, count} into slot `rank` of every rank's mailbox (one 8-byte P2P store per peer), and
  *     rn_loss_fwd_bwd(..., npos_dev = box[rank], ..., flags | RN_LOSS_NPOS_PEER_BOX, ...)
  * waits (on local memory, inside the kernel) until all `world` counts of the step have arrived and
- * uses their sum.  No NCCL call, no host synchronisation, CUDA-graph capturable.  All ranks must run
+ * uses their sum (RN_LOSS_PEER_LAG1: the sum of the step before the latest, so that the next batch's K1 +
+ * publish can be enqueued ahead of this batch's losses and the exchange leaves the critical path; up to 4 steps
+ * are kept).  No NCCL call, no host synchronisation, CUDA-graph capturable.  All ranks must run
  * the same sequence of publish / loss steps; a peer that never publishes turns the losses into NaN
  * after ~2 s instead of hanging the GPU.  world <= 16 (one NVSwitch domain).
  * ------------------------------------------------------------------------------------------- */

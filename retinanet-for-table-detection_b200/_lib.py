@@ -19,6 +19,7 @@ RN_BCE_LOGITS = 1
 RN_LOSS_SHARED_STATE = 1
 RN_LOSS_NPOS_PEER_BOX = 2
 RN_LOSS_FROM_LOGITS = 4
+RN_LOSS_PEER_LAG1 = 8
 RN_MAX_WORLD = 16
 
 

@@ -8,9 +8,14 @@
 // order (integer-valued floats: exact and identical on every rank).  No NCCL launch, no host round trip, and both
 // kernels stay capturable in CUDA graphs (the step number lives in device memory, not in a kernel argument).
 //
-// Slots are double-buffered by step parity.  Rank r can publish step s+2 only after its K2(s+1) has seen every
-// rank's step s+1, which each rank publishes after its own K2(s) in stream order -- so slot (s & 1) is never
-// overwritten before every rank has consumed step s.  All ranks must run the same sequence of steps.
+// Slots are indexed by step % 4.  Two schedules are supported, identical on all ranks:
+//   in order    K1(s) publish(s) K2(s) K1(s+1) publish(s+1) K2(s+1) ...           K2 reads its latest step (lag 0)
+//   pipelined   K1(s+1) publish(s+1) K2(s) K1(s+2) publish(s+2) K2(s+1) ...       K2 reads the step before (lag 1):
+//               the next batch's targets and count are produced while this batch's losses wait for nothing --
+//               the exchange latency and the skew between ranks leave the critical path.
+// Overwrite safety (pipelined, the stricter case): rank r stores step s+4 into slot s % 4 only after its own K2(s+2)
+// has returned, which has seen every rank p's publish(s+2), which p issues after its K2(s) in stream order -- so
+// every rank has consumed step s before anyone overwrites it.  All ranks must run the same sequence of steps.
 #include "rn_common.cuh"
 #include "peer_box.cuh"
 
@@ -28,7 +33,7 @@ __global__ void k_peer_publish(const float* value, RnPeerBox* local, const PeerP
     const unsigned long long step = s_step;
     const unsigned long long word = (step << 32) | (unsigned long long)__float_as_uint(__ldcg(value));
     if ((int)threadIdx.x < world) {
-        volatile unsigned long long* slot = &peers.p[threadIdx.x]->slots[step & 1ull][rank];
+        volatile unsigned long long* slot = &peers.p[threadIdx.x]->slots[step & (RN_PEER_SLOTS - 1)][rank];
         *slot = word;                               // one aligned 8-byte store per peer: count and step arrive together
     }
 }

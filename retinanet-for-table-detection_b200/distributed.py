@@ -31,6 +31,21 @@ def shard_pages(num_pages, rank=None, world_size=None):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def balanced_shards(weights, world_size):
+    """Load-aware page sharding: K1's cost grows with the number of GT tables on a page, and K2 of every rank waits
+    for the slowest rank's K1 (the normaliser is global), so pages are dealt out by descending weight in snake
+    order -- every rank gets the same number of pages (+-1) and nearly the same total weight.  ``weights``: one
+    number per page of the GLOBAL batch (e.g. its GT count).  Returns ``world_size`` ascending page-index lists;
+    deterministic, so every rank computes the same assignment from the annotations alone (no communication)."""
+    weights = [float(w) for w in weights]
+    order = sorted(range(len(weights)), key=lambda i: (-weights[i], i))
+    shards = [[] for _ in range(int(world_size))]
+    for k, page in enumerate(order):
+        rnd, pos = divmod(k, int(world_size))
+        shards[pos if rnd % 2 == 0 else int(world_size) - 1 - pos].append(page)
+    return [sorted(s) for s in shards]
+
+
 def global_positive_count(npos_per_page, group=None):
     """Sum of the per-page positive-anchor counts over all pages of all ranks, as a 1-element float32
     tensor on the same device (the ``normalizer`` argument of the loss functors)."""
@@ -67,11 +82,16 @@ class PeerCounter(object):
     @classmethod
     def create(cls, group=None):
         rank, world = (dist.get_rank(group), dist.get_world_size(group)) if (dist.is_available() and dist.is_initialized()) else (0, 1)
-        if world < 2 or world > _lib.RN_MAX_WORLD or os.environ.get("RN_B200_PEER_BOX", "1") == "0":
-            return None
-        if not torch.cuda.is_available():
+        mode = os.environ.get("RN_B200_PEER_BOX", "1")
+        if not torch.cuda.is_available() or world > _lib.RN_MAX_WORLD or mode == "0":
             return None
         lib = _lib.load()
+        if world < 2:
+            if mode != "force":                             # "force": a one-rank mailbox, for profiling the path on one GPU
+                return None
+            solo, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+            _lib.check(lib.rn_peer_box_create(1, ctypes.byref(solo), handle), "rn_peer_box_create")
+            return cls(0, 1, solo.value, [solo.value])
         box = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
         ok = lib.rn_peer_box_create(world, ctypes.byref(box), handle) == 0

@@ -120,7 +120,7 @@ def smooth_l1(sigma=3.0):
 
 def detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None,
                      alpha=0.25, gamma=2.0, sigma=3.0, bce="tf2", want_grads=True, out=None, workspace=None,
-                     shared_state=False, peer_box=None):
+                     shared_state=False, peer_box=None, peer_lag=0):
     """Both losses, forward + backward, in ONE launch of K2 (``rn_loss_fwd_bwd``).
 
     All tensors are float32 CUDA: ``y_true_reg`` (B,N,5), ``y_true_cls`` (B,N,C+1) in the order
@@ -133,7 +133,8 @@ def detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None
     outputs the result is identical and 20 B/anchor of reads disappear; keep ``False`` for foreign tensors.
 
     ``peer_box``: a :class:`distributed.PeerCounter` whose ``publish`` was enqueued for this step on every rank;
-    the kernel then takes the sum of the published counts as the normaliser (``normalizer`` is ignored)."""
+    the kernel then takes the sum of the published counts as the normaliser (``normalizer`` is ignored);
+    ``peer_lag=1`` selects the step published before the latest one (pipelined schedule, see ``pipeline``)."""
     device = cls_pred.device
     C = cls_pred.shape[-1]
     R = cls_pred.numel() // C
@@ -150,7 +151,7 @@ def detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None
     flags = _lib.RN_LOSS_SHARED_STATE if shared_state else 0
     if peer_box is not None:                              # normaliser = sum of the counts the ranks published
         npos_ptr = ctypes.c_void_p(peer_box.box)
-        flags |= _lib.RN_LOSS_NPOS_PEER_BOX
+        flags |= _lib.RN_LOSS_NPOS_PEER_BOX | (_lib.RN_LOSS_PEER_LAG1 if peer_lag else 0)
     else:
         npos = _norm_tensor(normalizer, device)
         npos_ptr = _lib.ptr(npos)

@@ -54,7 +54,9 @@ class TargetLossStep(object):
         self.kernel_launches_per_step = 2      # K1 + K2 (memsets and NCCL are not ours)
         # run_from_host(): copy stream, per-chunk events, per-chunk loss rows
         rank, world = _dist.world()
-        self.peer = _dist.PeerCounter.create() if (world > 1 and peer_box) else None   # NVLink mailbox or None
+        self.peer = _dist.PeerCounter.create() if peer_box else None   # NVLink mailbox; None with one rank / no peer access
+        # run_pipelined(): second set of target buffers, graphs per buffer
+        self._pipe = None
         self._copy_stream = None
         self._chunk_losses = None
         self._chunk_events = None
@@ -116,6 +118,72 @@ class TargetLossStep(object):
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         self._graphs = (self._capture(self._targets), self._capture(self._losses))
+
+    # ---- pipelined schedule for several ranks ------------------------------------------------------------
+    def _pipe_setup(self):
+        """Targets are double-buffered: K1 + publish of the NEXT batch are enqueued ahead of K2 of the current one,
+        which reads the mailbox with lag 1 -- the count exchange and the skew between ranks leave the critical
+        path (the reference's generator threads likewise prepare the next batch's targets during a train step)."""
+        d = self.device
+        bufs = [(self.y_reg, self.y_cls, self.npos_total),
+                (torch.empty_like(self.y_reg), torch.empty_like(self.y_cls), torch.zeros(1, dtype=torch.float32, device=d))]
+
+        def targets(i):
+            y_reg, y_cls, npos_total = bufs[i]
+            _anchors.anchor_targets_device(self.spec, self.d_boxes, self.d_labels, self.d_counts, self.d_hw, self.C,
+                                           self.neg, self.pos, out=(y_reg, y_cls), npos_total=npos_total)
+            self.peer.publish(npos_total, self.device)
+
+        def losses(i):
+            y_reg, y_cls, npos_total = bufs[i]
+            _losses.detection_losses(y_reg, y_cls, self.reg_pred, self.cls_pred, normalizer=npos_total,
+                                     out=(self.losses, self.grad_cls, self.grad_reg), workspace=self.loss_ws,
+                                     peer_box=self.peer, peer_lag=1, **self.loss_kw)
+        # warm-up outside capture keeps every rank's publish count equal: one full in-order-equivalent round
+        s = torch.cuda.Stream(d)
+        s.wait_stream(torch.cuda.current_stream(d))
+        with torch.cuda.stream(s):
+            targets(0)
+            targets(1)
+            losses(0)
+        torch.cuda.current_stream(d).wait_stream(s)
+        torch.cuda.synchronize(d)
+        if self.use_graph:
+            ga = [self._capture(lambda i=i: targets(i)) for i in range(2)]
+            gb = [self._capture(lambda i=i: losses(i)) for i in range(2)]
+            run_a, run_b = (lambda i: ga[i].replay()), (lambda i: gb[i].replay())
+        else:
+            run_a, run_b = targets, losses
+        # after the warm-up the latest published batch sits in buffer 1 (lag 0); prime: it becomes "current"
+        self._pipe = dict(bufs=bufs, run_a=run_a, run_b=run_b, cur=1)
+
+    def run_pipelined(self, events=None):
+        """One step of the pipelined schedule (several ranks with the peer mailbox only): enqueue K1 + publish for
+        the NEXT batch (the annotations currently loaded), then K2 for the batch whose targets were produced by the
+        previous call.  ``losses`` / ``grad_*`` then refer to that previous batch; ``targets_of_losses()`` returns
+        its target tensors."""
+        if self.peer is None:
+            raise _lib.RnError("run_pipelined() needs the peer mailbox (several ranks on one node); use run()")
+        if self._pipe is None:
+            self._pipe_setup()
+        pp = self._pipe
+        cur, nxt = pp['cur'], 1 - pp['cur']
+        if events is not None:
+            events[0].record()
+        pp['run_a'](nxt)                                    # K1(s+1) + publish(s+1)
+        if events is not None:
+            events[1].record()
+        pp['run_b'](cur)                                    # K2(s), mailbox lag 1
+        if events is not None:
+            events[2].record()
+        pp['cur'] = nxt
+        pp['done'] = cur
+        return self.losses
+
+    def targets_of_losses(self):
+        """(y_reg, y_cls) of the batch the last run_pipelined() computed the losses for."""
+        y_reg, y_cls, _ = self._pipe['bufs'][self._pipe['done']]
+        return y_reg, y_cls
 
     # ---- host inputs, copies overlapped with the kernels -----------------------------------------------
     def run_from_host(self, image_group, annotations_group, cls_host, reg_host, chunks=4):

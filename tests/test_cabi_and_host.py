@@ -126,3 +126,17 @@ def test_shard_pages(pkg):
         assert covered == list(range(pages))
         sizes = [hi - lo for lo, hi in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_balanced_shards(pkg):
+    """Load-aware sharding: every page exactly once, equal page counts, near-equal total weight."""
+    rs = np.random.RandomState(9)
+    for world, pages in ((8, 128), (4, 64), (2, 33), (3, 7)):
+        w = rs.randint(1, 23, pages)
+        shards = pkg.distributed.balanced_shards(w, world)
+        assert sorted(sum(shards, [])) == list(range(pages)) and all(s == sorted(s) for s in shards)
+        assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
+        totals = [int(w[s].sum()) for s in shards]
+        contiguous = [int(w[lo:hi].sum()) for lo, hi in (pkg.distributed.shard_pages(pages, r, world) for r in range(world))]
+        assert max(totals) - min(totals) <= max(w) and max(totals) <= max(contiguous)
+    assert pkg.distributed.balanced_shards([5, 1], 1) == [[0, 1]]
