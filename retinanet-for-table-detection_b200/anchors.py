@@ -254,10 +254,12 @@ def upload_annotations(boxes, labels, counts, img_hw, device):
 
 def anchor_targets_device(anchors, d_boxes, d_labels, d_counts, d_hw, num_classes,
                           negative_overlap=0.4, positive_overlap=0.5, want_argmax=False, out=None,
-                          npos_total=None):
+                          npos_total=None, npos_out=None):
     """Launch K1 on GT already resident on the device.  ``anchors``: an :class:`AnchorArray` /
     :class:`AnchorSpec` (generated in-kernel) or a CUDA float64 (N,4) tensor (explicit).
-    ``npos_total``: optional 1-float CUDA tensor receiving the batch's positive count (loss normaliser).
+    ``npos_total``: optional 1-float CUDA tensor receiving the batch's positive count (loss normaliser);
+    ``npos_out``: optional (B,) int32 tensor for the per-page counts (when it ends where ``npos_total`` starts the
+    library clears both with one memset).
     Returns ``(regression (B,N,5), labels (B,N,C+1), npos (B) int32, argmax (B,N) int32 | None)``."""
     lib = _lib.load()
     device = d_counts.device
@@ -279,7 +281,7 @@ def anchor_targets_device(anchors, d_boxes, d_labels, d_counts, d_hw, num_classe
         labels = torch.empty((B, N, num_classes + 1), dtype=torch.float32, device=device)
     else:
         regression, labels = out
-    npos = torch.empty((B,), dtype=torch.int32, device=device)
+    npos = torch.empty((B,), dtype=torch.int32, device=device) if npos_out is None else npos_out
     argmax = torch.empty((B, N), dtype=torch.int32, device=device) if want_argmax else None
     if N > 0:
         _lib.check(lib.rn_anchor_targets(_lib.ptr(base), hw_p, st_p, levels, per_cell,

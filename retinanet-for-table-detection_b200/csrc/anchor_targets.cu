@@ -706,13 +706,19 @@ extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* leve
     p.vec_ok = rn_aligned16(regression_out) && rn_aligned16(labels_out);
     RN_REQUIRE((reinterpret_cast<uintptr_t>(labels_out) & 7u) == 0, "labels_out must be 8-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    if (npos_out) {
-        cudaError_t e = cudaMemsetAsync(npos_out, 0, sizeof(int) * (size_t)B, s);
+    if (npos_out && npos_total_out && reinterpret_cast<char*>(npos_total_out) == reinterpret_cast<char*>(npos_out + B)) {
+        // the two counters are adjacent (as TargetLossStep allocates them): one memset node instead of two
+        cudaError_t e = cudaMemsetAsync(npos_out, 0, sizeof(int) * (size_t)B + sizeof(float), s);
         if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset npos: %s", cudaGetErrorString(e));
-    }
-    if (npos_total_out) {
-        cudaError_t e = cudaMemsetAsync(npos_total_out, 0, sizeof(float), s);
-        if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset npos_total: %s", cudaGetErrorString(e));
+    } else {
+        if (npos_out) {
+            cudaError_t e = cudaMemsetAsync(npos_out, 0, sizeof(int) * (size_t)B, s);
+            if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset npos: %s", cudaGetErrorString(e));
+        }
+        if (npos_total_out) {
+            cudaError_t e = cudaMemsetAsync(npos_total_out, 0, sizeof(float), s);
+            if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset npos_total: %s", cudaGetErrorString(e));
+        }
     }
     dim3 grid((unsigned)((num_anchors + K1_THREADS - 1) / K1_THREADS), (unsigned)B);
     if (anchors_dev) {

@@ -43,14 +43,17 @@ class TargetLossStep(object):
         self.reg_pred = torch.zeros((B, N, 4), dtype=torch.float32, device=d)
         self.y_reg = torch.empty((B, N, 5), dtype=torch.float32, device=d)
         self.y_cls = torch.empty((B, N, C + 1), dtype=torch.float32, device=d)
-        self.npos_total = torch.zeros(1, dtype=torch.float32, device=d)
-        self.npos = None
+        # per-page counts (B int32) and the batch total (1 float32) in one allocation: cleared by one memset node
+        self._counts = torch.zeros(B + 1, dtype=torch.int32, device=d)
+        self.npos = self._counts[:B]
+        self.npos_total = self._counts[B:].view(torch.float32)
         self.losses = torch.zeros(3, dtype=torch.float32, device=d)
         self.grad_cls = torch.empty_like(self.cls_pred)
         self.grad_reg = torch.empty_like(self.reg_pred)
         self.loss_ws = torch.zeros(int(_lib.load().rn_loss_workspace_bytes()), dtype=torch.uint8, device=d)
         self.use_graph = use_graph
         self._graphs = None
+        self._fused = None
         self.kernel_launches_per_step = 2      # K1 + K2 (memsets and NCCL are not ours)
         # run_from_host(): copy stream, per-chunk events, per-chunk loss rows
         rank, world = _dist.world()
@@ -86,9 +89,9 @@ class TargetLossStep(object):
 
     # ---- the two halves ----------------------------------------------------------------------------
     def _targets(self):
-        _, _, self.npos, _ = _anchors.anchor_targets_device(self.spec, self.d_boxes, self.d_labels, self.d_counts,
-                                                            self.d_hw, self.C, self.neg, self.pos,
-                                                            out=(self.y_reg, self.y_cls), npos_total=self.npos_total)
+        _anchors.anchor_targets_device(self.spec, self.d_boxes, self.d_labels, self.d_counts, self.d_hw, self.C,
+                                       self.neg, self.pos, out=(self.y_reg, self.y_cls), npos_total=self.npos_total,
+                                       npos_out=self.npos)
         if self.peer is not None:
             self.peer.publish(self.npos_total, self.device)     # this rank's count -> every rank's mailbox
 
@@ -118,6 +121,14 @@ class TargetLossStep(object):
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         self._graphs = (self._capture(self._targets), self._capture(self._losses))
+        # the whole step as ONE graph (one launch) when nothing has to happen between the halves on the host:
+        # one rank, or several ranks exchanging the count through the peer mailbox
+        self._fused = None
+        if self.peer is not None or _dist.world()[1] == 1:
+            def whole():
+                self._targets()
+                self._losses()
+            self._fused = self._capture(whole)
 
     # ---- pipelined schedule for several ranks ------------------------------------------------------------
     def _pipe_setup(self):
@@ -243,6 +254,9 @@ class TargetLossStep(object):
         rank, world = _dist.world()
         if self.use_graph and self._graphs is None:
             self._build_graphs()
+        if events is None and self.use_graph and self._fused is not None:
+            self._fused.replay()                            # K1 (+ publish) + K2: one graph launch
+            return self.losses
         if events is not None:
             events[0].record()
         if self.use_graph:
