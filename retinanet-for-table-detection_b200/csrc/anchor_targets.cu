@@ -573,9 +573,32 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the CTA's shared memory may go away after this
         }
         if (p.C != 1) {
-            for (int r2 = 0; r2 < nrows; ++r2)
-                store_labels_generic(p.lab, tile_row0 + (long long)r2 * W * A, cnt, p.C, true, nthreads,
-                                     s_state + r2 * 32 * A, s_hot + r2 * 32 * A);
+            // C > 1: a label row is C + 1 floats, all zero except the one-hot entry of a positive anchor and a non-zero
+            // state (~1 % of the anchors).  So the tile rows' label ranges are zero-filled with 128-bit stores -- no
+            // per-element row / column arithmetic -- and, after a barrier, the few non-zero entries are written.
+            const int CW = p.C + 1;
+            for (int r2 = 0; r2 < nrows; ++r2) {
+                const long long start = (tile_row0 + (long long)r2 * W * A) * CW;
+                const long long len = (long long)cnt * CW;
+                float* dst = p.lab + start;
+                int head = (int)((4 - (start & 3)) & 3);
+                if (head > len) head = (int)len;
+                if (tid < head) dst[tid] = 0.0f;
+                const long long nvec = (len - head) >> 2;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (long long v = tid; v < nvec; v += nthreads) rn_stg_stream4(dst + head + 4 * v, z);
+                const long long done = head + 4 * nvec;
+                if (tid < (int)(len - done)) dst[done + tid] = 0.0f;
+            }
+            __syncthreads();                                // orders the fix-ups below after the zero-fill (same CTA)
+            for (int j = tid; j < nrows * cnt; j += nthreads) {
+                const int r2 = j / cnt, k = j - r2 * cnt;
+                const float st = s_state[r2 * 32 * A + k];
+                const int hot = s_hot[r2 * 32 * A + k];
+                float* rowp = p.lab + (tile_row0 + (long long)r2 * W * A + k) * CW;
+                if (st != 0.0f) rowp[p.C] = st;
+                if (hot >= 0) rowp[hot] = 1.0f;
+            }
         }
         return;
     }
