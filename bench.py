@@ -37,6 +37,7 @@ HW = synthetic.CONFIGS[CFG]['hw']
 PAGES_PER_GPU = synthetic.CONFIGS[CFG]['batch']
 GMAX = synthetic.CONFIGS[CFG]['gmax'] + 2          # +2: the adversarial snapped duplicates
 CLASSES = 1
+E2E_GATHER = True                                  # smooth-L1 reads the positive anchors' regression rows straight from pinned host memory
 E2E_CHUNKS = 2                                     # page chunks of the overlapped host-input step
 METRIC = "pages/sec (anchor targets + focal/smooth-L1 fwd+bwd) @800x1333"
 WORKLOAD = "configs[1]: training-target path, 16 pages/GPU of 800x1333, 1 class, <=20 GT, 200700 anchors/page"
@@ -285,7 +286,7 @@ def run_ours(args):
     def e2e_step():
         # public API with HOST inputs: ragged GT (Python dicts) packed + copied, head outputs copied from pinned
         # memory chunk by chunk while K1 runs, K2 per chunk, 4 x 12 bytes of losses read back (synchronises)
-        return step.run_from_host(images, anns, cls_host, reg_host, chunks=E2E_CHUNKS)
+        return step.run_from_host(images, anns, cls_host, reg_host, chunks=E2E_CHUNKS, gather_reg_from_host=E2E_GATHER)
     e2e_steps = 0 if args.no_e2e else args.steps
     for _ in range(0 if args.no_e2e else max(args.warmup, 3)):
         e2e_step()
@@ -297,13 +298,29 @@ def run_ours(args):
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) if e2e_steps else float("nan")
-    h2d = gt_bytes + cls_host.numel() * 4 + reg_host.numel() * 4
+    # bytes that cross PCIe per step: the GT block, the classification tensor, and -- with the gather -- only the
+    # 16-byte regression rows of the positive anchors (K2 reads them in place); the full-copy variant is timed too
+    n_pos_rank = float(step.npos.sum().item())
+    h2d = gt_bytes + cls_host.numel() * 4 + (16 * n_pos_rank if E2E_GATHER else reg_host.numel() * 4)
+    full_ms = float("nan")
+    if E2E_GATHER and not args.no_e2e:
+        full_step = lambda: step.run_from_host(images, anns, cls_host, reg_host, chunks=E2E_CHUNKS)
+        for _ in range(3):
+            full_step()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            full_step()
+        f1.record()
+        barrier()
+        full_ms = f0.elapsed_time(f1)
     sampler.stop_flag = True
 
-    times = torch.tensor([total_ms, e2e_ms, k1_ms, k2_ms, split_ms], dtype=torch.float64, device=device)
+    times = torch.tensor([total_ms, e2e_ms, k1_ms, k2_ms, split_ms, full_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, k1_ms, k2_ms, split_ms = [float(x) for x in times.cpu()]
+    total_ms, e2e_ms, k1_ms, k2_ms, split_ms, full_ms = [float(x) for x in times.cpu()]
 
     # ---- N2 (extra object): K2 fed by the per-level head outputs, sigmoid fused ---------------------------
     levels = None
@@ -360,7 +377,11 @@ def run_ours(args):
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "pages/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 12 * E2E_CHUNKS, "ms_per_step": e2e_ms / args.steps,
                     "h2d_GBps": h2d / (e2e_ms / args.steps * 1e-3) / 1e9,
-                    "api": "TargetLossStep.run_from_host (copy stream overlapped with K1; K2 per page chunk)"},
+                    "api": "TargetLossStep.run_from_host (copy stream overlapped with GT packing and K1; K2 per page chunk)",
+                    "regression_rows": ("positive anchors' rows read in place from pinned host memory (model/losses.py:72-74 "
+                                        "gathers exactly those); the (B,N,4) tensor is not copied") if E2E_GATHER else "copied",
+                    "full_copy": {"value": world * B * args.steps / (full_ms * 1e-3), "ms_per_step": full_ms / args.steps,
+                                  "h2d_bytes_per_step": int(gt_bytes + cls_host.numel() * 4 + reg_host.numel() * 4)}},
             "gpu_launches": (3 if step.peer is not None else 2) * args.steps,   # `value` region: K1 (+ publish) + K2 per step
             # the dominant kernel of the step by time is K1 (~74 %, profiles/*_launches_value_region.md): it is
             # reported first although it is instruction-issue bound, not HBM bound; K2 (the HBM-bound loss kernel

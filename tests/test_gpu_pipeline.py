@@ -30,6 +30,13 @@ def test_run_from_host_matches_resident_run(rn, chunks):
     step2 = rn.pipeline.TargetLossStep(hw + (3,), B, 8, 1)
     for _ in range(2):                                   # twice: buffers are reused across steps
         got = step2.run_from_host(imgs, anns, cls_h, reg_h, chunks=chunks).numpy()
+    # regression rows of positive anchors fetched straight from the pinned host buffer: nothing changes
+    step3 = rn.pipeline.TargetLossStep(hw + (3,), B, 8, 1)
+    got3 = step3.run_from_host(imgs, anns, cls_h, reg_h, chunks=chunks, gather_reg_from_host=True).numpy()
+    assert np.array_equal(got3, got) and torch.equal(step3.grad_cls, step2.grad_cls) and torch.equal(step3.grad_reg, step2.grad_reg)
+    assert not step3.reg_pred.any()                      # the device copy of the regression tensor was never filled
+    with pytest.raises(ValueError):
+        step3.run_from_host(imgs, anns, cls_h, torch.from_numpy(reg), chunks=chunks, gather_reg_from_host=True)   # not pinned
     assert torch.equal(step2.y_reg, yr) and torch.equal(step2.y_cls, yc)
     assert torch.equal(step2.grad_cls, gc) and torch.equal(step2.grad_reg, gr)
     assert got[2] == want[2] and np.allclose(got[:2], want[:2], rtol=1e-6, atol=0)
