@@ -38,7 +38,7 @@ PAGES_PER_GPU = synthetic.CONFIGS[CFG]['batch']
 GMAX = synthetic.CONFIGS[CFG]['gmax'] + 2          # +2: the adversarial snapped duplicates
 CLASSES = 1
 E2E_GATHER = True                                  # smooth-L1 reads the positive anchors' regression rows straight from pinned host memory
-E2E_CHUNKS = 2                                     # page chunks of the overlapped host-input step
+E2E_CHUNKS = 1                                     # page chunks of the overlapped host-input step
 METRIC = "pages/sec (anchor targets + focal/smooth-L1 fwd+bwd) @800x1333"
 WORKLOAD = "configs[1]: training-target path, 16 pages/GPU of 800x1333, 1 class, <=20 GT, 200700 anchors/page"
 
