@@ -157,3 +157,29 @@ def test_empty_and_all_below_threshold(rn):
     b, s, l = head([(2,) + hw + (3,), reg, cls])
     assert head.last_indices.cpu().numpy()[1, 0] == 18 and (head.last_indices.cpu().numpy()[1, 1:] == -1).all()
     assert l.cpu().numpy()[1, 0] == 1
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_randomized_filter_detections(rn, seed):
+    """Random box sets with tight clusters (many IoUs near the threshold), quantised scores (many exact ties: order
+    must fall back to the anchor index), random class counts, thresholds, max_detections, class-specific or not,
+    NMS on or off -- boxes, scores, labels and selected indices bit for bit against the oracle."""
+    rs = np.random.RandomState(4000 + seed)
+    B = int(rs.randint(1, 4))
+    N = int(rs.choice([1, 37, 700, 3001, 9000]))
+    C = int(rs.choice([1, 2, 7]))
+    centers = rs.uniform(50, 950, (B, max(1, N // 40), 2))
+    which = rs.randint(0, centers.shape[1], (B, N))
+    cxy = centers[np.arange(B)[:, None], which] + rs.normal(0, 6, (B, N, 2))
+    wh = rs.uniform(20, 90, (B, N, 2)) * np.where(rs.uniform(size=(B, N, 1)) < 0.05, 0.0, 1.0)    # 5 % zero-area boxes
+    boxes = np.concatenate([cxy - wh / 2, cxy + wh / 2], axis=2).astype(np.float32)
+    flip = rs.uniform(size=(B, N)) < 0.1                                                    # corners in the other order
+    boxes[flip] = boxes[flip][:, [2, 3, 0, 1]]
+    cls = (np.round(rs.uniform(0, 1, (B, N, C)) ** 3 * 50) / 50).astype(np.float32)         # quantised: ties everywhere
+    kw = dict(class_specific_filter=bool(seed % 2 == 0), nms=bool(seed % 5 != 4),
+              score_threshold=float(rs.choice([0.05, 0.3, 0.0])), max_detections=int(rs.choice([300, 17, 1000])),
+              nms_threshold=float(rs.choice([0.5, 0.3, 0.75])))
+    want = L.filter_detections_batch(boxes, cls, **kw)
+    layer = rn.FilterDetections(**kw)
+    b, s, l = layer([torch.tensor(boxes, device="cuda"), torch.tensor(cls, device="cuda")])
+    assert same(layer.last_indices, want[3]) and same(l, want[2]) and same(s, want[1]) and same(b, want[0])

@@ -165,3 +165,46 @@ def test_bbox_transform_and_errors(rn):
         rn.anchor_targets_bbox(a, [synthetic.PageShape((64, 64, 3))], [], 1)
     with pytest.raises(AssertionError):
         rn.anchor_targets_bbox(a, [synthetic.PageShape((64, 64, 3))], [{'bboxes': np.zeros((0, 4))}], 1)
+
+
+@pytest.mark.parametrize("seed", list(range(14)))
+def test_randomized_shapes_and_parameters(rn, seed):
+    """Random page shapes, pyramid-level subsets, anchor parameter sets (1 to 30 anchors per cell: the 9-anchor
+    tile kernel, the generic tile kernel and the one-anchor-per-thread kernel), class counts and GT sets (boxes on
+    and across the page border, empty pages) -- every output bit for bit against the oracle.  Exercises tile
+    edges, every 16-byte phase of the bulk-store write-out and the exact-division fallback."""
+    rs = np.random.RandomState(1000 + seed)
+    H, W = int(rs.randint(17, 420)), int(rs.randint(17, 520))
+    all_levels = [3, 4, 5, 6, 7]
+    k = int(rs.randint(1, 6))
+    first = int(rs.randint(0, 6 - k))
+    levels = all_levels[first:first + k]
+    nr, ns = [(3, 3), (1, 1), (2, 2), (4, 3), (5, 6), (3, 1)][seed % 6]
+    ratios = np.sort(rs.uniform(0.3, 3.0, nr)).astype(np.float32)
+    scales = np.sort(rs.uniform(0.7, 1.9, ns)).astype(np.float32)
+    params = rn.AnchorParameters(sizes=[int(2 ** (l + 2) * rs.uniform(0.8, 1.3)) for l in levels],
+                                 strides=[2 ** l for l in levels], ratios=ratios, scales=scales)
+    oparams = O.AnchorParameters(params.sizes, params.strides, ratios, scales)
+    C = [1, 2, 5][seed % 3]
+    B = int(rs.randint(1, 5))
+    images, anns = [], []
+    for b in range(B):
+        h, w = int(H * rs.uniform(0.6, 1.0)) if b else H, int(W * rs.uniform(0.6, 1.0)) if b else W
+        images.append(synthetic.PageShape((h, w, 3)))
+        G = 0 if (b == 1 and seed % 2) else int(rs.randint(0, 41))
+        x1, y1 = rs.uniform(-5, w * 0.8, G), rs.uniform(-5, h * 0.8, G)
+        bw, bh = rs.uniform(2, w * 0.7, G), rs.uniform(2, h * 0.7, G)
+        boxes = np.stack([x1, y1, x1 + bw, y1 + bh], axis=1).reshape(-1, 4)
+        if G > 2:
+            boxes[1] = boxes[0]                                   # duplicate table: first index must win
+            boxes[2, 2:] = boxes[2, :2]                           # empty table
+        anns.append({'bboxes': boxes, 'labels': rs.randint(0, C, G).astype(np.float64)})
+    anchors = rn.anchors_for_shape((H, W, 3), pyramid_levels=levels, anchor_params=params)
+    oanchors = O.anchors_for_shape((H, W, 3), pyramid_levels=levels, anchor_params=oparams)
+    assert same(np.asarray(anchors), oanchors)
+    want_reg, want_lab = O.anchor_targets_bbox(oanchors, images, anns, C)
+    reg, lab = rn.anchor_targets_bbox(anchors, images, anns, C)
+    assert same(reg, want_reg) and same(lab, want_lab)
+    # the same through an explicit (N,4) array (no generation spec): one anchor per thread
+    reg2, lab2 = rn.anchor_targets_bbox(np.array(oanchors), images, anns, C)
+    assert same(reg2, want_reg) and same(lab2, want_lab)
