@@ -218,3 +218,38 @@ def test_per_level_heads_fused_sigmoid(rn, rows, from_logits):
     if not from_logits:                                                   # probabilities in: bit-identical to the concatenated path
         ref = rn.detection_losses(t(y_reg), t(y_cls), t(r), t(p), shared_state=True)
         assert torch.equal(torch.cat(g_cls, 1), ref[1]) and torch.equal(torch.cat(g_reg, 1), ref[2])
+
+
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_randomized_loss_parameters(rn, seed):
+    """Random alpha / gamma / sigma / cross-entropy form / class count / batch shape, soft labels sprinkled in, through
+    the fused entry point with and without the shared-state flag, the single-loss functors and an explicit
+    normaliser -- every variant against the oracle (1e-5 relative; gradients + 1e-7 of their maximum)."""
+    rs = np.random.RandomState(7000 + seed)
+    B, N, C = int(rs.randint(1, 4)), int(rs.choice([1, 5, 130, 2049, 10007])), int(rs.choice([1, 1, 2, 4, 21]))
+    alpha, gamma = float(rs.choice([0.25, 0.5, 0.9])), float(rs.choice([2.0, 2.0, 1.0, 1.5, 0.0]))
+    sigma, bce = float(rs.choice([3.0, 1.0, 2.0])), str(rs.choice(["tf2", "logits"]))
+    y_cls, p, y_reg, r = make_case(90 + seed, B, N, C, p_ignore=0.1, p_pos=0.15, logit_mu=float(rs.choice([-4.0, 0.0])))
+    soft = rs.uniform(size=y_cls[:, :, :C].shape) < 0.02
+    y_cls[:, :, :C] = np.where(soft, rs.uniform(0.05, 0.95, soft.shape).astype(np.float32), y_cls[:, :, :C])
+    y_reg[:, :, 4] = y_cls[:, :, C]
+    norm = None if seed % 2 else float(rs.randint(1, 500))
+    wf, wgf = OL.focal(alpha, gamma, bce=bce)(y_cls, p, return_grad=True, normalizer=norm)
+    ws, wgs = OL.smooth_l1(sigma)(y_reg, r, return_grad=True, normalizer=norm)
+    t = lambda a: torch.tensor(a, device="cuda")
+    nt = None if norm is None else torch.tensor([norm], dtype=torch.float32, device="cuda")
+    tol_f = dict(atol=1e-7 * float(np.abs(wgf).max()) + 1e-12)
+    for shared in (False, True):
+        losses, gc, gr = rn.detection_losses(t(y_reg), t(y_cls), t(r), t(p), normalizer=nt, alpha=alpha, gamma=gamma,
+                                             sigma=sigma, bce=bce, shared_state=shared)
+        l = losses.cpu().numpy()
+        assert close(l[0], wf, atol=1e-9) and close(l[1], ws, atol=1e-9), (seed, shared, l, wf, ws)
+        assert close(gc.cpu().numpy(), wgf, **tol_f) and close(gr.cpu().numpy(), wgs, atol=1e-9)
+    yp = t(p).requires_grad_()
+    lf = rn.focal(alpha, gamma, bce=bce)(t(y_cls), yp, normalizer=nt)
+    lf.backward()
+    assert close(lf.item(), wf, atol=1e-9) and close(yp.grad.cpu().numpy(), wgf, **tol_f)
+    rp = t(r).requires_grad_()
+    ls = rn.smooth_l1(sigma)(t(y_reg), rp, normalizer=nt)
+    ls.backward()
+    assert close(ls.item(), ws, atol=1e-9) and close(rp.grad.cpu().numpy(), wgs, atol=1e-9)
