@@ -269,78 +269,55 @@ __device__ __forceinline__ bool iou_exceeds(const float4 a, const float aa, cons
 
 
 // Descending bitonic sort of n (power of two, 128 <= n <= NMS_CHUNK) (key, slot) pairs in shared memory.
-// Each of the first n/4 threads keeps 4 consecutive elements in registers: compare-exchange distances 1-2
-// are thread-local, 4-64 are warp shuffles, only distances >= 128 go through shared memory -- 10 block-wide
-// exchange steps for n = 2048 instead of 66.  Keys are unique (zero padding excepted, which never swaps).
-// Must be called by all threads of the CTA.
+// Each of the first n/2 threads keeps 2 adjacent elements in registers (all 1024 threads are busy at n = 2048, so
+// shuffle and shared-memory latencies overlap across 32 warps): compare-exchange distance 1 is thread-local,
+// 2..32 are warp shuffles, distances >= 64 go through shared memory.  Keys are unique (zero padding excepted, which
+// never swaps).  Must be called by all threads of the CTA.
 __device__ __forceinline__ void ce_keep(unsigned long long& a, unsigned& av, unsigned long long b, unsigned bv, bool take_max) {
     const bool sw = take_max ? (b > a) : (b < a);
     if (sw) { a = b; av = bv; }
 }
 
-// (lo, hi) pair inside a thread: descending -> larger key first
-__device__ __forceinline__ void ce_local(unsigned long long& a, unsigned& av, unsigned long long& b, unsigned& bv, bool desc) {
-    const bool sw = desc ? (a < b) : (a > b);
-    if (sw) {
-        const unsigned long long tk = a; a = b; b = tk;
-        const unsigned tv = av; av = bv; bv = tv;
-    }
-}
-
 __device__ void sort_chunk_desc(unsigned long long* s_key, unsigned* s_slot, const int n, const int tid) {
-    const bool act = tid < (n >> 2);                 // warp-uniform: n/4 is a multiple of 32
-    const int i0 = tid * 4;
-    unsigned long long k4[4] = {0ull, 0ull, 0ull, 0ull};
-    unsigned v4[4] = {0u, 0u, 0u, 0u};
-    if (act) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { k4[e] = s_key[i0 + e]; v4[e] = s_slot[i0 + e]; }
-    }
+    const bool act = tid < (n >> 1);                 // warp-uniform: n/2 is a multiple of 32
+    const int i0 = tid * 2;
+    unsigned long long k0 = 0ull, k1 = 0ull;
+    unsigned v0 = 0u, v1 = 0u;
+    if (act) { k0 = s_key[i0]; k1 = s_key[i0 + 1]; v0 = s_slot[i0]; v1 = s_slot[i0 + 1]; }
     for (int k = 2; k <= n; k <<= 1) {
+        const bool desc = ((i0 & k) == 0);           // direction of this thread's pair in the k-merge (k >= 2: same for both)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= 128) {
-                if (act) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { s_key[i0 + e] = k4[e]; s_slot[i0 + e] = v4[e]; }
-                }
+            if (j >= 64) {
+                if (act) { s_key[i0] = k0; s_key[i0 + 1] = k1; s_slot[i0] = v0; s_slot[i0 + 1] = v1; }
                 __syncthreads();
                 if (act) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int i = i0 + e, x = i ^ j;
-                        ce_keep(k4[e], v4[e], s_key[x], s_slot[x], ((i & j) == 0) == ((i & k) == 0));
-                    }
+                    const int x0 = i0 ^ j, x1 = (i0 + 1) ^ j;
+                    const bool lower = ((i0 & j) == 0);                  // this thread holds the lower index of each pair
+                    ce_keep(k0, v0, s_key[x0], s_slot[x0], lower == desc);
+                    ce_keep(k1, v1, s_key[x1], s_slot[x1], lower == desc);
                 }
                 __syncthreads();
-            } else if (j >= 4) {
+            } else if (j >= 2) {
                 if (act) {
-                    const int lm = j >> 2;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int i = i0 + e;
-                        const unsigned long long b = __shfl_xor_sync(0xffffffffu, k4[e], lm);
-                        const unsigned bv = __shfl_xor_sync(0xffffffffu, v4[e], lm);
-                        ce_keep(k4[e], v4[e], b, bv, ((i & j) == 0) == ((i & k) == 0));
-                    }
+                    const int lm = j >> 1;
+                    const bool lower = ((i0 & j) == 0);
+                    const unsigned long long b0 = __shfl_xor_sync(0xffffffffu, k0, lm), b1 = __shfl_xor_sync(0xffffffffu, k1, lm);
+                    const unsigned w0 = __shfl_xor_sync(0xffffffffu, v0, lm), w1 = __shfl_xor_sync(0xffffffffu, v1, lm);
+                    ce_keep(k0, v0, b0, w0, lower == desc);
+                    ce_keep(k1, v1, b1, w1, lower == desc);
                 }
             } else if (act) {
-                // thread-local exchanges, written out so that k4 / v4 stay in registers (no dynamic indexing)
-                if (j == 2) {
-                    const bool d = ((i0 & k) == 0);                      // k >= 4: one direction per thread
-                    ce_local(k4[0], v4[0], k4[2], v4[2], d);
-                    ce_local(k4[1], v4[1], k4[3], v4[3], d);
-                } else {
-                    const bool d01 = ((i0 & k) == 0), d23 = (((i0 + 2) & k) == 0);   // differ only when k == 2
-                    ce_local(k4[0], v4[0], k4[1], v4[1], d01);
-                    ce_local(k4[2], v4[2], k4[3], v4[3], d23);
+                // j == 1: the pair inside the thread.  For k == 2 the direction alternates per pair ((i0 & 2) == 0).
+                const bool d = (k == 2) ? ((i0 & 2) == 0) : desc;
+                const bool sw = d ? (k0 < k1) : (k0 > k1);
+                if (sw) {
+                    const unsigned long long tk = k0; k0 = k1; k1 = tk;
+                    const unsigned tv = v0; v0 = v1; v1 = tv;
                 }
             }
         }
     }
-    if (act) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { s_key[i0 + e] = k4[e]; s_slot[i0 + e] = v4[e]; }
-    }
+    if (act) { s_key[i0] = k0; s_key[i0 + 1] = k1; s_slot[i0] = v0; s_slot[i0 + 1] = v1; }
     __syncthreads();
 }
 
