@@ -270,6 +270,19 @@ def run_ours(args):
     barrier()
     t_wall1 = time.perf_counter()
     total_ms = v0.elapsed_time(v1)
+    # extra: the overlapped schedule (K1 of the next batch concurrently with K2 of this one, two graph branches)
+    ov_ms = float("nan")
+    if world == 1:
+        for _ in range(5):
+            step.run_pipelined(overlap=True)
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        for i in range(args.steps):
+            step.run_pipelined(overlap=True)
+        o1.record()
+        barrier()
+        ov_ms = o0.elapsed_time(o1)
     # timed region 2 (per-kernel durations for the rooflines): the same K steps with the two halves replayed
     # separately and CUDA events between them (costs one more graph launch per step, so it is not the `value`)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
@@ -400,6 +413,9 @@ def run_ours(args):
                             "share_of_step": k2_ms / (k1_ms + k2_ms),
                             "achieved_survey_bytes": k2_bytes_survey / (k2_ms * 1e-3) / 1e9},
             "ms_per_step_split_graphs": split_ms / args.steps,
+            "overlapped_schedule": None if ov_ms != ov_ms else {
+                "pages_per_s": world * B * args.steps / (ov_ms * 1e-3), "ms_per_step": ov_ms / args.steps,
+                "note": "TargetLossStep.run_pipelined(overlap=True): K1 of batch s+1 and K2 of batch s as two branches of one graph"},
             "kernels": {"K1_anchor_targets": {"us": k1_ms * 1e3, "algorithmic_bytes": k1_bytes,
                                               "GBps": k1_bytes / (k1_ms * 1e-3) / 1e9},
                         "K2_losses": {"us": k2_ms * 1e3, "algorithmic_bytes": k2_bytes, "GBps": achieved}},

@@ -132,21 +132,24 @@ class TargetLossStep(object):
 
     # ---- pipelined schedule for several ranks ------------------------------------------------------------
     def _pipe_setup(self):
-        """Targets are double-buffered: K1 + publish of the NEXT batch are enqueued ahead of K2 of the current one,
-        which reads the mailbox with lag 1 -- the count exchange and the skew between ranks leave the critical
-        path (the reference's generator threads likewise prepare the next batch's targets during a train step)."""
+        """Targets are double-buffered: K1 (+ publish) of the NEXT batch is enqueued ahead of -- and, in the overlapped
+        form, concurrently with -- K2 of the current one (the reference's generator threads likewise prepare the next
+        batch's targets during a train step).  With several ranks K2 reads the mailbox with lag 1, so the count
+        exchange and the skew between ranks leave the critical path."""
         d = self.device
-        bufs = [(self.y_reg, self.y_cls, self.npos_total),
-                (torch.empty_like(self.y_reg), torch.empty_like(self.y_cls), torch.zeros(1, dtype=torch.float32, device=d))]
+        second = torch.zeros(self.B + 1, dtype=torch.int32, device=d)
+        bufs = [(self.y_reg, self.y_cls, self.npos, self.npos_total),
+                (torch.empty_like(self.y_reg), torch.empty_like(self.y_cls), second[:self.B], second[self.B:].view(torch.float32))]
 
         def targets(i):
-            y_reg, y_cls, npos_total = bufs[i]
+            y_reg, y_cls, npos, npos_total = bufs[i]
             _anchors.anchor_targets_device(self.spec, self.d_boxes, self.d_labels, self.d_counts, self.d_hw, self.C,
-                                           self.neg, self.pos, out=(y_reg, y_cls), npos_total=npos_total)
-            self.peer.publish(npos_total, self.device)
+                                           self.neg, self.pos, out=(y_reg, y_cls), npos_total=npos_total, npos_out=npos)
+            if self.peer is not None:
+                self.peer.publish(npos_total, self.device)
 
         def losses(i):
-            y_reg, y_cls, npos_total = bufs[i]
+            y_reg, y_cls, npos, npos_total = bufs[i]
             _losses.detection_losses(y_reg, y_cls, self.reg_pred, self.cls_pred, normalizer=npos_total,
                                      out=(self.losses, self.grad_cls, self.grad_reg), workspace=self.loss_ws,
                                      peer_box=self.peer, peer_lag=1, **self.loss_kw)
@@ -159,41 +162,63 @@ class TargetLossStep(object):
             losses(0)
         torch.cuda.current_stream(d).wait_stream(s)
         torch.cuda.synchronize(d)
+        side = (torch.cuda.Stream(d), torch.cuda.Stream(d))
+
+        def both(nxt, cur):
+            """K1 (+ publish) of the next batch and K2 of the current one on two streams: captured, they become two
+            parallel branches of one graph -- K1 is instruction-issue bound, K2 HBM-bound, so they share an SM well."""
+            main = torch.cuda.current_stream(d)
+            for st in side:
+                st.wait_stream(main)
+            with torch.cuda.stream(side[0]):
+                targets(nxt)
+            with torch.cuda.stream(side[1]):
+                losses(cur)
+            for st in side:
+                main.wait_stream(st)
+
         if self.use_graph:
             ga = [self._capture(lambda i=i: targets(i)) for i in range(2)]
             gb = [self._capture(lambda i=i: losses(i)) for i in range(2)]
-            run_a, run_b = (lambda i: ga[i].replay()), (lambda i: gb[i].replay())
+            gc = [self._capture(lambda i=i: both(i, 1 - i)) for i in range(2)]          # index = the NEXT batch's buffer
+            run_a, run_b, run_ab = (lambda i: ga[i].replay()), (lambda i: gb[i].replay()), (lambda i: gc[i].replay())
         else:
-            run_a, run_b = targets, losses
+            run_a, run_b, run_ab = targets, losses, (lambda i: both(i, 1 - i))
         # after the warm-up the latest published batch sits in buffer 1 (lag 0); prime: it becomes "current"
-        self._pipe = dict(bufs=bufs, run_a=run_a, run_b=run_b, cur=1)
+        self._pipe = dict(bufs=bufs, run_a=run_a, run_b=run_b, run_ab=run_ab, cur=1)
 
-    def run_pipelined(self, events=None):
-        """One step of the pipelined schedule (several ranks with the peer mailbox only): enqueue K1 + publish for
-        the NEXT batch (the annotations currently loaded), then K2 for the batch whose targets were produced by the
-        previous call.  ``losses`` / ``grad_*`` then refer to that previous batch; ``targets_of_losses()`` returns
-        its target tensors."""
-        if self.peer is None:
-            raise _lib.RnError("run_pipelined() needs the peer mailbox (several ranks on one node); use run()")
+    def run_pipelined(self, events=None, overlap=False):
+        """One step of the pipelined schedule: enqueue K1 (+ publish) for the NEXT batch (the annotations currently
+        loaded), then K2 for the batch whose targets were produced by the previous call.  ``losses`` / ``grad_*``
+        then refer to that previous batch; ``targets_of_losses()`` returns its target tensors.
+        ``overlap=True``: the two kernels run concurrently on two streams (one graph launch per step)."""
         if self._pipe is None:
             self._pipe_setup()
         pp = self._pipe
         cur, nxt = pp['cur'], 1 - pp['cur']
-        if events is not None:
-            events[0].record()
-        pp['run_a'](nxt)                                    # K1(s+1) + publish(s+1)
-        if events is not None:
-            events[1].record()
-        pp['run_b'](cur)                                    # K2(s), mailbox lag 1
-        if events is not None:
-            events[2].record()
+        if overlap:
+            if events is not None:
+                events[0].record()
+            pp['run_ab'](nxt)                               # K1(s+1) [+ publish(s+1)]  ||  K2(s)
+            if events is not None:
+                events[1].record()
+                events[2].record()
+        else:
+            if events is not None:
+                events[0].record()
+            pp['run_a'](nxt)                                # K1(s+1) + publish(s+1)
+            if events is not None:
+                events[1].record()
+            pp['run_b'](cur)                                # K2(s), mailbox lag 1
+            if events is not None:
+                events[2].record()
         pp['cur'] = nxt
         pp['done'] = cur
         return self.losses
 
     def targets_of_losses(self):
         """(y_reg, y_cls) of the batch the last run_pipelined() computed the losses for."""
-        y_reg, y_cls, _ = self._pipe['bufs'][self._pipe['done']]
+        y_reg, y_cls = self._pipe['bufs'][self._pipe['done']][:2]
         return y_reg, y_cls
 
     # ---- host inputs, copies overlapped with the kernels -----------------------------------------------
