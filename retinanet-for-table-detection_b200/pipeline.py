@@ -1,10 +1,19 @@
-"""The training-target step as one replayable unit: K1 (targets) -> normaliser -> K2 (losses fwd+bwd).
+"""The training-target step as one replayable unit: K1 (targets) -> count exchange -> K2 (losses fwd+bwd).
 
-``TargetLossStep`` owns static device buffers for one batch shape and, at world size 1, captures the two
-kernel launches into a CUDA graph so a step costs one ``cudaGraphLaunch`` instead of several Python-side
-launches (the kernels are ~tens of microseconds; launch overhead would otherwise dominate).  With several
-ranks the positive count is all-reduced between K1 and K2 (``distributed.global_positive_count``), the
-two halves being captured separately.
+``TargetLossStep`` owns static device buffers for one batch shape and captures the kernel launches into CUDA
+graphs (the kernels are tens of microseconds; launch overhead would otherwise dominate):
+
+* ``run()``            the whole step as ONE graph launch (K1 [+ publish] + K2); with ``events`` the two halves are
+                       replayed separately so that they can be timed;
+* ``run_from_host()``  inputs in (pinned) host memory: the classification tensor is copied on a copy stream while the
+                       GT list is packed and K1 runs; the regression rows of the positive anchors can be read in
+                       place from the host buffer (``gather_reg_from_host``);
+* ``run_pipelined()``  K1 of the NEXT batch ahead of (or, ``overlap=True``, concurrently with) K2 of the current one,
+                       double-buffered targets.
+
+With several ranks the positive count is exchanged through the NVLink peer mailbox
+(``distributed.PeerCounter``) -- graph-capturable, no NCCL call -- or, where peers cannot map each other's memory,
+all-reduced between the two halves.
 
 This is host plumbing around the C-ABI; it adds no arithmetic of its own.
 """
