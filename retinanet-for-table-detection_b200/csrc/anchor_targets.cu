@@ -331,7 +331,9 @@ struct K1Tiles {
 
 // MAXA bounds the block size (32 * A threads) so that the register budget can be set per instantiation:
 // <9, 3> is the RetinaNet default (288 threads, >= 3 CTAs per SM), <KT_MAX_A, 1> covers the rest
-template <int MAXA, int MINB>
+// C1: one class (the table-detection configuration) -- specialised so that the generic label path costs the common
+// instantiation no registers
+template <int MAXA, int MINB, bool C1>
 __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const K1Params p, const K1Tiles tl) {
     extern __shared__ __align__(16) float s_dyn[];
     __shared__ double s_gx1[KT_CHUNK], s_gy1[KT_CHUNK], s_gx2[KT_CHUNK], s_gy2[KT_CHUNK], s_ga[KT_CHUNK];
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                 const unsigned al = al0 + r * alw;          // first anchor of the staged row, mod 4 in the low bits
                 float* sr = s_reg + r * reg_stride + (int)(al & 3u) + k * 5;
                 sr[0] = t0; sr[1] = t1; sr[2] = t2; sr[3] = t3; sr[4] = state;
-                if (p.C == 1) {
+                if (C1) {
                     float* sl = s_lab + r * lab_stride + (int)((al & 1u) * 2u) + k * 2;
                     sl[0] = hot == 0 ? 1.0f : 0.0f; sl[1] = state;
                 } else {
@@ -561,7 +563,7 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
         const int job = tid;                                // jobs [0, KT_ROWS): regression rows, [KT_ROWS, 2 KT_ROWS): label rows
         const bool lab_job = job >= KT_ROWS;
         const int r = lab_job ? job - KT_ROWS : job;
-        if (job < 2 * KT_ROWS && r < nrows && !(lab_job && p.C != 1)) {
+        if (job < 2 * KT_ROWS && r < nrows && !(lab_job && !C1)) {
             const int per = lab_job ? 2 : 5;
             const long long start = (tile_row0 + (long long)r * W * A) * per;
             const int len = cnt * per, shift = (int)(start & 3);
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the CTA's shared memory may go away after this
         }
-        if (p.C != 1) {
+        if (!C1) {
             // C > 1: a label row is C + 1 floats, all zero except the one-hot entry of a positive anchor and a non-zero
             // state (~1 % of the anchors).  So the tile rows' label ranges are zero-filled with 128-bit stores -- no
             // per-element row / column arithmetic -- and, after a barrier, the few non-zero entries are written.
@@ -621,7 +623,7 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
             }
         }
     }
-    if (p.C == 1) {
+    if (C1) {
         const int len = cnt * 2, upr = (len + 3) / 4 + 1;
         for (int u = tid; u < nrows * upr; u += nthreads) {
             const int r = (u >= upr) + (u >= 2 * upr) + (u >= 3 * upr), v = u - r * upr;
@@ -772,20 +774,25 @@ extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* leve
         static bool attr_done = false;
         if (!attr_done) {
             const int big = (int)kt_dyn_smem(KT_MAX_A), small = (int)kt_dyn_smem(9);
-            cudaError_t ae = cudaFuncSetAttribute(k_anchor_targets_tiles<KT_MAX_A, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+            cudaError_t ae = cudaFuncSetAttribute(k_anchor_targets_tiles<KT_MAX_A, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<KT_MAX_A, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
             if (ae != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
             attr_done = true;
         }
+        const dim3 tgrid((unsigned)tiles, (unsigned)B);
         if (tiles > 0 && A <= 9) {
             static const int minb = getenv("RN_K1_MINB") ? atoi(getenv("RN_K1_MINB")) : 3;   // tuning knob (measured: 3 CTAs/SM is fastest)
-            if (minb >= 4) k_anchor_targets_tiles<9, 4><<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);
-            else if (minb == 3) k_anchor_targets_tiles<9, 3><<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);
-            else k_anchor_targets_tiles<9, 2><<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);
+            if (C != 1) k_anchor_targets_tiles<9, 3, false><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+            else if (minb >= 4) k_anchor_targets_tiles<9, 4, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+            else if (minb == 3) k_anchor_targets_tiles<9, 3, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+            else k_anchor_targets_tiles<9, 2, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
         } else if (tiles > 0) {
-            k_anchor_targets_tiles<KT_MAX_A, 1><<<dim3((unsigned)tiles, (unsigned)B), 32 * A, dyn, s>>>(p, tl);
+            if (C == 1) k_anchor_targets_tiles<KT_MAX_A, 1, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+            else k_anchor_targets_tiles<KT_MAX_A, 1, false><<<tgrid, 32 * A, dyn, s>>>(p, tl);
         }
     } else {
         k_anchor_targets<false><<<grid, K1_THREADS, 0, s>>>(p);
