@@ -331,6 +331,25 @@ struct K1Tiles {
 
 // MAXA bounds the block size (32 * A threads) so that the register budget can be set per instantiation:
 // <9, 3> is the RetinaNet default (288 threads, >= 3 CTAs per SM), <KT_MAX_A, 1> covers the rest
+// Write-out of a tile's staged rows when the output tensors are not 16-byte aligned: scalar stores (rows are staged
+// with the destination's phase, see the kernel).  Rare path, out of line so that it costs the kernel no registers.
+__device__ __noinline__ void write_out_unaligned(float* reg, float* lab, int C, const float* s_reg, const float* s_lab,
+                                                 const float* s_state, const int* s_hot, long long tile_row0, int row_anchors,
+                                                 int cnt, int nrows, int A, int tid, int nthreads) {
+    const int reg_stride = 32 * A * 5 + 4, lab_stride = 32 * A * 2 + 4;
+    for (int r = 0; r < nrows; ++r) {
+        const long long first = tile_row0 + (long long)r * row_anchors;
+        const float* sr = s_reg + r * reg_stride + (int)((first * 5) & 3);
+        for (int i = tid; i < cnt * 5; i += nthreads) reg[first * 5 + i] = sr[i];
+        if (C == 1) {
+            const float* sl = s_lab + r * lab_stride + (int)((first * 2) & 3);
+            for (int i = tid; i < cnt * 2; i += nthreads) lab[first * 2 + i] = sl[i];
+        } else {
+            store_labels_generic(lab, first, cnt, C, false, nthreads, s_state + r * 32 * A, s_hot + r * 32 * A);
+        }
+    }
+}
+
 // C1: one class (the table-detection configuration) -- specialised so that the generic label path costs the common
 // instantiation no registers
 template <int MAXA, int MINB, bool C1>
@@ -604,45 +623,8 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
         }
         return;
     }
-    // unaligned output tensors: plain stores
-    // Unit v of a row covers staged floats [4v, 4v+4) = global floats [start - shift + 4v, ...): whole units are
-    // one LDS.128 + one STG.128, the (<= 2) partial units at the ends of a row are written float by float.
-    {
-        const int len = cnt * 5, upr = (len + 3) / 4 + 1;   // units per row (upper bound incl. the shift)
-        for (int u = tid; u < nrows * upr; u += nthreads) {
-            const int r = (u >= upr) + (u >= 2 * upr) + (u >= 3 * upr), v = u - r * upr;      // KT_ROWS == 4
-            const long long start = (tile_row0 + (long long)r * W * A) * 5;
-            const int shift = p.vec_ok ? (int)(start & 3) : 0;
-            const float* sr = s_reg + r * reg_stride + (p.vec_ok ? 0 : (int)(start & 3));
-            float* dst = p.reg + (start - shift);
-            const int i = 4 * v;
-            if (p.vec_ok && i >= shift && i + 4 <= shift + len) {
-                rn_stg_stream4(dst + i, *reinterpret_cast<const float4*>(sr + i));
-            } else {
-                for (int k = max(i, shift); k < min(i + 4, shift + len); ++k) dst[k] = sr[k];
-            }
-        }
-    }
-    if (C1) {
-        const int len = cnt * 2, upr = (len + 3) / 4 + 1;
-        for (int u = tid; u < nrows * upr; u += nthreads) {
-            const int r = (u >= upr) + (u >= 2 * upr) + (u >= 3 * upr), v = u - r * upr;
-            const long long start = (tile_row0 + (long long)r * W * A) * 2;
-            const int shift = p.vec_ok ? (int)(start & 3) : 0;                    // 0 or 2
-            const float* sl = s_lab + r * lab_stride + (p.vec_ok ? 0 : (int)(start & 3));
-            float* dst = p.lab + (start - shift);
-            const int i = 4 * v;
-            if (p.vec_ok && i >= shift && i + 4 <= shift + len) {
-                rn_stg_stream4(dst + i, *reinterpret_cast<const float4*>(sl + i));
-            } else {
-                for (int k = max(i, shift); k < min(i + 4, shift + len); ++k) dst[k] = sl[k];
-            }
-        }
-    } else {
-        for (int r = 0; r < nrows; ++r)
-            store_labels_generic(p.lab, tile_row0 + (long long)r * W * A, cnt, p.C, p.vec_ok != 0, nthreads,
-                                 s_state + r * 32 * A, s_hot + r * 32 * A);
-    }
+    // unaligned output tensors (not 16-byte aligned: never the case for framework allocations): plain stores, out of line
+    write_out_unaligned(p.reg, p.lab, p.C, s_reg, s_lab, s_state, s_hot, tile_row0, W * A, cnt, nrows, A, tid, nthreads);
 }
 
 __global__ void k_anchors_f64(const RnLevels lv, const double* base, int N, double* out) {

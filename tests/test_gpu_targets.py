@@ -208,3 +208,29 @@ def test_randomized_shapes_and_parameters(rn, seed):
     # the same through an explicit (N,4) array (no generation spec): one anchor per thread
     reg2, lab2 = rn.anchor_targets_bbox(np.array(oanchors), images, anns, C)
     assert same(reg2, want_reg) and same(lab2, want_lab)
+
+
+@pytest.mark.parametrize("C", [1, 3])
+@pytest.mark.parametrize("off_reg,off_lab", [(1, 2), (3, 0), (2, 2)])
+def test_unaligned_output_tensors(rn, C, off_reg, off_lab):
+    """Output tensors that are not 16-byte aligned (a view into a larger buffer) take the plain-store write-out
+    instead of the TMA bulk stores: same bits."""
+    hw = (131, 203)
+    anchors = rn.anchors_for_shape(hw + (3,))
+    oanchors = O.anchors_for_shape(hw + (3,))
+    N = oanchors.shape[0]
+    imgs = [synthetic.PageShape(hw + (3,)), synthetic.PageShape((120, 180, 3))]
+    anns = [synthetic.gt_for_page(2, 40 + i, hw=hw, gmax=7, classes=C) for i in range(2)]
+    want_reg, want_lab = O.anchor_targets_bbox(oanchors, imgs, anns, C)
+    boxes, labels, counts, img_hw = rn.anchors.pack_annotations(imgs, anns, C)
+    d = rn.anchors.upload_annotations(boxes, labels, counts, img_hw, torch.device("cuda"))
+    big_r = torch.full((2 * N * 5 + 8,), 7.0, dtype=torch.float32, device="cuda")
+    big_l = torch.full((2 * N * (C + 1) + 8,), 7.0, dtype=torch.float32, device="cuda")
+    y_reg = big_r[off_reg:off_reg + 2 * N * 5].view(2, N, 5)
+    y_cls = big_l[off_lab:off_lab + 2 * N * (C + 1)].view(2, N, C + 1)
+    assert y_reg.data_ptr() % 16 != 0 or y_cls.data_ptr() % 16 != 0
+    rn.anchors.anchor_targets_device(anchors.spec, *d, C, out=(y_reg, y_cls))
+    assert same(y_reg.cpu().numpy(), want_reg) and same(y_cls.cpu().numpy(), want_lab)
+    # nothing outside the views was touched
+    assert float(big_r[:off_reg].sum()) == 7.0 * off_reg and float(big_r[off_reg + 2 * N * 5:].sum()) == 7.0 * (8 - off_reg)
+    assert float(big_l[:off_lab].sum()) == 7.0 * off_lab and float(big_l[off_lab + 2 * N * (C + 1):].sum()) == 7.0 * (8 - off_lab)
