@@ -352,7 +352,7 @@ __device__ __noinline__ void write_out_unaligned(float* reg, float* lab, int C, 
 
 // C1: one class (the table-detection configuration) -- specialised so that the generic label path costs the common
 // instantiation no registers
-template <int MAXA, int MINB, bool C1>
+template <int MAXA, int MINB, bool C1, bool AM>          // AM: the argmax tensor is wanted
 __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const K1Params p, const K1Tiles tl) {
     extern __shared__ __align__(16) float s_dyn[];
     __shared__ double s_gx1[KT_CHUNK], s_gy1[KT_CHUNK], s_gx2[KT_CHUNK], s_gy2[KT_CHUNK], s_ga[KT_CHUNK];
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                     s_hot[r * 32 * A + k] = hot;
                 }
                 my_pos += (state == 1.0f);
-                if (p.argmax)
+                if (AM && p.argmax)
                     p.argmax[(size_t)b * p.N + lstart + ((size_t)(cy0 + r) * W + cx0 + lane) * A + a] = arg[r];
             }
         }
@@ -756,25 +756,28 @@ extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* leve
         static bool attr_done = false;
         if (!attr_done) {
             const int big = (int)kt_dyn_smem(KT_MAX_A), small = (int)kt_dyn_smem(9);
-            cudaError_t ae = cudaFuncSetAttribute(k_anchor_targets_tiles<KT_MAX_A, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<KT_MAX_A, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+            cudaError_t ae = cudaFuncSetAttribute(k_anchor_targets_tiles<KT_MAX_A, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<KT_MAX_A, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
             if (ae != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
             attr_done = true;
         }
         const dim3 tgrid((unsigned)tiles, (unsigned)B);
+        // the common instantiation (9 anchors, one class, no argmax tensor) is specialised; the others share generic ones
         if (tiles > 0 && A <= 9) {
             static const int minb = getenv("RN_K1_MINB") ? atoi(getenv("RN_K1_MINB")) : 3;   // tuning knob (measured: 3 CTAs/SM is fastest)
-            if (C != 1) k_anchor_targets_tiles<9, 3, false><<<tgrid, 32 * A, dyn, s>>>(p, tl);
-            else if (minb >= 4) k_anchor_targets_tiles<9, 4, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
-            else if (minb == 3) k_anchor_targets_tiles<9, 3, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
-            else k_anchor_targets_tiles<9, 2, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+            if (C != 1) k_anchor_targets_tiles<9, 3, false, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+            else if (argmax_out) k_anchor_targets_tiles<9, 3, true, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+            else if (minb >= 4) k_anchor_targets_tiles<9, 4, true, false><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+            else if (minb == 3) k_anchor_targets_tiles<9, 3, true, false><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+            else k_anchor_targets_tiles<9, 2, true, false><<<tgrid, 32 * A, dyn, s>>>(p, tl);
         } else if (tiles > 0) {
-            if (C == 1) k_anchor_targets_tiles<KT_MAX_A, 1, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
-            else k_anchor_targets_tiles<KT_MAX_A, 1, false><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+            if (C == 1) k_anchor_targets_tiles<KT_MAX_A, 1, true, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+            else k_anchor_targets_tiles<KT_MAX_A, 1, false, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
         }
     } else {
         k_anchor_targets<false><<<grid, K1_THREADS, 0, s>>>(p);
