@@ -28,6 +28,10 @@ constexpr int K3_THREADS = 256;
 constexpr int NMS_THREADS = 1024;
 constexpr int NMS_WARPS = NMS_THREADS / 32;
 constexpr int NMS_CHUNK = 2048;    // candidates ordered per radix-select round
+#ifndef RN_NMS_CHUNK_NEXT
+#define RN_NMS_CHUNK_NEXT 256   // A/B at 64 pages x 5 k candidates: 256 -> 190 us, 512 -> 198 us, 1024 -> 197 us, 2048 -> 203 us
+#endif
+constexpr int NMS_CHUNK_NEXT = RN_NMS_CHUNK_NEXT;   // ... in the rounds after the first
 #ifndef RN_NMS_BATCH
 #define RN_NMS_BATCH 128         // A/B (64 pages, 5 k candidates each): 64 -> 217 us, 128 -> 203 us, 256 -> 214 us
 #endif
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     long long t_mark = p.timing ? clock64() : 0;
 #define RN_PHASE(k) do { if (p.timing && tid == 0) { const long long now = clock64(); atomicAdd(p.timing + (k), (unsigned long long)(now - t_mark)); t_mark = now; } } while (0)
     unsigned long long upper = ~0ull;   // keys >= upper have been visited
-    int visited = 0, nsel = 0;
+    int visited = 0, nsel = 0, round = 0;
     if (tid == 0) s_nsel = 0;
     // The slab's keys are read ONCE into registers (8 per thread) when the slab has <= 8192 candidates -- the
     // radix-select passes and the gathers of every round then run out of registers; larger slabs stream the
@@ -373,7 +377,11 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     __syncthreads();
 
     while (visited < limit && nsel < p.max_det) {
-        const int take = min(NMS_CHUNK, limit - visited);
+        // first round: the NMS_CHUNK best candidates.  Later rounds are only reached when those did not yield max_det
+        // selections -- typically a few hundred more are needed, not another 2048 -- so they start at NMS_CHUNK_NEXT
+        // and double (a select + sort round costs about the same as consuming 1000 candidates)
+        const int take = min(round == 0 ? NMS_CHUNK : min(NMS_CHUNK, NMS_CHUNK_NEXT << (round - 1)), limit - visited);
+        ++round;
         // ---------------- K4: radix select the `take` largest unvisited keys --------------------
         unsigned long long thr_key = 0ull;
         if (cnt - visited > take) {
