@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     __shared__ unsigned short s_pick[NMS_BATCH];
     __shared__ unsigned s_hist[256];
     __shared__ unsigned long long s_prefix;
-    __shared__ int s_want, s_loaded, s_nsel;
+    __shared__ int s_want, s_loaded, s_nsel, s_done;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int seg = blockIdx.x;
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
         // ---------------- K4: radix select the `take` largest unvisited keys --------------------
         unsigned long long thr_key = 0ull;
         if (cnt - visited > take) {
-            if (tid == 0) { s_prefix = 0ull; s_want = take; }
+            if (tid == 0) { s_prefix = 0ull; s_want = take; s_done = 0; }
             unsigned long long mask = 0ull;
             for (int shift = 56; shift >= 0; shift -= 8) {
                 if (tid < 256) s_hist[tid] = 0u;
@@ -414,18 +414,22 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                     for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
                     unsigned before = incl - run;          // keys in strictly higher digit groups of earlier lanes
                     const unsigned want = (unsigned)s_want;
-                    int digit = -1; unsigned rem = 0;
+                    int digit = -1; unsigned rem = 0; bool whole = false;
 #pragma unroll
                     for (int t = 0; t < 8; ++t) {
-                        if (digit < 0 && before + local[t] >= want && before < want) { digit = 255 - (lane * 8 + t); rem = want - before; }
+                        if (digit < 0 && before + local[t] >= want && before < want) {
+                            digit = 255 - (lane * 8 + t); rem = want - before;
+                            whole = (local[t] == rem);     // every key of this digit group is wanted: lower digits do not matter
+                        }
                         before += local[t];
                     }
-                    if (digit >= 0) { s_prefix = prefix | ((unsigned long long)digit << shift); s_want = (int)rem; }
+                    if (digit >= 0) { s_prefix = prefix | ((unsigned long long)digit << shift); s_want = (int)rem; s_done = whole ? 1 : 0; }
                 }
                 mask |= 255ull << shift;
                 __syncthreads();
+                if (s_done) break;       // block-uniform (scores are mostly distinct: the low 32 index bits rarely need passes)
             }
-            thr_key = s_prefix;          // exactly `take` unvisited keys are >= thr_key
+            thr_key = s_prefix;          // exactly `take` unvisited keys are >= thr_key (its undecided low digits are 0)
         }
         RN_PHASE(0);
         // ---------------- gather the chunk into shared memory ----------------------------------------
