@@ -8,9 +8,10 @@ forward and backward).  One "step" = one batch per GPU; per-GPU work is fixed as
 pages shard by image, the only exchange is the positive-anchor count (NVLink peer mailbox, or NCCL all-reduce).
 
 `value`  = pages/s with the batch's inputs resident in HBM (GT block + head outputs), CUDA events.
-`e2e`    = pages/s through the public Python API (TargetLossStep.run_from_host) with HOST inputs every step: the
-           ragged GT list is packed and copied, the head outputs are copied from pinned memory on a copy stream
-           while K1 runs, the loss scalars are read back.
+`e2e`    = pages/s through the public Python API (HostStepPipeline.submit / result) with HOST inputs every step: the
+           ragged GT list is packed and copied, the head outputs are copied from pinned memory on a copy stream, K1 +
+           K2 run, the loss scalars are read back; two steps are in flight so the copy of step s+1 overlaps the
+           kernels of step s (`e2e.synchronous` = one step at a time, TargetLossStep.run_from_host).
 `roofline` = K1, the dominant kernel of the step by time (instruction-issue bound): algorithmic bytes / its mean
            duration (CUDA events inside the timed region) against the measured HBM peak in MEASURED_PEAKS.json.
 `roofline_k2` = the same for K2, the HBM-bound loss kernel (north_star's 60 % target).
@@ -38,6 +39,7 @@ PAGES_PER_GPU = synthetic.CONFIGS[CFG]['batch']
 GMAX = synthetic.CONFIGS[CFG]['gmax'] + 2          # +2: the adversarial snapped duplicates
 CLASSES = 1
 E2E_GATHER = True                                  # smooth-L1 reads the positive anchors' regression rows straight from pinned host memory
+E2E_DEPTH = 2                                      # host-input steps in flight (HostStepPipeline slots)
 E2E_CHUNKS = 1                                     # page chunks of the overlapped host-input step
 METRIC = "pages/sec (anchor targets + focal/smooth-L1 fwd+bwd) @800x1333"
 WORKLOAD = "configs[1]: training-target path, 16 pages/GPU of 800x1333, 1 class, <=20 GT, 200700 anchors/page"
@@ -310,7 +312,32 @@ def run_ours(args):
         e2e_step()
     e1.record()
     barrier()
-    e2e_ms = e0.elapsed_time(e1) if e2e_steps else float("nan")
+    sync_ms = e0.elapsed_time(e1) if e2e_steps else float("nan")
+    # the headline e2e: the same step through HostStepPipeline, two steps in flight (submit step s+1, then take the
+    # result of step s) -- every step still copies its inputs from pinned host memory and reads its losses back
+    e2e_ms = float("nan")
+    if e2e_steps:
+        pipe = rn.pipeline.HostStepPipeline(HW + (3,), B, GMAX, C, depth=E2E_DEPTH)
+
+        def pipe_steps(n):
+            prev = None
+            for _ in range(n):
+                k = pipe.submit(images, anns, cls_host, reg_host, chunks=E2E_CHUNKS, gather_reg_from_host=E2E_GATHER)
+                if prev is not None:
+                    pipe.result(prev)
+                prev = k
+            return pipe.result(prev)
+        pipe_steps(max(args.warmup, 3))
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        pipe_losses = pipe_steps(e2e_steps)
+        p1.record()
+        barrier()
+        e2e_ms = p0.elapsed_time(p1)
+        sync_losses = step.run_from_host(images, anns, cls_host, reg_host, chunks=E2E_CHUNKS, gather_reg_from_host=E2E_GATHER)
+        assert np.array_equal(pipe_losses.numpy(), sync_losses.numpy()), (pipe_losses, sync_losses)
+        del pipe
     # bytes that cross PCIe per step: the GT block, the classification tensor, and -- with the gather -- only the
     # 16-byte regression rows of the positive anchors (K2 reads them in place); the full-copy variant is timed too
     n_pos_rank = float(step.npos.sum().item())
@@ -330,10 +357,10 @@ def run_ours(args):
         full_ms = f0.elapsed_time(f1)
     sampler.stop_flag = True
 
-    times = torch.tensor([total_ms, e2e_ms, k1_ms, k2_ms, split_ms, full_ms], dtype=torch.float64, device=device)
+    times = torch.tensor([total_ms, e2e_ms, k1_ms, k2_ms, split_ms, full_ms, sync_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, k1_ms, k2_ms, split_ms, full_ms = [float(x) for x in times.cpu()]
+    total_ms, e2e_ms, k1_ms, k2_ms, split_ms, full_ms, sync_ms = [float(x) for x in times.cpu()]
 
     # ---- N2 (extra object): K2 fed by the per-level head outputs, sigmoid fused ---------------------------
     levels = None
@@ -390,7 +417,11 @@ def run_ours(args):
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "pages/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 12 * E2E_CHUNKS, "ms_per_step": e2e_ms / args.steps,
                     "h2d_GBps": h2d / (e2e_ms / args.steps * 1e-3) / 1e9,
-                    "api": "TargetLossStep.run_from_host (copy stream overlapped with GT packing and K1; K2 per page chunk)",
+                    "api": "HostStepPipeline.submit / result (%d steps in flight: the copy of step s+1 runs during K1 / K2 of "
+                           "step s; per step: GT packed + copied, classification tensor copied from pinned memory, K1, K2, "
+                           "loss rows read back)" % E2E_DEPTH,
+                    "synchronous": {"value": world * B * args.steps / (sync_ms * 1e-3), "ms_per_step": sync_ms / args.steps,
+                                    "api": "TargetLossStep.run_from_host (one step at a time, host waits for the losses)"},
                     "regression_rows": ("positive anchors' rows read in place from pinned host memory (model/losses.py:72-74 "
                                         "gathers exactly those); the (B,N,4) tensor is not copied") if E2E_GATHER else "copied",
                     "full_copy": {"value": world * B * args.steps / (full_ms * 1e-3), "ms_per_step": full_ms / args.steps,

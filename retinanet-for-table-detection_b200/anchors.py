@@ -196,36 +196,78 @@ class _Staging(object):
 _staging = {}
 
 
-def pack_annotations(image_group, annotations_group, num_classes):
+_hw_cache = {}        # tuple of page (H, W) -> (B, 2) int32 array (pure conversion, memoised)
+
+
+def pack_annotations(image_group, annotations_group, num_classes, out=None):
     """Validate like the reference (``model/anchors.py:56-60``) and flatten the ragged GT list.
     Returns ``(boxes (B,G,4) f64, labels (B,G) i32, counts (B) i32, img_hw (B,2) i32)`` numpy arrays,
     with G = max(1, max GT per page).  Labels follow numpy fancy-index rules: ``.astype(int)``
-    truncation, negative values wrap over the C+1 columns, anything else raises IndexError."""
+    truncation, negative values wrap over the C+1 columns, anything else raises IndexError.
+
+    ``out``: four preallocated arrays of those dtypes, ``(B, Gcap, 4)``, ``(B, Gcap)``, ``(B,)``, ``(B, 2)`` with
+    ``Gcap >= G`` (e.g. views of a pinned staging block) that are filled instead; ValueError if they do not fit."""
     assert (len(image_group) == len(annotations_group)), "The length of the images and annotations need to be equal."
     assert (len(annotations_group) > 0), "No data received to compute anchor targets for."
     for annotations in annotations_group:
         assert ('bboxes' in annotations), "Annotations should contain bboxes."
         assert ('labels' in annotations), "Annotations should contain labels."
     B = len(image_group)
-    counts = np.array([np.asarray(a['bboxes']).shape[0] for a in annotations_group], dtype=np.int32)
-    G = max(1, int(counts.max()))
-    boxes = np.zeros((B, G, 4), dtype=np.float64)
-    labels = np.zeros((B, G), dtype=np.int32)
-    img_hw = np.zeros((B, 2), dtype=np.int32)
+    parts = [np.asarray(a['bboxes']) for a in annotations_group]
+    cnt = [p.shape[0] for p in parts]
+    G = max(1, max(cnt))
+    if out is None:
+        boxes = np.zeros((B, G, 4), dtype=np.float64)
+        labels = np.zeros((B, G), dtype=np.int32)
+        counts = np.empty(B, dtype=np.int32)
+        img_hw = np.empty((B, 2), dtype=np.int32)
+    else:
+        boxes, labels, counts, img_hw = out
+        if boxes.shape[0] != B or boxes.shape[1] < G:
+            raise ValueError("batch of %d pages / %d GT does not fit the staging block (%d pages, %d GT)"
+                             % (B, G, boxes.shape[0], boxes.shape[1]))
+        boxes[...] = 0.0
+        labels[...] = 0
+    counts[:] = cnt
     width = num_classes + 1
-    for b, (image, ann) in enumerate(zip(image_group, annotations_group)):
-        g = int(counts[b])
-        if g:
-            boxes[b, :g] = np.asarray(ann['bboxes'], dtype=np.float64).reshape(g, -1)[:, :4]
-            lab = np.asarray(ann['labels']).astype(int).reshape(-1)[:g]
-            if lab.size and (lab.max() >= width or lab.min() < -width):
-                raise IndexError("label out of bounds for %d classes" % num_classes)
-            labels[b, :g] = np.where(lab < 0, lab + width, lab)
-        shape = tuple(image.shape)
-        if shape:
-            img_hw[b, 0], img_hw[b, 1] = int(shape[0]), int(shape[1])
-        else:
-            img_hw[b] = np.iinfo(np.int32).max      # `if image.shape:` false -> no border rule
+    total = sum(cnt)
+    if total:
+        # This runs on the host once per step, so the common case -- every page's boxes a (g, 4) array and labels a
+        # (g,) array -- is one concatenation, one conversion / range check and one masked assignment for the batch.
+        lparts = [np.asarray(a['labels']) for a in annotations_group]
+        flat = lab = None
+        if all(p.ndim == 2 and p.shape[1] == 4 for p in parts) and [l.shape for l in lparts] == [(c,) for c in cnt]:
+            flat = np.concatenate(parts)
+            lab = np.concatenate(lparts).astype(int)
+        else:                                           # ragged shapes: the reference's per-page conversions
+            fl, ll = [], []
+            for b in range(B):
+                g = cnt[b]
+                if g:
+                    fl.append(np.asarray(parts[b], dtype=np.float64).reshape(g, -1)[:, :4])
+                    l = lparts[b].astype(int).reshape(-1)[:g]
+                    if l.size != g:
+                        if l.size != 1:                 # numpy's assignment would refuse to broadcast these
+                            raise ValueError("page %d: %d labels for %d boxes" % (b, l.size, g))
+                        l = np.repeat(l, g)
+                    ll.append(l)
+            flat, lab = np.concatenate(fl), np.concatenate(ll)
+        lo, hi = lab.min(), lab.max()
+        if hi >= width or lo < -width:
+            raise IndexError("label out of bounds for %d classes" % num_classes)
+        if lo < 0:
+            lab = np.where(lab < 0, lab + width, lab)
+        mask = np.arange(boxes.shape[1]) < counts[:, None]       # row-major order == concatenation order
+        boxes[mask] = flat
+        labels[mask] = lab
+    shapes = tuple(tuple(image.shape)[:2] for image in image_group)
+    hw = _hw_cache.get(shapes)
+    if hw is None:
+        no_rule = np.iinfo(np.int32).max                # `if image.shape:` false -> no border rule
+        hw = np.array([(int(s[0]), int(s[1])) if s else (no_rule, no_rule) for s in shapes], dtype=np.int32)
+        if len(_hw_cache) < 64:
+            _hw_cache[shapes] = hw
+    img_hw[...] = hw
     return boxes, labels, counts, img_hw
 
 

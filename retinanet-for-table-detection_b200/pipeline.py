@@ -43,6 +43,11 @@ class TargetLossStep(object):
         total = self.nb + self.nl + self.nc + self.ni
         self.gt_host = torch.zeros(total, dtype=torch.uint8, pin_memory=True)
         self.gt_dev = torch.zeros(total, dtype=torch.uint8, device=d)
+        hv = self.gt_host.numpy()
+        self._gt_views = (hv[:self.nb].view(np.float64).reshape(B, G, 4),
+                          hv[self.nb:self.nb + self.nl].view(np.int32).reshape(B, G),
+                          hv[self.nb + self.nl:self.nb + self.nl + self.nc].view(np.int32),
+                          hv[self.nb + self.nl + self.nc:].view(np.int32).reshape(B, 2))
         o = 0
         self.d_boxes = self.gt_dev[o:o + self.nb].view(torch.float64).view(B, G, 4); o += self.nb
         self.d_labels = self.gt_dev[o:o + self.nl].view(torch.int32).view(B, G); o += self.nl
@@ -73,21 +78,12 @@ class TargetLossStep(object):
         self._chunk_losses = None
         self._chunk_events = None
         self._losses_host = None
+        self._done_event = None
 
     # ---- inputs ---------------------------------------------------------------------------------
     def load_annotations(self, image_group, annotations_group):
         """Pack the ragged GT list (reference format) and copy it to the static device block (async)."""
-        boxes, labels, counts, img_hw = _anchors.pack_annotations(image_group, annotations_group, self.C)
-        B, G = labels.shape
-        if B != self.B or G > self.G:
-            raise ValueError("batch of %d pages / %d GT does not fit this step (%d pages, %d GT)" % (B, G, self.B, self.G))
-        hv = self.gt_host.numpy()
-        hb = hv[:self.nb].view(np.float64).reshape(self.B, self.G, 4)
-        hl = hv[self.nb:self.nb + self.nl].view(np.int32).reshape(self.B, self.G)
-        hb[:, :G] = boxes
-        hl[:, :G] = labels
-        hv[self.nb + self.nl:self.nb + self.nl + self.nc].view(np.int32)[:] = counts
-        hv[self.nb + self.nl + self.nc:].view(np.int32).reshape(self.B, 2)[:] = img_hw
+        _anchors.pack_annotations(image_group, annotations_group, self.C, out=self._gt_views)   # straight into the pinned block
         self.gt_dev.copy_(self.gt_host, non_blocking=True)
         return self.gt_host.numel()
 
@@ -245,7 +241,14 @@ class TargetLossStep(object):
         exactly those, ``model/losses.py:72-74``; ~0.1 % of the rows), so K2 fetches those 16-byte rows straight
         from the pinned host buffer over PCIe (unified addressing): 51 MB of the step's 64 MB never cross the
         bus.  Losses and gradients are bit-identical to the copying path."""
-        rank, world = _dist.world()
+        self._enqueue_from_host(image_group, annotations_group, cls_host, reg_host, chunks, gather_reg_from_host)
+        return self._finish_from_host()
+
+    def _enqueue_from_host(self, image_group, annotations_group, cls_host, reg_host, chunks=4, gather_reg_from_host=False,
+                           wait_compute=True):
+        """Everything of :meth:`run_from_host` except the final wait: copies, K1, K2 per chunk and the D2H copy of the
+        loss rows are enqueued, ``_done_event`` is recorded behind them.  (``HostStepPipeline`` keeps several steps
+        in flight this way.)"""
         dev = self.device
         chunks = max(1, min(int(chunks), self.B))
         if self._copy_stream is None:
@@ -254,22 +257,25 @@ class TargetLossStep(object):
             self._chunk_losses = torch.zeros((chunks, 3), dtype=torch.float32, device=dev)
             self._losses_host = torch.zeros((chunks, 3), dtype=torch.float32).pin_memory()
             self._chunk_events = [torch.cuda.Event() for _ in range(chunks)]
+            self._done_event = torch.cuda.Event()
         if self.use_graph and self._graphs is None:
             self._build_graphs()
         if gather_reg_from_host and not (reg_host.is_pinned() and self.loss_kw.get("shared_state") and self.C == 1):
             raise ValueError("gather_reg_from_host needs a pinned reg_host and the C == 1 shared-state loss path "
                              "(the only one that reads regression rows of positive anchors only)")
         compute = torch.cuda.current_stream(dev)
-        self._copy_stream.wait_stream(compute)              # the previous step's K2 has consumed the buffers
+        if wait_compute:                                    # HostStepPipeline has already waited for this slot's last step
+            self._copy_stream.wait_stream(compute)          # the previous step's K2 has consumed the buffers
         # the 64 MB of head outputs go first: the PCIe link is the bottleneck of this step, so it starts before
         # the (Python) GT packing, which then runs on the CPU while the copies are in flight
         bounds = [(self.B * i) // chunks for i in range(chunks + 1)]
         with torch.cuda.stream(self._copy_stream):
             for i in range(chunks):
                 lo, hi = bounds[i], bounds[i + 1]
-                self.cls_pred[lo:hi].copy_(cls_host[lo:hi], non_blocking=True)
+                sl = (lambda t: t) if chunks == 1 else (lambda t: t[lo:hi])
+                sl(self.cls_pred).copy_(sl(cls_host), non_blocking=True)
                 if not gather_reg_from_host:
-                    self.reg_pred[lo:hi].copy_(reg_host[lo:hi], non_blocking=True)
+                    sl(self.reg_pred).copy_(sl(reg_host), non_blocking=True)
                 self._chunk_events[i].record(self._copy_stream)
         self.load_annotations(image_group, annotations_group)
         if self.use_graph:
@@ -277,16 +283,20 @@ class TargetLossStep(object):
         else:
             self._targets()
         self._exchange()
+        reg_src = reg_host if gather_reg_from_host else self.reg_pred
         for i in range(chunks):
             lo, hi = bounds[i], bounds[i + 1]
             compute.wait_event(self._chunk_events[i])
-            reg_src = reg_host if gather_reg_from_host else self.reg_pred
-            _losses.detection_losses(self.y_reg[lo:hi], self.y_cls[lo:hi], reg_src[lo:hi], self.cls_pred[lo:hi],
+            sl = (lambda t: t) if chunks == 1 else (lambda t: t[lo:hi])     # one chunk: no views to build
+            _losses.detection_losses(sl(self.y_reg), sl(self.y_cls), sl(reg_src), sl(self.cls_pred),
                                      normalizer=self.npos_total,
-                                     out=(self._chunk_losses[i], self.grad_cls[lo:hi], self.grad_reg[lo:hi]),
+                                     out=(self._chunk_losses[i], sl(self.grad_cls), sl(self.grad_reg)),
                                      workspace=self.loss_ws, peer_box=self.peer, **self.loss_kw)
         self._losses_host.copy_(self._chunk_losses, non_blocking=True)
-        compute.synchronize()
+        self._done_event.record(compute)
+
+    def _finish_from_host(self):
+        self._done_event.synchronize()
         out = self._losses_host.sum(dim=0)
         out[2] = self._losses_host[0, 2]                    # the normaliser is the same in every row
         return out
@@ -318,3 +328,62 @@ class TargetLossStep(object):
         if events is not None:
             events[2].record()
         return self.losses
+
+
+class HostStepPipeline(object):
+    """Several training-target steps with HOST inputs in flight at once (what a training loop with a prefetching
+    generator does): ``depth`` independent ``TargetLossStep`` slots -- own GT block, head-output buffers, targets,
+    gradients and loss rows each -- share ONE compute stream and ONE copy stream.
+
+    ``submit()`` enqueues a step into the next slot and returns at once; ``result()`` waits for that step's loss
+    rows.  While step s runs K1/K2, the copy engine is already moving the classification tensor of step s+1, so the
+    step rate is the PCIe copy rate instead of copy + kernels + launch latency.  The arithmetic is the one of
+    ``TargetLossStep.run_from_host`` (same kernels, same order per step): losses and gradients are bit-identical.
+    Kernels of different steps stay in order on the one compute stream, so with several ranks the count exchange
+    behaves exactly as in the unpipelined schedule."""
+
+    def __init__(self, image_shape, batch, gmax, num_classes, depth=2, device=None, **step_kw):
+        _lib.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.depth = max(1, int(depth))
+        self.slots = [TargetLossStep(image_shape, batch, gmax, num_classes, device=self.device, **step_kw)
+                      for _ in range(self.depth)]
+        self.compute = torch.cuda.Stream(self.device)
+        copy = torch.cuda.Stream(self.device)
+        for s in self.slots:
+            s._copy_stream = copy
+            if s.use_graph:
+                s._build_graphs()
+        self._busy = [False] * self.depth
+        self._next = 0
+
+    def submit(self, image_group, annotations_group, cls_host, reg_host, chunks=1, gather_reg_from_host=False):
+        """Enqueue one step; returns the slot index to pass to :meth:`result`.  ``cls_host`` / ``reg_host`` must stay
+        untouched until the step's result has been taken.  If the slot still holds an unfinished step, that step is
+        waited for first (its result is dropped)."""
+        k = self._next
+        self._next = (k + 1) % self.depth
+        slot = self.slots[k]
+        if self._busy[k]:
+            slot._finish_from_host()
+        with torch.cuda.stream(self.compute):
+            # no device-side wait of the copy stream for the compute stream: the slot's previous step has finished (host
+            # wait above), and waiting for the OTHER slots' kernels would serialise the copy behind them
+            slot._enqueue_from_host(image_group, annotations_group, cls_host, reg_host, chunks, gather_reg_from_host,
+                                    wait_compute=False)
+        self._busy[k] = True
+        return k
+
+    def result(self, k):
+        """``[focal, smooth_l1, normaliser]`` of the step submitted into slot ``k`` (waits for it); the slot's
+        gradients / targets are ``slots[k].grad_cls`` / ``grad_reg`` / ``y_reg`` / ``y_cls`` until it is reused."""
+        if not self._busy[k]:
+            raise RuntimeError("slot %d holds no submitted step" % k)
+        out = self.slots[k]._finish_from_host()
+        self._busy[k] = False
+        return out
+
+    def drain(self):
+        """Wait for every step in flight; returns their results oldest first."""
+        order = [(self._next + i) % self.depth for i in range(self.depth)]
+        return [self.result(k) for k in order if self._busy[k]]

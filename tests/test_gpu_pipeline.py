@@ -46,3 +46,40 @@ def test_run_from_host_matches_resident_run(rn, chunks):
     assert yr.cpu().numpy().tobytes() == oreg.tobytes() and yc.cpu().numpy().tobytes() == olab.tobytes()
     wf, ws = OL.focal()(olab, cls), OL.smooth_l1()(oreg, reg)
     assert abs(got[0] - wf) <= 1e-5 * abs(wf) and abs(got[1] - ws) <= 1e-5 * abs(ws)
+
+
+@pytest.mark.parametrize("gather", [False, True])
+def test_host_step_pipeline_matches_run_from_host(rn, gather):
+    """Two steps in flight (different batches in the two slots): every step's losses, gradients and targets are
+    bit-identical to the unpipelined host-input step on the same batch."""
+    import synthetic
+    hw, B = (256, 320), 4
+    N = rn.anchors_for_shape(hw + (3,)).shape[0]
+    imgs = [synthetic.PageShape(hw + (3,)) for _ in range(B)]
+    batches = []
+    for s in range(5):
+        anns = [synthetic.gt_for_page(2, 10 * s + i, hw=hw, gmax=6) for i in range(B)]
+        cls, reg = synthetic.training_predictions(20 + s, B, N, classes=1)
+        batches.append((anns, torch.from_numpy(cls).pin_memory(), torch.from_numpy(reg).pin_memory()))
+    ref = rn.pipeline.TargetLossStep(hw + (3,), B, 8, 1)
+    want = []
+    for anns, c, r in batches:
+        l = ref.run_from_host(imgs, anns, c, r, chunks=1, gather_reg_from_host=gather).numpy().copy()
+        want.append((l, ref.grad_cls.clone(), ref.grad_reg.clone(), ref.y_reg.clone(), ref.y_cls.clone()))
+
+    pipe = rn.pipeline.HostStepPipeline(hw + (3,), B, 8, 1, depth=2)
+    with pytest.raises(RuntimeError):
+        pipe.result(0)                                    # nothing submitted yet
+    pending = []
+    for s, (anns, c, r) in enumerate(batches):
+        pending.append((s, pipe.submit(imgs, anns, c, r, chunks=1, gather_reg_from_host=gather)))
+        if len(pending) == 2:                             # take the older step's result while the newer one runs
+            t, k = pending.pop(0)
+            got = pipe.result(k).numpy()
+            slot = pipe.slots[k]
+            assert np.array_equal(got, want[t][0])
+            assert torch.equal(slot.grad_cls, want[t][1]) and torch.equal(slot.grad_reg, want[t][2])
+            assert torch.equal(slot.y_reg, want[t][3]) and torch.equal(slot.y_cls, want[t][4])
+    rest = pipe.drain()
+    assert len(rest) == 1 and np.array_equal(rest[0].numpy(), want[-1][0])
+    assert pipe.drain() == []
