@@ -333,14 +333,14 @@ class TargetLossStep(object):
 class HostStepPipeline(object):
     """Several training-target steps with HOST inputs in flight at once (what a training loop with a prefetching
     generator does): ``depth`` independent ``TargetLossStep`` slots -- own GT block, head-output buffers, targets,
-    gradients and loss rows each -- share ONE compute stream and ONE copy stream.
+    gradients and loss rows each -- share ONE copy stream (the PCIe link is the bottleneck; copies stay in order).
 
     ``submit()`` enqueues a step into the next slot and returns at once; ``result()`` waits for that step's loss
     rows.  While step s runs K1/K2, the copy engine is already moving the classification tensor of step s+1, so the
     step rate is the PCIe copy rate instead of copy + kernels + launch latency.  The arithmetic is the one of
     ``TargetLossStep.run_from_host`` (same kernels, same order per step): losses and gradients are bit-identical.
-    Kernels of different steps stay in order on the one compute stream, so with several ranks the count exchange
-    behaves exactly as in the unpipelined schedule."""
+    With several ranks the kernels of all steps stay in order on one compute stream, so the count exchange behaves
+    exactly as in the unpipelined schedule."""
 
     def __init__(self, image_shape, batch, gmax, num_classes, depth=2, device=None, **step_kw):
         _lib.require_cuda()
@@ -348,7 +348,13 @@ class HostStepPipeline(object):
         self.depth = max(1, int(depth))
         self.slots = [TargetLossStep(image_shape, batch, gmax, num_classes, device=self.device, **step_kw)
                       for _ in range(self.depth)]
+        # One rank: every slot has its own compute stream, so K1 of step s+1 is not held behind K2 of step s (which,
+        # with ``gather_reg_from_host``, spends most of its time waiting for PCIe reads that compete with the bulk
+        # copy).  Several ranks: one compute stream for all slots -- kernels of different steps stay in order, so a
+        # K2 waiting in its prologue for the peers' counts can never occupy the SMs ahead of an earlier step's K1.
+        one = _dist.world()[1] > 1
         self.compute = torch.cuda.Stream(self.device)
+        self.streams = [self.compute if (one or k == 0) else torch.cuda.Stream(self.device) for k in range(self.depth)]
         copy = torch.cuda.Stream(self.device)
         for s in self.slots:
             s._copy_stream = copy
@@ -366,7 +372,7 @@ class HostStepPipeline(object):
         slot = self.slots[k]
         if self._busy[k]:
             slot._finish_from_host()
-        with torch.cuda.stream(self.compute):
+        with torch.cuda.stream(self.streams[k]):
             # no device-side wait of the copy stream for the compute stream: the slot's previous step has finished (host
             # wait above), and waiting for the OTHER slots' kernels would serialise the copy behind them
             slot._enqueue_from_host(image_group, annotations_group, cls_host, reg_host, chunks, gather_reg_from_host,
