@@ -393,3 +393,57 @@ class HostStepPipeline(object):
         """Wait for every step in flight; returns their results oldest first."""
         order = [(self._next + i) % self.depth for i in range(self.depth)]
         return [self.result(k) for k in order if self._busy[k]]
+
+
+class HostDetectionPipeline(object):
+    """The inference tail (``layers.DetectionHead``) as a serving loop over HOST head outputs with several batches in
+    flight: every slot has its own stream, device classification buffer and pinned result buffers.
+
+    ``submit(regression_host, classification_host)`` (both PINNED float32) copies the classification tensor, runs the
+    fused decode + filter kernels -- the regression rows of the candidates are read in place from the pinned buffer,
+    see ``DetectionHead`` -- and copies the (B, max_detections, .) results back, all asynchronously; ``result(k)``
+    waits and returns ``[boxes, scores, labels]`` as pinned host tensors (valid until the slot is reused).  While
+    batch s is in its NMS kernel the copy of batch s+1 is under way, and two NMS kernels (one CTA per page and class)
+    can share the GPU.  Results are bit-identical to calling the head directly."""
+
+    def __init__(self, head, batch, image_hw, num_classes=1, depth=2, device=None):
+        _lib.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.head, self.depth = head, max(1, int(depth))
+        self.shape = (int(batch), int(image_hw[0]), int(image_hw[1]), 3)
+        N, M, d = head.spec_for(image_hw).num_anchors, int(head.max_detections), self.device
+        self.streams = [torch.cuda.Stream(d) for _ in range(self.depth)]
+        self.cls_dev = [torch.empty((batch, N, num_classes), dtype=torch.float32, device=d) for _ in range(self.depth)]
+        self.out = [[torch.empty((batch, M, 4), dtype=torch.float32).pin_memory(),
+                     torch.empty((batch, M), dtype=torch.float32).pin_memory(),
+                     torch.empty((batch, M), dtype=torch.int32).pin_memory()] for _ in range(self.depth)]
+        self.events = [torch.cuda.Event() for _ in range(self.depth)]
+        self._busy = [False] * self.depth
+        self._next = 0
+
+    def submit(self, regression_host, classification_host):
+        k = self._next
+        self._next = (k + 1) % self.depth
+        if self._busy[k]:
+            self.events[k].synchronize()
+        if not (regression_host.is_pinned() and classification_host.is_pinned()):
+            raise ValueError("HostDetectionPipeline needs pinned host tensors")
+        with torch.cuda.stream(self.streams[k]):
+            self.cls_dev[k].copy_(classification_host, non_blocking=True)
+            res = self.head([self.shape, regression_host, self.cls_dev[k]])
+            for dst, src in zip(self.out[k], res):
+                dst.copy_(src, non_blocking=True)
+            self.events[k].record(self.streams[k])
+        self._busy[k] = True
+        return k
+
+    def result(self, k):
+        if not self._busy[k]:
+            raise RuntimeError("slot %d holds no submitted batch" % k)
+        self.events[k].synchronize()
+        self._busy[k] = False
+        return self.out[k]
+
+    def drain(self):
+        order = [(self._next + i) % self.depth for i in range(self.depth)]
+        return [[t.clone() for t in self.result(k)] for k in order if self._busy[k]]

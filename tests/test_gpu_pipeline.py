@@ -83,3 +83,31 @@ def test_host_step_pipeline_matches_run_from_host(rn, gather):
     rest = pipe.drain()
     assert len(rest) == 1 and np.array_equal(rest[0].numpy(), want[-1][0])
     assert pipe.drain() == []
+
+
+def test_host_detection_pipeline_matches_direct_head(rn):
+    """Batches in flight on two streams give the detections of the direct DetectionHead call, bit for bit."""
+    import synthetic
+    hw, B = (256, 320), 3
+    anchors = np.asarray(rn.anchors_for_shape(hw + (3,)))
+    head = rn.DetectionHead()
+    batches, want = [], []
+    for s in range(4):
+        anns = [synthetic.gt_for_page(3, 7 * s + i, hw=hw, gmax=5) for i in range(B)]
+        cls, reg = synthetic.inference_predictions(3, B, anchors, anns, classes=1, first_page=5 * s)
+        cls_h, reg_h = torch.from_numpy(cls).pin_memory(), torch.from_numpy(reg).pin_memory()
+        batches.append((reg_h, cls_h))
+        want.append([t.cpu() for t in head([(B,) + hw + (3,), reg_h.cuda(), cls_h.cuda()])])
+    pipe = rn.pipeline.HostDetectionPipeline(head, B, hw, depth=2)
+    pend = []
+    for s, (reg_h, cls_h) in enumerate(batches):
+        pend.append((s, pipe.submit(reg_h, cls_h)))
+        if len(pend) == 2:
+            t, k = pend.pop(0)
+            got = pipe.result(k)
+            assert all(torch.equal(g, w) for g, w in zip(got, want[t]))
+            assert int((got[1] >= 0).sum()) > 0
+    rest = pipe.drain()
+    assert len(rest) == 1 and all(torch.equal(g, w) for g, w in zip(rest[0], want[-1]))
+    with pytest.raises(ValueError):
+        pipe.submit(torch.zeros(1), batches[0][1])           # not pinned
