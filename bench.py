@@ -202,6 +202,10 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
+    # stdout carries ONE JSON line: everything else written to fd 1 (NCCL prints its version banner there) goes to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -460,7 +464,8 @@ def run_ours(args):
             line["per_level_heads"] = levels
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_leg()
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
