@@ -264,7 +264,8 @@ def run_ours(args):
         else:
             dist.all_reduce(check)
         assert float(check) == float(step.losses[2]) or float(check) < 1.0, (float(check), float(step.losses[2]))
-        exchange = "NVLink peer mailbox (rn_peer_publish + K2 prologue)" if step.peer is not None else "NCCL all_reduce"
+        exchange = ("NVLink peer mailbox, " + ("send + wait fused into K2 (CTA 0 stores the count into every rank's mailbox, all CTAs "
+                    "wait on local memory)" if step.peer_fused else "rn_peer_publish kernel + K2 prologue")) if step.peer is not None else "NCCL all_reduce"
     # timed region 1 (`value`): K steps of the product call -- step.run() replays ONE graph per step (K1 [+ publish] + K2)
     barrier()
     t_wall0 = time.perf_counter()
@@ -430,7 +431,7 @@ def run_ours(args):
                                         "gathers exactly those); the (B,N,4) tensor is not copied") if E2E_GATHER else "copied",
                     "full_copy": {"value": world * B * args.steps / (full_ms * 1e-3), "ms_per_step": full_ms / args.steps,
                                   "h2d_bytes_per_step": int(gt_bytes + cls_host.numel() * 4 + reg_host.numel() * 4)}},
-            "gpu_launches": (3 if step.peer is not None else 2) * args.steps,   # `value` region: K1 (+ publish) + K2 per step
+            "gpu_launches": step.kernel_launches_per_step * args.steps,   # `value` region: K1 + K2 per step (+ publish when not fused into K2)
             # the dominant kernel of the step by time is K1 (~74 %, profiles/*_launches_value_region.md): it is
             # reported first although it is instruction-issue bound, not HBM bound; K2 (the HBM-bound loss kernel
             # north_star sets the 60 % target for) follows

@@ -121,6 +121,11 @@ int rn_smooth_l1_fwd_bwd(const float* y_true_reg /*(R,5)*/, const float* y_pred 
                                     the sum of the counts all ranks published for the current step           */
 #define RN_LOSS_PEER_LAG1     8   /* with RN_LOSS_NPOS_PEER_BOX: use the step published BEFORE the latest one
                                     (pipelined schedule: K1 + publish of the next batch run ahead of this K2)  */
+#define RN_LOSS_PEER_PUBLISH  16  /* with RN_LOSS_NPOS_PEER_BOX on a mailbox prepared by rn_peer_box_bind: FUSED publish --
+                                    this launch itself stores the rank's count into every rank's mailbox (CTA 0, P2P
+                                    stores over NVLink) before all CTAs wait for the ranks' counts, and completes the
+                                    step when its last CTA finishes; rn_peer_publish is not called for such steps.
+                                    Send, wait and loss arithmetic are one kernel.  Not combinable with PEER_LAG1.      */
 int rn_loss_fwd_bwd(const float* y_true_cls, const float* cls_pred, const float* y_true_reg,
                     const float* reg_pred, long long R, int C,
                     float alpha, float gamma, int bce_mode, float sigma,
@@ -232,7 +237,12 @@ int rn_rescale_cut(const float* boxes, const float* scores, const float* image_s
  * waits (on local memory, inside the kernel) until all `world` counts of the step have arrived and
  * uses their sum (RN_LOSS_PEER_LAG1: the sum of the step before the latest, so that the next batch's K1 +
  * publish can be enqueued ahead of this batch's losses and the exchange leaves the critical path; up to 4 steps
- * are kept).  No NCCL call, no host synchronisation, CUDA-graph capturable.  All ranks must run
+ * are kept).  Fused form (the in-order schedule's default): rn_peer_box_bind(box[rank], boxes, rank, world,
+ * npos_total_dev) once, then per step only
+ *     rn_loss_fwd_bwd(..., npos_dev = box[rank], ..., flags | RN_LOSS_NPOS_PEER_BOX | RN_LOSS_PEER_PUBLISH, ...)
+ * -- the loss kernel sends this rank's count itself (no publish launch between K1 and K2).  A step's further loss
+ * launches (page chunks) pass RN_LOSS_NPOS_PEER_BOX alone and read the completed step.
+ * No NCCL call, no host synchronisation, CUDA-graph capturable.  All ranks must run
  * the same sequence of publish / loss steps; a peer that never publishes turns the losses into NaN
  * after ~2 s instead of hanging the GPU.  world <= 16 (one NVSwitch domain).
  * ------------------------------------------------------------------------------------------- */
@@ -241,6 +251,10 @@ int rn_peer_box_create(int world, void** box_out, void* ipc_handle_out64);
 int rn_peer_box_open(const void* ipc_handle64, void** peer_box_out);
 int rn_peer_box_close(void* peer_box);
 int rn_peer_box_destroy(void* box);
+/* records in the local mailbox what RN_LOSS_PEER_PUBLISH needs: every rank's mailbox pointer (as mapped into this
+ * process, boxes_of_all_ranks[rank] == local_box), this rank, and the device float it publishes.  Synchronous, once. */
+int rn_peer_box_bind(void* local_box, void* const* boxes_of_all_ranks /* host, (world) */, int rank, int world,
+                     const float* value_dev);
 int rn_peer_publish(const float* value_dev, void* local_box, void* const* boxes_of_all_ranks /* host, (world) */,
                     int rank, int world, void* stream);
 

@@ -20,6 +20,7 @@ RN_LOSS_SHARED_STATE = 1
 RN_LOSS_NPOS_PEER_BOX = 2
 RN_LOSS_FROM_LOGITS = 4
 RN_LOSS_PEER_LAG1 = 8
+RN_LOSS_PEER_PUBLISH = 16
 RN_MAX_WORLD = 16
 
 
@@ -66,6 +67,7 @@ SIGNATURES = {
     "rn_peer_box_open": (c_int, [c_void_p, POINTER(c_void_p)]),
     "rn_peer_box_close": (c_int, [c_void_p]),
     "rn_peer_box_destroy": (c_int, [c_void_p]),
+    "rn_peer_box_bind": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, _P]),
     "rn_peer_publish": (c_int, [_P, c_void_p, POINTER(c_void_p), c_int, c_int, _P]),
 }
 

@@ -8,6 +8,10 @@
 // order (integer-valued floats: exact and identical on every rank).  No NCCL launch, no host round trip, and both
 // kernels stay capturable in CUDA graphs (the step number lives in device memory, not in a kernel argument).
 //
+// Fused publish (rn_peer_box_bind + RN_LOSS_PEER_PUBLISH, the in-order schedule's default): the publish kernel
+// disappears -- K2's CTA 0 stores the word into every mailbox in its prologue, right before all CTAs start waiting,
+// and K2's last CTA bumps the step counter; see rn_peer_box_sum_warp().  Send, wait and the loss arithmetic are ONE kernel.
+//
 // Slots are indexed by step % 4.  Two schedules are supported, identical on all ranks:
 //   in order    K1(s) publish(s) K2(s) K1(s+1) publish(s+1) K2(s+1) ...           K2 reads its latest step (lag 0)
 //   pipelined   K1(s+1) publish(s+1) K2(s) K1(s+2) publish(s+2) K2(s+1) ...       K2 reads the step before (lag 1):
@@ -16,6 +20,7 @@
 // Overwrite safety (pipelined, the stricter case): rank r stores step s+4 into slot s % 4 only after its own K2(s+2)
 // has returned, which has seen every rank p's publish(s+2), which p issues after its K2(s) in stream order -- so
 // every rank has consumed step s before anyone overwrites it.  All ranks must run the same sequence of steps.
+#include <stddef.h>
 #include "rn_common.cuh"
 #include "peer_box.cuh"
 
@@ -55,6 +60,25 @@ extern "C" int rn_peer_box_create(int world, void** box_out, void* ipc_handle_ou
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(ipc_handle_out64), d);
     if (e != cudaSuccess) { cudaFree(d); return rn_fail(RN_ERR_CUDA, "peer box setup: %s", cudaGetErrorString(e)); }
     *box_out = d;
+    return RN_OK;
+}
+
+extern "C" int rn_peer_box_bind(void* local_box, void* const* boxes_of_all_ranks, int rank, int world, const float* value_dev) {
+    RN_REQUIRE(local_box && boxes_of_all_ranks && value_dev, "NULL pointer");
+    RN_REQUIRE(world >= 1 && world <= RN_MAX_WORLD && rank >= 0 && rank < world, "bad rank / world (%d / %d)", rank, world);
+    RN_REQUIRE(boxes_of_all_ranks[rank] == local_box, "boxes_of_all_ranks[rank] must be the local box");
+    RnPeerBox host = {};
+    host.rank = rank;
+    host.value = value_dev;
+    for (int r = 0; r < world; ++r) {
+        RN_REQUIRE(boxes_of_all_ranks[r] != nullptr, "box of rank %d is NULL", r);
+        host.peers[r] = reinterpret_cast<RnPeerBox*>(boxes_of_all_ranks[r]);
+    }
+    // rank, value and peers are contiguous in the struct: one copy, `step`, `world` and the slots stay untouched
+    const size_t off = offsetof(RnPeerBox, rank), len = offsetof(RnPeerBox, slots) - off;
+    cudaError_t e = cudaMemcpy(reinterpret_cast<char*>(local_box) + off, reinterpret_cast<const char*>(&host) + off, len,
+                               cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "peer box bind: %s", cudaGetErrorString(e));
     return RN_OK;
 }
 

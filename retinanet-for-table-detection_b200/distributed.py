@@ -78,6 +78,7 @@ class PeerCounter(object):
     def __init__(self, rank, world, box, peers):
         self.rank, self.world, self.box, self.peers = rank, world, box, peers
         self._arr = (ctypes.c_void_p * world)(*peers)
+        self.bound = None
 
     @classmethod
     def create(cls, group=None):
@@ -120,6 +121,14 @@ class PeerCounter(object):
                 lib.rn_peer_box_destroy(box)
             return None
         return cls(rank, world, box.value, peers)
+
+    def bind(self, value):
+        """Prepare the FUSED publish: record the peers' mailboxes, this rank and the 1-float device tensor ``value``
+        (K1's positive count) in the local mailbox, so that the loss kernel launched with ``peer_publish=True`` sends
+        the count itself -- no publish launch between K1 and K2.  ``value`` must stay allocated."""
+        _lib.check(_lib.load().rn_peer_box_bind(ctypes.c_void_p(self.box), self._arr, self.rank, self.world, _lib.ptr(value)),
+                   "rn_peer_box_bind")
+        self.bound = value
 
     def publish(self, value, device=None):
         """Enqueue the publication of the 1-float device tensor ``value`` (this rank's positive count)."""

@@ -120,7 +120,7 @@ def smooth_l1(sigma=3.0):
 
 def detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None,
                      alpha=0.25, gamma=2.0, sigma=3.0, bce="tf2", want_grads=True, out=None, workspace=None,
-                     shared_state=False, peer_box=None, peer_lag=0):
+                     shared_state=False, peer_box=None, peer_lag=0, peer_publish=False):
     """Both losses, forward + backward, in ONE launch of K2 (``rn_loss_fwd_bwd``).
 
     All tensors are float32 CUDA: ``y_true_reg`` (B,N,5), ``y_true_cls`` (B,N,C+1) in the order
@@ -134,7 +134,9 @@ def detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None
 
     ``peer_box``: a :class:`distributed.PeerCounter` whose ``publish`` was enqueued for this step on every rank;
     the kernel then takes the sum of the published counts as the normaliser (``normalizer`` is ignored);
-    ``peer_lag=1`` selects the step published before the latest one (pipelined schedule, see ``pipeline``)."""
+    ``peer_lag=1`` selects the step published before the latest one (pipelined schedule, see ``pipeline``).
+    ``peer_publish=True`` (``peer_box.bind(count)`` done once): fused publish -- this launch sends the rank's count
+    itself and completes the step, ``publish`` is not called for it."""
     device = cls_pred.device
     C = cls_pred.shape[-1]
     R = cls_pred.numel() // C
@@ -152,6 +154,10 @@ def detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None
     if peer_box is not None:                              # normaliser = sum of the counts the ranks published
         npos_ptr = ctypes.c_void_p(peer_box.box)
         flags |= _lib.RN_LOSS_NPOS_PEER_BOX | (_lib.RN_LOSS_PEER_LAG1 if peer_lag else 0)
+        if peer_publish:
+            if peer_lag or peer_box.bound is None:
+                raise ValueError("peer_publish needs peer_box.bind(count) and is not combinable with peer_lag")
+            flags |= _lib.RN_LOSS_PEER_PUBLISH
     else:
         npos = _norm_tensor(normalizer, device)
         npos_ptr = _lib.ptr(npos)

@@ -17,6 +17,8 @@ all-reduced between the two halves.
 
 This is host plumbing around the C-ABI; it adds no arithmetic of its own.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -72,6 +74,13 @@ class TargetLossStep(object):
         # run_from_host(): copy stream, per-chunk events, per-chunk loss rows
         rank, world = _dist.world()
         self.peer = _dist.PeerCounter.create() if peer_box else None   # NVLink mailbox; None with one rank / no peer access
+        # fused publish: K2 sends this rank's count itself (CTA 0, P2P stores) before waiting for the others' --
+        # no publish launch between K1 and K2 (RN_B200_PEER_FUSED=0: the separate rn_peer_publish kernel)
+        self.peer_fused = self.peer is not None and os.environ.get("RN_B200_PEER_FUSED", "1") != "0"
+        if self.peer_fused:
+            self.peer.bind(self.npos_total)
+        else:
+            self.kernel_launches_per_step += 1 if self.peer is not None else 0
         # run_pipelined(): second set of target buffers, graphs per buffer
         self._pipe = None
         self._copy_stream = None
@@ -97,7 +106,7 @@ class TargetLossStep(object):
         _anchors.anchor_targets_device(self.spec, self.d_boxes, self.d_labels, self.d_counts, self.d_hw, self.C,
                                        self.neg, self.pos, out=(self.y_reg, self.y_cls), npos_total=self.npos_total,
                                        npos_out=self.npos)
-        if self.peer is not None:
+        if self.peer is not None and not self.peer_fused:
             self.peer.publish(self.npos_total, self.device)     # this rank's count -> every rank's mailbox
 
     def _exchange(self):
@@ -108,7 +117,7 @@ class TargetLossStep(object):
     def _losses(self):
         _losses.detection_losses(self.y_reg, self.y_cls, self.reg_pred, self.cls_pred, normalizer=self.npos_total,
                                  out=(self.losses, self.grad_cls, self.grad_reg), workspace=self.loss_ws,
-                                 peer_box=self.peer, **self.loss_kw)
+                                 peer_box=self.peer, peer_publish=self.peer_fused, **self.loss_kw)
 
     def _capture(self, fn):
         g = torch.cuda.CUDAGraph()
@@ -291,7 +300,9 @@ class TargetLossStep(object):
             _losses.detection_losses(sl(self.y_reg), sl(self.y_cls), sl(reg_src), sl(self.cls_pred),
                                      normalizer=self.npos_total,
                                      out=(self._chunk_losses[i], sl(self.grad_cls), sl(self.grad_reg)),
-                                     workspace=self.loss_ws, peer_box=self.peer, **self.loss_kw)
+                                     workspace=self.loss_ws, peer_box=self.peer,
+                                     peer_publish=self.peer_fused and i == 0,     # the step's first launch sends the count
+                                     **self.loss_kw)
         self._losses_host.copy_(self._chunk_losses, non_blocking=True)
         self._done_event.record(compute)
 

@@ -111,3 +111,39 @@ def test_host_detection_pipeline_matches_direct_head(rn):
     assert len(rest) == 1 and all(torch.equal(g, w) for g, w in zip(rest[0], want[-1]))
     with pytest.raises(ValueError):
         pipe.submit(torch.zeros(1), batches[0][1])           # not pinned
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_peer_mailbox_one_rank(rn, monkeypatch, fused):
+    """The count exchange through the peer mailbox on ONE GPU (a one-rank mailbox: publish to self, wait on self), with
+    the publish fused into K2 and as a separate kernel: same losses / gradients as without a mailbox, over several
+    steps (the slots rotate), through the one-graph step, the split graphs and the chunked host-input step."""
+    import synthetic
+    hw, B = (256, 320), 4
+    N = rn.anchors_for_shape(hw + (3,)).shape[0]
+    imgs = [synthetic.PageShape(hw + (3,)) for _ in range(B)]
+    cls, reg = synthetic.training_predictions(5, B, N, classes=1)
+    cls_h, reg_h = torch.from_numpy(cls).pin_memory(), torch.from_numpy(reg).pin_memory()
+    plain = rn.pipeline.TargetLossStep(hw + (3,), B, 8, 1)
+    assert plain.peer is None
+    monkeypatch.setenv("RN_B200_PEER_BOX", "force")
+    monkeypatch.setenv("RN_B200_PEER_FUSED", fused)
+    boxed = rn.pipeline.TargetLossStep(hw + (3,), B, 8, 1)
+    assert boxed.peer is not None and boxed.peer_fused == (fused == "1")
+    assert boxed.kernel_launches_per_step == (2 if fused == "1" else 3)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for s in range(7):                                    # > RN_PEER_SLOTS steps
+        anns = [synthetic.gt_for_page(2, 10 * s + i, hw=hw, gmax=6) for i in range(B)]
+        for st in (plain, boxed):
+            st.load_annotations(imgs, anns)
+            st.load_predictions(cls_h, reg_h)
+        want = plain.run().cpu().numpy().copy()
+        if s % 3 == 0:
+            got = boxed.run().cpu().numpy()
+        elif s % 3 == 1:
+            got = boxed.run(events=evs).cpu().numpy()
+        else:
+            got = boxed.run_from_host(imgs, anns, cls_h, reg_h, chunks=3).numpy()
+        assert got[2] == want[2] and want[2] >= 1
+        assert np.allclose(got[:2], want[:2], rtol=1e-6, atol=0)
+        assert torch.equal(boxed.grad_cls, plain.grad_cls) and torch.equal(boxed.grad_reg, plain.grad_reg)
