@@ -7,7 +7,9 @@ Workload (BASELINE.json configs[1]): the training-target path on a batch of 16 p
 forward and backward).  One "step" = one batch per GPU; per-GPU work is fixed as N grows (weak scaling),
 pages shard by image, the only exchange is the positive-anchor count (NVLink peer mailbox, or NCCL all-reduce).
 
-`value`  = pages/s with the batch's inputs resident in HBM (GT block + head outputs), CUDA events.
+`value`  = pages/s with the batch's inputs resident in HBM (GT block + head outputs), CUDA events.  Every step launches
+           one K1 and one K2 as two branches of one CUDA graph: K1 on the batch loaded now, K2 on the batch before it
+           (double-buffered targets; bit-identical to `in_order`, which is K1(s) then K2(s) and reported beside it).
 `e2e`    = pages/s through the public Python API (HostStepPipeline.submit / result) with HOST inputs every step: the
            ragged GT list is packed and copied, the head outputs are copied from pinned memory on a copy stream, K1 +
            K2 run, the loss scalars are read back; two steps are in flight so the copy of step s+1 overlaps the
@@ -224,12 +226,12 @@ def run_ours(args):
     N = anchors.shape[0]
     first = rank * B
     if world > 1 and not args.contiguous_shards:
-        # the global batch (world x 16 pages) is sharded by GT count so that every rank's K1 takes about the same
+        # the global batch (world x 16 pages) is sharded by estimated K1 cost so that every rank's K1 takes about the same
         # time (distributed.balanced_shards); every rank derives the same assignment from the annotations
         g_images, g_anns = synthetic.training_batch(CFG, batch=world * B, anchors=np.asarray(anchors), first_page=0)
-        mine = rn.distributed.balanced_shards([len(a['labels']) for a in g_anns], world)[rank]
+        mine = rn.distributed.balanced_shards(rn.distributed.page_cost(g_anns, HW), world)[rank]
         images, anns = [g_images[i] for i in mine], [g_anns[i] for i in mine]
-        sharding = "pages of the global batch dealt out by GT count (balanced_shards)"
+        sharding = "pages of the global batch dealt out by estimated K1 cost (distributed.page_cost + balanced_shards)"
     else:
         images, anns = synthetic.training_batch(CFG, batch=B, anchors=np.asarray(anchors), first_page=first)
         sharding = "contiguous page ranges"
@@ -278,8 +280,11 @@ def run_ours(args):
     t_wall1 = time.perf_counter()
     total_ms = v0.elapsed_time(v1)
     # extra: the overlapped schedule (K1 of the next batch concurrently with K2 of this one, two graph branches)
-    ov_ms = float("nan")
-    if world == 1:
+    ov_ms, ov_match = float("nan"), None
+    inorder_losses = step.losses.clone()
+    if world == 1 or step.peer_fused:
+        # (several ranks: K2 of batch s sends and collects the counts of batch s itself while K1 of batch s+1 runs beside
+        # it -- fused publish -- so the exchange and the skew between ranks hide behind the longer kernel)
         for _ in range(5):
             step.run_pipelined(overlap=True)
         barrier()
@@ -290,6 +295,8 @@ def run_ours(args):
         o1.record()
         barrier()
         ov_ms = o0.elapsed_time(o1)
+        ov_match = bool(torch.equal(step.losses, inorder_losses))     # same batch every step -> same bits as in order
+        t_wall1 = time.perf_counter()
     # timed region 2 (per-kernel durations for the rooflines): the same K steps with the two halves replayed
     # separately and CUDA events between them (costs one more graph launch per step, so it is not the `value`)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
@@ -362,10 +369,14 @@ def run_ours(args):
         full_ms = f0.elapsed_time(f1)
     sampler.stop_flag = True
 
-    times = torch.tensor([total_ms, e2e_ms, k1_ms, k2_ms, split_ms, full_ms, sync_ms], dtype=torch.float64, device=device)
+    times = torch.tensor([total_ms, e2e_ms, k1_ms, k2_ms, split_ms, full_ms, sync_ms, ov_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, k1_ms, k2_ms, split_ms, full_ms, sync_ms = [float(x) for x in times.cpu()]
+    total_ms, e2e_ms, k1_ms, k2_ms, split_ms, full_ms, sync_ms, ov_ms = [float(x) for x in times.cpu()]
+    # `value`: the overlapped schedule (K1 of batch s+1 beside K2 of batch s: one K1 + one K2 per step, one graph launch)
+    # unless --schedule in-order or the schedule is unavailable (several ranks without the peer mailbox)
+    overlapped = args.schedule == "overlapped" and ov_ms == ov_ms and not pipelined
+    value_ms = ov_ms if overlapped else total_ms
 
     # ---- N2 (extra object): K2 fed by the per-level head outputs, sigmoid fused ---------------------------
     levels = None
@@ -410,15 +421,20 @@ def run_ours(args):
         k1_bytes = 4 * (5 + C + 1) * N * B            # 28 B/anchor at C=1
         achieved = k2_bytes / (k2_ms * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": world * B * args.steps / (total_ms * 1e-3), "unit": "pages/s",
+            "metric": METRIC, "value": world * B * args.steps / (value_ms * 1e-3), "unit": "pages/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": value_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64 matching + f32 targets/losses", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pages_per_gpu": B, "anchors_per_page": N, "classes": C,
                        "l2": "working set per step ~%d MB (> 126 MB L2), no explicit flush" % ((k1_bytes + k2_bytes) // (1 << 20)),
                        "cuda_graphs": True, "count_exchange": exchange, "sharding": sharding,
-                       "schedule": ("pipelined: K1 + publish of batch s+1 enqueued ahead of K2 of batch s (mailbox lag 1, "
-                                    "double-buffered targets)") if pipelined else "in order: K1(s), K2(s)"},
+                       "schedule": ("overlapped: every step launches K1 of batch s+1 and K2 of batch s as two branches of one "
+                                    "graph (TargetLossStep.run_pipelined(overlap=True), double-buffered targets; bit-identical "
+                                    "to in order)") if overlapped else
+                                   ("pipelined: K1 of batch s+1 enqueued ahead of K2 of batch s (double-buffered targets)"
+                                    if pipelined else "in order: K1(s), K2(s)")},
+            "in_order": {"pages_per_s": world * B * args.steps / (total_ms * 1e-3), "ms_per_step": total_ms / args.steps,
+                         "note": "TargetLossStep.run(): K1(s) then K2(s), one graph launch per step"},
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "pages/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 12 * E2E_CHUNKS, "ms_per_step": e2e_ms / args.steps,
                     "h2d_GBps": h2d / (e2e_ms / args.steps * 1e-3) / 1e9,
@@ -451,7 +467,9 @@ def run_ours(args):
             "ms_per_step_split_graphs": split_ms / args.steps,
             "overlapped_schedule": None if ov_ms != ov_ms else {
                 "pages_per_s": world * B * args.steps / (ov_ms * 1e-3), "ms_per_step": ov_ms / args.steps,
-                "note": "TargetLossStep.run_pipelined(overlap=True): K1 of batch s+1 and K2 of batch s as two branches of one graph"},
+                "losses_equal_in_order": ov_match,
+                "note": "TargetLossStep.run_pipelined(overlap=True): K1 of batch s+1 and K2 of batch s as two branches of one graph"
+                        + ("; K2 sends and collects the ranks' positive counts itself (fused publish), hidden behind K1" if world > 1 else "")},
             "kernels": {"K1_anchor_targets": {"us": k1_ms * 1e3, "algorithmic_bytes": k1_bytes,
                                               "GBps": k1_bytes / (k1_ms * 1e-3) / 1e9},
                         "K2_losses": {"us": k2_ms * 1e3, "algorithmic_bytes": k2_bytes, "GBps": achieved}},
@@ -584,6 +602,8 @@ def main():
     ap.add_argument("--no-inference", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--contiguous-shards", action="store_true", help="several ranks: rank r takes pages [16r, 16r+16) instead of the load-aware deal")
+    ap.add_argument("--schedule", default="overlapped", choices=["overlapped", "in-order"],
+                    help="what `value` times: K1 of batch s+1 beside K2 of batch s (default) or K1(s) then K2(s); both are measured")
     ap.add_argument("--pipelined", action="store_true", help="several ranks: enqueue K1 + publish of batch s+1 ahead of K2 of batch s "
                     "(TargetLossStep.run_pipelined; measured 3 %% slower than in order at N = 2 and 8, so not the default)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-input leg (used for the ncu launch list of the `value` region)")

@@ -252,9 +252,15 @@ int rn_peer_box_open(const void* ipc_handle64, void** peer_box_out);
 int rn_peer_box_close(void* peer_box);
 int rn_peer_box_destroy(void* box);
 /* records in the local mailbox what RN_LOSS_PEER_PUBLISH needs: every rank's mailbox pointer (as mapped into this
- * process, boxes_of_all_ranks[rank] == local_box), this rank, and the device float it publishes.  Synchronous, once. */
+ * process, boxes_of_all_ranks[rank] == local_box), this rank, and the device floats it publishes: the loss launch that
+ * completes step t (steps count from 1, rn_peer_box_step() + 1 is the next) sends value_even_dev for even t and
+ * value_odd_dev for odd t -- pass the same pointer twice unless the targets are double-buffered (pipelined schedule:
+ * K1 of the next batch runs concurrently with this batch's loss launch).  Synchronous (cudaMemcpy); the stream that
+ * uses the mailbox must be idle. */
 int rn_peer_box_bind(void* local_box, void* const* boxes_of_all_ranks /* host, (world) */, int rank, int world,
-                     const float* value_dev);
+                     const float* value_even_dev, const float* value_odd_dev);
+/* number of steps this rank has completed / published so far (synchronous read of the device counter) */
+int rn_peer_box_step(const void* local_box, unsigned long long* step_out);
 int rn_peer_publish(const float* value_dev, void* local_box, void* const* boxes_of_all_ranks /* host, (world) */,
                     int rank, int world, void* stream);
 

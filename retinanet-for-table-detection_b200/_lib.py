@@ -67,7 +67,8 @@ SIGNATURES = {
     "rn_peer_box_open": (c_int, [c_void_p, POINTER(c_void_p)]),
     "rn_peer_box_close": (c_int, [c_void_p]),
     "rn_peer_box_destroy": (c_int, [c_void_p]),
-    "rn_peer_box_bind": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, _P]),
+    "rn_peer_box_bind": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, _P, _P]),
+    "rn_peer_box_step": (c_int, [c_void_p, POINTER(ctypes.c_ulonglong)]),
     "rn_peer_publish": (c_int, [_P, c_void_p, POINTER(c_void_p), c_int, c_int, _P]),
 }
 

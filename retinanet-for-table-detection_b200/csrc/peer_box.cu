@@ -63,13 +63,23 @@ extern "C" int rn_peer_box_create(int world, void** box_out, void* ipc_handle_ou
     return RN_OK;
 }
 
-extern "C" int rn_peer_box_bind(void* local_box, void* const* boxes_of_all_ranks, int rank, int world, const float* value_dev) {
-    RN_REQUIRE(local_box && boxes_of_all_ranks && value_dev, "NULL pointer");
+extern "C" int rn_peer_box_step(const void* local_box, unsigned long long* step_out) {
+    RN_REQUIRE(local_box && step_out, "NULL pointer");
+    cudaError_t e = cudaMemcpy(step_out, reinterpret_cast<const char*>(local_box) + offsetof(RnPeerBox, step), sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "peer box step: %s", cudaGetErrorString(e));
+    return RN_OK;
+}
+
+extern "C" int rn_peer_box_bind(void* local_box, void* const* boxes_of_all_ranks, int rank, int world,
+                                const float* value_even_dev, const float* value_odd_dev) {
+    RN_REQUIRE(local_box && boxes_of_all_ranks && value_even_dev && value_odd_dev, "NULL pointer");
     RN_REQUIRE(world >= 1 && world <= RN_MAX_WORLD && rank >= 0 && rank < world, "bad rank / world (%d / %d)", rank, world);
     RN_REQUIRE(boxes_of_all_ranks[rank] == local_box, "boxes_of_all_ranks[rank] must be the local box");
     RnPeerBox host = {};
     host.rank = rank;
-    host.value = value_dev;
+    host.value[0] = value_even_dev;
+    host.value[1] = value_odd_dev;
     for (int r = 0; r < world; ++r) {
         RN_REQUIRE(boxes_of_all_ranks[r] != nullptr, "box of rank %d is NULL", r);
         host.peers[r] = reinterpret_cast<RnPeerBox*>(boxes_of_all_ranks[r]);

@@ -9,7 +9,8 @@ struct RnPeerBox {
     unsigned long long step;                        // last step this rank published (bumped on the device)
     int world;
     int rank;                                       // fused publish (rn_peer_box_bind): this rank,
-    const float* value;                             //   the device float it publishes (K1's positive count),
+    const float* value[2];                          //   the device float it publishes for a step: value[step & 1] (K1's
+                                                    //   positive count; two so that double-buffered targets alternate),
     RnPeerBox* peers[RN_MAX_WORLD];                 //   and every rank's mailbox as mapped into this process
     unsigned long long slots[RN_PEER_SLOTS][RN_MAX_WORLD];   // [step % 4][rank] = step << 32 | float bits of the rank's value
 };
@@ -35,7 +36,7 @@ __device__ __forceinline__ float rn_peer_box_sum_warp(const RnPeerBox* box, int 
     const unsigned long long step = publish ? b->step + 1ull : b->step - (unsigned long long)lag;   // lag 1: the step published before the latest one
     const int world = b->world, lane = threadIdx.x & 31;
     if (publish && blockIdx.x == 0 && lane < world) {
-        const unsigned long long word = (step << 32) | (unsigned long long)__float_as_uint(__ldcg(box->value));
+        const unsigned long long word = (step << 32) | (unsigned long long)__float_as_uint(__ldcg(box->value[step & 1]));
         volatile unsigned long long* slot = &box->peers[lane]->slots[step & (RN_PEER_SLOTS - 1)][box->rank];
         *slot = word;                               // one aligned 8-byte store per peer: count and step arrive together
     }

@@ -9,6 +9,7 @@ any ``torch.distributed`` backend (NCCL over NVLink on the GPU box; gloo in the 
 import ctypes
 import os
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -44,6 +45,43 @@ def balanced_shards(weights, world_size):
         rnd, pos = divmod(k, int(world_size))
         shards[pos if rnd % 2 == 0 else int(world_size) - 1 - pos].append(page)
     return [sorted(s) for s in shards]
+
+
+def page_cost(annotations_group, image_hw, anchor_params=None, pyramid_levels=None, fixed=None):
+    """K1's cost of each page, for :func:`balanced_shards`: the kernel does a fixed amount of work per anchor plus one
+    IoU per (anchor, GT table) pair that overlaps, so the estimate is ``fixed + pairs`` with
+    ``pairs = sum over tables, levels, anchor types of (w + aw)(h + ah) / stride^2`` (the number of anchor centres whose
+    box can touch the table; closed form, no anchors are generated).  ``fixed`` defaults to the measured ratio
+    (``profiles/k1_page_cost.py``): the per-anchor work of a page equals ~PAIRS_PER_FIXED overlapping pairs.
+    Deterministic from the annotations alone, so every rank derives the same sharding without communication."""
+    from . import anchors as _anchors
+    ap = anchor_params or _anchors.AnchorParameters_default
+    levels = pyramid_levels or [3, 4, 5, 6, 7]
+    ratios, scales = np.asarray(ap.ratios, dtype=np.float64), np.asarray(ap.scales, dtype=np.float64)
+    aw, ah, inv_s2 = [], [], []
+    for size, stride in zip(ap.sizes, ap.strides):
+        base = _anchors.generate_anchors(size, ap.ratios, ap.scales)
+        aw.append(base[:, 2] - base[:, 0])
+        ah.append(base[:, 3] - base[:, 1])
+        inv_s2.append(np.full(base.shape[0], 1.0 / (float(stride) * float(stride))))
+    aw, ah, inv_s2 = np.concatenate(aw), np.concatenate(ah), np.concatenate(inv_s2)
+    H, W = float(image_hw[0]), float(image_hw[1])
+    if fixed is None:
+        n_anchors = sum(len(ratios) * len(scales) * (-(-int(H) // s)) * (-(-int(W) // s)) for s in ap.strides[:len(levels)])
+        fixed = PAIRS_PER_FIXED * n_anchors
+    out = []
+    for ann in annotations_group:
+        bb = np.asarray(ann['bboxes'], dtype=np.float64).reshape(-1, 4) if len(ann['bboxes']) else np.zeros((0, 4))
+        w = np.clip(bb[:, 2] - bb[:, 0], 0, None)[:, None]
+        h = np.clip(bb[:, 3] - bb[:, 1], 0, None)[:, None]
+        pairs = (np.minimum(w + aw, W + aw) * np.minimum(h + ah, H + ah) * inv_s2).sum()
+        out.append(float(fixed + pairs))
+    return out
+
+
+# K1 on 16 copies of one 800x1333 page: 43.3 us + 3.68e-5 us per overlapping (anchor, table) pair of the page (32 pages,
+# rms error 1.5 us; profiles/k1_page_cost.py), i.e. the fixed per-anchor work of a page equals 5.9 pairs per anchor
+PAIRS_PER_FIXED = 5.9
 
 
 def global_positive_count(npos_per_page, group=None):
@@ -122,13 +160,22 @@ class PeerCounter(object):
             return None
         return cls(rank, world, box.value, peers)
 
-    def bind(self, value):
+    def bind(self, value, value_odd=None):
         """Prepare the FUSED publish: record the peers' mailboxes, this rank and the 1-float device tensor ``value``
         (K1's positive count) in the local mailbox, so that the loss kernel launched with ``peer_publish=True`` sends
-        the count itself -- no publish launch between K1 and K2.  ``value`` must stay allocated."""
-        _lib.check(_lib.load().rn_peer_box_bind(ctypes.c_void_p(self.box), self._arr, self.rank, self.world, _lib.ptr(value)),
-                   "rn_peer_box_bind")
-        self.bound = value
+        the count itself -- no publish launch between K1 and K2.  With ``value_odd`` the launch completing an odd
+        step sends that tensor instead (double-buffered targets, see ``pipeline``).  Synchronous; the tensors must stay
+        allocated and the stream using the mailbox must be idle."""
+        odd = value if value_odd is None else value_odd
+        _lib.check(_lib.load().rn_peer_box_bind(ctypes.c_void_p(self.box), self._arr, self.rank, self.world, _lib.ptr(value),
+                                                _lib.ptr(odd)), "rn_peer_box_bind")
+        self.bound = (value, odd)
+
+    def steps(self):
+        """Steps this rank has completed / published so far (synchronous read of the device counter)."""
+        out = ctypes.c_ulonglong(0)
+        _lib.check(_lib.load().rn_peer_box_step(ctypes.c_void_p(self.box), ctypes.byref(out)), "rn_peer_box_step")
+        return int(out.value)
 
     def publish(self, value, device=None):
         """Enqueue the publication of the 1-float device tensor ``value`` (this rank's positive count)."""

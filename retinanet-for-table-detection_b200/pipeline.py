@@ -77,8 +77,9 @@ class TargetLossStep(object):
         # fused publish: K2 sends this rank's count itself (CTA 0, P2P stores) before waiting for the others' --
         # no publish launch between K1 and K2 (RN_B200_PEER_FUSED=0: the separate rn_peer_publish kernel)
         self.peer_fused = self.peer is not None and os.environ.get("RN_B200_PEER_FUSED", "1") != "0"
+        self._peer_mode = None                 # what the mailbox's value pointers are bound for: 'inorder' / 'pipe'
         if self.peer_fused:
-            self.peer.bind(self.npos_total)
+            self._bind_inorder()
         else:
             self.kernel_launches_per_step += 1 if self.peer is not None else 0
         # run_pipelined(): second set of target buffers, graphs per buffer
@@ -88,6 +89,13 @@ class TargetLossStep(object):
         self._chunk_events = None
         self._losses_host = None
         self._done_event = None
+
+    def _bind_inorder(self):
+        """Fused publish, in-order schedule: every step's loss launch sends ``npos_total``."""
+        if self._peer_mode != 'inorder':
+            torch.cuda.synchronize(self.device)
+            self.peer.bind(self.npos_total)
+            self._peer_mode = 'inorder'
 
     # ---- inputs ---------------------------------------------------------------------------------
     def load_annotations(self, image_group, annotations_group):
@@ -159,21 +167,37 @@ class TargetLossStep(object):
             y_reg, y_cls, npos, npos_total = bufs[i]
             _anchors.anchor_targets_device(self.spec, self.d_boxes, self.d_labels, self.d_counts, self.d_hw, self.C,
                                            self.neg, self.pos, out=(y_reg, y_cls), npos_total=npos_total, npos_out=npos)
-            if self.peer is not None:
+            if self.peer is not None and not self.peer_fused:
                 self.peer.publish(npos_total, self.device)
 
         def losses(i):
             y_reg, y_cls, npos, npos_total = bufs[i]
+            # fused publish: the loss launch of batch s sends the count of batch s itself (from the buffer bound for the
+            # step's parity) and waits for the other ranks' -- while K1 of batch s+1 runs beside it, so the exchange and
+            # the skew between ranks are hidden behind the longer kernel.  Separate publish kernel: mailbox lag 1.
             _losses.detection_losses(y_reg, y_cls, self.reg_pred, self.cls_pred, normalizer=npos_total,
                                      out=(self.losses, self.grad_cls, self.grad_reg), workspace=self.loss_ws,
-                                     peer_box=self.peer, peer_lag=1, **self.loss_kw)
+                                     peer_box=self.peer, peer_lag=0 if self.peer_fused else 1,
+                                     peer_publish=self.peer_fused, **self.loss_kw)
+        if self.peer_fused:
+            # the loss launch completing step t sends value[t & 1]: bind the two count buffers so that the warm-up's
+            # losses(0) (step t0 = steps() + 1) reads buffer 0 and the following steps alternate 1, 0, 1, ...
+            torch.cuda.synchronize(d)
+            t0 = self.peer.steps() + 1
+            pair = (bufs[0][3], bufs[1][3]) if t0 % 2 == 0 else (bufs[1][3], bufs[0][3])
+            self.peer.bind(*pair)
+            self._peer_mode = 'pipe'
         # warm-up outside capture keeps every rank's publish count equal: one full in-order-equivalent round
         s = torch.cuda.Stream(d)
         s.wait_stream(torch.cuda.current_stream(d))
         with torch.cuda.stream(s):
             targets(0)
-            targets(1)
-            losses(0)
+            if self.peer_fused:
+                losses(0)
+                targets(1)
+            else:
+                targets(1)
+                losses(0)
         torch.cuda.current_stream(d).wait_stream(s)
         torch.cuda.synchronize(d)
         side = (torch.cuda.Stream(d), torch.cuda.Stream(d))
@@ -206,9 +230,20 @@ class TargetLossStep(object):
         loaded), then K2 for the batch whose targets were produced by the previous call.  ``losses`` / ``grad_*``
         then refer to that previous batch; ``targets_of_losses()`` returns its target tensors.
         ``overlap=True``: the two kernels run concurrently on two streams (one graph launch per step)."""
+        if overlap and self.peer is not None and not self.peer_fused:
+            raise ValueError("overlap=True with several ranks needs the fused publish (the separate publish kernel would "
+                             "bump the step counter while K2 of the previous batch reads it)")
         if self._pipe is None:
             self._pipe_setup()
         pp = self._pipe
+        if self.peer_fused and self._peer_mode != 'pipe':
+            # in-order steps ran in between: bind the count buffers again so that the next loss launch (step t) reads
+            # the buffer of the batch it consumes
+            torch.cuda.synchronize(self.device)
+            t = self.peer.steps() + 1
+            mine, other = pp['bufs'][pp['cur']][3], pp['bufs'][1 - pp['cur']][3]
+            self.peer.bind(*((mine, other) if t % 2 == 0 else (other, mine)))
+            self._peer_mode = 'pipe'
         cur, nxt = pp['cur'], 1 - pp['cur']
         if overlap:
             if events is not None:
@@ -259,6 +294,8 @@ class TargetLossStep(object):
         loss rows are enqueued, ``_done_event`` is recorded behind them.  (``HostStepPipeline`` keeps several steps
         in flight this way.)"""
         dev = self.device
+        if self.peer_fused:
+            self._bind_inorder()
         chunks = max(1, min(int(chunks), self.B))
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(dev)
@@ -317,7 +354,8 @@ class TargetLossStep(object):
         ``grad_cls``, ``grad_reg``, ``y_reg``, ``y_cls`` (static tensors, overwritten every step).
         ``events``: optional 3 CUDA events recorded before K1, between K1 and K2 (after the all-reduce
         when there are several ranks) and after K2 -- used by the benchmark's roofline accounting."""
-        rank, world = _dist.world()
+        if self.peer_fused:
+            self._bind_inorder()
         if self.use_graph and self._graphs is None:
             self._build_graphs()
         if events is None and self.use_graph and self._fused is not None:

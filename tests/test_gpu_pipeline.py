@@ -147,3 +147,57 @@ def test_peer_mailbox_one_rank(rn, monkeypatch, fused):
         assert got[2] == want[2] and want[2] >= 1
         assert np.allclose(got[:2], want[:2], rtol=1e-6, atol=0)
         assert torch.equal(boxed.grad_cls, plain.grad_cls) and torch.equal(boxed.grad_reg, plain.grad_reg)
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_peer_mailbox_pipelined_schedule(rn, monkeypatch, fused):
+    """run_pipelined (K1 of the next batch ahead of / beside K2 of the current one) with the one-rank mailbox: call s
+    returns the losses of batch s-1, bit-identical gradients; switching between the in-order and the pipelined schedule
+    re-binds the mailbox's count buffers (fused publish sends value[step & 1])."""
+    import synthetic
+    hw, B = (256, 320), 4
+    N = rn.anchors_for_shape(hw + (3,)).shape[0]
+    imgs = [synthetic.PageShape(hw + (3,)) for _ in range(B)]
+    cls, reg = synthetic.training_predictions(6, B, N, classes=1)
+    cls_h, reg_h = torch.from_numpy(cls).pin_memory(), torch.from_numpy(reg).pin_memory()
+    batches = [[synthetic.gt_for_page(2, 10 * s + i, hw=hw, gmax=6) for i in range(B)] for s in range(9)]
+    plain = rn.pipeline.TargetLossStep(hw + (3,), B, 8, 1)
+    plain.load_predictions(cls_h, reg_h)
+    want = []
+    for anns in batches:
+        plain.load_annotations(imgs, anns)
+        l = plain.run().cpu().numpy().copy()
+        want.append((l, plain.grad_cls.clone(), plain.grad_reg.clone()))
+    assert len(set(float(w[0][2]) for w in want)) > 3        # the batches have different positive counts
+
+    monkeypatch.setenv("RN_B200_PEER_BOX", "force")
+    monkeypatch.setenv("RN_B200_PEER_FUSED", fused)
+    boxed = rn.pipeline.TargetLossStep(hw + (3,), B, 8, 1)
+    boxed.load_predictions(cls_h, reg_h)
+
+    def check(got, s):
+        got = got.cpu().numpy()
+        assert got[2] == want[s][0][2], (s, got, want[s][0])
+        assert np.allclose(got[:2], want[s][0][:2], rtol=1e-6, atol=0)
+        assert torch.equal(boxed.grad_cls, want[s][1]) and torch.equal(boxed.grad_reg, want[s][2])
+
+    overlap_ok = fused == "1"
+    boxed.load_annotations(imgs, batches[0])
+    check(boxed.run_pipelined(), 0)                           # the warm-up's targets are batch 0's
+    for s in (1, 2, 3):
+        boxed.load_annotations(imgs, batches[s])
+        check(boxed.run_pipelined(overlap=overlap_ok and s % 2 == 1), s - 1)
+    if not overlap_ok:
+        # separate publish kernel: K2 takes "the step before the latest" (lag 1), so the two schedules cannot be mixed
+        # on one step object, and the overlapped form is refused
+        with pytest.raises(ValueError):
+            boxed.run_pipelined(overlap=True)
+        return
+    for s in (4, 5, 6):                                       # in order again (odd number of steps: the parity flips)
+        boxed.load_annotations(imgs, batches[s])
+        check(boxed.run(), s)
+    boxed.load_annotations(imgs, batches[7])
+    boxed.run_pipelined(overlap=overlap_ok)                   # consumes the targets left in the pipeline (batch 3)
+    check(boxed.losses, 3)
+    boxed.load_annotations(imgs, batches[8])
+    check(boxed.run_pipelined(overlap=overlap_ok), 7)
