@@ -315,10 +315,11 @@ __device__ __forceinline__ void rn_bulk_store_row(float* dst, const float* src, 
 // stores.
 // ------------------------------------------------------------------------------------------------
 constexpr int KT_ROWS = 4;             // the write-out's row decode assumes 4
-#ifndef KT_PASSES
-#define KT_PASSES 1                    // a CTA walks KT_PASSES vertically adjacent KT_ROWS-row tiles (tile decode, column geometry,
-#endif                                 // staged GT tables and x targets shared by the passes).  Measured: 13 % fewer instructions at 2
-                                       // passes but 56.6 -> 60.3 us (3: 62.9, 4: 64.6) -- the kernel is latency-, not issue-bound -- so 1.
+// (A/B, profiles/sweep_k1.py: a CTA walking 2 / 3 / 4 vertically adjacent 4-row tiles -- tile decode, column geometry,
+// staged GT tables and x targets shared by the passes, 13 % fewer instructions at 2 -- took 60.3 / 62.9 / 64.6 us
+// against 56.6: the kernel is latency-, not issue-bound, and longer CTAs drain worse.  Requesting the GT chunk before
+// the tile decode changed nothing.  A page with one small table costs 43 us per 16 pages, the heaviest 77 us:
+// 3/4 of the time is the per-anchor work (targets, state, staging, write-out), not the matching; profiles/k1_page_cost.py.)
 constexpr int KT_MAX_A = 24;
 constexpr int KT_CHUNK = 256;          // GT tables staged per round
 
@@ -392,8 +393,8 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
     const int ty = rn_div(t, tiles_x, inv_tiles_x);
     const int tx = t - ty * tiles_x;
     const double stride = (double)istride;
-    const int cx0 = tx * 32, cy_base = ty * (KT_ROWS * KT_PASSES);
-    const int ncols = min(32, W - cx0);
+    const int cx0 = tx * 32, cy0 = ty * KT_ROWS;
+    const int ncols = min(32, W - cx0), nrows = min(KT_ROWS, H - cy0);
     const bool valid_x = lane < ncols;
     int G = p.gt_count[b];
     G = max(0, min(G, p.Gmax));
@@ -404,32 +405,17 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
     const double sx = ((double)(cx0 + lane) + 0.5) * stride;
     const double ax1 = b0 + sx, ax2 = b2 + sx;
     const double aw = ax2 - ax1;
-    const bool match_x = valid_x && (aw > 0.0);
-    // exact bounding box of the warp's anchors (first / last valid column, first / last valid row)
-    const double wx1 = b0 + ((double)cx0 + 0.5) * stride, wx2 = b2 + ((double)(cx0 + ncols - 1) + 0.5) * stride;
-    double* ihw = s_ih + (size_t)a * (KT_ROWS * 32);       // this warp's [KT_ROWS][32] intersection heights
-    const double* gtb = p.gt + (size_t)b * p.Gmax * 4;
-    const double (*row)[3] = s_row[a];
-    const bool gt_staged = G <= KT_CHUNK;                   // the (only) chunk stays in shared memory
-    int my_pos = 0;
-    int prev = -1;                                          // the x targets depend on the column and the table only
-    float t0 = 0.f, t2 = 0.f;
-    double gy1 = 0.0, gy2 = 0.0;
-    const int cnt = ncols * A;
-
-#pragma unroll 1
-    for (int pass = 0; pass < KT_PASSES; ++pass) {
-    const int cy0 = cy_base + pass * KT_ROWS;
-    if (cy0 >= H) break;                                    // block-uniform
-    const int nrows = min(KT_ROWS, H - cy0);
     // row geometry is the same for the whole warp: keep it in shared memory, not in 24 registers per thread
-    __syncwarp();                                           // the previous pass's readers of s_row are done
     if (lane < KT_ROWS) {
         const double sy = ((double)(cy0 + lane) + 0.5) * stride;
         const double y1 = b1 + sy, y2 = b3 + sy;
         s_row[a][lane][0] = y1; s_row[a][lane][1] = y2; s_row[a][lane][2] = y2 - y1;
     }
     __syncwarp();
+    const double (*row)[3] = s_row[a];
+    const bool match_x = valid_x && (aw > 0.0);
+    // exact bounding box of the warp's anchors (first / last valid column, first / last valid row)
+    const double wx1 = b0 + ((double)cx0 + 0.5) * stride, wx2 = b2 + ((double)(cx0 + ncols - 1) + 0.5) * stride;
 
     // ---- matching -------------------------------------------------------------------------------------
     // The y half of every (anchor, table) overlap depends only on (anchor type, tile row, table): it is the
@@ -440,19 +426,19 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
     int arg[KT_ROWS];
 #pragma unroll
     for (int r = 0; r < KT_ROWS; ++r) { best[r] = 0.0f; arg[r] = 0; }   // all-zero IoU row -> argmax 0
+    double* ihw = s_ih + (size_t)a * (KT_ROWS * 32);       // this warp's [KT_ROWS][32] intersection heights
+    const double* gtb = p.gt + (size_t)b * p.Gmax * 4;
     for (int g0 = 0; g0 < G; g0 += KT_CHUNK) {
         const int chunk = min(KT_CHUNK, G - g0);
-        if (pass == 0 || !gt_staged) {                     // a single chunk is staged once for all passes
-            if (g0 || pass) __syncthreads();               // previous chunk consumed (nothing has been staged before the first)
-            for (int j = tid; j < chunk; j += nthreads) {
-                const double sx1 = __ldg(gtb + 4 * (g0 + j)), sy1 = __ldg(gtb + 4 * (g0 + j) + 1);
-                const double sx2 = __ldg(gtb + 4 * (g0 + j) + 2), sy2 = __ldg(gtb + 4 * (g0 + j) + 3);
-                s_gx1[j] = sx1; s_gy1[j] = sy1; s_gx2[j] = sx2; s_gy2[j] = sy2;
-                s_ga[j] = (sx2 - sx1) * (sy2 - sy1);
-                s_glab[j] = __ldg(p.gt_labels + (size_t)b * p.Gmax + g0 + j);
-            }
-            __syncthreads();
+        if (g0) __syncthreads();                           // previous chunk consumed (nothing has been staged before the first)
+        for (int j = tid; j < chunk; j += nthreads) {
+            const double gx1 = __ldg(gtb + 4 * (g0 + j)), gy1 = __ldg(gtb + 4 * (g0 + j) + 1);
+            const double gx2 = __ldg(gtb + 4 * (g0 + j) + 2), gy2 = __ldg(gtb + 4 * (g0 + j) + 3);
+            s_gx1[j] = gx1; s_gy1[j] = gy1; s_gx2[j] = gx2; s_gy2[j] = gy2;
+            s_ga[j] = (gx2 - gx1) * (gy2 - gy1);
+            s_glab[j] = __ldg(p.gt_labels + (size_t)b * p.Gmax + g0 + j);
         }
+        __syncthreads();
         for (int q0 = 0; q0 < chunk; q0 += 32) {
             const int j = q0 + lane;
             unsigned rows_hit = 0u;
@@ -510,12 +496,13 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
     }
 
     // ---- state, one-hot class, regression targets, border rule ------------------------------------------
-    if (pass) __syncthreads();          // the TMA engine has read the previous pass's staged rows (wait_group.read below)
+    int my_pos = 0;
     // misalignment (in anchors, mod 4) of the tile's first anchor and of one feature-map row; unsigned wrap-around
     // keeps the low two bits right.  Row r is staged shifted by ((al0 + r * alw) * 5) & 3 = (al0 + r * alw) & 3 floats
     // (regression) and ((al0 + r * alw) * 2) & 3 floats (labels).
     const unsigned al0 = ((unsigned)b * (unsigned)p.N + (unsigned)lstart + ((unsigned)cy0 * (unsigned)W + (unsigned)cx0) * (unsigned)A) & 3u;
     const unsigned alw = ((unsigned)W * (unsigned)A) & 3u;
+    const bool gt_staged = G <= KT_CHUNK;                   // the (only) chunk is still in shared memory
     // 5/width, 5/height for the regression fast path: the base box's stand in for the anchor's own (they
     // differ by rounding only) when that is far inside the fast path's tolerance (see the wrapper)
     const double bw = __ldg(bs + 2) - __ldg(bs), bh = __ldg(bs + 3) - __ldg(bs + 1);     // re-read: not kept live across the matching loop
@@ -529,6 +516,9 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
             out_x = ((ax1 + ax2) / 2.0) >= (double)p.img_hw[2 * b + 1];
             img_h = (double)p.img_hw[2 * b];
         }
+        int prev = -1;                                      // the x targets depend on the column and the table only
+        float t0 = 0.f, t2 = 0.f;
+        double gy1 = 0.0, gy2 = 0.0;
 #pragma unroll
         for (int r = 0; r < KT_ROWS; ++r) {
             if (r < nrows) {
@@ -575,9 +565,18 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
             }
         }
     }
+    if (p.npos || p.npos_total) {
+        my_pos = rn_warp_sum(my_pos);
+        if (lane == 0 && my_pos) atomicAdd(&s_npos, my_pos);
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the staged rows are read by the TMA engine below
     __syncthreads();
+    if (tid == 0 && s_npos) {
+        if (p.npos) atomicAdd(p.npos + b, s_npos);
+        if (p.npos_total) atomicAdd(p.npos_total, (float)s_npos);   // integer-valued: exact, order-independent
+    }
 
+    const int cnt = ncols * A;
     const long long tile_row0 = (long long)b * p.N + lstart + ((long long)cy0 * W + cx0) * A;
     // ---- write-out: each tile row is one contiguous anchor range, staged with the destination's 16-byte phase.
     if (p.vec_ok) {
@@ -627,21 +626,10 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                 if (hot >= 0) rowp[hot] = 1.0f;
             }
         }
-    } else {
-        // unaligned output tensors (not 16-byte aligned: never the case for framework allocations): plain stores, out of line
-        write_out_unaligned(p.reg, p.lab, p.C, s_reg, s_lab, s_state, s_hot, tile_row0, W * A, cnt, nrows, A, tid, nthreads);
+        return;
     }
-    }   // pass
-
-    if (p.npos || p.npos_total) {
-        my_pos = rn_warp_sum(my_pos);
-        if (lane == 0 && my_pos) atomicAdd(&s_npos, my_pos);
-        __syncthreads();
-        if (tid == 0 && s_npos) {
-            if (p.npos) atomicAdd(p.npos + b, s_npos);
-            if (p.npos_total) atomicAdd(p.npos_total, (float)s_npos);   // integer-valued: exact, order-independent
-        }
-    }
+    // unaligned output tensors (not 16-byte aligned: never the case for framework allocations): plain stores, out of line
+    write_out_unaligned(p.reg, p.lab, p.C, s_reg, s_lab, s_state, s_hot, tile_row0, W * A, cnt, nrows, A, tid, nthreads);
 }
 
 __global__ void k_anchors_f64(const RnLevels lv, const double* base, int N, double* out) {
@@ -764,7 +752,7 @@ extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* leve
             tl.tile_start[l] = tiles;
             tl.tiles_x[l] = (w + 31) / 32 > 0 ? (w + 31) / 32 : 1;
             tl.inv_tiles_x[l] = 1.0f / (float)tl.tiles_x[l];
-            tiles += ((w + 31) / 32) * ((h + KT_ROWS * KT_PASSES - 1) / (KT_ROWS * KT_PASSES));
+            tiles += ((w + 31) / 32) * ((h + KT_ROWS - 1) / KT_ROWS);
         }
         for (int l = num_levels; l <= RN_MAX_LEVELS; ++l) tl.tile_start[l] = tiles;
         p.max_coord = max_coord;
