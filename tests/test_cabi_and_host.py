@@ -140,3 +140,85 @@ def test_balanced_shards(pkg):
         contiguous = [int(w[lo:hi].sum()) for lo, hi in (pkg.distributed.shard_pages(pages, r, world) for r in range(world))]
         assert max(totals) - min(totals) <= max(w) and max(totals) <= max(contiguous)
     assert pkg.distributed.balanced_shards([5, 1], 1) == [[0, 1]]
+
+
+def test_page_cost_tracks_exact_overlap_count(pkg):
+    """distributed.page_cost: fixed per-anchor work + the closed-form number of overlapping (anchor, table) pairs.
+    The pair estimate must stay within a few per cent of the exact count (oracle anchors, numpy); an empty page costs
+    exactly the fixed part."""
+    import synthetic
+    from oracle import anchors_np as OA
+    hw = (800, 1333)
+    anchors = OA.anchors_for_shape(hw + (3,))
+    _, anns = synthetic.training_batch(2, batch=6, anchors=anchors)
+    est = pkg.distributed.page_cost(anns, hw, fixed=0.0)
+    exact = []
+    for a in anns:
+        n = 0
+        for g in np.asarray(a['bboxes']):
+            iw = np.minimum(anchors[:, 2], g[2]) - np.maximum(anchors[:, 0], g[0])
+            ih = np.minimum(anchors[:, 3], g[3]) - np.maximum(anchors[:, 1], g[1])
+            n += int(((iw > 0) & (ih > 0)).sum())
+        exact.append(n)
+    for e, x in zip(est, exact):
+        assert abs(e - x) <= 0.06 * x + 2000, (e, x)
+    assert np.corrcoef(est, exact)[0, 1] > 0.995
+    empty = {'bboxes': np.zeros((0, 4)), 'labels': np.zeros((0,))}
+    full = pkg.distributed.page_cost(anns[:1] + [empty], hw)
+    assert full[1] == pytest.approx(pkg.distributed.PAIRS_PER_FIXED * anchors.shape[0]) and full[0] > full[1]
+    shards = pkg.distributed.balanced_shards(pkg.distributed.page_cost(anns, hw), 2)
+    assert sorted(sum(shards, [])) == list(range(6))
+
+
+def test_pack_annotations_fast_and_ragged_paths_agree(pkg):
+    """anchors.pack_annotations: the batch-wide fast path (every page a (g,4) / (g,) array pair), the per-page path
+    (lists, extra columns, scalar label broadcast, 1-D empty boxes) and the `out=` form give what a plain loop over the
+    reference's conversions gives; errors keep their types."""
+    A = pkg.anchors
+
+    class Shape(object):
+        def __init__(self, shape):
+            self.shape = shape
+
+    rs = np.random.RandomState(3)
+    pages, images = [], []
+    for g in (3, 0, 7, 1, 5):
+        pages.append({'bboxes': rs.rand(g, 4) * 100, 'labels': rs.randint(-2, 2, g).astype(np.float64)})
+        images.append(Shape((60 + g, 80 + g, 3)))
+
+    def loop(pages, images, C):
+        G = max(1, max(len(p['labels']) if np.ndim(p['labels']) else 1 for p in pages), max(np.asarray(p['bboxes']).shape[0] for p in pages))
+        boxes, labels = np.zeros((len(pages), G, 4)), np.zeros((len(pages), G), np.int32)
+        counts = np.array([np.asarray(p['bboxes']).shape[0] for p in pages], np.int32)
+        for b, p in enumerate(pages):
+            g = int(counts[b])
+            if g:
+                boxes[b, :g] = np.asarray(p['bboxes'], dtype=np.float64).reshape(g, -1)[:, :4]
+                lab = np.asarray(p['labels']).astype(int).reshape(-1)[:g]
+                labels[b, :g] = np.where(lab < 0, lab + C + 1, lab)
+        hw = np.array([[im.shape[0], im.shape[1]] if im.shape else [np.iinfo(np.int32).max] * 2 for im in images], np.int32)
+        return boxes[:, :max(1, counts.max())], labels[:, :max(1, counts.max())], counts, hw
+
+    def same(got, want):
+        return all(np.array_equal(g, w) and g.dtype == w.dtype for g, w in zip(got, want))
+
+    assert same(A.pack_annotations(images, pages, 2), loop(pages, images, 2))                      # fast path
+    ragged = [dict(p) for p in pages]
+    ragged[0] = {'bboxes': np.hstack([pages[0]['bboxes'], np.ones((3, 1))]).tolist(), 'labels': pages[0]['labels'].tolist()}
+    ragged[1] = {'bboxes': np.array([]), 'labels': np.array([])}                                   # 1-D empty
+    ragged[3] = {'bboxes': pages[3]['bboxes'], 'labels': np.array(pages[3]['labels'][0])}          # 0-d label
+    assert same(A.pack_annotations(images + [Shape(())], ragged + [ragged[1]], 2),
+                loop(pages + [pages[1]], images + [Shape(())], 2))
+    out = (np.full((5, 9, 4), 7.0), np.full((5, 9), 7, np.int32), np.zeros(5, np.int32), np.zeros((5, 2), np.int32))
+    got = A.pack_annotations(images, pages, 2, out=out)
+    want = loop(pages, images, 2)
+    assert got[0] is out[0] and np.array_equal(out[0][:, :7], want[0]) and not out[0][:, 7:].any() and not out[1][:, 7:].any()
+    assert np.array_equal(out[1][:, :7], want[1]) and np.array_equal(out[2], want[2]) and np.array_equal(out[3], want[3])
+    with pytest.raises(ValueError):
+        A.pack_annotations(images, pages, 2, out=(np.zeros((5, 4, 4)), np.zeros((5, 4), np.int32), out[2], out[3]))   # 7 GT do not fit
+    with pytest.raises(IndexError):
+        A.pack_annotations(images[:1], [{'bboxes': np.ones((1, 4)), 'labels': np.array([3.0])}], 2)
+    with pytest.raises(AssertionError):
+        A.pack_annotations(images[:2], pages[:1], 2)
+    with pytest.raises(AssertionError):
+        A.pack_annotations(images[:1], [{'bboxes': np.ones((1, 4))}], 2)
