@@ -357,7 +357,7 @@ __device__ __noinline__ void write_out_unaligned(float* reg, float* lab, int C, 
 
 // C1: one class (the table-detection configuration) -- specialised so that the generic label path costs the common
 // instantiation no registers
-template <int MAXA, int MINB, bool C1, bool AM>          // AM: the argmax tensor is wanted
+template <int MAXA, int MINB, bool C1, bool AM, bool AX = false>   // AM: the argmax tensor is wanted; AX: exactly MAXA anchors per cell
 __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const K1Params p, const K1Tiles tl) {
     extern __shared__ __align__(16) float s_dyn[];
     __shared__ double s_gx1[KT_CHUNK], s_gy1[KT_CHUNK], s_gx2[KT_CHUNK], s_gy2[KT_CHUNK], s_ga[KT_CHUNK];
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
     __shared__ int s_npos;
 
     const int tid = threadIdx.x, lane = tid & 31, a = tid >> 5;
-    const int A = p.lv.anchors_per_cell, L = p.lv.num_levels;
+    const int A = AX ? MAXA : p.lv.anchors_per_cell, L = p.lv.num_levels;   // AX: a compile-time 9 folds the staging / index arithmetic
     const int nthreads = 32 * A;
     const int b = blockIdx.y;
     // staging rows are shifted by the destination's misalignment (start & 3 floats) so that 16-byte units of
@@ -767,6 +767,7 @@ extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* leve
             if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
             if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
             if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
             if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
             if (ae != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
             attr_done = true;
@@ -778,6 +779,9 @@ extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* leve
             if (C != 1) k_anchor_targets_tiles<9, 3, false, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
             else if (argmax_out) k_anchor_targets_tiles<9, 3, true, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
             else if (minb >= 4) k_anchor_targets_tiles<9, 4, true, false><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+#ifdef KT_AEXACT
+            else if (minb == 3 && A == 9) k_anchor_targets_tiles<9, 3, true, false, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+#endif
             else if (minb == 3) k_anchor_targets_tiles<9, 3, true, false><<<tgrid, 32 * A, dyn, s>>>(p, tl);
             else k_anchor_targets_tiles<9, 2, true, false><<<tgrid, 32 * A, dyn, s>>>(p, tl);
         } else if (tiles > 0) {
