@@ -168,7 +168,14 @@ __global__ void __launch_bounds__(K3_THREADS) k_threshold_compact(const K3Params
             while (hits) {
                 const int j = __ffs(hits) - 1;
                 hits &= hits - 1u;
-                s_elem[at++] = tile0 + (((j >> 2) * K3_THREADS + tid) << 2) + (j & 3);
+                const int e = tile0 + (((j >> 2) * K3_THREADS + tid) << 2) + (j & 3);
+                s_elem[at++] = e;
+#ifdef K3_PREFETCH_ROWS
+                // (A/B for the next sweep, off) request the candidate's regression row now: phase 2 is bound by the number of
+                // scattered rows in flight, and this puts them in flight one barrier + one list pass earlier
+                if (DECODE && p.C == 1)
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const float4*>(p.reg) + (size_t)b * p.N + e));
+#endif
             }
         }
     } else {
