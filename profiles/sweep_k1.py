@@ -47,7 +47,7 @@ if __name__ == "__main__":
         libdir = os.path.join(ROOT, "retinanet-for-table-detection_b200")
         variants = [""] + sorted(f for f in os.listdir(libdir) if f.startswith("librn_b200.") and f != "librn_b200.so"
                                  and f.endswith(".so"))
-        for rep in range(2):
+        for rep in range(int(os.environ.get("SWEEP_REPS", "2"))):
             for lib in variants:
                 env = dict(os.environ)
                 if lib:

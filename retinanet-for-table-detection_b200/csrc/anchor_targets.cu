@@ -119,20 +119,37 @@ __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : 
 __device__ __noinline__ float reg_target_exact(double d, double len) { return (float)((d / len) / 0.2); }
 __device__ __noinline__ float iou_exact(double inter, double uni) { return (float)(inter / uni); }
 
-// same with the reciprocal pre-multiplied by 5 (r5 ~ 5/len to < 2^-40 relative)
-__device__ __forceinline__ float reg_target5(double g, double a, double len, double r5) {
-    const double d = g - a;
-    const double approx = d * r5;
-    if (f32_rounding_safe(approx)) return (float)approx;     // d == 0 gives exponent 0 -> exact path (signed zero)
-    return reg_target_exact(d, len);
-}
-
 // one regression target: ((g - a) / len) / 0.2 rounded to fp32 (model/anchors.py:300-311)
 __device__ __forceinline__ float reg_target(double g, double a, double len, double rlen) {
     const double d = g - a;
     const double approx = (d * rlen) * 5.0;
     if (d != 0.0 && f32_rounding_safe(approx)) return (float)approx;
     return reg_target_exact(d, len);                          // also the exact (signed) zero
+}
+
+// Regression targets with the reciprocal pre-multiplied by 5 (r5 ~ 5/len to < 2^-40 relative; d == 0 gives exponent 0 ->
+// exact path, signed zero) and IoUs:
+// two quotients at a time with ONE rarely taken branch behind both conversions instead of a branch (a convergence region
+// the scheduler cannot move instructions across) after each: the two dependency chains -- subtract, multiply, mantissa
+// check, convert -- overlap.  Same values, same fall-back, bit for bit (profiles/sweep_k1.py: 55.2 -> 53.5 us, equal checksums).
+__device__ __forceinline__ void reg_target5_pair(double ga, double aa, double gb, double ab, double len, double r5, float& ta, float& tb) {
+    const double da = ga - aa, db = gb - ab;
+    const double pa = da * r5, pb = db * r5;
+    const bool oka = f32_rounding_safe(pa), okb = f32_rounding_safe(pb);
+    ta = (float)pa; tb = (float)pb;
+    if (!(oka && okb)) {
+        if (!oka) ta = reg_target_exact(da, len);
+        if (!okb) tb = reg_target_exact(db, len);
+    }
+}
+__device__ __forceinline__ void iou_pair(double i0, double u0, double i1, double u1, float& iou0, float& iou1) {
+    const double q0 = i0 * rcp_fast(u0), q1 = i1 * rcp_fast(u1);
+    const bool ok0 = f32_rounding_safe(q0), ok1 = f32_rounding_safe(q1);
+    iou0 = (float)q0; iou1 = (float)q1;
+    if (!(ok0 && ok1)) {
+        if (!ok0) iou0 = iou_exact(i0, u0);
+        if (!ok1) iou1 = iou_exact(i1, u1);
+    }
 }
 
 template <bool EXPLICIT>
@@ -471,9 +488,8 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                         for (int r = 0; r < KT_ROWS; r += 2) {          // two rows at a time: ILP without spilling
                             const double i0 = iw * ihw[r * 32 + ml], i1 = iw * ihw[(r + 1) * 32 + ml];
                             const double u0 = aw * row[r][2] + ga - i0, u1 = aw * row[r + 1][2] + ga - i1;
-                            const double q0v = i0 * rcp_fast(u0), q1v = i1 * rcp_fast(u1);
-                            const float iou0 = f32_rounding_safe(q0v) ? (float)q0v : iou_exact(i0, u0);
-                            const float iou1 = f32_rounding_safe(q1v) ? (float)q1v : iou_exact(i1, u1);
+                            float iou0, iou1;
+                            iou_pair(i0, u0, i1, u1, iou0, iou1);
                             if (iou0 > best[r]) { best[r] = iou0; arg[r] = g0 + m; }
                             if (iou1 > best[r + 1]) { best[r + 1] = iou1; arg[r + 1] = g0 + m; }
                         }
@@ -539,13 +555,11 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                             const double* g = gtb + 4 * (size_t)m;
                             gx1 = __ldg(g); gy1 = __ldg(g + 1); gx2 = __ldg(g + 2); gy2 = __ldg(g + 3);
                         }
-                        t0 = reg_target5(gx1, ax1, aw, r5w);
-                        t2 = reg_target5(gx2, ax2, aw, r5w);
+                        reg_target5_pair(gx1, ax1, gx2, ax2, aw, r5w, t0, t2);
                     }
                     if (is_pos) hot = gt_staged ? s_glab[m] : __ldg(p.gt_labels + (size_t)b * p.Gmax + m);
                     const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(hh);
-                    t1 = reg_target5(gy1, y1, hh, r5h);
-                    t3 = reg_target5(gy2, y2, hh, r5h);
+                    reg_target5_pair(gy1, y1, gy2, y2, hh, r5h, t1, t3);
                 }
                 if (p.img_hw && (out_x || ((y1 + y2) / 2.0) >= img_h)) state = -1.0f;
                 const int k = lane * A + a;                 // reference order within the tile row
