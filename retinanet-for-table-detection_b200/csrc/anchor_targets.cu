@@ -535,6 +535,13 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
         int prev = -1;                                      // the x targets depend on the column and the table only
         float t0 = 0.f, t2 = 0.f;
         double gy1 = 0.0, gy2 = 0.0;
+#ifdef KT_EPI_BATCH
+        // (A/B for the next sweep, off.)  The y targets of all rows take the fast path unconditionally and only record
+        // which of them it could not certify (2 bits per row); ONE rarely taken branch behind the row loop recomputes
+        // those exactly and overwrites the staged values.  With the label fetched by a select, a row's body has no
+        // convergence region left except the table change, so the rows' fp64 chains can overlap.
+        unsigned bad = 0u;
+#endif
 #pragma unroll
         for (int r = 0; r < KT_ROWS; ++r) {
             if (r < nrows) {
@@ -557,9 +564,17 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                         }
                         reg_target5_pair(gx1, ax1, gx2, ax2, aw, r5w, t0, t2);
                     }
-                    if (is_pos) hot = gt_staged ? s_glab[m] : __ldg(p.gt_labels + (size_t)b * p.Gmax + m);
                     const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(hh);
+#ifdef KT_EPI_BATCH
+                    if (gt_staged) hot = is_pos ? s_glab[m] : -1;
+                    else if (is_pos) hot = __ldg(p.gt_labels + (size_t)b * p.Gmax + m);
+                    const double pa = (gy1 - y1) * r5h, pb = (gy2 - y2) * r5h;
+                    t1 = (float)pa; t3 = (float)pb;
+                    bad |= (f32_rounding_safe(pa) ? 0u : 1u << (2 * r)) | (f32_rounding_safe(pb) ? 0u : 2u << (2 * r));
+#else
+                    if (is_pos) hot = gt_staged ? s_glab[m] : __ldg(p.gt_labels + (size_t)b * p.Gmax + m);
                     reg_target5_pair(gy1, y1, gy2, y2, hh, r5h, t1, t3);
+#endif
                 }
                 if (p.img_hw && (out_x || ((y1 + y2) / 2.0) >= img_h)) state = -1.0f;
                 const int k = lane * A + a;                 // reference order within the tile row
@@ -578,6 +593,22 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                     p.argmax[(size_t)b * p.N + lstart + ((size_t)(cy0 + r) * W + cx0 + lane) * A + a] = arg[r];
             }
         }
+#ifdef KT_EPI_BATCH
+        if (bad) {                                          // ~0.4 % of the threads; a set bit implies r < nrows and G > 0
+#pragma unroll
+            for (int r = 0; r < KT_ROWS; ++r) {
+                const unsigned bits = (bad >> (2 * r)) & 3u;
+                if (bits) {
+                    const int m = arg[r];
+                    const double g1 = gt_staged ? s_gy1[m] : __ldg(gtb + 4 * (size_t)m + 1);
+                    const double g2 = gt_staged ? s_gy2[m] : __ldg(gtb + 4 * (size_t)m + 3);
+                    float* sr = s_reg + r * reg_stride + (int)((al0 + r * alw) & 3u) + (lane * A + a) * 5;
+                    if (bits & 1u) sr[1] = reg_target_exact(g1 - row[r][0], row[r][2]);
+                    if (bits & 2u) sr[3] = reg_target_exact(g2 - row[r][1], row[r][2]);
+                }
+            }
+        }
+#endif
     }
     if (p.npos || p.npos_total) {
         my_pos = rn_warp_sum(my_pos);
