@@ -564,15 +564,16 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                         }
                         reg_target5_pair(gx1, ax1, gx2, ax2, aw, r5w, t0, t2);
                     }
-                    const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(hh);
 #ifdef KT_EPI_BATCH
                     if (gt_staged) hot = is_pos ? s_glab[m] : -1;
                     else if (is_pos) hot = __ldg(p.gt_labels + (size_t)b * p.Gmax + m);
+                    const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(hh);
                     const double pa = (gy1 - y1) * r5h, pb = (gy2 - y2) * r5h;
                     t1 = (float)pa; t3 = (float)pb;
                     bad |= (f32_rounding_safe(pa) ? 0u : 1u << (2 * r)) | (f32_rounding_safe(pb) ? 0u : 2u << (2 * r));
 #else
                     if (is_pos) hot = gt_staged ? s_glab[m] : __ldg(p.gt_labels + (size_t)b * p.Gmax + m);
+                    const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(hh);
                     reg_target5_pair(gy1, y1, gy2, y2, hh, r5h, t1, t3);
 #endif
                 }
