@@ -443,6 +443,9 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
     int arg[KT_ROWS];
 #pragma unroll
     for (int r = 0; r < KT_ROWS; ++r) { best[r] = 0.0f; arg[r] = 0; }   // all-zero IoU row -> argmax 0
+#ifdef KT_EMPTY_WARP
+    unsigned any_live = 0u;                                 // warp-uniform: some table reaches some anchor of this warp
+#endif
     double* ihw = s_ih + (size_t)a * (KT_ROWS * 32);       // this warp's [KT_ROWS][32] intersection heights
     const double* gtb = p.gt + (size_t)b * p.Gmax * 4;
     for (int g0 = 0; g0 < G; g0 += KT_CHUNK) {
@@ -472,6 +475,9 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                 }
             }
             unsigned live = __ballot_sync(0xffffffffu, rows_hit != 0u);   // also orders the s_ih writes
+#ifdef KT_EMPTY_WARP
+            any_live |= live;
+#endif
             while (live) {                                 // warp-uniform, ascending GT order
                 const int ml = __ffs(live) - 1;
                 live &= live - 1u;
@@ -525,6 +531,61 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
     const bool table_ok = (bw > 0.0) && (bh > 0.0) && (p.max_coord < 4096.0 * fmin(bw, bh));
     const double r5w = 5.0 * rcp_fast(table_ok ? bw : aw);
     const double r5h_tab = table_ok ? 5.0 * rcp_fast(bh) : 0.0;
+#ifdef KT_EMPTY_WARP
+    // (A/B for the next sweep, off.)  No table reaches any anchor of this warp (every warp of a page with one or two
+    // small tables): all its IoUs are 0, every argmax is table 0, so the x targets are per column, the y targets per
+    // row -- 4 lanes compute the rows' pairs, shuffles hand them out -- and the state is the same for all anchors but
+    // the border ones.  Expression for expression what the general path below computes with best = 0, arg = 0.
+    if (!any_live) {
+        float t0 = 0.f, t2 = 0.f, ty1 = 0.f, ty3 = 0.f, state0 = 0.0f;
+        int hot0 = -1;
+        if (G > 0) {
+            const bool is_pos = 0.0f >= p.pos;
+            const bool is_ign = (0.0f > p.neg) && !is_pos;
+            state0 = is_pos ? 1.0f : (is_ign ? -1.0f : 0.0f);
+            double gx1, gy1, gx2, gy2;
+            if (gt_staged) {
+                gx1 = s_gx1[0]; gy1 = s_gy1[0]; gx2 = s_gx2[0]; gy2 = s_gy2[0];
+            } else {
+                gx1 = __ldg(gtb); gy1 = __ldg(gtb + 1); gx2 = __ldg(gtb + 2); gy2 = __ldg(gtb + 3);
+            }
+            if (is_pos) hot0 = gt_staged ? s_glab[0] : __ldg(p.gt_labels + (size_t)b * p.Gmax);
+            reg_target5_pair(gx1, ax1, gx2, ax2, aw, r5w, t0, t2);
+            const int rr = lane & (KT_ROWS - 1);            // lanes 0 .. KT_ROWS-1 are read below, the others repeat them
+            const double hh = row[rr][2];
+            const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(hh);
+            reg_target5_pair(gy1, row[rr][0], gy2, row[rr][1], hh, r5h, ty1, ty3);
+        }
+        bool out_x = false;
+        double img_h = 0.0;
+        if (p.img_hw) {
+            out_x = ((ax1 + ax2) / 2.0) >= (double)p.img_hw[2 * b + 1];
+            img_h = (double)p.img_hw[2 * b];
+        }
+#pragma unroll
+        for (int r = 0; r < KT_ROWS; ++r) {
+            const float t1 = __shfl_sync(0xffffffffu, ty1, r), t3 = __shfl_sync(0xffffffffu, ty3, r);
+            if (valid_x && r < nrows) {
+                float state = state0;
+                if (p.img_hw && (out_x || ((row[r][0] + row[r][1]) / 2.0) >= img_h)) state = -1.0f;
+                const int k = lane * A + a;
+                const unsigned al = al0 + r * alw;
+                float* sr = s_reg + r * reg_stride + (int)(al & 3u) + k * 5;
+                sr[0] = t0; sr[1] = t1; sr[2] = t2; sr[3] = t3; sr[4] = state;
+                if (C1) {
+                    float* sl = s_lab + r * lab_stride + (int)((al & 1u) * 2u) + k * 2;
+                    sl[0] = hot0 == 0 ? 1.0f : 0.0f; sl[1] = state;
+                } else {
+                    s_state[r * 32 * A + k] = state;
+                    s_hot[r * 32 * A + k] = hot0;
+                }
+                my_pos += (state == 1.0f);
+                if (AM && p.argmax)
+                    p.argmax[(size_t)b * p.N + lstart + ((size_t)(cy0 + r) * W + cx0 + lane) * A + a] = 0;
+            }
+        }
+    } else
+#endif
     if (valid_x) {
         bool out_x = false;
         double img_h = 0.0;
