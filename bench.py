@@ -285,7 +285,7 @@ def run_ours(args):
     if world == 1 or step.peer_fused:
         # (several ranks: K2 of batch s sends and collects the counts of batch s itself while K1 of batch s+1 runs beside
         # it -- fused publish -- so the exchange and the skew between ranks hide behind the longer kernel)
-        for _ in range(5):
+        for _ in range(max(args.warmup, 3)):
             step.run_pipelined(overlap=True)
         barrier()
         o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
