@@ -16,8 +16,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librn_b200.so")
 STAMP = LIB + ".stamp"
+# -cudart shared: the CUDA runtime is NOT linked into the library (the process' libcudart.so.12 -- torch's -- is used; the
+# rpath covers a plain ctypes load without torch), so the artefact carries none of the runtime's own entry points
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false",
-              "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+              "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared",
+              "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
 
 
 def _sources():

@@ -20,7 +20,7 @@
 // (probability ~5e-4 per value) the exact IEEE expression of the reference is evaluated.  The result is
 // bit-identical to always dividing.
 #include "rn_common.cuh"
-#include <stdlib.h>
+#include <atomic>
 
 namespace {
 
@@ -372,9 +372,70 @@ __device__ __noinline__ void write_out_unaligned(float* reg, float* lab, int C, 
     }
 }
 
+// Write-out of a tile's staged rows (shared by the tile kernels).  Each tile row is one contiguous anchor range, staged
+// with the destination's 16-byte phase.
+template <bool C1>
+__device__ __forceinline__ void tile_write_out(const K1Params& p, const float* s_reg, const float* s_lab, const float* s_state,
+                                               const int* s_hot, int b, int lstart, int cy0, int cx0, int W, int A, int ncols,
+                                               int nrows, int reg_stride, int lab_stride, int tid, int nthreads) {
+    const int cnt = ncols * A;
+    const long long tile_row0 = (long long)b * p.N + lstart + ((long long)cy0 * W + cx0) * A;
+    if (p.vec_ok) {
+        // TMA bulk stores: ONE thread per (row, tensor) hands its staged row to the copy engine --
+        // cp.async.bulk.global.shared::cta for the 16-byte aligned interior, the sm_100 .cp_mask form (a byte mask
+        // inside one 16-byte chunk) for the partial chunks at the two ends -- instead of every thread looping
+        // over LDS.128 / STG.128 pairs (that loop was ~15 % of the kernel's instructions).
+        const int job = tid;                                // jobs [0, KT_ROWS): regression rows, [KT_ROWS, 2 KT_ROWS): label rows
+        const bool lab_job = job >= KT_ROWS;
+        const int r = lab_job ? job - KT_ROWS : job;
+        if (job < 2 * KT_ROWS && r < nrows && !(lab_job && !C1)) {
+            const int per = lab_job ? 2 : 5;
+            const long long start = (tile_row0 + (long long)r * W * A) * per;
+            const int len = cnt * per, shift = (int)(start & 3);
+            const float* src = lab_job ? s_lab + r * lab_stride : s_reg + r * reg_stride;
+            float* dst = (lab_job ? p.lab : p.reg) + (start - shift);
+            const int end = shift + len;                    // staged floats [shift, end) are valid
+            rn_bulk_store_row(dst, src, shift, end);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the CTA's shared memory may go away after this
+        }
+        if (!C1) {
+            // C > 1: a label row is C + 1 floats, all zero except the one-hot entry of a positive anchor and a non-zero
+            // state (~1 % of the anchors).  So the tile rows' label ranges are zero-filled with 128-bit stores -- no
+            // per-element row / column arithmetic -- and, after a barrier, the few non-zero entries are written.
+            const int CW = p.C + 1;
+            for (int r2 = 0; r2 < nrows; ++r2) {
+                const long long start = (tile_row0 + (long long)r2 * W * A) * CW;
+                const long long len = (long long)cnt * CW;
+                float* dst = p.lab + start;
+                int head = (int)((4 - (start & 3)) & 3);
+                if (head > len) head = (int)len;
+                if (tid < head) dst[tid] = 0.0f;
+                const long long nvec = (len - head) >> 2;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (long long v = tid; v < nvec; v += nthreads) rn_stg_stream4(dst + head + 4 * v, z);
+                const long long done = head + 4 * nvec;
+                if (tid < (int)(len - done)) dst[done + tid] = 0.0f;
+            }
+            __syncthreads();                                // orders the fix-ups below after the zero-fill (same CTA)
+            for (int j = tid; j < nrows * cnt; j += nthreads) {
+                const int r2 = j / cnt, k = j - r2 * cnt;
+                const float st = s_state[r2 * 32 * A + k];
+                const int hot = s_hot[r2 * 32 * A + k];
+                float* rowp = p.lab + (tile_row0 + (long long)r2 * W * A + k) * CW;
+                if (st != 0.0f) rowp[p.C] = st;
+                if (hot >= 0) rowp[hot] = 1.0f;
+            }
+        }
+        return;
+    }
+    // unaligned output tensors (not 16-byte aligned: never the case for framework allocations): plain stores, out of line
+    write_out_unaligned(p.reg, p.lab, p.C, s_reg, s_lab, s_state, s_hot, tile_row0, W * A, cnt, nrows, A, tid, nthreads);
+}
+
 // C1: one class (the table-detection configuration) -- specialised so that the generic label path costs the common
 // instantiation no registers
-template <int MAXA, int MINB, bool C1, bool AM, bool AX = false>   // AM: the argmax tensor is wanted; AX: exactly MAXA anchors per cell
+template <int MAXA, int MINB, bool C1, bool AM>   // AM: the argmax tensor is wanted
 __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const K1Params p, const K1Tiles tl) {
     extern __shared__ __align__(16) float s_dyn[];
     __shared__ double s_gx1[KT_CHUNK], s_gy1[KT_CHUNK], s_gx2[KT_CHUNK], s_gy2[KT_CHUNK], s_ga[KT_CHUNK];
@@ -383,7 +444,7 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
     __shared__ int s_npos;
 
     const int tid = threadIdx.x, lane = tid & 31, a = tid >> 5;
-    const int A = AX ? MAXA : p.lv.anchors_per_cell, L = p.lv.num_levels;   // AX: a compile-time 9 folds the staging / index arithmetic
+    const int A = p.lv.anchors_per_cell, L = p.lv.num_levels;
     const int nthreads = 32 * A;
     const int b = blockIdx.y;
     // staging rows are shifted by the destination's misalignment (start & 3 floats) so that 16-byte units of
@@ -443,9 +504,6 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
     int arg[KT_ROWS];
 #pragma unroll
     for (int r = 0; r < KT_ROWS; ++r) { best[r] = 0.0f; arg[r] = 0; }   // all-zero IoU row -> argmax 0
-#ifdef KT_EMPTY_WARP
-    unsigned any_live = 0u;                                 // warp-uniform: some table reaches some anchor of this warp
-#endif
     double* ihw = s_ih + (size_t)a * (KT_ROWS * 32);       // this warp's [KT_ROWS][32] intersection heights
     const double* gtb = p.gt + (size_t)b * p.Gmax * 4;
     for (int g0 = 0; g0 < G; g0 += KT_CHUNK) {
@@ -475,9 +533,6 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                 }
             }
             unsigned live = __ballot_sync(0xffffffffu, rows_hit != 0u);   // also orders the s_ih writes
-#ifdef KT_EMPTY_WARP
-            any_live |= live;
-#endif
             while (live) {                                 // warp-uniform, ascending GT order
                 const int ml = __ffs(live) - 1;
                 live &= live - 1u;
@@ -531,61 +586,6 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
     const bool table_ok = (bw > 0.0) && (bh > 0.0) && (p.max_coord < 4096.0 * fmin(bw, bh));
     const double r5w = 5.0 * rcp_fast(table_ok ? bw : aw);
     const double r5h_tab = table_ok ? 5.0 * rcp_fast(bh) : 0.0;
-#ifdef KT_EMPTY_WARP
-    // (A/B for the next sweep, off.)  No table reaches any anchor of this warp (every warp of a page with one or two
-    // small tables): all its IoUs are 0, every argmax is table 0, so the x targets are per column, the y targets per
-    // row -- 4 lanes compute the rows' pairs, shuffles hand them out -- and the state is the same for all anchors but
-    // the border ones.  Expression for expression what the general path below computes with best = 0, arg = 0.
-    if (!any_live) {
-        float t0 = 0.f, t2 = 0.f, ty1 = 0.f, ty3 = 0.f, state0 = 0.0f;
-        int hot0 = -1;
-        if (G > 0) {
-            const bool is_pos = 0.0f >= p.pos;
-            const bool is_ign = (0.0f > p.neg) && !is_pos;
-            state0 = is_pos ? 1.0f : (is_ign ? -1.0f : 0.0f);
-            double gx1, gy1, gx2, gy2;
-            if (gt_staged) {
-                gx1 = s_gx1[0]; gy1 = s_gy1[0]; gx2 = s_gx2[0]; gy2 = s_gy2[0];
-            } else {
-                gx1 = __ldg(gtb); gy1 = __ldg(gtb + 1); gx2 = __ldg(gtb + 2); gy2 = __ldg(gtb + 3);
-            }
-            if (is_pos) hot0 = gt_staged ? s_glab[0] : __ldg(p.gt_labels + (size_t)b * p.Gmax);
-            reg_target5_pair(gx1, ax1, gx2, ax2, aw, r5w, t0, t2);
-            const int rr = lane & (KT_ROWS - 1);            // lanes 0 .. KT_ROWS-1 are read below, the others repeat them
-            const double hh = row[rr][2];
-            const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(hh);
-            reg_target5_pair(gy1, row[rr][0], gy2, row[rr][1], hh, r5h, ty1, ty3);
-        }
-        bool out_x = false;
-        double img_h = 0.0;
-        if (p.img_hw) {
-            out_x = ((ax1 + ax2) / 2.0) >= (double)p.img_hw[2 * b + 1];
-            img_h = (double)p.img_hw[2 * b];
-        }
-#pragma unroll
-        for (int r = 0; r < KT_ROWS; ++r) {
-            const float t1 = __shfl_sync(0xffffffffu, ty1, r), t3 = __shfl_sync(0xffffffffu, ty3, r);
-            if (valid_x && r < nrows) {
-                float state = state0;
-                if (p.img_hw && (out_x || ((row[r][0] + row[r][1]) / 2.0) >= img_h)) state = -1.0f;
-                const int k = lane * A + a;
-                const unsigned al = al0 + r * alw;
-                float* sr = s_reg + r * reg_stride + (int)(al & 3u) + k * 5;
-                sr[0] = t0; sr[1] = t1; sr[2] = t2; sr[3] = t3; sr[4] = state;
-                if (C1) {
-                    float* sl = s_lab + r * lab_stride + (int)((al & 1u) * 2u) + k * 2;
-                    sl[0] = hot0 == 0 ? 1.0f : 0.0f; sl[1] = state;
-                } else {
-                    s_state[r * 32 * A + k] = state;
-                    s_hot[r * 32 * A + k] = hot0;
-                }
-                my_pos += (state == 1.0f);
-                if (AM && p.argmax)
-                    p.argmax[(size_t)b * p.N + lstart + ((size_t)(cy0 + r) * W + cx0 + lane) * A + a] = 0;
-            }
-        }
-    } else
-#endif
     if (valid_x) {
         bool out_x = false;
         double img_h = 0.0;
@@ -596,13 +596,6 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
         int prev = -1;                                      // the x targets depend on the column and the table only
         float t0 = 0.f, t2 = 0.f;
         double gy1 = 0.0, gy2 = 0.0;
-#ifdef KT_EPI_BATCH
-        // (A/B for the next sweep, off.)  The y targets of all rows take the fast path unconditionally and only record
-        // which of them it could not certify (2 bits per row); ONE rarely taken branch behind the row loop recomputes
-        // those exactly and overwrites the staged values.  With the label fetched by a select, a row's body has no
-        // convergence region left except the table change, so the rows' fp64 chains can overlap.
-        unsigned bad = 0u;
-#endif
 #pragma unroll
         for (int r = 0; r < KT_ROWS; ++r) {
             if (r < nrows) {
@@ -625,18 +618,9 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                         }
                         reg_target5_pair(gx1, ax1, gx2, ax2, aw, r5w, t0, t2);
                     }
-#ifdef KT_EPI_BATCH
-                    if (gt_staged) hot = is_pos ? s_glab[m] : -1;
-                    else if (is_pos) hot = __ldg(p.gt_labels + (size_t)b * p.Gmax + m);
-                    const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(hh);
-                    const double pa = (gy1 - y1) * r5h, pb = (gy2 - y2) * r5h;
-                    t1 = (float)pa; t3 = (float)pb;
-                    bad |= (f32_rounding_safe(pa) ? 0u : 1u << (2 * r)) | (f32_rounding_safe(pb) ? 0u : 2u << (2 * r));
-#else
                     if (is_pos) hot = gt_staged ? s_glab[m] : __ldg(p.gt_labels + (size_t)b * p.Gmax + m);
                     const double r5h = table_ok ? r5h_tab : 5.0 * rcp_fast(hh);
                     reg_target5_pair(gy1, y1, gy2, y2, hh, r5h, t1, t3);
-#endif
                 }
                 if (p.img_hw && (out_x || ((y1 + y2) / 2.0) >= img_h)) state = -1.0f;
                 const int k = lane * A + a;                 // reference order within the tile row
@@ -655,22 +639,6 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
                     p.argmax[(size_t)b * p.N + lstart + ((size_t)(cy0 + r) * W + cx0 + lane) * A + a] = arg[r];
             }
         }
-#ifdef KT_EPI_BATCH
-        if (bad) {                                          // ~0.4 % of the threads; a set bit implies r < nrows and G > 0
-#pragma unroll
-            for (int r = 0; r < KT_ROWS; ++r) {
-                const unsigned bits = (bad >> (2 * r)) & 3u;
-                if (bits) {
-                    const int m = arg[r];
-                    const double g1 = gt_staged ? s_gy1[m] : __ldg(gtb + 4 * (size_t)m + 1);
-                    const double g2 = gt_staged ? s_gy2[m] : __ldg(gtb + 4 * (size_t)m + 3);
-                    float* sr = s_reg + r * reg_stride + (int)((al0 + r * alw) & 3u) + (lane * A + a) * 5;
-                    if (bits & 1u) sr[1] = reg_target_exact(g1 - row[r][0], row[r][2]);
-                    if (bits & 2u) sr[3] = reg_target_exact(g2 - row[r][1], row[r][2]);
-                }
-            }
-        }
-#endif
     }
     if (p.npos || p.npos_total) {
         my_pos = rn_warp_sum(my_pos);
@@ -683,60 +651,251 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
         if (p.npos_total) atomicAdd(p.npos_total, (float)s_npos);   // integer-valued: exact, order-independent
     }
 
-    const int cnt = ncols * A;
-    const long long tile_row0 = (long long)b * p.N + lstart + ((long long)cy0 * W + cx0) * A;
-    // ---- write-out: each tile row is one contiguous anchor range, staged with the destination's 16-byte phase.
-    if (p.vec_ok) {
-        // TMA bulk stores: ONE thread per (row, tensor) hands its staged row to the copy engine --
-        // cp.async.bulk.global.shared::cta for the 16-byte aligned interior, the sm_100 .cp_mask form (a byte mask
-        // inside one 16-byte chunk) for the partial chunks at the two ends -- instead of every thread looping
-        // over LDS.128 / STG.128 pairs (that loop was ~15 % of the kernel's instructions).
-        const int job = tid;                                // jobs [0, KT_ROWS): regression rows, [KT_ROWS, 2 KT_ROWS): label rows
-        const bool lab_job = job >= KT_ROWS;
-        const int r = lab_job ? job - KT_ROWS : job;
-        if (job < 2 * KT_ROWS && r < nrows && !(lab_job && !C1)) {
-            const int per = lab_job ? 2 : 5;
-            const long long start = (tile_row0 + (long long)r * W * A) * per;
-            const int len = cnt * per, shift = (int)(start & 3);
-            const float* src = lab_job ? s_lab + r * lab_stride : s_reg + r * reg_stride;
-            float* dst = (lab_job ? p.lab : p.reg) + (start - shift);
-            const int end = shift + len;                    // staged floats [shift, end) are valid
-            rn_bulk_store_row(dst, src, shift, end);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the CTA's shared memory may go away after this
+    tile_write_out<C1>(p, s_reg, s_lab, s_state, s_hot, b, lstart, cy0, cx0, W, A, ncols, nrows, reg_stride, lab_stride, tid, nthreads);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 for pages with at most 32 GT tables and at most 9 anchor types per cell -- the table-detection case.  Same tiling and,
+// operation for operation, the same arithmetic as k_anchor_targets_tiles (which stays the general path: any number of
+// tables, up to 24 anchor types); what differs is WHO computes what:
+//  * one GT group: no chunk / group loops, the staged tables stay valid for the epilogue;
+//  * the y half of a regression target depends on (anchor type, tile row, table) only -- it is the same for all 32 lanes of
+//    a warp.  After the matching the warp computes it ONCE per (row, table that can be an argmax of the warp: table 0 and the
+//    tables that reach the warp), lane = (table slot, row), 8 tables per pass, usually one pass, into a table in shared
+//    memory (it takes over the intersection heights' space).  A thread's epilogue then costs one 64-bit shared-memory load
+//    per anchor instead of two fp64 quotients with their rounding certificates (model/anchors.py:300-311);
+//  * the row half of the border rule (model/anchors.py:85-90) is a per-warp bit mask: 4 lanes + one ballot;
+//  * the one-hot label of the (rare) positive anchors is written behind ONE branch after the row loop, so a row's body has
+//    no convergence region but the change of the argmax table.
+// ------------------------------------------------------------------------------------------------
+constexpr int K32_G = 32;
+constexpr int K32_A = 9;
+
+template <bool C1, bool AM>
+__global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const K1Params p, const K1Tiles tl) {
+    extern __shared__ __align__(16) float s_dyn[];
+    __shared__ double s_gx1[K32_G], s_gy1[K32_G], s_gx2[K32_G], s_gy2[K32_G], s_ga[K32_G];
+    __shared__ int s_glab[K32_G];
+    __shared__ double s_row[K32_A][KT_ROWS][3];             // per (anchor type, tile row): y1, y2, height
+    __shared__ unsigned char s_list[K32_A][32];             // per warp: the tables that can be an argmax, ascending
+    __shared__ int s_npos;
+
+    const int tid = threadIdx.x, lane = tid & 31, a = tid >> 5;
+    const int A = p.lv.anchors_per_cell, L = p.lv.num_levels;
+    const int nthreads = 32 * A;
+    const int b = blockIdx.y;
+    const int reg_stride = 32 * A * 5 + 4, lab_stride = 32 * A * 2 + 4;     // floats per staged tile row (multiples of 4)
+    float* s_reg = s_dyn;                                   // [KT_ROWS][reg_stride]
+    float* s_lab = s_reg + KT_ROWS * reg_stride;            // C == 1: [KT_ROWS][lab_stride] {one-hot, state} pairs
+    float* s_state = s_lab;                                 // C  > 1: [KT_ROWS][32][A] states, then the hot classes
+    int* s_hot = reinterpret_cast<int*>(s_lab + KT_ROWS * 32 * A);
+    double* s_ih = reinterpret_cast<double*>(s_lab + KT_ROWS * lab_stride);   // [A][KT_ROWS][32]; 8-byte aligned
+    if (tid == 0) s_npos = 0;
+
+    // ---- tile -> (level, tile x, tile y): block-uniform (static indices only, see k_anchor_targets_tiles) ----
+    int level = 0, tstart = 0, tiles_x = tl.tiles_x[0], W = p.lv.w[0], H = p.lv.h[0], istride = p.lv.stride[0], lstart = p.lv.start[0];
+    float inv_tiles_x = tl.inv_tiles_x[0];
+#pragma unroll
+    for (int l = 1; l < RN_MAX_LEVELS; ++l)
+        if (l < L && (int)blockIdx.x >= tl.tile_start[l]) {
+            level = l; tstart = tl.tile_start[l]; tiles_x = tl.tiles_x[l]; inv_tiles_x = tl.inv_tiles_x[l];
+            W = p.lv.w[l]; H = p.lv.h[l]; istride = p.lv.stride[l]; lstart = p.lv.start[l];
         }
-        if (!C1) {
-            // C > 1: a label row is C + 1 floats, all zero except the one-hot entry of a positive anchor and a non-zero
-            // state (~1 % of the anchors).  So the tile rows' label ranges are zero-filled with 128-bit stores -- no
-            // per-element row / column arithmetic -- and, after a barrier, the few non-zero entries are written.
-            const int CW = p.C + 1;
-            for (int r2 = 0; r2 < nrows; ++r2) {
-                const long long start = (tile_row0 + (long long)r2 * W * A) * CW;
-                const long long len = (long long)cnt * CW;
-                float* dst = p.lab + start;
-                int head = (int)((4 - (start & 3)) & 3);
-                if (head > len) head = (int)len;
-                if (tid < head) dst[tid] = 0.0f;
-                const long long nvec = (len - head) >> 2;
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (long long v = tid; v < nvec; v += nthreads) rn_stg_stream4(dst + head + 4 * v, z);
-                const long long done = head + 4 * nvec;
-                if (tid < (int)(len - done)) dst[done + tid] = 0.0f;
-            }
-            __syncthreads();                                // orders the fix-ups below after the zero-fill (same CTA)
-            for (int j = tid; j < nrows * cnt; j += nthreads) {
-                const int r2 = j / cnt, k = j - r2 * cnt;
-                const float st = s_state[r2 * 32 * A + k];
-                const int hot = s_hot[r2 * 32 * A + k];
-                float* rowp = p.lab + (tile_row0 + (long long)r2 * W * A + k) * CW;
-                if (st != 0.0f) rowp[p.C] = st;
-                if (hot >= 0) rowp[hot] = 1.0f;
-            }
-        }
-        return;
+    const int t = blockIdx.x - tstart;
+    const int ty = rn_div(t, tiles_x, inv_tiles_x);
+    const int tx = t - ty * tiles_x;
+    const double stride = (double)istride;
+    const int cx0 = tx * 32, cy0 = ty * KT_ROWS;
+    const int ncols = min(32, W - cx0), nrows = min(KT_ROWS, H - cy0);
+    const bool valid_x = lane < ncols;
+    int G = p.gt_count[b];
+    G = max(0, min(G, min(p.Gmax, K32_G)));
+
+    // ---- the page's tables -> shared memory (one per thread) -------------------------------------------
+    const double* gtb = p.gt + (size_t)b * p.Gmax * 4;
+    if (tid < G) {
+        const double gx1 = __ldg(gtb + 4 * tid), gy1 = __ldg(gtb + 4 * tid + 1);
+        const double gx2 = __ldg(gtb + 4 * tid + 2), gy2 = __ldg(gtb + 4 * tid + 3);
+        s_gx1[tid] = gx1; s_gy1[tid] = gy1; s_gx2[tid] = gx2; s_gy2[tid] = gy2;
+        s_ga[tid] = (gx2 - gx1) * (gy2 - gy1);
+        s_glab[tid] = __ldg(p.gt_labels + (size_t)b * p.Gmax + tid);
     }
-    // unaligned output tensors (not 16-byte aligned: never the case for framework allocations): plain stores, out of line
-    write_out_unaligned(p.reg, p.lab, p.C, s_reg, s_lab, s_state, s_hot, tile_row0, W * A, cnt, nrows, A, tid, nthreads);
+
+    // ---- geometry: base box (warp-uniform), column extent (per thread), row extents (warp-uniform) -----
+    const double* bs = p.base + ((size_t)level * A + a) * 4;
+    const double b0 = __ldg(bs), b1 = __ldg(bs + 1), b2 = __ldg(bs + 2), b3 = __ldg(bs + 3);
+    const double sx = ((double)(cx0 + lane) + 0.5) * stride;
+    const double ax1 = b0 + sx, ax2 = b2 + sx;
+    const double aw = ax2 - ax1;
+    if (lane < KT_ROWS) {
+        const double sy = ((double)(cy0 + lane) + 0.5) * stride;
+        const double y1 = b1 + sy, y2 = b3 + sy;
+        s_row[a][lane][0] = y1; s_row[a][lane][1] = y2; s_row[a][lane][2] = y2 - y1;
+    }
+    __syncthreads();                                        // staged tables, row geometry, s_npos
+    const double (*row)[3] = s_row[a];
+    const bool match_x = valid_x && (aw > 0.0);
+    const double wx1 = b0 + ((double)cx0 + 0.5) * stride, wx2 = b2 + ((double)(cx0 + ncols - 1) + 0.5) * stride;
+
+    // ---- matching: lane j prepares table j's intersection heights with the warp's rows, then the live tables are
+    //      walked in GT order with warp-uniform control flow (first maximum wins) -------------------------------
+    float best[KT_ROWS];
+    int arg[KT_ROWS];
+#pragma unroll
+    for (int r = 0; r < KT_ROWS; ++r) { best[r] = 0.0f; arg[r] = 0; }   // all-zero IoU row -> argmax 0
+    double* ihw = s_ih + (size_t)a * (KT_ROWS * 32);       // this warp's [KT_ROWS][32] intersection heights
+    unsigned rows_hit = 0u;
+    if (lane < G) {
+        const double gx1 = s_gx1[lane], gy1 = s_gy1[lane], gx2 = s_gx2[lane], gy2 = s_gy2[lane];
+        // empty tables and tables outside the warp's x range have zero intersection with all its anchors
+        if ((gx2 > gx1) && (gy2 > gy1) && (gx2 > wx1) && (gx1 < wx2)) {
+#pragma unroll
+            for (int r = 0; r < KT_ROWS; ++r) {
+                const double y1 = row[r][0], y2 = row[r][1], hh = row[r][2];
+                ihw[r * 32 + lane] = dmin(y2, gy2) - dmax(y1, gy1);
+                if (r < nrows && gy2 > y1 && gy1 < y2 && hh > 0.0) rows_hit |= 1u << r;
+            }
+        }
+    }
+    __syncwarp();                                           // the intersection heights are visible to the whole warp
+    unsigned live = __ballot_sync(0xffffffffu, rows_hit != 0u);
+    const unsigned cand = live | 1u;                        // possible argmax tables of this warp: table 0 (nothing overlaps) + live
+    while (live) {                                          // warp-uniform, ascending GT order
+        const int m = __ffs(live) - 1;
+        live &= live - 1u;
+        const unsigned rmask = __shfl_sync(0xffffffffu, rows_hit, m);
+        const double g1 = s_gx1[m], g2 = s_gx2[m];
+        if (match_x && g2 > ax1 && g1 < ax2) {
+            const double iw = dmin(ax2, g2) - dmax(ax1, g1);
+            const double ga = s_ga[m];
+            if (rmask == (1u << KT_ROWS) - 1u) {
+                // every row of the tile overlaps (the common case inside a table): no per-row branches, so
+                // pairs of reciprocal chains (MUFU -> DFMA -> DFMA -> DMUL) overlap each other
+#pragma unroll
+                for (int r = 0; r < KT_ROWS; r += 2) {
+                    const double i0 = iw * ihw[r * 32 + m], i1 = iw * ihw[(r + 1) * 32 + m];
+                    const double u0 = aw * row[r][2] + ga - i0, u1 = aw * row[r + 1][2] + ga - i1;
+                    float iou0, iou1;
+                    iou_pair(i0, u0, i1, u1, iou0, iou1);
+                    if (iou0 > best[r]) { best[r] = iou0; arg[r] = m; }
+                    if (iou1 > best[r + 1]) { best[r + 1] = iou1; arg[r + 1] = m; }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < KT_ROWS; ++r) {
+                    if (rmask & (1u << r)) {
+                        const double inter = iw * ihw[r * 32 + m];
+                        const double uni = aw * row[r][2] + ga - inter;
+                        const double q = inter * rcp_fast(uni);
+                        const float iou = f32_rounding_safe(q) ? (float)q : iou_exact(inter, uni);
+                        if (iou > best[r]) { best[r] = iou; arg[r] = m; }
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();                                           // the intersection heights are dead: their space becomes the y-target table
+
+    // ---- y targets per (row, candidate table), computed by the warp once ---------------------------------
+    // 5/width, 5/height for the regression fast path: the base box's stand in for the anchor's own (they
+    // differ by rounding only) when that is far inside the fast path's tolerance (see the wrapper)
+    const double bw = __ldg(bs + 2) - __ldg(bs), bh = __ldg(bs + 3) - __ldg(bs + 1);     // re-read: not kept live across the matching loop
+    const bool table_ok = (bw > 0.0) && (bh > 0.0) && (p.max_coord < 4096.0 * fmin(bw, bh));
+    const double r5w = 5.0 * rcp_fast(table_ok ? bw : aw);
+    float2* tyw = reinterpret_cast<float2*>(ihw);           // [KT_ROWS][32]: {t1, t3} of (row, table)
+    unsigned out_y = 0u;                                    // bit r: the centres of tile row r lie below the page
+    bool out_x = false;
+    {
+        const int r = lane & (KT_ROWS - 1);
+        const double y1 = row[r][0], y2 = row[r][1], hh = row[r][2];
+        if (G > 0) {
+            const int ncand = __popc(cand);
+            if ((cand >> lane) & 1u) s_list[a][__popc(cand & ((1u << lane) - 1u))] = (unsigned char)lane;
+            __syncwarp();
+            const double r5h = table_ok ? 5.0 * rcp_fast(bh) : 5.0 * rcp_fast(hh);
+            for (int k = lane >> 2; k < ncand; k += 8) {    // lane = (table slot, row)
+                const int m = s_list[a][k];
+                float t1, t3;
+                reg_target5_pair(s_gy1[m], y1, s_gy2[m], y2, hh, r5h, t1, t3);
+                tyw[r * 32 + m] = make_float2(t1, t3);
+            }
+        }
+        if (p.img_hw) {
+            out_y = __ballot_sync(0xffffffffu, (lane < KT_ROWS) && (((y1 + y2) / 2.0) >= (double)p.img_hw[2 * b]));
+            out_x = ((ax1 + ax2) / 2.0) >= (double)p.img_hw[2 * b + 1];
+        }
+        __syncwarp();                                       // the table is complete and visible to the whole warp
+    }
+
+    // ---- state, regression targets, border rule, staging --------------------------------------------------
+    int my_pos = 0;
+    // misalignment (in anchors, mod 4) of the tile's first anchor and of one feature-map row; unsigned wrap-around
+    // keeps the low two bits right.  Row r is staged shifted by ((al0 + r * alw) * 5) & 3 = (al0 + r * alw) & 3 floats
+    // (regression) and ((al0 + r * alw) * 2) & 3 floats (labels).
+    const unsigned al0 = ((unsigned)b * (unsigned)p.N + (unsigned)lstart + ((unsigned)cy0 * (unsigned)W + (unsigned)cx0) * (unsigned)A) & 3u;
+    const unsigned alw = ((unsigned)W * (unsigned)A) & 3u;
+    if (valid_x) {
+        const int k = lane * A + a;                         // reference order within the tile row
+        int prev = -1;                                      // the x targets depend on the column and the table only
+        float t0 = 0.f, t2 = 0.f;
+        unsigned posbits = 0u;
+#pragma unroll
+        for (int r = 0; r < KT_ROWS; ++r) {
+            if (r < nrows) {
+                float state = 0.0f, t1 = 0.f, t3 = 0.f;
+                if (G > 0) {
+                    const int m = arg[r];
+                    const bool is_pos = best[r] >= p.pos;
+                    const bool is_ign = (best[r] > p.neg) && !is_pos;
+                    state = is_pos ? 1.0f : (is_ign ? -1.0f : 0.0f);
+                    posbits |= is_pos ? (1u << r) : 0u;
+                    if (m != prev) {                        // x targets change with the table only
+                        prev = m;
+                        reg_target5_pair(s_gx1[m], ax1, s_gx2[m], ax2, aw, r5w, t0, t2);
+                    }
+                    const float2 ty2 = tyw[r * 32 + m];
+                    t1 = ty2.x; t3 = ty2.y;
+                }
+                if (out_x || ((out_y >> r) & 1u)) state = -1.0f;
+                const unsigned al = al0 + r * alw;          // first anchor of the staged row, mod 4 in the low bits
+                float* sr = s_reg + r * reg_stride + (int)(al & 3u) + k * 5;
+                sr[0] = t0; sr[1] = t1; sr[2] = t2; sr[3] = t3; sr[4] = state;
+                if (C1) {
+                    *reinterpret_cast<float2*>(s_lab + r * lab_stride + (int)((al & 1u) * 2u) + k * 2) = make_float2(0.0f, state);
+                } else {
+                    s_state[r * 32 * A + k] = state;
+                    s_hot[r * 32 * A + k] = -1;
+                }
+                my_pos += (state == 1.0f);
+                if (AM && p.argmax)
+                    p.argmax[(size_t)b * p.N + lstart + ((size_t)(cy0 + r) * W + cx0 + lane) * A + a] = arg[r];
+            }
+        }
+        if (posbits) {                                      // positives are ~0.2 % of the anchors
+#pragma unroll
+            for (int r = 0; r < KT_ROWS; ++r) {
+                if (posbits & (1u << r)) {
+                    const int hot = s_glab[arg[r]];
+                    if (C1) {
+                        if (hot == 0) s_lab[r * lab_stride + (int)(((al0 + r * alw) & 1u) * 2u) + k * 2] = 1.0f;
+                    } else {
+                        s_hot[r * 32 * A + k] = hot;
+                    }
+                }
+            }
+        }
+    }
+    if (p.npos || p.npos_total) {
+        my_pos = rn_warp_sum(my_pos);
+        if (lane == 0 && my_pos) atomicAdd(&s_npos, my_pos);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the staged rows are read by the TMA engine below
+    __syncthreads();
+    if (tid == 0 && s_npos) {
+        if (p.npos) atomicAdd(p.npos + b, s_npos);
+        if (p.npos_total) atomicAdd(p.npos_total, (float)s_npos);   // integer-valued: exact, order-independent
+    }
+    tile_write_out<C1>(p, s_reg, s_lab, s_state, s_hot, b, lstart, cy0, cx0, W, A, ncols, nrows, reg_stride, lab_stride, tid, nthreads);
 }
 
 __global__ void k_anchors_f64(const RnLevels lv, const double* base, int N, double* out) {
@@ -776,6 +935,28 @@ __global__ void k_bbox_transform(const double* anchors, const double* gt, long l
         out[4 * i + 2] = ((gt[4 * i + 2] - ax2) / aw - nm.mean[2]) / nm.std[2];
         out[4 * i + 3] = ((gt[4 * i + 3] - ay2) / ah - nm.mean[3]) / nm.std[3];
     }
+}
+
+// The tile kernels' static + dynamic shared memory exceeds the 48 KB default: opt in.  The attribute is per DEVICE, so the
+// "done" flags are a bit per device ordinal (a process may drive several GPUs; devices >= 64 simply set it every call).
+static int k1_opt_in_shared_memory() {
+    static std::atomic<unsigned long long> done{0ull};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+    const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+    if (bit && (done.load(std::memory_order_acquire) & bit)) return RN_OK;
+    const int big = (int)kt_dyn_smem(KT_MAX_A), small = (int)kt_dyn_smem(9);
+    cudaError_t ae = cudaFuncSetAttribute(k_anchor_targets_tiles<KT_MAX_A, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<KT_MAX_A, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles32<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles32<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles32<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+    if (ae != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
+    if (bit) done.fetch_or(bit, std::memory_order_release);
+    return RN_OK;
 }
 
 }  // namespace
@@ -864,33 +1045,18 @@ extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* leve
         for (int l = num_levels; l <= RN_MAX_LEVELS; ++l) tl.tile_start[l] = tiles;
         p.max_coord = max_coord;
         const size_t dyn = kt_dyn_smem(A);
-        // static + dynamic shared memory exceeds the 48 KB default: opt in once per instantiation
-        static bool attr_done = false;
-        if (!attr_done) {
-            const int big = (int)kt_dyn_smem(KT_MAX_A), small = (int)kt_dyn_smem(9);
-            cudaError_t ae = cudaFuncSetAttribute(k_anchor_targets_tiles<KT_MAX_A, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<KT_MAX_A, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-            if (ae != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
-            attr_done = true;
-        }
+        int rc = k1_opt_in_shared_memory();
+        if (rc) return rc;
         const dim3 tgrid((unsigned)tiles, (unsigned)B);
-        // the common instantiation (9 anchors, one class, no argmax tensor) is specialised; the others share generic ones
-        if (tiles > 0 && A <= 9) {
-            static const int minb = getenv("RN_K1_MINB") ? atoi(getenv("RN_K1_MINB")) : 3;   // tuning knob (measured: 3 CTAs/SM is fastest)
-            if (C != 1) k_anchor_targets_tiles<9, 3, false, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
-            else if (argmax_out) k_anchor_targets_tiles<9, 3, true, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
-            else if (minb >= 4) k_anchor_targets_tiles<9, 4, true, false><<<tgrid, 32 * A, dyn, s>>>(p, tl);
-#ifdef KT_AEXACT
-            else if (minb == 3 && A == 9) k_anchor_targets_tiles<9, 3, true, false, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
-#endif
-            else if (minb == 3) k_anchor_targets_tiles<9, 3, true, false><<<tgrid, 32 * A, dyn, s>>>(p, tl);
-            else k_anchor_targets_tiles<9, 2, true, false><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+        // <= 9 anchor types and <= 32 tables per page (the table-detection case): the y-target-table kernel; the common
+        // instantiation (one class, no argmax tensor) is specialised; everything else goes through the general tile kernel
+        if (tiles > 0 && A <= K32_A && Gmax <= K32_G) {
+            if (C != 1) k_anchor_targets_tiles32<false, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+            else if (argmax_out) k_anchor_targets_tiles32<true, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+            else k_anchor_targets_tiles32<true, false><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+        } else if (tiles > 0 && A <= 9) {
+            if (C == 1) k_anchor_targets_tiles<9, 3, true, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+            else k_anchor_targets_tiles<9, 3, false, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
         } else if (tiles > 0) {
             if (C == 1) k_anchor_targets_tiles<KT_MAX_A, 1, true, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
             else k_anchor_targets_tiles<KT_MAX_A, 1, false, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
