@@ -213,6 +213,14 @@ int rn_nms(const float* boxes /*(K,4)*/, const float* scores /*(K)*/, long long 
            int max_output, float iou_threshold, int* out_indices, int* out_count_dev,
            void* workspace, size_t workspace_bytes, void* stream);
 
+/* profiling aid: when enabled, k_segment_nms adds its per-phase clock64() ticks (thread 0 of every CTA) to the first
+ * 8 uint64 of the filter workspace (select, gather, sort, group fetch, suppression tests, resolve).  Off by default. */
+int rn_debug_nms_timing(int enable);
+/* measurement hook (process-wide, not for concurrent use): four cudaEvent_t handles that every following filter call records on
+ * its stream before k_threshold_keys, after it, after k_segment_nms and after k_merge_topk; NULLs switch it off.  This is how
+ * bench.py times the three kernels of one call individually (rn_nms records only the last two). */
+int rn_debug_filter_events(void* before_k3, void* after_k3, void* after_nms, void* after_merge);
+
 /* ---------------------------------------------------------------------------------------------
  * N3  the reference's host post-step on the detections (RetinaNet.py:366-377):
  *     boxes /= image_scale (fp32 division, per page) and the score cut -- the reference walks the

@@ -1,8 +1,7 @@
-"""Per-phase clock64 breakdown of k_segment_nms (RN_NMS_TIMING=1) at the benchmark's inference sizes."""
+"""Per-phase clock64 breakdown of k_segment_nms (rn_debug_nms_timing) at the benchmark's inference sizes."""
 import os
 import sys
 
-os.environ["RN_NMS_TIMING"] = "1"
 import numpy as np
 import torch
 
@@ -16,7 +15,8 @@ anchors = np.asarray(rn.anchors_for_shape(HW + (3,)))
 _, anns = synthetic.training_batch(3, batch=B)
 cls, reg = synthetic.inference_predictions(3, B, anchors, anns, classes=1)
 cls_d, reg_d = torch.from_numpy(cls).cuda(), torch.from_numpy(reg).cuda()
-names = ["radix select", "gather", "bitonic sort", "batch load", "(a) vs selected", "(b) bit-matrix", "(c) resolve"]
+names = ["bisection select", "gather", "bitonic sort", "group fetch/decode", "(a) suppression tests", "(b) resolve", "-", "-"]
+rn._lib.load().rn_debug_nms_timing(1)
 for topk in (0, 1000):
     head = rn.DetectionHead(pre_nms_top_k=topk)
     for _ in range(3):

@@ -61,6 +61,8 @@ SIGNATURES = {
                                             c_int, c_longlong, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "rn_nms_workspace_bytes": (c_size_t, [c_longlong, c_int]),
     "rn_nms": (c_int, [_P, _P, c_longlong, c_int, c_float, _P, _P, _P, c_size_t, _P]),
+    "rn_debug_nms_timing": (c_int, [c_int]),
+    "rn_debug_filter_events": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "rn_rescale_cut": (c_int, [_P, _P, _P, c_int, c_int, c_float, _P, _P, _P]),
     "rn_peer_box_bytes": (c_size_t, []),
     "rn_peer_box_create": (c_int, [c_int, POINTER(c_void_p), c_void_p]),

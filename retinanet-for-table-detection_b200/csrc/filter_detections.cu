@@ -1,42 +1,35 @@
 // K3 + K4 + K5: FilterDetections (reference model/layers.py:177-264, :298-332) for a whole batch,
 // no host synchronisation anywhere.
 //
-//   K3  k_threshold_compact   one pass over classification (B,N,C): score > thr (strict, fp32);
-//                             survivors are decoded (RegressBoxes + ClipBoxes fused, anchors generated
-//                             in-kernel in fp32 like the Anchors layer) or gathered from a dense box
-//                             tensor, and appended to the (page,class) candidate slab with
-//                             warp-aggregated atomics.  The 16-byte regression row of an anchor is only
-//                             fetched when that anchor survives the threshold.
-//   K4  block radix top-k     inside k_segment_nms: 8-bit MSD radix select over the slab's 64-bit keys
-//                             (score bits | ~anchor index) picks the next <= 2048 best candidates, a
-//                             shared-memory bitonic network orders them (score desc, anchor asc).
-//   K5  bitmask NMS           same kernel: candidates are visited 128 at a time; each is tested against
-//                             the boxes selected so far, survivors get a 128x128 suppression bit-matrix
-//                             built with __ballot_sync, one warp resolves the greedy order by scanning
-//                             set bits only.  Stops at max_detections (TF's max_output_size early stop).
-//   k_merge_topk              per page: class-major concatenation + tf.nn.top_k (ties -> earlier
-//                             position) done as a C-way merge of the per-class lists; pad with -1.
+//   K3  k_threshold_keys      ONE streaming pass over classification (B,N,C): score > thr (strict, fp32); the survivors'
+//                             64-bit sort keys (score bits | ~anchor index) are appended to the (page,class) slab --
+//                             nothing else is read or written: the kernel is a pure HBM stream of the scores.
+//   K4  approximate select    inside k_segment_nms: a 4-way bisection on the key VALUE (three pivots per pass, counts by
+//       + bitonic sort        comparison and __reduce_add_sync -- no histogram, no same-address atomics) finds a threshold
+//                             that keeps between 1536 and 2048 of the unvisited keys; a bitonic network orders them.
+//   K5  bitmask NMS           same kernel.  The boxes of the ordered candidates are fetched LAZILY, 256 at a time and one
+//                             group ahead of their use: only candidates that are actually visited are ever decoded
+//                             (RegressBoxes + ClipBoxes fused, anchors generated in-kernel in fp32 like the Anchors layer)
+//                             or gathered from a dense box tensor.  Greedy NMS runs 32 candidates at a time: warp i owns
+//                             candidate i -- its lanes split the list of boxes selected so far, one ballot gives the
+//                             32-bit row of the in-batch suppression matrix -- and one warp resolves the order in registers
+//                             (no loop at all when the batch has no internal conflict).  Stops at max_detections.
+//   k_merge_topk              per page: class-major concatenation + tf.nn.top_k (ties -> earlier position) done as a
+//                             C-way merge of the per-class lists; pad with -1.
 //
-// Semantics restated from tf.image.non_max_suppression / tf.nn.top_k: see oracle/layers_np.py.
+// Semantics restated from tf.image.non_max_suppression / tf.nn.top_k (third-party, un-pinned): see oracle/layers_np.py.
 // Compiled with -fmad=false: IoU and decode are evaluated in the reference's fp32 operation order.
 #include "rn_common.cuh"
-#include <stdlib.h>
+#include <atomic>
 
 namespace {
 
 constexpr int K3_THREADS = 256;
 constexpr int NMS_THREADS = 1024;
 constexpr int NMS_WARPS = NMS_THREADS / 32;
-constexpr int NMS_CHUNK = 2048;    // candidates ordered per radix-select round
-#ifndef RN_NMS_CHUNK_NEXT
-#define RN_NMS_CHUNK_NEXT 256   // A/B at 64 pages x 5 k candidates: 256 -> 190 us, 512 -> 198 us, 1024 -> 197 us, 2048 -> 203 us
-#endif
-constexpr int NMS_CHUNK_NEXT = RN_NMS_CHUNK_NEXT;   // ... in the rounds after the first
-#ifndef RN_NMS_BATCH
-#define RN_NMS_BATCH 128         // A/B (64 pages, 5 k candidates each): 64 -> 217 us, 128 -> 203 us, 256 -> 214 us
-#endif
-constexpr int NMS_BATCH = RN_NMS_BATCH;     // candidates resolved per bit-matrix
-constexpr int NMS_WORDS = NMS_BATCH / 32;
+constexpr int NMS_CHUNK = 2048;    // candidates ordered per round (shared-memory capacity of the sorted chunk)
+constexpr int NMS_GROUP = 256;     // boxes fetched / decoded per step, one group ahead of the greedy loop
+constexpr int NMS_BATCH = 32;      // candidates resolved per greedy step: warp i <-> candidate i
 constexpr int MAX_DET_LIMIT = 1024;
 
 struct Norm4 { float mean[4]; float std[4]; };
@@ -58,19 +51,15 @@ __device__ __forceinline__ float key_score(unsigned long long k) { return ord2f(
 struct Slabs {
     int* counts;                 // (S)
     unsigned long long* keys;    // (S, cap)
-    float4* boxes;               // (S, cap)   [compact mode]   or the caller's (K) boxes [direct mode]
     int* labels;                 // (S, cap)   only for class-agnostic filtering
     long long cap;
 };
 
+// ------------------------------------------------------------------------------------------------
+// K3: threshold + key compaction
+// ------------------------------------------------------------------------------------------------
 struct K3Params {
     const float* cls;      // (B, N, C)
-    const float* boxes;    // (B, N, 4) dense, or nullptr when decoding
-    const float* reg;      // (B, N, 4) regression (decode mode)
-    const float* base32;   // (L, A, 4) float32 base anchors (decode mode)
-    RnLevels lv;
-    Norm4 nm;
-    float clipW, clipH;
     int B, N, C;
     int class_specific;
     float thr;
@@ -79,49 +68,16 @@ struct K3Params {
     Slabs sl;
 };
 
-template <bool DECODE>
-__device__ __forceinline__ float4 candidate_box(const K3Params& p, int b, int n) {
-    if (!DECODE) return __ldg(reinterpret_cast<const float4*>(p.boxes) + (size_t)b * p.N + n);
-    int level, cx, cy, a;
-    rn_locate(p.lv, n, level, cx, cy, a);
-    const float* bs = p.base32 + ((size_t)level * p.lv.anchors_per_cell + a) * 4;
-    const float sx = ((float)cx + 0.5f) * (float)p.lv.stride[level];
-    const float sy = ((float)cy + 0.5f) * (float)p.lv.stride[level];
-    const float ax1 = __ldg(bs) + sx, ay1 = __ldg(bs + 1) + sy, ax2 = __ldg(bs + 2) + sx, ay2 = __ldg(bs + 3) + sy;
-    // scattered 16-byte rows (~2.5 % of the anchors): no L1 allocation and the smallest L2 fetch granularity
-    float4 d;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(d.x), "=f"(d.y), "=f"(d.z), "=f"(d.w) : "l"(reinterpret_cast<const float4*>(p.reg) + (size_t)b * p.N + n));
-    const float w = ax2 - ax1, h = ay2 - ay1;
-    float4 o;
-    o.x = ax1 + (d.x * p.nm.std[0] + p.nm.mean[0]) * w;
-    o.y = ay1 + (d.y * p.nm.std[1] + p.nm.mean[1]) * h;
-    o.z = ax2 + (d.z * p.nm.std[2] + p.nm.mean[2]) * w;
-    o.w = ay2 + (d.w * p.nm.std[3] + p.nm.mean[3]) * h;
-    o.x = fminf(fmaxf(o.x, 0.0f), p.clipW);
-    o.y = fminf(fmaxf(o.y, 0.0f), p.clipH);
-    o.z = fminf(fmaxf(o.z, 0.0f), p.clipW);
-    o.w = fminf(fmaxf(o.w, 0.0f), p.clipH);
-    return o;
-}
-
-// Measured (profiles/k3_probe.py, 64 pages): streaming the 51 MB of scores alone takes 12.5-14.5 us; the 326 k
-// candidates add ~13 us, which is the HBM random-access rate for their scattered 16-byte regression rows
-// (~22 G rows/s), not instruction issue or atomics -- a persistent, warp-autonomous, software-pipelined variant
-// (no block barriers, next chunk's loads in flight during the candidate phase, 4 candidates per lane in flight)
-// streamed faster (12.5 us) but took 34 us with candidates and was not kept.
-// grid = (tiles of a page, pages).  Two phases per CTA so that the sparse candidates (~2.5 % of the scores)
-// never make whole warps walk the divergent decode path:
-//   1. every thread streams K3_VEC float4 groups of scores (all loads issued up front) and pushes the
-//      survivors of `score > thr` into a shared-memory list (shared-memory atomics);
-//   2. the list is consumed densely, one candidate per thread: slot reservation (ONE global atomic per CTA
-//      when all candidates feed the same slab, i.e. C == 1 or class-agnostic; one per candidate otherwise),
-//      box decode, key/box store.
+// grid = (tiles of a page, pages).  Two phases per CTA:
+//   1. every thread streams K3_VEC float4 groups of scores (all loads issued up front), the survivors of `score > thr` are
+//      ranked with a warp prefix sum and pushed into a shared-memory list (ONE shared-memory atomic per warp);
+//   2. the list is consumed densely, one candidate per thread: slot reservation (ONE global atomic per CTA when all
+//      candidates feed the same slab, i.e. C == 1 or class-agnostic; one per candidate otherwise) and the key store.
+// Algorithmic bytes: 4 per score read + 8 per candidate written (~2.5 % of the scores).
 constexpr int K3_VEC = 4;                                   // float4 groups per thread
 constexpr int K3_TILE = K3_THREADS * K3_VEC * 4;            // scores per CTA (class-specific path)
 
-template <bool DECODE>
-__global__ void __launch_bounds__(K3_THREADS) k_threshold_compact(const K3Params p) {
+__global__ void __launch_bounds__(K3_THREADS) k_threshold_keys(const K3Params p) {
     __shared__ int s_elem[K3_TILE];
     __shared__ float s_score[K3_THREADS * K3_VEC];          // class-agnostic path only (score = max over classes)
     __shared__ int s_label[K3_THREADS * K3_VEC];            // class-agnostic path only
@@ -130,8 +86,8 @@ __global__ void __launch_bounds__(K3_THREADS) k_threshold_compact(const K3Params
     if (tid == 0) s_count = 0;
     __syncthreads();
     const bool one_slab = (p.C == 1) || !p.class_specific;
+    const int total = p.N * p.C;                            // scores of this page, < 2^31 (checked on the host)
     if (p.class_specific) {
-        const int total = p.N * p.C;                        // scores of this page, < 2^31 (checked on the host)
         const float* src = p.cls + (size_t)b * total;
         const int tile0 = blockIdx.x * K3_TILE;
         float sv[K3_VEC][4];
@@ -159,23 +115,15 @@ __global__ void __launch_bounds__(K3_THREADS) k_threshold_compact(const K3Params
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
         const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
-        int at = 0;
         if (warp_total) {                                   // warp-uniform
+            int at = 0;
             if (lane == 31) at = atomicAdd(&s_count, warp_total);
             at = __shfl_sync(0xffffffffu, at, 31) + incl - mine;
-            // only the element index is staged; the score is re-read (an L2 hit) by the thread that takes the
-            // candidate, together with its regression row
+            // only the element index is staged; the score is re-read (an L2 hit) by the thread that stores the key
             while (hits) {
                 const int j = __ffs(hits) - 1;
                 hits &= hits - 1u;
-                const int e = tile0 + (((j >> 2) * K3_THREADS + tid) << 2) + (j & 3);
-                s_elem[at++] = e;
-#ifdef K3_PREFETCH_ROWS
-                // (A/B for the next sweep, off) request the candidate's regression row now: phase 2 is bound by the number of
-                // scattered rows in flight, and this puts them in flight one barrier + one list pass earlier
-                if (DECODE && p.C == 1)
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const float4*>(p.reg) + (size_t)b * p.N + e));
-#endif
+                s_elem[at++] = tile0 + (((j >> 2) * K3_THREADS + tid) << 2) + (j & 3);
             }
         }
     } else {
@@ -197,42 +145,75 @@ __global__ void __launch_bounds__(K3_THREADS) k_threshold_compact(const K3Params
     }
     __syncthreads();
     const int found = s_count;
-    if (found == 0) return;
-    // slot reservation (one global atomic per CTA when all candidates feed one slab) is issued first and only
-    // waited for after the candidates' boxes have been fetched and decoded: the two round trips overlap
-    if (one_slab && tid == 0) s_base = atomicAdd(p.sl.counts + b, found);
-    for (int i0 = 0; i0 < found; i0 += K3_THREADS) {
-        const int i = i0 + tid;
-        const bool act = i < found;
-        int n = 0, c = 0, seg = b;
-        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-        float score = 0.f;
-        long long slot = 0;
-        if (act) {
-            const int e = s_elem[i];
-            n = e;
-            score = p.class_specific ? __ldg(p.cls + (size_t)b * p.N * p.C + e) : s_score[i];
-            if (one_slab) {
-                if (!p.class_specific) c = s_label[i];
-            } else {
-                n = rn_div(e, p.C, p.inv_c);
-                c = e - n * p.C;
-                seg = b * p.C + c;
-                slot = atomicAdd(p.sl.counts + seg, 1);
-            }
-            box = candidate_box<DECODE>(p, b, n);
+    if (found == 0) return;                                 // block-uniform
+    if (one_slab) {
+        if (tid == 0) s_base = atomicAdd(p.sl.counts + b, found);
+        __syncthreads();
+    }
+    for (int i = tid; i < found; i += K3_THREADS) {
+        const int e = s_elem[i];
+        int n = e, c = 0, seg = b;
+        const float score = p.class_specific ? __ldg(p.cls + (size_t)b * total + e) : s_score[i];
+        long long slot;
+        if (one_slab) {
+            if (!p.class_specific) c = s_label[i];
+            slot = (long long)s_base + i;
+        } else {
+            n = rn_div(e, p.C, p.inv_c);
+            c = e - n * p.C;
+            seg = b * p.C + c;
+            slot = atomicAdd(p.sl.counts + seg, 1);
         }
-        if (one_slab && i0 == 0) __syncthreads();           // s_base has arrived
-        if (act) {
-            if (one_slab) slot = (long long)s_base + i;
-            if (slot < p.sl.cap) {                          // dropped when the slab is full; the count keeps
-                const size_t dst = (size_t)seg * p.sl.cap + slot;   // growing so k_segment_nms reports the overflow
-                p.sl.keys[dst] = make_key(score, (unsigned)n);
-                p.sl.boxes[dst] = box;
-                if (p.sl.labels) p.sl.labels[dst] = c;
-            }
+        if (slot < p.sl.cap) {                              // dropped when the slab is full; the count keeps
+            const size_t dst = (size_t)seg * p.sl.cap + slot;   // growing so k_segment_nms reports the overflow
+            p.sl.keys[dst] = make_key(score, (unsigned)n);
+            if (p.sl.labels) p.sl.labels[dst] = c;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// where a candidate's box comes from: a dense (pages, N, 4) tensor, or the fused decode (Anchors + RegressBoxes + ClipBoxes)
+// ------------------------------------------------------------------------------------------------
+struct BoxSource {
+    const float* rows;     // (pages, N, 4): boxes (dense mode) or regression deltas (decode mode)
+    const float* base32;   // (L, A, 4) float32 base anchors (decode mode)
+    RnLevels lv;
+    Norm4 nm;
+    float clipW, clipH;
+    int N;
+};
+
+// the candidate's 16-byte row.  Scattered (~1 % of the rows are ever visited): no L1 allocation, smallest L2 fetch granularity
+__device__ __forceinline__ float4 fetch_row(const BoxSource& s, int page, int n) {
+    float4 d;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(d.x), "=f"(d.y), "=f"(d.z), "=f"(d.w) : "l"(reinterpret_cast<const float4*>(s.rows) + (size_t)page * s.N + n));
+    return d;
+}
+
+// row -> box.  Decode mode: fp32 anchor as the Anchors layer computes it (model/utils.py:51-80), a + (d * std + mean) * len
+// in the reference's order (model/utils.py:102-110), clip to [0, W] x [0, H] (model/layers.py:166-169).
+template <bool DECODE>
+__device__ __forceinline__ float4 finish_box(const BoxSource& s, int n, const float4 d) {
+    if (!DECODE) return d;
+    int level, cx, cy, a;
+    rn_locate(s.lv, n, level, cx, cy, a);
+    const float* bs = s.base32 + ((size_t)level * s.lv.anchors_per_cell + a) * 4;
+    const float sx = ((float)cx + 0.5f) * (float)s.lv.stride[level];
+    const float sy = ((float)cy + 0.5f) * (float)s.lv.stride[level];
+    const float ax1 = __ldg(bs) + sx, ay1 = __ldg(bs + 1) + sy, ax2 = __ldg(bs + 2) + sx, ay2 = __ldg(bs + 3) + sy;
+    const float w = ax2 - ax1, h = ay2 - ay1;
+    float4 o;
+    o.x = ax1 + (d.x * s.nm.std[0] + s.nm.mean[0]) * w;
+    o.y = ay1 + (d.y * s.nm.std[1] + s.nm.mean[1]) * h;
+    o.z = ax2 + (d.z * s.nm.std[2] + s.nm.mean[2]) * w;
+    o.w = ay2 + (d.w * s.nm.std[3] + s.nm.mean[3]) * h;
+    o.x = fminf(fmaxf(o.x, 0.0f), s.clipW);
+    o.y = fminf(fmaxf(o.y, 0.0f), s.clipH);
+    o.z = fminf(fmaxf(o.z, 0.0f), s.clipW);
+    o.w = fminf(fmaxf(o.w, 0.0f), s.clipH);
+    return o;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -240,9 +221,9 @@ __global__ void __launch_bounds__(K3_THREADS) k_threshold_compact(const K3Params
 // ------------------------------------------------------------------------------------------------
 struct NmsParams {
     Slabs sl;
+    BoxSource src;
     int S;                 // segments
     int segs_per_page;     // C (class specific) or 1
-    int direct_boxes;      // 1: sl.boxes is the caller's box array indexed by anchor idx (rn_nms)
     int nms;
     float iou_thr;
     int max_det;
@@ -335,6 +316,16 @@ __device__ void sort_chunk_desc(unsigned long long* s_key, unsigned* s_slot, con
     __syncthreads();
 }
 
+// number of unvisited keys (0 < k < upper) at or above each of three pivots, for the keys this thread looks at
+__device__ __forceinline__ void count3(unsigned long long k, unsigned long long upper, unsigned long long q1, unsigned long long q2,
+                                       unsigned long long q3, unsigned& c1, unsigned& c2, unsigned& c3) {
+    const bool live = (k != 0ull) && (k < upper);
+    c1 += (live && k >= q1) ? 1u : 0u;
+    c2 += (live && k >= q2) ? 1u : 0u;
+    c3 += (live && k >= q3) ? 1u : 0u;
+}
+
+template <bool DECODE>
 __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // dynamic: selected boxes (normalised corners) + areas, sized by max_det
@@ -343,35 +334,34 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
 
     __shared__ unsigned long long s_key[NMS_CHUNK];
     __shared__ unsigned s_slot[NMS_CHUNK];
-    __shared__ float4 s_cbox[NMS_BATCH];      // corner-normalised
-    __shared__ float4 s_craw[NMS_BATCH];      // as stored
-    __shared__ float s_carea[NMS_BATCH];
-    __shared__ int s_alive[NMS_BATCH];
-    __shared__ unsigned s_mask[NMS_BATCH * NMS_WORDS];
-    __shared__ unsigned short s_pick[NMS_BATCH];
-    __shared__ unsigned s_hist[256];
-    __shared__ unsigned long long s_prefix;
-    __shared__ int s_want, s_loaded, s_nsel, s_done;
+    __shared__ float4 s_gbox[NMS_GROUP];      // the group's boxes, corner-normalised
+    __shared__ float4 s_graw[NMS_GROUP];      // ... as decoded / stored
+    __shared__ float s_garea[NMS_GROUP];
+    __shared__ unsigned s_vict[NMS_BATCH];    // per batch member: the later members it suppresses
+    __shared__ int s_dead[NMS_BATCH];         // per batch member: suppressed by an earlier selection
+    __shared__ unsigned s_cnt[3][4];          // pivot counts of the bisection, three rotating sets
+    __shared__ int s_loaded, s_nsel;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int seg = blockIdx.x;
     const int total = p.sl.counts[seg];
     const int cnt = (int)min((long long)total, p.sl.cap);
-    if (total > cnt && p.status && tid == 0) p.status[seg / p.segs_per_page] = 1;
+    const int page = seg / p.segs_per_page;
+    if (total > cnt && p.status && tid == 0) p.status[page] = 1;
     const int limit = p.pre_nms_top_k > 0 ? min(cnt, p.pre_nms_top_k) : cnt;
     const unsigned long long* keys = p.sl.keys + (size_t)seg * p.sl.cap;
-    const float4* boxes = p.direct_boxes ? p.sl.boxes : p.sl.boxes + (size_t)seg * p.sl.cap;
     const int* labels = p.sl.labels ? p.sl.labels + (size_t)seg * p.sl.cap : nullptr;
-    const int seg_label = seg % p.segs_per_page;
+    const int seg_label = seg - page * p.segs_per_page;
 
-    // optional phase timing (RN_NMS_TIMING=1): thread 0 accumulates clock64() deltas per phase
+    // optional phase timing (rn_debug_nms_timing(1)): thread 0 accumulates clock64() deltas per phase
     long long t_mark = p.timing ? clock64() : 0;
 #define RN_PHASE(k) do { if (p.timing && tid == 0) { const long long now = clock64(); atomicAdd(p.timing + (k), (unsigned long long)(now - t_mark)); t_mark = now; } } while (0)
-    unsigned long long upper = ~0ull;   // keys >= upper have been visited
-    int visited = 0, nsel = 0, round = 0;
+    unsigned long long upper = ~0ull;   // keys >= upper have been visited (no key equals ~0: its score bits would be a NaN's)
+    int visited = 0, nsel = 0, round = 0, bis = 0;
     if (tid == 0) s_nsel = 0;
+    if (tid < 4) s_cnt[0][tid] = 0u;
     // The slab's keys are read ONCE into registers (8 per thread) when the slab has <= 8192 candidates -- the
-    // radix-select passes and the gathers of every round then run out of registers; larger slabs stream the
+    // bisection passes and the gathers of every round then run out of registers; larger slabs stream the
     // keys from global memory (L2) in every pass.
     constexpr int KPT = 8;
     const bool in_regs = cnt <= KPT * NMS_THREADS;
@@ -384,192 +374,182 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     __syncthreads();
 
     while (visited < limit && nsel < p.max_det) {
-        // first round: the NMS_CHUNK best candidates.  Later rounds are only reached when those did not yield max_det
-        // selections -- typically a few hundred more are needed, not another 2048 -- so they start at NMS_CHUNK_NEXT
-        // and double (a select + sort round costs about the same as consuming 1000 candidates)
-        const int take = min(round == 0 ? NMS_CHUNK : min(NMS_CHUNK, NMS_CHUNK_NEXT << (round - 1)), limit - visited);
+        // ---------------- K4: a threshold key that keeps between `lo` and `hi` of the unvisited keys ----------------
+        // The first round takes (up to) a full chunk; later rounds are only reached when its candidates did not yield
+        // max_det selections -- typically a few hundred more are needed -- so they start small and double.
+        // (with pre_nms_top_k only `need` more candidates may be visited at all: the chunk is sized for them)
+        const int need = limit - visited;
+        int hi = round == 0 ? NMS_CHUNK : min(NMS_CHUNK, 512 << (round - 1));
+        while (hi >= 256 && (hi >> 1) >= need) hi >>= 1;
+        const int lo = min(hi - (hi >> 2), need);
         ++round;
-        // ---------------- K4: radix select the `take` largest unvisited keys --------------------
-        unsigned long long thr_key = 0ull;
-        if (cnt - visited > take) {
-            if (tid == 0) { s_prefix = 0ull; s_want = take; s_done = 0; }
-            unsigned long long mask = 0ull;
-            for (int shift = 56; shift >= 0; shift -= 8) {
-                if (tid < 256) s_hist[tid] = 0u;
-                __syncthreads();
-                const unsigned long long prefix = s_prefix;
+        const int remaining = cnt - visited;
+        unsigned long long thr_key = 0ull;                   // remaining <= hi: everything that is left
+        if (remaining > hi) {
+            // c(x) = #{unvisited k >= x} falls from `remaining` (> hi) at x = 0 to 0 (< lo) at x = upper; keys are unique, so
+            // c steps by one and some x has lo <= c(x) <= hi.  Each pass evaluates c at the three quartile points of [L, H)
+            // and either accepts one of them or keeps the quarter that brackets the window.
+            unsigned long long L = 0ull, H = upper;
+            for (int pass = 0; pass < 96; ++pass, ++bis) {
+                const int set = bis % 3;                          // `bis` runs on across rounds: the rotation never restarts on a used set
+                if (tid < 4) s_cnt[(bis + 1) % 3][tid] = 0u;      // the next pass's set (last read two barriers ago)
+                const unsigned long long span = H - L;
+                const unsigned long long q1 = L + (span >> 2), q2 = L + (span >> 1), q3 = q2 + (span >> 2);
+                unsigned c1 = 0u, c2 = 0u, c3 = 0u;
                 if (in_regs) {
 #pragma unroll
-                    for (int t = 0; t < KPT; ++t) {
-                        const unsigned long long k = rk[t];
-                        if (k != 0ull && k < upper && (k & mask) == prefix) atomicAdd(&s_hist[(unsigned)(k >> shift) & 255u], 1u);
-                    }
+                    for (int t = 0; t < KPT; ++t) count3(rk[t], upper, q1, q2, q3, c1, c2, c3);
                 } else {
-                    for (int i = tid; i < cnt; i += NMS_THREADS) {
-                        const unsigned long long k = __ldcg(keys + i);
-                        if (k < upper && (k & mask) == prefix) atomicAdd(&s_hist[(unsigned)(k >> shift) & 255u], 1u);
-                    }
+                    for (int i = tid; i < cnt; i += NMS_THREADS) count3(__ldcg(keys + i), upper, q1, q2, q3, c1, c2, c3);
+                }
+                c1 = __reduce_add_sync(0xffffffffu, c1);
+                c2 = __reduce_add_sync(0xffffffffu, c2);
+                c3 = __reduce_add_sync(0xffffffffu, c3);
+                if (lane == 0) {
+                    if (c1) atomicAdd(&s_cnt[set][0], c1);
+                    if (c2) atomicAdd(&s_cnt[set][1], c2);
+                    if (c3) atomicAdd(&s_cnt[set][2], c3);
                 }
                 __syncthreads();
-                if (warp == 0) {
-                    // suffix sums over the 256 bins, 8 bins per lane, highest digit first
-                    unsigned local[8], run = 0;
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) { local[t] = s_hist[255 - (lane * 8 + t)]; run += local[t]; }
-                    unsigned incl = run;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-                    unsigned before = incl - run;          // keys in strictly higher digit groups of earlier lanes
-                    const unsigned want = (unsigned)s_want;
-                    int digit = -1; unsigned rem = 0; bool whole = false;
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        if (digit < 0 && before + local[t] >= want && before < want) {
-                            digit = 255 - (lane * 8 + t); rem = want - before;
-                            whole = (local[t] == rem);     // every key of this digit group is wanted: lower digits do not matter
-                        }
-                        before += local[t];
-                    }
-                    if (digit >= 0) { s_prefix = prefix | ((unsigned long long)digit << shift); s_want = (int)rem; s_done = whole ? 1 : 0; }
-                }
-                mask |= 255ull << shift;
-                __syncthreads();
-                if (s_done) break;       // block-uniform (scores are mostly distinct: the low 32 index bits rarely need passes)
+                const int n1 = (int)s_cnt[set][0], n2 = (int)s_cnt[set][1], n3 = (int)s_cnt[set][2];   // n1 >= n2 >= n3
+                if (n1 >= lo && n1 <= hi) { thr_key = q1; ++bis; break; }
+                if (n2 >= lo && n2 <= hi) { thr_key = q2; ++bis; break; }
+                if (n3 >= lo && n3 <= hi) { thr_key = q3; ++bis; break; }
+                if (n1 < lo) H = q1;                         // c(L) > hi, c(q1) < lo
+                else if (n2 < lo) { L = q1; H = q2; }        // n1 > hi
+                else if (n3 < lo) { L = q2; H = q3; }
+                else L = q3;                                 // n3 > hi
+                thr_key = L;                                 // (only used if the pass limit is ever hit: more than `hi` keys, the gather truncates)
             }
-            thr_key = s_prefix;          // exactly `take` unvisited keys are >= thr_key (its undecided low digits are 0)
         }
         RN_PHASE(0);
-        // ---------------- gather the chunk into shared memory ----------------------------------------
+        // ---------------- gather the chunk into shared memory (one shared-memory atomic per warp and key slot) ----------
         if (tid == 0) s_loaded = 0;
         __syncthreads();
         if (in_regs) {
 #pragma unroll
             for (int t = 0; t < KPT; ++t) {
                 const unsigned long long k = rk[t];
-                if (k != 0ull && k < upper && k >= thr_key) {
-                    const int at = atomicAdd(&s_loaded, 1);
-                    if (at < NMS_CHUNK) { s_key[at] = k; s_slot[at] = (unsigned)(t * NMS_THREADS + tid); }
+                const bool in = (k != 0ull) && (k < upper) && (k >= thr_key);
+                const unsigned m = __ballot_sync(0xffffffffu, in);
+                if (m) {                                    // warp-uniform
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_loaded, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const int at = base + __popc(m & ((1u << lane) - 1u));
+                    if (in && at < NMS_CHUNK) { s_key[at] = k; s_slot[at] = (unsigned)(t * NMS_THREADS + tid); }
                 }
             }
         } else {
-            for (int i = tid; i < cnt; i += NMS_THREADS) {
-                const unsigned long long k = __ldcg(keys + i);
-                if (k < upper && k >= thr_key) {
-                    const int at = atomicAdd(&s_loaded, 1);
-                    if (at < NMS_CHUNK) { s_key[at] = k; s_slot[at] = (unsigned)i; }
+            for (int i0 = warp * 32; i0 < cnt; i0 += NMS_THREADS) {      // warp-uniform trip count
+                const int i = i0 + lane;
+                const unsigned long long k = i < cnt ? __ldcg(keys + i) : 0ull;
+                const bool in = (k != 0ull) && (k < upper) && (k >= thr_key);
+                const unsigned m = __ballot_sync(0xffffffffu, in);
+                if (m) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_loaded, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const int at = base + __popc(m & ((1u << lane) - 1u));
+                    if (in && at < NMS_CHUNK) { s_key[at] = k; s_slot[at] = (unsigned)i; }
                 }
             }
         }
         __syncthreads();
         const int loaded = min(s_loaded, NMS_CHUNK);
-        int n2 = 128;
-        while (n2 < loaded) n2 <<= 1;
-        for (int i = loaded + tid; i < n2; i += NMS_THREADS) { s_key[i] = 0ull; s_slot[i] = 0u; }
+        if (s_loaded > NMS_CHUNK && p.status && tid == 0) p.status[page] = 2;   // cannot happen (see the bisection); never silent
+        int n2p = 128;
+        while (n2p < loaded) n2p <<= 1;
+        for (int i = loaded + tid; i < n2p; i += NMS_THREADS) { s_key[i] = 0ull; s_slot[i] = 0u; }
         __syncthreads();
         RN_PHASE(1);
         // ---------------- bitonic network, descending (keys are unique) ----------------------------
-        sort_chunk_desc(s_key, s_slot, n2, tid);
-        const int chunk_n = min(loaded, take);
+        sort_chunk_desc(s_key, s_slot, n2p, tid);
+        const int chunk_n = min(loaded, limit - visited);
         RN_PHASE(2);
-        // ---------------- K5: greedy NMS over the ordered chunk, 256 candidates per round --------------
-        for (int s0 = 0; s0 < chunk_n && nsel < p.max_det; s0 += NMS_BATCH) {
-            const int bn = min(NMS_BATCH, chunk_n - s0);
-            if (tid < NMS_BATCH) {
-                int alive = 0;
-                if (tid < bn) {
-                    const unsigned slot = s_slot[s0 + tid];
-                    const float4 r = p.direct_boxes ? __ldg(boxes + key_idx(s_key[s0 + tid])) : __ldcg(boxes + slot);
+        // ---------------- K5: greedy NMS over the ordered chunk -------------------------------------------
+        // boxes arrive one group (256 candidates) ahead: the row is requested here, decoded when its group starts
+        float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < NMS_GROUP && tid < chunk_n) nxt = fetch_row(p.src, page, (int)key_idx(s_key[tid]));
+        for (int g0 = 0; g0 < chunk_n && nsel < p.max_det; g0 += NMS_GROUP) {
+            const int gn = min(NMS_GROUP, chunk_n - g0);
+            if (tid < NMS_GROUP) {
+                if (tid < gn) {
+                    const float4 r = finish_box<DECODE>(p.src, (int)key_idx(s_key[g0 + tid]), nxt);
                     float4 c;
                     c.x = fminf(r.x, r.z); c.y = fminf(r.y, r.w); c.z = fmaxf(r.x, r.z); c.w = fmaxf(r.y, r.w);
-                    s_craw[tid] = r; s_cbox[tid] = c;
-                    s_carea[tid] = (c.z - c.x) * (c.w - c.y);
-                    alive = 1;
+                    s_graw[tid] = r; s_gbox[tid] = c;
+                    s_garea[tid] = (c.z - c.x) * (c.w - c.y);
                 }
-                s_alive[tid] = alive;
+                const int nx = g0 + NMS_GROUP + tid;
+                if (nx < chunk_n) nxt = fetch_row(p.src, page, (int)key_idx(s_key[nx]));
             }
             __syncthreads();
-            if (p.nms) {
-                RN_PHASE(3);
-                // (a) against everything selected so far: 2 threads per candidate split the list
-                {
-                    const int c = tid & (NMS_BATCH - 1), part = tid / NMS_BATCH;
-                    if (c < bn) {
-                        const float4 cb = s_cbox[c];
-                        const float ca = s_carea[c];
-                        bool dead = false;
-                        for (int s = part; s < nsel && !dead; s += NMS_THREADS / NMS_BATCH)
-                            dead = iou_exceeds(cb, ca, s_selbox[s], s_selarea[s], p.iou_thr);
-                        if (dead) s_alive[c] = 0;
+            RN_PHASE(3);
+            for (int b0 = 0; b0 < gn && nsel < p.max_det; b0 += NMS_BATCH) {
+                const int bn = min(NMS_BATCH, gn - b0);
+                // (a) warp w owns batch member w: its lanes split the selected list (early exit), then one ballot over the
+                //     later batch members gives row w of the in-batch suppression matrix
+                if (warp < bn) {                            // warp-uniform
+                    bool dead = false;
+                    unsigned vict = 0u;
+                    if (p.nms) {
+                        const float4 mb = s_gbox[b0 + warp];
+                        const float ma = s_garea[b0 + warp];
+                        for (int s0 = 0; s0 < nsel; s0 += 32) {
+                            const int s = s0 + lane;
+                            const bool hit = (s < nsel) && iou_exceeds(mb, ma, s_selbox[s], s_selarea[s], p.iou_thr);
+                            if (__any_sync(0xffffffffu, hit)) { dead = true; break; }
+                        }
+                        if (!dead) {                        // a suppressed candidate suppresses nothing
+                            const int j = b0 + lane;
+                            const bool hit = (lane > warp) && (lane < bn) && iou_exceeds(mb, ma, s_gbox[j], s_garea[j], p.iou_thr);
+                            vict = __ballot_sync(0xffffffffu, hit);
+                        }
                     }
+                    if (lane == 0) { s_dead[warp] = dead ? 1 : 0; s_vict[warp] = vict; }
                 }
                 __syncthreads();
                 RN_PHASE(4);
-                // (b) suppression bit-matrix among the survivors (upper triangle), one ballot per word
-                unsigned aw[NMS_WORDS];                     // alive columns, 32 per word (warp-uniform)
-#pragma unroll
-                for (int w = 0; w < NMS_WORDS; ++w) aw[w] = __ballot_sync(0xffffffffu, s_alive[w * 32 + lane] != 0);
-                for (int i = warp; i < bn; i += NMS_WARPS) {
-                    if (!s_alive[i]) continue;
-                    const float4 bi = s_cbox[i];
-                    const float ai = s_carea[i];
-                    const int w_first = i >> 5;
-#pragma unroll
-                    for (int w = 0; w < NMS_WORDS; ++w) {      // unrolled: the 8 words are independent
-                        if (w < w_first) continue;
-                        unsigned word = 0u;
-                        if (aw[w]) {
-                            const int j = w * 32 + lane;
-                            const bool hit = (j > i) && ((aw[w] >> lane) & 1u) &&
-                                             iou_exceeds(bi, ai, s_cbox[j], s_carea[j], p.iou_thr);
-                            word = __ballot_sync(0xffffffffu, hit);
+                // (b) one warp resolves the greedy order in registers; the survivors join the selected list
+                if (warp == 0) {
+                    const bool alive = (lane < bn) && (s_dead[lane] == 0);
+                    const unsigned vict = (lane < bn) ? s_vict[lane] : 0u;
+                    const unsigned rem = __ballot_sync(0xffffffffu, alive);
+                    unsigned keep = rem;
+                    if (__any_sync(0xffffffffu, alive && (vict & rem) != 0u)) {      // conflicts inside the batch: walk it
+                        keep = 0u;
+                        unsigned r = rem;
+                        while (r) {                         // warp-uniform
+                            const int i = __ffs(r) - 1;
+                            keep |= 1u << i;
+                            r &= ~(1u << i);
+                            r &= ~__shfl_sync(0xffffffffu, vict, i);
                         }
-                        if (lane == 0) s_mask[i * NMS_WORDS + w] = word;
                     }
+                    int extra = __popc(keep) - (p.max_det - nsel);       // TF stops at max_output_size: the first ones in order
+                    while (extra-- > 0) keep &= ~(0x80000000u >> __clz(keep));
+                    if ((keep >> lane) & 1u) {
+                        const int pos = nsel + __popc(keep & ((1u << lane) - 1u));
+                        const int c = b0 + lane;
+                        s_selbox[pos] = s_gbox[c];
+                        s_selarea[pos] = s_garea[c];
+                        const size_t at = (size_t)seg * p.max_det + pos;
+                        p.kept_key[at] = s_key[g0 + c];
+                        p.kept_box[at] = s_graw[c];
+                        p.kept_label[at] = labels ? labels[s_slot[g0 + c]] : seg_label;
+                    }
+                    if (lane == 0) s_nsel = nsel + __popc(keep);
                 }
                 __syncthreads();
+                nsel = s_nsel;
+                RN_PHASE(5);
             }
-            RN_PHASE(5);
-            // (c) one warp walks the surviving bits in order
-            if (warp == 0) {
-                unsigned mine = 0u;
-#pragma unroll
-                for (int w = 0; w < NMS_WORDS; ++w) {
-                    const unsigned word = __ballot_sync(0xffffffffu, s_alive[w * 32 + lane] != 0);
-                    if (lane == w) mine = word;
-                }
-                int ns = nsel;
-                while (ns < p.max_det) {
-                    const unsigned has = __ballot_sync(0xffffffffu, mine != 0u) & ((1u << NMS_WORDS) - 1u);
-                    if (!has) break;
-                    const int w0 = __ffs(has) - 1;
-                    const unsigned word = __shfl_sync(0xffffffffu, mine, w0);
-                    const int bit = __ffs(word) - 1;
-                    const int i = w0 * 32 + bit;
-                    if (lane == 0) s_pick[ns - nsel] = (unsigned short)i;
-                    ++ns;
-                    if (lane == w0) mine &= ~(1u << bit);
-                    if (p.nms && lane < NMS_WORDS && lane >= w0) mine &= ~s_mask[i * NMS_WORDS + lane];
-                }
-                if (lane == 0) s_nsel = ns;
-            }
-            __syncthreads();
-            // the picked candidates join the selected list / the kept arrays, one thread each
-            for (int t = tid; t < s_nsel - nsel; t += NMS_THREADS) {
-                const int i = s_pick[t], ns = nsel + t;
-                s_selbox[ns] = s_cbox[i];
-                s_selarea[ns] = s_carea[i];
-                const size_t at = (size_t)seg * p.max_det + ns;
-                p.kept_key[at] = s_key[s0 + i];
-                p.kept_box[at] = s_craw[i];
-                p.kept_label[at] = labels ? labels[s_slot[s0 + i]] : seg_label;
-            }
-            __syncthreads();
-            nsel = s_nsel;
-            RN_PHASE(6);
         }
-        visited += take;
-        upper = (loaded > 0) ? s_key[chunk_n - 1] : 0ull;
+        visited += chunk_n;
+        upper = (chunk_n > 0) ? s_key[chunk_n - 1] : 0ull;
         __syncthreads();
+        if (chunk_n == 0) break;                            // defensive: no progress is impossible while visited < limit
     }
     if (tid == 0) p.kept_count[seg] = nsel;
 #undef RN_PHASE
@@ -674,7 +654,7 @@ __global__ void k_keys_from_scores(const float* scores, long long K, unsigned lo
 struct FilterWs {
     unsigned long long* timing;
     int* counts; int* kept_count; int* status;
-    unsigned long long* keys; float4* boxes; int* labels;
+    unsigned long long* keys; int* labels;
     unsigned long long* kept_key; float4* kept_box; int* kept_label;
     size_t bytes;
 };
@@ -691,7 +671,6 @@ FilterWs carve(void* ws, int B, int S, long long cap, int max_det, bool agnostic
     w.kept_count = reinterpret_cast<int*>(take(sizeof(int) * S));
     w.status = reinterpret_cast<int*>(take(sizeof(int) * B));
     w.keys = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * (size_t)S * cap));
-    w.boxes = reinterpret_cast<float4*>(take(sizeof(float4) * (size_t)S * cap));
     w.labels = agnostic ? reinterpret_cast<int*>(take(sizeof(int) * (size_t)S * cap)) : nullptr;
     w.kept_key = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * (size_t)S * max_det));
     w.kept_box = reinterpret_cast<float4*>(take(sizeof(float4) * (size_t)S * max_det));
@@ -702,37 +681,67 @@ FilterWs carve(void* ws, int B, int S, long long cap, int max_det, bool agnostic
 
 size_t nms_dynamic_smem(int max_det) { return (size_t)max_det * (sizeof(float4) + sizeof(float)); }
 
-int run_back_end(const FilterWs& w, int B, int S, int segs_per_page, long long cap, int direct_boxes, const float4* direct,
+std::atomic<int> g_phase_timing{0};
+// measurement hook (rn_debug_filter_events): four cudaEvent_t recorded around the three kernels of a filter call
+std::atomic<void*> g_events[4];
+
+int record_event(int k, cudaStream_t s) {
+    void* ev = g_events[k].load(std::memory_order_relaxed);
+    if (ev == nullptr) return RN_OK;
+    cudaError_t e = cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev), s);
+    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(e));
+    return RN_OK;
+}
+
+// static (~34 KB) + dynamic shared memory can exceed the 48 KB default: opt in once per DEVICE (bit per device ordinal)
+int nms_opt_in_shared_memory() {
+    static std::atomic<unsigned long long> done{0ull};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+    const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+    if (bit && (done.load(std::memory_order_acquire) & bit)) return RN_OK;
+    const int big = (int)nms_dynamic_smem(MAX_DET_LIMIT);
+    cudaError_t ae = cudaFuncSetAttribute(k_segment_nms<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_segment_nms<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (ae != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
+    if (bit) done.fetch_or(bit, std::memory_order_release);
+    return RN_OK;
+}
+
+int run_back_end(const FilterWs& w, const BoxSource& src, bool decode, int B, int S, int segs_per_page, long long cap,
                  int nms, float nms_thr, int max_det, int pre_nms_top_k,
                  float* out_boxes, float* out_scores, int* out_labels, int* out_indices, int* out_count,
                  int* status, cudaStream_t s) {
     NmsParams np;
-    np.sl.counts = w.counts; np.sl.keys = w.keys; np.sl.boxes = direct_boxes ? const_cast<float4*>(direct) : w.boxes;
-    np.sl.labels = w.labels; np.sl.cap = cap;
-    np.S = S; np.segs_per_page = segs_per_page; np.direct_boxes = direct_boxes; np.nms = nms; np.iou_thr = nms_thr;
+    np.sl.counts = w.counts; np.sl.keys = w.keys; np.sl.labels = w.labels; np.sl.cap = cap;
+    np.src = src;
+    np.S = S; np.segs_per_page = segs_per_page; np.nms = nms; np.iou_thr = nms_thr;
     np.max_det = max_det; np.pre_nms_top_k = pre_nms_top_k;
     np.kept_count = w.kept_count; np.kept_key = w.kept_key; np.kept_box = w.kept_box; np.kept_label = w.kept_label;
     np.status = status;
-    static const bool timing_on = getenv("RN_NMS_TIMING") != nullptr;
-    np.timing = timing_on ? w.timing : nullptr;
+    np.timing = g_phase_timing.load(std::memory_order_relaxed) ? w.timing : nullptr;
     const size_t dyn = nms_dynamic_smem(max_det);
-    // static (~43 KB) + dynamic shared memory exceeds the 48 KB default: opt in (227 KB per CTA on sm_100a)
-    cudaError_t ae = cudaFuncSetAttribute(k_segment_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_dynamic_smem(MAX_DET_LIMIT));
-    if (ae != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
-    k_segment_nms<<<S, NMS_THREADS, dyn, s>>>(np);
-    int rc = rn_check_launch("k_segment_nms");
+    int rc = nms_opt_in_shared_memory();
     if (rc) return rc;
+    if (decode) k_segment_nms<true><<<S, NMS_THREADS, dyn, s>>>(np);
+    else k_segment_nms<false><<<S, NMS_THREADS, dyn, s>>>(np);
+    rc = rn_check_launch("k_segment_nms");
+    if (rc) return rc;
+    if ((rc = record_event(2, s)) != RN_OK) return rc;
     MergeParams mp;
     mp.pages = B; mp.segs_per_page = segs_per_page; mp.max_det = max_det;
     mp.kept_count = w.kept_count; mp.kept_key = w.kept_key; mp.kept_box = w.kept_box; mp.kept_label = w.kept_label;
     mp.out_boxes = out_boxes; mp.out_scores = out_scores; mp.out_labels = out_labels; mp.out_indices = out_indices;
     mp.out_count = out_count;
     k_merge_topk<<<B, 256, sizeof(int) * (size_t)segs_per_page, s>>>(mp);
-    return rn_check_launch("k_merge_topk");
+    rc = rn_check_launch("k_merge_topk");
+    if (rc) return rc;
+    return record_event(3, s);
 }
 
-int filter_common(K3Params kp, bool decode, int nms, float nms_thr, int max_det, int pre_nms_top_k, long long cand_cap,
-                  float* out_boxes, float* out_scores, int* out_labels, int* out_indices, int* status_out,
+int filter_common(K3Params kp, const BoxSource& src, bool decode, int nms, float nms_thr, int max_det, int pre_nms_top_k,
+                  long long cand_cap, float* out_boxes, float* out_scores, int* out_labels, int* out_indices, int* status_out,
                   void* workspace, size_t workspace_bytes, cudaStream_t s) {
     const int B = kp.B, C = kp.C;
     RN_REQUIRE(B >= 1 && kp.N >= 1 && C >= 1, "bad shape");
@@ -749,14 +758,14 @@ int filter_common(K3Params kp, bool decode, int nms, float nms_thr, int max_det,
     const int S = (int)S64;
     FilterWs w = carve(workspace, B, S, cand_cap, max_det, !kp.class_specific);
     if (workspace_bytes < w.bytes) return rn_fail(RN_ERR_WORKSPACE, "filter workspace too small: %zu < %zu", workspace_bytes, w.bytes);
-    // counts, kept_count, status are contiguous at the front of the workspace
+    // timing, counts, kept_count, status are contiguous at the front of the workspace
     cudaError_t e = cudaMemsetAsync(w.timing, 0, (size_t)((char*)w.keys - (char*)w.timing), s);
     if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
     if (status_out) {
         e = cudaMemsetAsync(status_out, 0, sizeof(int) * (size_t)B, s);
         if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
     }
-    kp.sl.counts = w.counts; kp.sl.keys = w.keys; kp.sl.boxes = w.boxes; kp.sl.labels = w.labels; kp.sl.cap = cand_cap;
+    kp.sl.counts = w.counts; kp.sl.keys = w.keys; kp.sl.labels = w.labels; kp.sl.cap = cand_cap;
     RN_REQUIRE((long long)kp.N * C < (1ll << 31) - 4096, "N * C too large for one page");
     RN_REQUIRE(B <= 65535, "B must be <= 65535");
     kp.inv_c = 1.0f / (float)C;
@@ -764,16 +773,28 @@ int filter_common(K3Params kp, bool decode, int nms, float nms_thr, int max_det,
     const long long tiles = kp.class_specific ? ((long long)kp.N * C + K3_TILE - 1) / K3_TILE
                                               : ((long long)kp.N + K3_THREADS * K3_VEC - 1) / (K3_THREADS * K3_VEC);
     const dim3 grid((unsigned)tiles, (unsigned)B);
-    if (decode) k_threshold_compact<true><<<grid, K3_THREADS, 0, s>>>(kp);
-    else k_threshold_compact<false><<<grid, K3_THREADS, 0, s>>>(kp);
-    int rc = rn_check_launch("k_threshold_compact");
+    int rc = record_event(0, s);
     if (rc) return rc;
-    return run_back_end(w, B, S, spp, cand_cap, 0, nullptr, nms, nms_thr, max_det, pre_nms_top_k,
+    k_threshold_keys<<<grid, K3_THREADS, 0, s>>>(kp);
+    rc = rn_check_launch("k_threshold_keys");
+    if (rc) return rc;
+    if ((rc = record_event(1, s)) != RN_OK) return rc;
+    return run_back_end(w, src, decode, B, S, spp, cand_cap, nms, nms_thr, max_det, pre_nms_top_k,
                         out_boxes, out_scores, out_labels, out_indices, nullptr,
                         status_out ? status_out : w.status, s);
 }
 
 }  // namespace
+
+extern "C" int rn_debug_nms_timing(int enable) {
+    g_phase_timing.store(enable ? 1 : 0, std::memory_order_relaxed);
+    return RN_OK;
+}
+
+extern "C" int rn_debug_filter_events(void* before_k3, void* after_k3, void* after_nms, void* after_merge) {
+    g_events[0].store(before_k3); g_events[1].store(after_k3); g_events[2].store(after_nms); g_events[3].store(after_merge);
+    return RN_OK;
+}
 
 extern "C" size_t rn_filter_workspace_bytes(int B, long long N, int C, int class_specific, long long cand_cap, int max_detections) {
     if (B < 1 || N < 1 || C < 1 || max_detections < 1) return 0;
@@ -790,11 +811,13 @@ extern "C" int rn_filter_detections(const float* boxes, const float* classificat
                                     int* status_out_dev, void* workspace, size_t workspace_bytes, void* stream) {
     RN_REQUIRE(boxes && classification, "NULL input");
     RN_REQUIRE(rn_aligned16(boxes), "boxes must be 16-byte aligned");
-    RN_REQUIRE(N < (1ll << 31), "N too large");
+    RN_REQUIRE(N >= 1 && N < (1ll << 31), "N out of range");
     K3Params kp = {};
-    kp.cls = classification; kp.boxes = boxes; kp.B = B; kp.N = (int)N; kp.C = C;
+    kp.cls = classification; kp.B = B; kp.N = (int)N; kp.C = C;
     kp.class_specific = class_specific ? 1 : 0; kp.thr = score_threshold;
-    return filter_common(kp, false, nms ? 1 : 0, nms_threshold, max_detections, pre_nms_top_k, cand_cap,
+    BoxSource src = {};
+    src.rows = boxes; src.N = (int)N;
+    return filter_common(kp, src, false, nms ? 1 : 0, nms_threshold, max_detections, pre_nms_top_k, cand_cap,
                          out_boxes, out_scores, out_labels, out_indices, status_out_dev,
                          workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -811,15 +834,16 @@ extern "C" int rn_decode_filter_detections(const float* base_anchors_f32_dev, co
                                            int* status_out_dev, void* workspace, size_t workspace_bytes, void* stream) {
     RN_REQUIRE(base_anchors_f32_dev && regression && classification && mean4 && std4, "NULL input");
     RN_REQUIRE(rn_aligned16(regression), "regression must be 16-byte aligned");
-    K3Params kp = {};
-    int rc = rn_make_levels(&kp.lv, level_hw, level_stride, num_levels, anchors_per_cell);
+    BoxSource src = {};
+    int rc = rn_make_levels(&src.lv, level_hw, level_stride, num_levels, anchors_per_cell);
     if (rc) return rc;
-    RN_REQUIRE(kp.lv.start[num_levels] == N, "N (%lld) does not match the level table (%d)", N, kp.lv.start[num_levels]);
-    kp.cls = classification; kp.reg = regression; kp.base32 = base_anchors_f32_dev;
-    for (int i = 0; i < 4; ++i) { kp.nm.mean[i] = mean4[i]; kp.nm.std[i] = std4[i]; }
-    kp.clipW = clip_width; kp.clipH = clip_height;
-    kp.B = B; kp.N = (int)N; kp.C = C; kp.class_specific = class_specific ? 1 : 0; kp.thr = score_threshold;
-    return filter_common(kp, true, nms ? 1 : 0, nms_threshold, max_detections, pre_nms_top_k, cand_cap,
+    RN_REQUIRE(src.lv.start[num_levels] == N, "N (%lld) does not match the level table (%d)", N, src.lv.start[num_levels]);
+    src.rows = regression; src.base32 = base_anchors_f32_dev; src.N = (int)N;
+    for (int i = 0; i < 4; ++i) { src.nm.mean[i] = mean4[i]; src.nm.std[i] = std4[i]; }
+    src.clipW = clip_width; src.clipH = clip_height;
+    K3Params kp = {};
+    kp.cls = classification; kp.B = B; kp.N = (int)N; kp.C = C; kp.class_specific = class_specific ? 1 : 0; kp.thr = score_threshold;
+    return filter_common(kp, src, true, nms ? 1 : 0, nms_threshold, max_detections, pre_nms_top_k, cand_cap,
                          out_boxes, out_scores, out_labels, out_indices, status_out_dev,
                          workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -855,6 +879,8 @@ extern "C" int rn_nms(const float* boxes, const float* scores, long long K, int 
         int rc = rn_check_launch("k_keys_from_scores");
         if (rc) return rc;
     }
-    return run_back_end(w, 1, 1, 1, cap, 1, reinterpret_cast<const float4*>(boxes), 1, iou_threshold, max_output, 0,
+    BoxSource src = {};
+    src.rows = boxes; src.N = (int)cap;
+    return run_back_end(w, src, false, 1, 1, 1, cap, 1, iou_threshold, max_output, 0,
                         sc_boxes, sc_scores, sc_labels, out_indices, out_count_dev, w.status, s);
 }

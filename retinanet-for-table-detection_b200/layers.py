@@ -159,22 +159,30 @@ def _gather_other(other, indices, max_detections):
     return outs
 
 
+def filter_outputs(B, M, device):
+    """The five result tensors of one filter call: boxes (B,M,4) f32, scores (B,M) f32, labels (B,M) i32, selected anchor
+    indices (B,M) i32, per-page status (B) i32."""
+    return (torch.empty((B, M, 4), dtype=torch.float32, device=device), torch.empty((B, M), dtype=torch.float32, device=device),
+            torch.empty((B, M), dtype=torch.int32, device=device), torch.empty((B, M), dtype=torch.int32, device=device),
+            torch.empty((B,), dtype=torch.int32, device=device))
+
+
 def _run_filter(boxes, classification, class_specific_filter, nms, score_threshold, max_detections,
-                nms_threshold, pre_nms_top_k, cand_cap, decode=None):
-    """Shared launcher.  ``decode`` = None (boxes given) or dict(spec, regression, mean, std, clip_hw)."""
+                nms_threshold, pre_nms_top_k, cand_cap, decode=None, out=None, workspace=None):
+    """Shared launcher.  ``decode`` = None (boxes given) or dict(spec, regression, mean, std, clip_hw).
+    ``out`` (see :func:`filter_outputs`) / ``workspace``: caller-owned static buffers (``pipeline.DetectionStep``);
+    allocated per call otherwise."""
     lib = _lib.load()
     cls = _cuda(classification)
     device = cls.device
     B, N, C = int(cls.shape[0]), int(cls.shape[1]), int(cls.shape[2])
     M = int(max_detections)
     cap = N if cand_cap is None else int(cand_cap)
-    out_boxes = torch.empty((B, M, 4), dtype=torch.float32, device=device)
-    out_scores = torch.empty((B, M), dtype=torch.float32, device=device)
-    out_labels = torch.empty((B, M), dtype=torch.int32, device=device)
-    out_idx = torch.empty((B, M), dtype=torch.int32, device=device)
-    status = torch.empty((B,), dtype=torch.int32, device=device)
+    out_boxes, out_scores, out_labels, out_idx, status = filter_outputs(B, M, device) if out is None else out
     ws_bytes = int(lib.rn_filter_workspace_bytes(B, N, C, int(bool(class_specific_filter)), cap, M))
-    ws = _lib.scratch("filter", ws_bytes, device)
+    ws = _lib.scratch("filter", ws_bytes, device) if workspace is None else workspace
+    if ws.numel() < ws_bytes:
+        raise ValueError("filter workspace too small: %d < %d bytes" % (ws.numel(), ws_bytes))
     thr = float(np.float32(score_threshold))
     nthr = float(np.float32(nms_threshold))
     if decode is None:
@@ -318,14 +326,21 @@ class DetectionHead(_Layer):
             self._specs[key] = spec
         return spec
 
-    def forward(self, inputs, check=True, **kwargs):
+    def workspace_bytes(self, batch, image_hw, num_classes):
+        """Size of the filter workspace for a (batch, image shape, classes) configuration (static-buffer callers)."""
+        N = self.spec_for(image_hw).num_anchors
+        cap = N if self.cand_cap is None else int(self.cand_cap)
+        return int(_lib.load().rn_filter_workspace_bytes(int(batch), N, int(num_classes), int(bool(self.class_specific_filter)),
+                                                         cap, int(self.max_detections)))
+
+    def forward(self, inputs, check=True, out=None, workspace=None, **kwargs):
         image, regression, classification, other = inputs[0], inputs[1], inputs[2], list(inputs[3:])
         shape = _shape_of(image)
         hw = (int(shape[1]), int(shape[2])) if len(shape) == 4 else (int(shape[0]), int(shape[1]))
         decode = dict(spec=self.spec_for(hw), regression=regression, mean=self.mean, std=self.std, clip_hw=hw)
         ob, osc, ol, oi, status = _run_filter(None, classification, self.class_specific_filter, self.nms,
                                               self.score_threshold, self.max_detections, self.nms_threshold,
-                                              self.pre_nms_top_k, self.cand_cap, decode=decode)
+                                              self.pre_nms_top_k, self.cand_cap, decode=decode, out=out, workspace=workspace)
         if check:
             _raise_on_overflow(status, self.cand_cap)
         self.last_indices = oi

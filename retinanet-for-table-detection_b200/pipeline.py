@@ -444,6 +444,63 @@ class HostStepPipeline(object):
         return [self.result(k) for k in order if self._busy[k]]
 
 
+class DetectionStep(object):
+    """The inference tail (``layers.DetectionHead``: decode + clip + threshold + sort + NMS + merge) for one batch shape
+    as a replayable unit, like ``TargetLossStep`` for the training half: static device buffers for the head outputs
+    (``cls_pred`` (B,N,C), ``reg_pred`` (B,N,4)), the results (``boxes`` (B,M,4), ``scores`` (B,M), ``labels`` (B,M),
+    ``indices`` (B,M), ``status`` (B)) and the workspace, and the three kernel launches captured into ONE CUDA graph.
+    ``run()`` replays it on the current stream; ``load_predictions`` copies new head outputs in (async).  Results are
+    bit-identical to calling the head directly."""
+
+    def __init__(self, image_hw, batch, num_classes=1, head=None, use_graph=True, device=None, **head_kw):
+        from . import layers as _layers
+        _lib.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.head = head if head is not None else _layers.DetectionHead(**head_kw)
+        self.hw = (int(image_hw[0]), int(image_hw[1]))
+        self.B, self.C = int(batch), int(num_classes)
+        self.N, M, d = self.head.spec_for(self.hw).num_anchors, int(self.head.max_detections), self.device
+        self.cls_pred = torch.zeros((self.B, self.N, self.C), dtype=torch.float32, device=d)
+        self.reg_pred = torch.zeros((self.B, self.N, 4), dtype=torch.float32, device=d)
+        self.out = _layers.filter_outputs(self.B, M, d)
+        self.boxes, self.scores, self.labels, self.indices, self.status = self.out
+        self.workspace = torch.empty(max(256, self.head.workspace_bytes(self.B, self.hw, self.C)), dtype=torch.uint8, device=d)
+        self.use_graph = use_graph
+        self._graph = None
+        self.kernel_launches_per_step = 3       # k_threshold_keys, k_segment_nms, k_merge_topk
+
+    def load_predictions(self, cls_pred, reg_pred):
+        self.cls_pred.copy_(cls_pred, non_blocking=True)
+        self.reg_pred.copy_(reg_pred, non_blocking=True)
+
+    def _launch(self):
+        self.head([(self.B,) + self.hw + (3,), self.reg_pred, self.cls_pred], check=False, out=self.out, workspace=self.workspace)
+
+    def run(self):
+        """One batch on the current stream; returns ``[boxes, scores, labels]`` (static tensors, overwritten per call)."""
+        if not self.use_graph:
+            self._launch()
+        else:
+            if self._graph is None:
+                s = torch.cuda.Stream(self.device)
+                s.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(s):
+                    self._launch()                          # warm-up outside capture (lazy module loading, attributes)
+                torch.cuda.current_stream(self.device).wait_stream(s)
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch()
+                self._graph = g
+            self._graph.replay()
+        return [self.boxes, self.scores, self.labels]
+
+    def check(self):
+        """Raises when a candidate slab overflowed in the last batch (only possible with ``cand_cap``); synchronises."""
+        from . import layers as _layers
+        _layers._raise_on_overflow(self.status, self.head.cand_cap)
+
+
 class HostDetectionPipeline(object):
     """The inference tail (``layers.DetectionHead``) as a serving loop over HOST head outputs with several batches in
     flight: every slot has its own stream, device classification buffer and pinned result buffers.

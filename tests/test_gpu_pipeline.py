@@ -201,3 +201,27 @@ def test_peer_mailbox_pipelined_schedule(rn, monkeypatch, fused):
     check(boxed.losses, 3)
     boxed.load_annotations(imgs, batches[8])
     check(boxed.run_pipelined(overlap=overlap_ok), 7)
+
+
+def test_detection_step_graph_matches_direct_head(rn):
+    """DetectionStep (static buffers, the three kernels of the inference tail replayed as one CUDA graph) gives the
+    detections of the direct DetectionHead call, bit for bit, batch after batch."""
+    import synthetic
+    hw, B = (256, 320), 3
+    anchors = np.asarray(rn.anchors_for_shape(hw + (3,)))
+    head = rn.DetectionHead()
+    step = rn.pipeline.DetectionStep(hw, B, 1)
+    eager = rn.pipeline.DetectionStep(hw, B, 1, use_graph=False)
+    for s in range(3):
+        anns = [synthetic.gt_for_page(3, 11 * s + i, hw=hw, gmax=5) for i in range(B)]
+        cls, reg = synthetic.inference_predictions(3, B, anchors, anns, classes=1, first_page=3 * s)
+        cls_d, reg_d = torch.from_numpy(cls).cuda(), torch.from_numpy(reg).cuda()
+        want = head([(B,) + hw + (3,), reg_d, cls_d])
+        for st in (step, eager):
+            st.load_predictions(cls_d, reg_d)
+            got = st.run()
+            torch.cuda.synchronize()
+            assert all(torch.equal(g, w) for g, w in zip(got, want))
+            assert torch.equal(st.indices, head.last_indices)
+            st.check()
+        assert int((want[1] >= 0).sum()) > 0
