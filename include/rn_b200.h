@@ -121,6 +121,10 @@ int rn_smooth_l1_fwd_bwd(const float* y_true_reg /*(R,5)*/, const float* y_pred 
                                     the sum of the counts all ranks published for the current step           */
 #define RN_LOSS_PEER_LAG1     8   /* with RN_LOSS_NPOS_PEER_BOX: use the step published BEFORE the latest one
                                     (pipelined schedule: K1 + publish of the next batch run ahead of this K2)  */
+#define RN_LOSS_PEER_LOSSES   32  /* with RN_LOSS_NPOS_PEER_BOX: the two loss sums are exchanged through the mailbox as well (by
+                                   * the kernel's last CTA, added in rank order), so losses_out is the loss of the whole merged
+                                   * batch on every rank (model/losses.py:44, :90 with RetinaNet.py:106-112).  At most ONE such
+                                   * launch per exchanged step (not for page-chunked launches). */
 #define RN_LOSS_PEER_PUBLISH  16  /* with RN_LOSS_NPOS_PEER_BOX on a mailbox prepared by rn_peer_box_bind: FUSED publish --
                                     this launch itself stores the rank's count into every rank's mailbox (CTA 0, P2P
                                     stores over NVLink) before all CTAs wait for the ranks' counts, and completes the
@@ -251,8 +255,10 @@ int rn_rescale_cut(const float* boxes, const float* scores, const float* image_s
  * -- the loss kernel sends this rank's count itself (no publish launch between K1 and K2).  A step's further loss
  * launches (page chunks) pass RN_LOSS_NPOS_PEER_BOX alone and read the completed step.
  * No NCCL call, no host synchronisation, CUDA-graph capturable.  All ranks must run
- * the same sequence of publish / loss steps; a peer that never publishes turns the losses into NaN
- * after ~2 s instead of hanging the GPU.  world <= 16 (one NVSwitch domain).
+ * the same sequence of publish / loss steps.  A wait that outlasts the mailbox's timeout (default 30 s,
+ * rn_peer_box_set_timeout) never hangs the GPU: it sets a STICKY error flag in the mailbox (rn_peer_box_status) and the
+ * step's losses are NaN; once the flag is set every further wait of this rank gives up at once, until it is cleared.
+ * world <= 16 (one NVSwitch domain).
  * ------------------------------------------------------------------------------------------- */
 size_t rn_peer_box_bytes(void);
 int rn_peer_box_create(int world, void** box_out, void* ipc_handle_out64);
@@ -267,6 +273,10 @@ int rn_peer_box_destroy(void* box);
  * uses the mailbox must be idle. */
 int rn_peer_box_bind(void* local_box, void* const* boxes_of_all_ranks /* host, (world) */, int rank, int world,
                      const float* value_even_dev, const float* value_odd_dev);
+/* how long a device-side wait on the mailbox may last (seconds, > 0; default 30).  Synchronous. */
+int rn_peer_box_set_timeout(void* local_box, double seconds);
+/* *timed_out = 1 when a wait of this rank has timed out since the flag was last cleared; clear != 0 resets it.  Synchronous. */
+int rn_peer_box_status(void* local_box, int* timed_out, int clear);
 /* number of steps this rank has completed / published so far (synchronous read of the device counter) */
 int rn_peer_box_step(const void* local_box, unsigned long long* step_out);
 int rn_peer_publish(const float* value_dev, void* local_box, void* const* boxes_of_all_ranks /* host, (world) */,

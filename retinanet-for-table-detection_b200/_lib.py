@@ -21,6 +21,7 @@ RN_LOSS_NPOS_PEER_BOX = 2
 RN_LOSS_FROM_LOGITS = 4
 RN_LOSS_PEER_LAG1 = 8
 RN_LOSS_PEER_PUBLISH = 16
+RN_LOSS_PEER_LOSSES = 32
 RN_MAX_WORLD = 16
 
 
@@ -70,6 +71,8 @@ SIGNATURES = {
     "rn_peer_box_close": (c_int, [c_void_p]),
     "rn_peer_box_destroy": (c_int, [c_void_p]),
     "rn_peer_box_bind": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, _P, _P]),
+    "rn_peer_box_set_timeout": (c_int, [c_void_p, c_double]),
+    "rn_peer_box_status": (c_int, [c_void_p, POINTER(c_int), c_int]),
     "rn_peer_box_step": (c_int, [c_void_p, POINTER(ctypes.c_ulonglong)]),
     "rn_peer_publish": (c_int, [_P, c_void_p, POINTER(c_void_p), c_int, c_int, _P]),
 }

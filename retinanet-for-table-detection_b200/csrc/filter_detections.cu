@@ -21,6 +21,7 @@
 // Compiled with -fmad=false: IoU and decode are evaluated in the reference's fp32 operation order.
 #include "rn_common.cuh"
 #include <atomic>
+#include <string.h>
 
 namespace {
 
@@ -172,6 +173,81 @@ __global__ void __launch_bounds__(K3_THREADS) k_threshold_keys(const K3Params p)
     }
 }
 
+// The class-specific path (the reference's default) when page rows are 16-byte aligned: a PERSISTENT, warp-autonomous
+// stream.  grid = SMs x resident CTAs; a warp walks warp-tiles (32 lanes x one float4 = 128 consecutive scores of one page)
+// strided by the number of warps, with the loads of the next two tiles already in flight while it handles the current one
+// -- no shared memory, no block barrier.  Survivors are ranked inside the warp with three ballots (a lane has 0..4 of them);
+// one global atomic per warp-tile reserves their slab slots when all of them feed one slab (C == 1), one per candidate
+// otherwise.  The slab order is arbitrary by design: keys are unique, the NMS kernel orders them.
+constexpr int K3S_TILE = 128;                               // scores per warp-tile
+constexpr int K3S_CTAS_PER_SM = 8;
+
+struct K3Stream {
+    int tiles_per_page;
+    float inv_tiles_per_page;
+    int ntiles;                                             // tiles_per_page * B, < 2^31 (checked on the host)
+};
+
+__device__ __forceinline__ float4 k3s_load(const K3Params& p, const K3Stream& st, int tile, int lane, int total) {
+    const float ninf = __int_as_float(0xff800000);
+    float4 v = make_float4(ninf, ninf, ninf, ninf);         // out of range: never above any threshold
+    if (tile < st.ntiles) {
+        const int page = rn_div(tile, st.tiles_per_page, st.inv_tiles_per_page);
+        const int e = (tile - page * st.tiles_per_page) * K3S_TILE + lane * 4;
+        if (e < total) v = rn_ldg_stream4(p.cls + (size_t)page * total + e);     // total % 4 == 0: all four or none
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(K3_THREADS, K3S_CTAS_PER_SM) k_threshold_keys_stream(const K3Params p, const K3Stream st) {
+    const int lane = threadIdx.x & 31;
+    const int nw = gridDim.x * (K3_THREADS / 32);
+    const int total = p.N * p.C;                            // scores of one page
+    int tile = blockIdx.x * (K3_THREADS / 32) + (threadIdx.x >> 5);
+    float4 v0 = k3s_load(p, st, tile, lane, total);
+    float4 v1 = k3s_load(p, st, tile + nw, lane, total);
+    for (; tile < st.ntiles; tile += nw) {
+        const float4 cur = v0;
+        v0 = v1;
+        v1 = k3s_load(p, st, tile + 2 * nw, lane, total);   // two tiles ahead
+        const unsigned hits = (cur.x > p.thr ? 1u : 0u) | (cur.y > p.thr ? 2u : 0u) | (cur.z > p.thr ? 4u : 0u) | (cur.w > p.thr ? 8u : 0u);
+        if (!__any_sync(0xffffffffu, hits != 0u)) continue;  // warp-uniform
+        const int page = rn_div(tile, st.tiles_per_page, st.inv_tiles_per_page);
+        const int e0 = (tile - page * st.tiles_per_page) * K3S_TILE + lane * 4;
+        const float sc[4] = {cur.x, cur.y, cur.z, cur.w};
+        if (p.C == 1) {
+            // exclusive prefix of the lanes' survivor counts (0..4 = 3 bits): three ballots, no shuffles
+            const unsigned mine = (unsigned)__popc(hits);
+            const unsigned b0 = __ballot_sync(0xffffffffu, mine & 1u), b1 = __ballot_sync(0xffffffffu, mine & 2u),
+                           b2 = __ballot_sync(0xffffffffu, mine & 4u);
+            const unsigned lt = (1u << lane) - 1u;
+            int at = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+            const int tot = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(p.sl.counts + page, tot);
+            at += __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (hits & (1u << j)) {
+                    if (at < p.sl.cap) p.sl.keys[(size_t)page * p.sl.cap + at] = make_key(sc[j], (unsigned)(e0 + j));
+                    ++at;                                   // dropped when the slab is full; the count keeps growing (overflow is reported)
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (hits & (1u << j)) {
+                    const int e = e0 + j;
+                    const int n = rn_div(e, p.C, p.inv_c);
+                    const int seg = page * p.C + (e - n * p.C);
+                    const long long slot = atomicAdd(p.sl.counts + seg, 1);
+                    if (slot < p.sl.cap) p.sl.keys[(size_t)seg * p.sl.cap + slot] = make_key(sc[j], (unsigned)n);
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // where a candidate's box comes from: a dense (pages, N, 4) tensor, or the fused decode (Anchors + RegressBoxes + ClipBoxes)
 // ------------------------------------------------------------------------------------------------
@@ -228,6 +304,7 @@ struct NmsParams {
     float iou_thr;
     int max_det;
     int pre_nms_top_k;
+    unsigned key_floor_hi;         // every key's upper (score) word is >= this (the score threshold's image; 0 = unknown)
     // per-segment results
     int* kept_count;               // (S)
     unsigned long long* kept_key;  // (S, max_det)
@@ -237,12 +314,15 @@ struct NmsParams {
     unsigned long long* timing;    // 8 phase counters (clock64 ticks of thread 0, summed over CTAs) or nullptr
 };
 
-// TF non_max_suppression_op.cc IOU on corner-normalised boxes with precomputed areas
-// Exact fast rejects first (they never change the outcome): a non-positive area or an empty intersection
-// gives IoU 0; and since IoU <= min(area)/max(area), boxes whose areas differ by more than the threshold
-// allows (0.1 % safety margin over fp32 rounding) cannot exceed it.  Only the remaining pairs pay the divide.
+// TF non_max_suppression_op.cc IOU on corner-normalised boxes with precomputed areas: IoU = 0 when an area is not
+// positive, else inter / (area_a + area_b - inter); suppression iff IoU > thr (strict).  The quotient is only evaluated
+// when the product form cannot decide: inter > thr * union * (1 + 1e-4) implies RN(inter / union) > thr and
+// inter < thr * union * (1 - 1e-4) implies RN(inter / union) <= thr (fp32 rounding errors are ~1e-7), so the main path is
+// straight-line code without a divide and the outcome is bit-identical to always dividing.
+__device__ __noinline__ bool iou_exceeds_exact(float inter, float uni, float thr) { return inter / uni > thr; }
+
 __device__ __forceinline__ bool iou_exceeds(const float4 a, const float aa, const float4 b, const float ab, const float thr) {
-    if (thr < 0.0f) {                       // degenerate threshold: fall back to the plain formula
+    if (thr < 0.0f) {                       // degenerate threshold (kernel-uniform): the plain formula
         float iou = 0.0f;
         if (aa > 0.0f && ab > 0.0f) {
             const float iw = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.0f);
@@ -252,14 +332,16 @@ __device__ __forceinline__ bool iou_exceeds(const float4 a, const float aa, cons
         }
         return iou > thr;
     }
-    if (!(aa > 0.0f && ab > 0.0f)) return false;
-    if (fminf(aa, ab) < thr * fmaxf(aa, ab) * 0.999f) return false;
     const float iw = fminf(a.z, b.z) - fmaxf(a.x, b.x);
-    if (!(iw > 0.0f)) return false;
     const float ih = fminf(a.w, b.w) - fmaxf(a.y, b.y);
-    if (!(ih > 0.0f)) return false;
     const float inter = iw * ih;
-    return inter / (aa + ab - inter) > thr;
+    const float uni = aa + ab - inter;
+    const float t = thr * uni;
+    const bool overlap = (iw > 0.0f) && (ih > 0.0f) && (aa > 0.0f) && (ab > 0.0f);
+    const bool sure = overlap && (inter > t * 1.0001f);
+    const bool maybe = overlap && !sure && (inter > t * 0.9999f);
+    if (maybe) return iou_exceeds_exact(inter, uni, thr);    // ~1e-4 of the overlapping pairs
+    return sure;
 }
 
 
@@ -268,28 +350,31 @@ __device__ __forceinline__ bool iou_exceeds(const float4 a, const float aa, cons
 // shuffle and shared-memory latencies overlap across 32 warps): compare-exchange distance 1 is thread-local,
 // 2..32 are warp shuffles, distances >= 64 go through shared memory.  Keys are unique (zero padding excepted, which
 // never swaps).  Must be called by all threads of the CTA.
+template <bool SLOT>
 __device__ __forceinline__ void ce_keep(unsigned long long& a, unsigned& av, unsigned long long b, unsigned bv, bool take_max) {
     const bool sw = take_max ? (b > a) : (b < a);
-    if (sw) { a = b; av = bv; }
+    if (sw) { a = b; if (SLOT) av = bv; }
 }
 
-__device__ void sort_chunk_desc(unsigned long long* s_key, unsigned* s_slot, const int n, const int tid) {
+// SLOT: the 32-bit payload (slab slot, needed for the labels of class-agnostic filtering) travels with the keys
+template <bool SLOT>
+__device__ __forceinline__ void sort_chunk_desc(unsigned long long* s_key, unsigned* s_slot, const int n, const int tid) {
     const bool act = tid < (n >> 1);                 // warp-uniform: n/2 is a multiple of 32
     const int i0 = tid * 2;
     unsigned long long k0 = 0ull, k1 = 0ull;
     unsigned v0 = 0u, v1 = 0u;
-    if (act) { k0 = s_key[i0]; k1 = s_key[i0 + 1]; v0 = s_slot[i0]; v1 = s_slot[i0 + 1]; }
+    if (act) { k0 = s_key[i0]; k1 = s_key[i0 + 1]; if (SLOT) { v0 = s_slot[i0]; v1 = s_slot[i0 + 1]; } }
     for (int k = 2; k <= n; k <<= 1) {
         const bool desc = ((i0 & k) == 0);           // direction of this thread's pair in the k-merge (k >= 2: same for both)
         for (int j = k >> 1; j > 0; j >>= 1) {
             if (j >= 64) {
-                if (act) { s_key[i0] = k0; s_key[i0 + 1] = k1; s_slot[i0] = v0; s_slot[i0 + 1] = v1; }
+                if (act) { s_key[i0] = k0; s_key[i0 + 1] = k1; if (SLOT) { s_slot[i0] = v0; s_slot[i0 + 1] = v1; } }
                 __syncthreads();
                 if (act) {
                     const int x0 = i0 ^ j, x1 = (i0 + 1) ^ j;
                     const bool lower = ((i0 & j) == 0);                  // this thread holds the lower index of each pair
-                    ce_keep(k0, v0, s_key[x0], s_slot[x0], lower == desc);
-                    ce_keep(k1, v1, s_key[x1], s_slot[x1], lower == desc);
+                    ce_keep<SLOT>(k0, v0, s_key[x0], SLOT ? s_slot[x0] : 0u, lower == desc);
+                    ce_keep<SLOT>(k1, v1, s_key[x1], SLOT ? s_slot[x1] : 0u, lower == desc);
                 }
                 __syncthreads();
             } else if (j >= 2) {
@@ -297,9 +382,10 @@ __device__ void sort_chunk_desc(unsigned long long* s_key, unsigned* s_slot, con
                     const int lm = j >> 1;
                     const bool lower = ((i0 & j) == 0);
                     const unsigned long long b0 = __shfl_xor_sync(0xffffffffu, k0, lm), b1 = __shfl_xor_sync(0xffffffffu, k1, lm);
-                    const unsigned w0 = __shfl_xor_sync(0xffffffffu, v0, lm), w1 = __shfl_xor_sync(0xffffffffu, v1, lm);
-                    ce_keep(k0, v0, b0, w0, lower == desc);
-                    ce_keep(k1, v1, b1, w1, lower == desc);
+                    unsigned w0 = 0u, w1 = 0u;
+                    if (SLOT) { w0 = __shfl_xor_sync(0xffffffffu, v0, lm); w1 = __shfl_xor_sync(0xffffffffu, v1, lm); }
+                    ce_keep<SLOT>(k0, v0, b0, w0, lower == desc);
+                    ce_keep<SLOT>(k1, v1, b1, w1, lower == desc);
                 }
             } else if (act) {
                 // j == 1: the pair inside the thread.  For k == 2 the direction alternates per pair ((i0 & 2) == 0).
@@ -312,20 +398,45 @@ __device__ void sort_chunk_desc(unsigned long long* s_key, unsigned* s_slot, con
             }
         }
     }
-    if (act) { s_key[i0] = k0; s_key[i0 + 1] = k1; s_slot[i0] = v0; s_slot[i0 + 1] = v1; }
+    if (act) { s_key[i0] = k0; s_key[i0 + 1] = k1; if (SLOT) { s_slot[i0] = v0; s_slot[i0 + 1] = v1; } }
     __syncthreads();
 }
 
-// number of unvisited keys (0 < k < upper) at or above each of three pivots, for the keys this thread looks at
-__device__ __forceinline__ void count3(unsigned long long k, unsigned long long upper, unsigned long long q1, unsigned long long q2,
-                                       unsigned long long q3, unsigned& c1, unsigned& c2, unsigned& c3) {
-    const bool live = (k != 0ull) && (k < upper);
+// ---- bisection helpers: #{keys >= pivot} for three pivots at once -------------------------------------------------
+// keys held in registers: visited keys have been zeroed, so "unvisited" needs no test (every pivot is >= 1)
+__device__ __forceinline__ void count3_hi(unsigned khi, unsigned q1, unsigned q2, unsigned q3, unsigned& c1, unsigned& c2, unsigned& c3) {
+    c1 += (khi >= q1) ? 1u : 0u;
+    c2 += (khi >= q2) ? 1u : 0u;
+    c3 += (khi >= q3) ? 1u : 0u;
+}
+__device__ __forceinline__ void count3(unsigned long long k, unsigned long long q1, unsigned long long q2, unsigned long long q3,
+                                       unsigned& c1, unsigned& c2, unsigned& c3) {
+    const bool live = k != 0ull;
     c1 += (live && k >= q1) ? 1u : 0u;
     c2 += (live && k >= q2) ? 1u : 0u;
     c3 += (live && k >= q3) ? 1u : 0u;
 }
 
-template <bool DECODE>
+// Candidates c = tid & 255 of the current group that are still alive are tested against the selected boxes [s_lo, s_hi):
+// four threads per candidate split the list (thread-serial loops over broadcast shared-memory reads: every lane does useful
+// work), a hit clears the candidate's alive bit (one shared-memory atomic per warp).  Callers separate this from the next read
+// of the alive bits with a block barrier.
+__device__ __forceinline__ void suppress_group(const float4* s_gbox, const float* s_garea, unsigned* s_alive, int gn,
+                                               const float4* s_selbox, const float* s_selarea, int s_lo, int s_hi, float thr,
+                                               int tid, int lane) {
+    const int c = tid & (NMS_GROUP - 1), part = tid >> 8;   // NMS_THREADS / NMS_GROUP = 4 parts
+    bool dead = false;
+    if (c < gn && ((s_alive[c >> 5] >> (c & 31)) & 1u)) {
+        const float4 cb = s_gbox[c];
+        const float ca = s_garea[c];
+        for (int s = s_lo + part; s < s_hi && !dead; s += NMS_THREADS / NMS_GROUP)
+            dead = iou_exceeds(cb, ca, s_selbox[s], s_selarea[s], thr);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, dead);
+    if (m != 0u && lane == 0) atomicAnd(&s_alive[c >> 5], ~m);      // a warp's 32 candidates are one word of the bit set
+}
+
+template <bool DECODE, bool SLOT>
 __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // dynamic: selected boxes (normalised corners) + areas, sized by max_det
@@ -333,13 +444,14 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     float* s_selarea = reinterpret_cast<float*>(s_selbox + p.max_det);
 
     __shared__ unsigned long long s_key[NMS_CHUNK];
-    __shared__ unsigned s_slot[NMS_CHUNK];
+    __shared__ unsigned s_slot[SLOT ? NMS_CHUNK : 1];
     __shared__ float4 s_gbox[NMS_GROUP];      // the group's boxes, corner-normalised
     __shared__ float4 s_graw[NMS_GROUP];      // ... as decoded / stored
     __shared__ float s_garea[NMS_GROUP];
+    __shared__ unsigned s_alive[NMS_GROUP / 32];   // bit set: candidate of the group neither consumed nor suppressed yet
     __shared__ unsigned s_vict[NMS_BATCH];    // per batch member: the later members it suppresses
-    __shared__ int s_dead[NMS_BATCH];         // per batch member: suppressed by an earlier selection
     __shared__ unsigned s_cnt[3][4];          // pivot counts of the bisection, three rotating sets
+    __shared__ unsigned s_kmax;
     __shared__ int s_loaded, s_nsel;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -358,20 +470,29 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
 #define RN_PHASE(k) do { if (p.timing && tid == 0) { const long long now = clock64(); atomicAdd(p.timing + (k), (unsigned long long)(now - t_mark)); t_mark = now; } } while (0)
     unsigned long long upper = ~0ull;   // keys >= upper have been visited (no key equals ~0: its score bits would be a NaN's)
     int visited = 0, nsel = 0, round = 0, bis = 0;
-    if (tid == 0) s_nsel = 0;
+    if (tid == 0) { s_nsel = 0; s_kmax = 0u; }
     if (tid < 4) s_cnt[0][tid] = 0u;
+    __syncthreads();
     // The slab's keys are read ONCE into registers (8 per thread) when the slab has <= 8192 candidates -- the
-    // bisection passes and the gathers of every round then run out of registers; larger slabs stream the
-    // keys from global memory (L2) in every pass.
+    // bisection passes and the gathers of every round then run out of registers (visited keys are zeroed there);
+    // larger slabs stream the keys from global memory (L2) in every pass.
     constexpr int KPT = 8;
     const bool in_regs = cnt <= KPT * NMS_THREADS;
     unsigned long long rk[KPT];
+    {
+        unsigned mx = 0u;
 #pragma unroll
-    for (int t = 0; t < KPT; ++t) {
-        const int i = t * NMS_THREADS + tid;
-        rk[t] = (in_regs && i < cnt) ? __ldcg(keys + i) : 0ull;      // 0 never matches (real keys are > 0)
+        for (int t = 0; t < KPT; ++t) {
+            const int i = t * NMS_THREADS + tid;
+            rk[t] = (in_regs && i < cnt) ? __ldcg(keys + i) : 0ull;      // 0 never matches (real keys are > 0)
+            mx = max(mx, (unsigned)(rk[t] >> 32));
+        }
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0 && mx) atomicMax(&s_kmax, mx);
     }
     __syncthreads();
+    // every key's score word lies in [key_floor_hi, kmax]: the first bracket of the bisection
+    const unsigned long long top = in_regs ? (((unsigned long long)s_kmax + 1ull) << 32) : 0ull;   // 0: no bound known (also on overflow)
 
     while (visited < limit && nsel < p.max_det) {
         // ---------------- K4: a threshold key that keeps between `lo` and `hi` of the unvisited keys ----------------
@@ -386,21 +507,37 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
         const int remaining = cnt - visited;
         unsigned long long thr_key = 0ull;                   // remaining <= hi: everything that is left
         if (remaining > hi) {
-            // c(x) = #{unvisited k >= x} falls from `remaining` (> hi) at x = 0 to 0 (< lo) at x = upper; keys are unique, so
+            // c(x) = #{unvisited k >= x} falls from `remaining` (> hi) at x = L to 0 (< lo) at x = H; keys are unique, so
             // c steps by one and some x has lo <= c(x) <= hi.  Each pass evaluates c at the three quartile points of [L, H)
-            // and either accepts one of them or keeps the quarter that brackets the window.
-            unsigned long long L = 0ull, H = upper;
+            // and either accepts one of them or keeps the quarter that brackets the window.  While the bracket spans at
+            // least four values of the keys' upper (score) word the pivots are multiples of 2^32, so a 32-bit compare of
+            // that word decides k >= pivot; only ties in the score ever need the 64-bit form.
+            unsigned long long L = (unsigned long long)p.key_floor_hi << 32, H = upper;
+            if (top != 0ull && top < H) H = top;
             for (int pass = 0; pass < 96; ++pass, ++bis) {
                 const int set = bis % 3;                          // `bis` runs on across rounds: the rotation never restarts on a used set
                 if (tid < 4) s_cnt[(bis + 1) % 3][tid] = 0u;      // the next pass's set (last read two barriers ago)
                 const unsigned long long span = H - L;
-                const unsigned long long q1 = L + (span >> 2), q2 = L + (span >> 1), q3 = q2 + (span >> 2);
+                const bool wide = in_regs && (span >> 34) != 0ull;
+                unsigned long long q1, q2, q3;
                 unsigned c1 = 0u, c2 = 0u, c3 = 0u;
-                if (in_regs) {
+                if (wide) {
+                    const unsigned long long Lh = L >> 32, sh = span >> 32;
+                    const unsigned long long h1 = Lh + (sh >> 2), h2 = Lh + (sh >> 1), h3 = h2 + (sh >> 2);
+                    q1 = h1 << 32; q2 = h2 << 32; q3 = h3 << 32;
 #pragma unroll
-                    for (int t = 0; t < KPT; ++t) count3(rk[t], upper, q1, q2, q3, c1, c2, c3);
+                    for (int t = 0; t < KPT; ++t) count3_hi((unsigned)(rk[t] >> 32), (unsigned)h1, (unsigned)h2, (unsigned)h3, c1, c2, c3);
                 } else {
-                    for (int i = tid; i < cnt; i += NMS_THREADS) count3(__ldcg(keys + i), upper, q1, q2, q3, c1, c2, c3);
+                    q1 = L + (span >> 2); q2 = L + (span >> 1); q3 = q2 + (span >> 2);
+                    if (in_regs) {
+#pragma unroll
+                        for (int t = 0; t < KPT; ++t) count3(rk[t], q1, q2, q3, c1, c2, c3);
+                    } else {
+                        for (int i = tid; i < cnt; i += NMS_THREADS) {
+                            const unsigned long long k = __ldcg(keys + i);
+                            if (k < upper) count3(k, q1, q2, q3, c1, c2, c3);
+                        }
+                    }
                 }
                 c1 = __reduce_add_sync(0xffffffffu, c1);
                 c2 = __reduce_add_sync(0xffffffffu, c2);
@@ -430,14 +567,14 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
 #pragma unroll
             for (int t = 0; t < KPT; ++t) {
                 const unsigned long long k = rk[t];
-                const bool in = (k != 0ull) && (k < upper) && (k >= thr_key);
+                const bool in = (k != 0ull) && (k >= thr_key);
                 const unsigned m = __ballot_sync(0xffffffffu, in);
                 if (m) {                                    // warp-uniform
                     int base = 0;
                     if (lane == 0) base = atomicAdd(&s_loaded, __popc(m));
                     base = __shfl_sync(0xffffffffu, base, 0);
                     const int at = base + __popc(m & ((1u << lane) - 1u));
-                    if (in && at < NMS_CHUNK) { s_key[at] = k; s_slot[at] = (unsigned)(t * NMS_THREADS + tid); }
+                    if (in && at < NMS_CHUNK) { s_key[at] = k; if (SLOT) s_slot[at] = (unsigned)(t * NMS_THREADS + tid); }
                 }
             }
         } else {
@@ -451,7 +588,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                     if (lane == 0) base = atomicAdd(&s_loaded, __popc(m));
                     base = __shfl_sync(0xffffffffu, base, 0);
                     const int at = base + __popc(m & ((1u << lane) - 1u));
-                    if (in && at < NMS_CHUNK) { s_key[at] = k; s_slot[at] = (unsigned)i; }
+                    if (in && at < NMS_CHUNK) { s_key[at] = k; if (SLOT) s_slot[at] = (unsigned)i; }
                 }
             }
         }
@@ -460,11 +597,11 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
         if (s_loaded > NMS_CHUNK && p.status && tid == 0) p.status[page] = 2;   // cannot happen (see the bisection); never silent
         int n2p = 128;
         while (n2p < loaded) n2p <<= 1;
-        for (int i = loaded + tid; i < n2p; i += NMS_THREADS) { s_key[i] = 0ull; s_slot[i] = 0u; }
+        for (int i = loaded + tid; i < n2p; i += NMS_THREADS) { s_key[i] = 0ull; if (SLOT) s_slot[i] = 0u; }
         __syncthreads();
         RN_PHASE(1);
         // ---------------- bitonic network, descending (keys are unique) ----------------------------
-        sort_chunk_desc(s_key, s_slot, n2p, tid);
+        sort_chunk_desc<SLOT>(s_key, s_slot, n2p, tid);
         const int chunk_n = min(loaded, limit - visited);
         RN_PHASE(2);
         // ---------------- K5: greedy NMS over the ordered chunk -------------------------------------------
@@ -483,41 +620,53 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                 }
                 const int nx = g0 + NMS_GROUP + tid;
                 if (nx < chunk_n) nxt = fetch_row(p.src, page, (int)key_idx(s_key[nx]));
+                if (tid < NMS_GROUP / 32) {
+                    const int left = gn - tid * 32;
+                    s_alive[tid] = left >= 32 ? ~0u : (left > 0 ? (1u << left) - 1u : 0u);
+                }
             }
             __syncthreads();
             RN_PHASE(3);
-            for (int b0 = 0; b0 < gn && nsel < p.max_det; b0 += NMS_BATCH) {
-                const int bn = min(NMS_BATCH, gn - b0);
-                // (a) warp w owns batch member w: its lanes split the selected list (early exit), then one ballot over the
-                //     later batch members gives row w of the in-batch suppression matrix
+            // (0) whatever an earlier selection suppresses leaves the group before its order is ever looked at
+            if (p.nms && nsel > 0) suppress_group(s_gbox, s_garea, s_alive, gn, s_selbox, s_selarea, 0, nsel, p.iou_thr, tid, lane);
+            while (nsel < p.max_det) {
+                __syncthreads();                            // the alive bits are final
+                // (a) the next <= 32 alive candidates, in order: every warp derives their positions from the 8 alive words
+                const unsigned aw = lane < NMS_GROUP / 32 ? s_alive[lane] : 0u;
+                int incl = __popc(aw);
+#pragma unroll
+                for (int o = 1; o < NMS_GROUP / 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                const int alive_total = __shfl_sync(0xffffffffu, incl, NMS_GROUP / 32 - 1);
+                if (alive_total == 0) break;                // block-uniform: every warp reads the same words
+                const int bn = min(NMS_BATCH, alive_total);
+                int word = 0, before = 0;                   // lane l looks for the l-th alive candidate
+#pragma unroll
+                for (int w8 = 0; w8 < NMS_GROUP / 32 - 1; ++w8) {
+                    const int inc = __shfl_sync(0xffffffffu, incl, w8);
+                    if (inc <= lane) { word = w8 + 1; before = inc; }
+                }
+                const unsigned wbits = __shfl_sync(0xffffffffu, aw, word);
+                const int pos = lane < bn ? (word << 5) + (int)__fns(wbits, 0u, lane - before + 1) : 0;
+                // warp w owns batch member w: one ballot over the later members gives row w of the in-batch suppression matrix
                 if (warp < bn) {                            // warp-uniform
-                    bool dead = false;
                     unsigned vict = 0u;
                     if (p.nms) {
-                        const float4 mb = s_gbox[b0 + warp];
-                        const float ma = s_garea[b0 + warp];
-                        for (int s0 = 0; s0 < nsel; s0 += 32) {
-                            const int s = s0 + lane;
-                            const bool hit = (s < nsel) && iou_exceeds(mb, ma, s_selbox[s], s_selarea[s], p.iou_thr);
-                            if (__any_sync(0xffffffffu, hit)) { dead = true; break; }
-                        }
-                        if (!dead) {                        // a suppressed candidate suppresses nothing
-                            const int j = b0 + lane;
-                            const bool hit = (lane > warp) && (lane < bn) && iou_exceeds(mb, ma, s_gbox[j], s_garea[j], p.iou_thr);
-                            vict = __ballot_sync(0xffffffffu, hit);
-                        }
+                        const int mine = __shfl_sync(0xffffffffu, pos, warp);
+                        const bool hit = (lane > warp) && (lane < bn) &&
+                                         iou_exceeds(s_gbox[mine], s_garea[mine], s_gbox[pos], s_garea[pos], p.iou_thr);
+                        vict = __ballot_sync(0xffffffffu, hit);
                     }
-                    if (lane == 0) { s_dead[warp] = dead ? 1 : 0; s_vict[warp] = vict; }
+                    if (lane == 0) s_vict[warp] = vict;
                 }
                 __syncthreads();
                 RN_PHASE(4);
                 // (b) one warp resolves the greedy order in registers; the survivors join the selected list
+                const int n_old = nsel;
                 if (warp == 0) {
-                    const bool alive = (lane < bn) && (s_dead[lane] == 0);
                     const unsigned vict = (lane < bn) ? s_vict[lane] : 0u;
-                    const unsigned rem = __ballot_sync(0xffffffffu, alive);
+                    const unsigned rem = bn >= 32 ? ~0u : (1u << bn) - 1u;      // every batch member is alive
                     unsigned keep = rem;
-                    if (__any_sync(0xffffffffu, alive && (vict & rem) != 0u)) {      // conflicts inside the batch: walk it
+                    if (__any_sync(0xffffffffu, vict != 0u)) {   // conflicts inside the batch: walk it
                         keep = 0u;
                         unsigned r = rem;
                         while (r) {                         // warp-uniform
@@ -530,24 +679,32 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                     int extra = __popc(keep) - (p.max_det - nsel);       // TF stops at max_output_size: the first ones in order
                     while (extra-- > 0) keep &= ~(0x80000000u >> __clz(keep));
                     if ((keep >> lane) & 1u) {
-                        const int pos = nsel + __popc(keep & ((1u << lane) - 1u));
-                        const int c = b0 + lane;
-                        s_selbox[pos] = s_gbox[c];
-                        s_selarea[pos] = s_garea[c];
-                        const size_t at = (size_t)seg * p.max_det + pos;
-                        p.kept_key[at] = s_key[g0 + c];
-                        p.kept_box[at] = s_graw[c];
-                        p.kept_label[at] = labels ? labels[s_slot[g0 + c]] : seg_label;
+                        const int at_sel = nsel + __popc(keep & ((1u << lane) - 1u));
+                        s_selbox[at_sel] = s_gbox[pos];
+                        s_selarea[at_sel] = s_garea[pos];
+                        const size_t at = (size_t)seg * p.max_det + at_sel;
+                        p.kept_key[at] = s_key[g0 + pos];
+                        p.kept_box[at] = s_graw[pos];
+                        p.kept_label[at] = (SLOT && labels) ? labels[s_slot[g0 + pos]] : seg_label;
                     }
+                    if (lane < bn) atomicAnd(&s_alive[pos >> 5], ~(1u << (pos & 31)));   // the whole batch is consumed
                     if (lane == 0) s_nsel = nsel + __popc(keep);
                 }
                 __syncthreads();
                 nsel = s_nsel;
+                // (c) the new selections act on the rest of the group at once
+                if (p.nms && nsel > n_old && nsel < p.max_det)
+                    suppress_group(s_gbox, s_garea, s_alive, gn, s_selbox, s_selarea, n_old, nsel, p.iou_thr, tid, lane);
                 RN_PHASE(5);
             }
+            __syncthreads();                                // the group's arrays are rewritten next
         }
         visited += chunk_n;
         upper = (chunk_n > 0) ? s_key[chunk_n - 1] : 0ull;
+        if (in_regs) {
+#pragma unroll
+            for (int t = 0; t < KPT; ++t) if (rk[t] >= upper) rk[t] = 0ull;     // visited
+        }
         __syncthreads();
         if (chunk_n == 0) break;                            // defensive: no progress is impossible while visited < limit
     }
@@ -679,6 +836,13 @@ FilterWs carve(void* ws, int B, int S, long long cap, int max_det, bool agnostic
     return w;
 }
 
+// host image of f2ord(): scores > thr have upper key words >= this
+unsigned host_f2ord(float f) {
+    unsigned u;
+    memcpy(&u, &f, sizeof(u));
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
 size_t nms_dynamic_smem(int max_det) { return (size_t)max_det * (sizeof(float4) + sizeof(float)); }
 
 std::atomic<int> g_phase_timing{0};
@@ -702,30 +866,33 @@ int nms_opt_in_shared_memory() {
     const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
     if (bit && (done.load(std::memory_order_acquire) & bit)) return RN_OK;
     const int big = (int)nms_dynamic_smem(MAX_DET_LIMIT);
-    cudaError_t ae = cudaFuncSetAttribute(k_segment_nms<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_segment_nms<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaError_t ae = cudaFuncSetAttribute(k_segment_nms<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_segment_nms<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_segment_nms<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_segment_nms<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     if (ae != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
     if (bit) done.fetch_or(bit, std::memory_order_release);
     return RN_OK;
 }
 
 int run_back_end(const FilterWs& w, const BoxSource& src, bool decode, int B, int S, int segs_per_page, long long cap,
-                 int nms, float nms_thr, int max_det, int pre_nms_top_k,
+                 int nms, float nms_thr, int max_det, int pre_nms_top_k, unsigned key_floor_hi,
                  float* out_boxes, float* out_scores, int* out_labels, int* out_indices, int* out_count,
                  int* status, cudaStream_t s) {
     NmsParams np;
     np.sl.counts = w.counts; np.sl.keys = w.keys; np.sl.labels = w.labels; np.sl.cap = cap;
     np.src = src;
     np.S = S; np.segs_per_page = segs_per_page; np.nms = nms; np.iou_thr = nms_thr;
-    np.max_det = max_det; np.pre_nms_top_k = pre_nms_top_k;
+    np.max_det = max_det; np.pre_nms_top_k = pre_nms_top_k; np.key_floor_hi = key_floor_hi;
     np.kept_count = w.kept_count; np.kept_key = w.kept_key; np.kept_box = w.kept_box; np.kept_label = w.kept_label;
     np.status = status;
     np.timing = g_phase_timing.load(std::memory_order_relaxed) ? w.timing : nullptr;
     const size_t dyn = nms_dynamic_smem(max_det);
     int rc = nms_opt_in_shared_memory();
     if (rc) return rc;
-    if (decode) k_segment_nms<true><<<S, NMS_THREADS, dyn, s>>>(np);
-    else k_segment_nms<false><<<S, NMS_THREADS, dyn, s>>>(np);
+    const bool slot = w.labels != nullptr;              // only class-agnostic filtering reads per-candidate labels
+    if (decode) { if (slot) k_segment_nms<true, true><<<S, NMS_THREADS, dyn, s>>>(np); else k_segment_nms<true, false><<<S, NMS_THREADS, dyn, s>>>(np); }
+    else { if (slot) k_segment_nms<false, true><<<S, NMS_THREADS, dyn, s>>>(np); else k_segment_nms<false, false><<<S, NMS_THREADS, dyn, s>>>(np); }
     rc = rn_check_launch("k_segment_nms");
     if (rc) return rc;
     if ((rc = record_event(2, s)) != RN_OK) return rc;
@@ -770,16 +937,28 @@ int filter_common(K3Params kp, const BoxSource& src, bool decode, int nms, float
     RN_REQUIRE(B <= 65535, "B must be <= 65535");
     kp.inv_c = 1.0f / (float)C;
     kp.vec_ok = (((long long)kp.N * C) % 4 == 0) ? 1 : 0;
-    const long long tiles = kp.class_specific ? ((long long)kp.N * C + K3_TILE - 1) / K3_TILE
-                                              : ((long long)kp.N + K3_THREADS * K3_VEC - 1) / (K3_THREADS * K3_VEC);
-    const dim3 grid((unsigned)tiles, (unsigned)B);
     int rc = record_event(0, s);
     if (rc) return rc;
-    k_threshold_keys<<<grid, K3_THREADS, 0, s>>>(kp);
+    const long long page_tiles = ((long long)kp.N * C + K3S_TILE - 1) / K3S_TILE;
+    if (kp.class_specific && kp.vec_ok && page_tiles * B < (1ll << 31) - 4 * RN_NUM_SMS * K3S_CTAS_PER_SM * (K3_THREADS / 32)) {
+        K3Stream st;
+        st.tiles_per_page = (int)page_tiles;
+        st.inv_tiles_per_page = 1.0f / (float)page_tiles;
+        st.ntiles = (int)(page_tiles * B);
+        const long long ctas = (st.ntiles + K3_THREADS / 32 - 1) / (K3_THREADS / 32);
+        const int grid = (int)(ctas < RN_NUM_SMS * K3S_CTAS_PER_SM ? ctas : RN_NUM_SMS * K3S_CTAS_PER_SM);
+        k_threshold_keys_stream<<<grid, K3_THREADS, 0, s>>>(kp, st);
+    } else {
+        // class-agnostic filtering (max over classes per anchor) or unaligned page rows: the tile-per-CTA kernel
+        const long long tiles = kp.class_specific ? ((long long)kp.N * C + K3_TILE - 1) / K3_TILE
+                                                  : ((long long)kp.N + K3_THREADS * K3_VEC - 1) / (K3_THREADS * K3_VEC);
+        const dim3 grid((unsigned)tiles, (unsigned)B);
+        k_threshold_keys<<<grid, K3_THREADS, 0, s>>>(kp);
+    }
     rc = rn_check_launch("k_threshold_keys");
     if (rc) return rc;
     if ((rc = record_event(1, s)) != RN_OK) return rc;
-    return run_back_end(w, src, decode, B, S, spp, cand_cap, nms, nms_thr, max_det, pre_nms_top_k,
+    return run_back_end(w, src, decode, B, S, spp, cand_cap, nms, nms_thr, max_det, pre_nms_top_k, host_f2ord(kp.thr),
                         out_boxes, out_scores, out_labels, out_indices, nullptr,
                         status_out ? status_out : w.status, s);
 }
@@ -881,6 +1060,6 @@ extern "C" int rn_nms(const float* boxes, const float* scores, long long K, int 
     }
     BoxSource src = {};
     src.rows = boxes; src.N = (int)cap;
-    return run_back_end(w, src, false, 1, 1, 1, cap, 1, iou_threshold, max_output, 0,
+    return run_back_end(w, src, false, 1, 1, 1, cap, 1, iou_threshold, max_output, 0, 0u,
                         sc_boxes, sc_scores, sc_labels, out_indices, out_count_dev, w.status, s);
 }

@@ -12,6 +12,10 @@
 // disappears -- K2's CTA 0 stores the word into every mailbox in its prologue, right before all CTAs start waiting,
 // and K2's last CTA bumps the step counter; see rn_peer_box_sum_warp().  Send, wait and the loss arithmetic are ONE kernel.
 //
+// With RN_LOSS_PEER_LOSSES the two loss sums make the same trip at the END of the loss kernel (its last CTA; loss_slots), so
+// that every rank's `losses` is the loss of the merged batch.  A wait that outlasts the mailbox's timeout (default 30 s,
+// rn_peer_box_set_timeout) sets a STICKY error flag (rn_peer_box_status) and yields NaN losses; it never hangs the GPU.
+//
 // Slots are indexed by step % 4.  Two schedules are supported, identical on all ranks:
 //   in order    K1(s) publish(s) K2(s) K1(s+1) publish(s+1) K2(s+1) ...           K2 reads its latest step (lag 0)
 //   pipelined   K1(s+1) publish(s+1) K2(s) K1(s+2) publish(s+2) K2(s+1) ...       K2 reads the step before (lag 1):
@@ -56,10 +60,31 @@ extern "C" int rn_peer_box_create(int world, void** box_out, void* ipc_handle_ou
     if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
     RnPeerBox init = {};
     init.world = world;
+    init.timeout_ns = 30ull * 1000000000ull;          // see rn_peer_box_set_timeout
     e = cudaMemcpy(d, &init, sizeof(init), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(ipc_handle_out64), d);
     if (e != cudaSuccess) { cudaFree(d); return rn_fail(RN_ERR_CUDA, "peer box setup: %s", cudaGetErrorString(e)); }
     *box_out = d;
+    return RN_OK;
+}
+
+extern "C" int rn_peer_box_set_timeout(void* local_box, double seconds) {
+    RN_REQUIRE(local_box, "NULL pointer");
+    RN_REQUIRE(seconds > 0.0 && seconds < 1e9, "timeout must be positive");
+    const unsigned long long ns = (unsigned long long)(seconds * 1e9);
+    cudaError_t e = cudaMemcpy(reinterpret_cast<char*>(local_box) + offsetof(RnPeerBox, timeout_ns), &ns, sizeof(ns), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "peer box timeout: %s", cudaGetErrorString(e));
+    return RN_OK;
+}
+
+extern "C" int rn_peer_box_status(void* local_box, int* timed_out, int clear) {
+    RN_REQUIRE(local_box && timed_out, "NULL pointer");
+    unsigned int flag = 0u;
+    char* at = reinterpret_cast<char*>(local_box) + offsetof(RnPeerBox, error);
+    cudaError_t e = cudaMemcpy(&flag, at, sizeof(flag), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && flag && clear) { const unsigned int zero = 0u; e = cudaMemcpy(at, &zero, sizeof(zero), cudaMemcpyHostToDevice); }
+    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "peer box status: %s", cudaGetErrorString(e));
+    *timed_out = flag ? 1 : 0;
     return RN_OK;
 }
 
