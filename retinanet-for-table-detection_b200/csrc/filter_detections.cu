@@ -173,47 +173,57 @@ __global__ void __launch_bounds__(K3_THREADS) k_threshold_keys(const K3Params p)
     }
 }
 
-// The class-specific path (the reference's default) when page rows are 16-byte aligned: a PERSISTENT, warp-autonomous
-// stream.  grid = SMs x resident CTAs; a warp walks warp-tiles (32 lanes x one float4 = 128 consecutive scores of one page)
-// strided by the number of warps, with the loads of the next two tiles already in flight while it handles the current one
-// -- no shared memory, no block barrier.  Survivors are ranked inside the warp with three ballots (a lane has 0..4 of them);
-// one global atomic per warp-tile reserves their slab slots when all of them feed one slab (C == 1), one per candidate
-// otherwise.  The slab order is arbitrary by design: keys are unique, the NMS kernel orders them.
+// The class-specific path (the reference's default) when page rows are 16-byte aligned: a warp-autonomous stream.
+// grid = (CTAs per page, pages), about SMs x 8 CTAs in total; a CTA owns a contiguous slice of one page's scores, its 8 warps
+// interleave warp-tiles (32 lanes x one float4 = 128 consecutive scores) of the slice, each with the loads of its next two
+// tiles already in flight while it handles the current one -- no block barrier anywhere.  Survivors are ranked inside the
+// warp with three ballots (a lane has 0..4 of them) and collected in a warp-private shared-memory buffer; ONE global atomic
+// per flush reserves their slab slots (same-address atomics are what limits this kernel otherwise: one per warp-tile made
+// it 4x slower), and the keys leave with coalesced stores.  C > 1: candidates of a warp feed different slabs, one atomic each.
+// The slab order is arbitrary by design: keys are unique, the NMS kernel orders them.
 constexpr int K3S_TILE = 128;                               // scores per warp-tile
 constexpr int K3S_CTAS_PER_SM = 8;
+constexpr int K3S_BUF = 192;                                // keys a warp buffers before it flushes (a tile adds <= 128)
 
-struct K3Stream {
-    int tiles_per_page;
-    float inv_tiles_per_page;
-    int ntiles;                                             // tiles_per_page * B, < 2^31 (checked on the host)
-};
-
-__device__ __forceinline__ float4 k3s_load(const K3Params& p, const K3Stream& st, int tile, int lane, int total) {
+__device__ __forceinline__ float4 k3s_load(const float* src, int t, int t_end, int lane, int total) {
     const float ninf = __int_as_float(0xff800000);
     float4 v = make_float4(ninf, ninf, ninf, ninf);         // out of range: never above any threshold
-    if (tile < st.ntiles) {
-        const int page = rn_div(tile, st.tiles_per_page, st.inv_tiles_per_page);
-        const int e = (tile - page * st.tiles_per_page) * K3S_TILE + lane * 4;
-        if (e < total) v = rn_ldg_stream4(p.cls + (size_t)page * total + e);     // total % 4 == 0: all four or none
+    if (t < t_end) {
+        const int e = t * K3S_TILE + lane * 4;
+        if (e < total) v = rn_ldg_stream4(src + e);         // total % 4 == 0: all four or none
     }
     return v;
 }
 
-__global__ void __launch_bounds__(K3_THREADS, K3S_CTAS_PER_SM) k_threshold_keys_stream(const K3Params p, const K3Stream st) {
-    const int lane = threadIdx.x & 31;
-    const int nw = gridDim.x * (K3_THREADS / 32);
+__device__ __forceinline__ void k3s_flush(const K3Params& p, int page, const unsigned long long* buf, int n, int lane) {
+    __syncwarp();
+    int base = 0;
+    if (lane == 0) base = atomicAdd(p.sl.counts + page, n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int i = lane; i < n; i += 32)                      // dropped when the slab is full; the count keeps growing (overflow is reported)
+        if ((long long)base + i < p.sl.cap) p.sl.keys[(size_t)page * p.sl.cap + base + i] = buf[i];
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(K3_THREADS, K3S_CTAS_PER_SM) k_threshold_keys_stream(const K3Params p, int tiles_per_page, int tiles_per_cta) {
+    __shared__ unsigned long long s_buf[K3_THREADS / 32][K3S_BUF];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int page = blockIdx.y;
     const int total = p.N * p.C;                            // scores of one page
-    int tile = blockIdx.x * (K3_THREADS / 32) + (threadIdx.x >> 5);
-    float4 v0 = k3s_load(p, st, tile, lane, total);
-    float4 v1 = k3s_load(p, st, tile + nw, lane, total);
-    for (; tile < st.ntiles; tile += nw) {
+    const float* src = p.cls + (size_t)page * total;
+    const int t_begin = blockIdx.x * tiles_per_cta, t_end = min(tiles_per_page, t_begin + tiles_per_cta);
+    unsigned long long* buf = s_buf[warp];
+    int fill = 0;                                           // warp-uniform
+    int t = t_begin + warp;
+    float4 v0 = k3s_load(src, t, t_end, lane, total);
+    float4 v1 = k3s_load(src, t + K3_THREADS / 32, t_end, lane, total);
+    for (; t < t_end; t += K3_THREADS / 32) {
         const float4 cur = v0;
         v0 = v1;
-        v1 = k3s_load(p, st, tile + 2 * nw, lane, total);   // two tiles ahead
+        v1 = k3s_load(src, t + 2 * (K3_THREADS / 32), t_end, lane, total);      // two tiles ahead
         const unsigned hits = (cur.x > p.thr ? 1u : 0u) | (cur.y > p.thr ? 2u : 0u) | (cur.z > p.thr ? 4u : 0u) | (cur.w > p.thr ? 8u : 0u);
         if (!__any_sync(0xffffffffu, hits != 0u)) continue;  // warp-uniform
-        const int page = rn_div(tile, st.tiles_per_page, st.inv_tiles_per_page);
-        const int e0 = (tile - page * st.tiles_per_page) * K3S_TILE + lane * 4;
+        const int e0 = t * K3S_TILE + lane * 4;
         const float sc[4] = {cur.x, cur.y, cur.z, cur.w};
         if (p.C == 1) {
             // exclusive prefix of the lanes' survivor counts (0..4 = 3 bits): three ballots, no shuffles
@@ -221,18 +231,13 @@ __global__ void __launch_bounds__(K3_THREADS, K3S_CTAS_PER_SM) k_threshold_keys_
             const unsigned b0 = __ballot_sync(0xffffffffu, mine & 1u), b1 = __ballot_sync(0xffffffffu, mine & 2u),
                            b2 = __ballot_sync(0xffffffffu, mine & 4u);
             const unsigned lt = (1u << lane) - 1u;
-            int at = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
             const int tot = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-            int base = 0;
-            if (lane == 0) base = atomicAdd(p.sl.counts + page, tot);
-            at += __shfl_sync(0xffffffffu, base, 0);
+            if (fill + tot > K3S_BUF) { k3s_flush(p, page, buf, fill, lane); fill = 0; }
+            int at = fill + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (hits & (1u << j)) {
-                    if (at < p.sl.cap) p.sl.keys[(size_t)page * p.sl.cap + at] = make_key(sc[j], (unsigned)(e0 + j));
-                    ++at;                                   // dropped when the slab is full; the count keeps growing (overflow is reported)
-                }
-            }
+            for (int j = 0; j < 4; ++j)
+                if (hits & (1u << j)) buf[at++] = make_key(sc[j], (unsigned)(e0 + j));
+            fill += tot;
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -246,6 +251,7 @@ __global__ void __launch_bounds__(K3_THREADS, K3S_CTAS_PER_SM) k_threshold_keys_
             }
         }
     }
+    if (fill) k3s_flush(p, page, buf, fill, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -417,19 +423,21 @@ __device__ __forceinline__ void count3(unsigned long long k, unsigned long long 
     c3 += (live && k >= q3) ? 1u : 0u;
 }
 
-// Candidates c = tid & 255 of the current group that are still alive are tested against the selected boxes [s_lo, s_hi):
-// four threads per candidate split the list (thread-serial loops over broadcast shared-memory reads: every lane does useful
-// work), a hit clears the candidate's alive bit (one shared-memory atomic per warp).  Callers separate this from the next read
-// of the alive bits with a block barrier.
-__device__ __forceinline__ void suppress_group(const float4* s_gbox, const float* s_garea, unsigned* s_alive, int gn,
-                                               const float4* s_selbox, const float* s_selarea, int s_lo, int s_hi, float thr,
-                                               int tid, int lane) {
-    const int c = tid & (NMS_GROUP - 1), part = tid >> 8;   // NMS_THREADS / NMS_GROUP = 4 parts
+// The alive candidates [w0, w0 + wn) of the current group (wn <= 256, w0 a multiple of 32) are tested against the selected
+// boxes [s_lo, s_hi): NMS_THREADS / wp threads per candidate split the list (wp = wn rounded up to a power of two >= 32;
+// thread-serial loops over broadcast shared-memory reads: every lane does useful work), a hit clears the candidate's alive
+// bit (one shared-memory atomic per warp).  Callers separate this from the next read of the alive bits with a block barrier.
+__device__ __forceinline__ void suppress_window(const float4* s_gbox, const float* s_garea, unsigned* s_alive, int w0, int wn,
+                                                const float4* s_selbox, const float* s_selarea, int s_lo, int s_hi, float thr,
+                                                int tid, int lane) {
+    int wp = 32, sh = 5;
+    while (wp < wn) { wp <<= 1; ++sh; }
+    const int c = w0 + (tid & (wp - 1)), part = tid >> sh, parts = NMS_THREADS >> sh;
     bool dead = false;
-    if (c < gn && ((s_alive[c >> 5] >> (c & 31)) & 1u)) {
+    if (c < w0 + wn && ((s_alive[c >> 5] >> (c & 31)) & 1u)) {
         const float4 cb = s_gbox[c];
         const float ca = s_garea[c];
-        for (int s = s_lo + part; s < s_hi && !dead; s += NMS_THREADS / NMS_GROUP)
+        for (int s = s_lo + part; s < s_hi && !dead; s += parts)
             dead = iou_exceeds(cb, ca, s_selbox[s], s_selarea[s], thr);
     }
     const unsigned m = __ballot_sync(0xffffffffu, dead);
@@ -620,15 +628,15 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                 }
                 const int nx = g0 + NMS_GROUP + tid;
                 if (nx < chunk_n) nxt = fetch_row(p.src, page, (int)key_idx(s_key[nx]));
-                if (tid < NMS_GROUP / 32) {
-                    const int left = gn - tid * 32;
-                    s_alive[tid] = left >= 32 ? ~0u : (left > 0 ? (1u << left) - 1u : 0u);
-                }
+                if (tid < NMS_GROUP / 32) s_alive[tid] = 0u;
             }
             __syncthreads();
             RN_PHASE(3);
-            // (0) whatever an earlier selection suppresses leaves the group before its order is ever looked at
-            if (p.nms && nsel > 0) suppress_group(s_gbox, s_garea, s_alive, gn, s_selbox, s_selarea, 0, nsel, p.iou_thr, tid, lane);
+            // The group is opened window by window: a window's candidates are first tested against everything selected so
+            // far (what an earlier selection suppresses leaves before its order is ever looked at), then consumed 32 alive
+            // candidates at a time.  A window is no wider than what can still be needed -- about (max_det - nsel) more
+            // selections -- so candidates behind the stopping point are (almost) never tested.
+            int gdone = 0;                                  // candidates of the group whose window has been opened
             while (nsel < p.max_det) {
                 __syncthreads();                            // the alive bits are final
                 // (a) the next <= 32 alive candidates, in order: every warp derives their positions from the 8 alive words
@@ -637,7 +645,21 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
 #pragma unroll
                 for (int o = 1; o < NMS_GROUP / 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
                 const int alive_total = __shfl_sync(0xffffffffu, incl, NMS_GROUP / 32 - 1);
-                if (alive_total == 0) break;                // block-uniform: every warp reads the same words
+                if (alive_total == 0) {                     // block-uniform: every warp reads the same words
+                    if (gdone >= gn) break;
+                    const int room = p.max_det - nsel;
+                    int wn = min(gn - gdone, (room + (room >> 2) + 47) & ~31);      // a multiple of 32 unless it ends the group
+                    __syncthreads();                        // everybody has read the (empty) alive words
+                    if (tid < NMS_GROUP / 32) {
+                        const int left = gdone + wn - tid * 32, skip = gdone - tid * 32;    // gdone is a multiple of 32
+                        s_alive[tid] = (skip > 0 || left <= 0) ? 0u : (left >= 32 ? ~0u : (1u << left) - 1u);
+                    }
+                    __syncthreads();
+                    if (p.nms && nsel > 0)
+                        suppress_window(s_gbox, s_garea, s_alive, gdone, wn, s_selbox, s_selarea, 0, nsel, p.iou_thr, tid, lane);
+                    gdone += wn;
+                    continue;
+                }
                 const int bn = min(NMS_BATCH, alive_total);
                 int word = 0, before = 0;                   // lane l looks for the l-th alive candidate
 #pragma unroll
@@ -692,9 +714,9 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                 }
                 __syncthreads();
                 nsel = s_nsel;
-                // (c) the new selections act on the rest of the group at once
+                // (c) the new selections act on the rest of the open window at once
                 if (p.nms && nsel > n_old && nsel < p.max_det)
-                    suppress_group(s_gbox, s_garea, s_alive, gn, s_selbox, s_selarea, n_old, nsel, p.iou_thr, tid, lane);
+                    suppress_window(s_gbox, s_garea, s_alive, 0, gdone, s_selbox, s_selarea, n_old, nsel, p.iou_thr, tid, lane);
                 RN_PHASE(5);
             }
             __syncthreads();                                // the group's arrays are rewritten next
@@ -940,14 +962,15 @@ int filter_common(K3Params kp, const BoxSource& src, bool decode, int nms, float
     int rc = record_event(0, s);
     if (rc) return rc;
     const long long page_tiles = ((long long)kp.N * C + K3S_TILE - 1) / K3S_TILE;
-    if (kp.class_specific && kp.vec_ok && page_tiles * B < (1ll << 31) - 4 * RN_NUM_SMS * K3S_CTAS_PER_SM * (K3_THREADS / 32)) {
-        K3Stream st;
-        st.tiles_per_page = (int)page_tiles;
-        st.inv_tiles_per_page = 1.0f / (float)page_tiles;
-        st.ntiles = (int)(page_tiles * B);
-        const long long ctas = (st.ntiles + K3_THREADS / 32 - 1) / (K3_THREADS / 32);
-        const int grid = (int)(ctas < RN_NUM_SMS * K3S_CTAS_PER_SM ? ctas : RN_NUM_SMS * K3S_CTAS_PER_SM);
-        k_threshold_keys_stream<<<grid, K3_THREADS, 0, s>>>(kp, st);
+    if (kp.class_specific && kp.vec_ok) {
+        // about SMs x 8 CTAs over all pages, each CTA a contiguous slice of one page (at least one tile per warp)
+        long long per_page = (RN_NUM_SMS * K3S_CTAS_PER_SM + B - 1) / B;
+        const long long most = (page_tiles + K3_THREADS / 32 - 1) / (K3_THREADS / 32);
+        if (per_page > most) per_page = most;
+        if (per_page < 1) per_page = 1;
+        const int tiles_per_cta = (int)((page_tiles + per_page - 1) / per_page);
+        const dim3 grid((unsigned)((page_tiles + tiles_per_cta - 1) / tiles_per_cta), (unsigned)B);
+        k_threshold_keys_stream<<<grid, K3_THREADS, 0, s>>>(kp, (int)page_tiles, tiles_per_cta);
     } else {
         // class-agnostic filtering (max over classes per anchor) or unaligned page rows: the tile-per-CTA kernel
         const long long tiles = kp.class_specific ? ((long long)kp.N * C + K3_TILE - 1) / K3_TILE

@@ -117,6 +117,26 @@ class PeerCounter(object):
         self.rank, self.world, self.box, self.peers = rank, world, box, peers
         self._arr = (ctypes.c_void_p * world)(*peers)
         self.bound = None
+        # how long a device-side wait for a peer may last before it gives up (sticky error flag + NaN losses instead of a
+        # hung GPU).  Rank skew of seconds is normal (checkpointing, evaluation callbacks, a stalled loader): default 30 s.
+        self.set_timeout(float(os.environ.get("RN_B200_PEER_TIMEOUT_S", "30")))
+
+    def set_timeout(self, seconds):
+        _lib.check(_lib.load().rn_peer_box_set_timeout(ctypes.c_void_p(self.box), float(seconds)), "rn_peer_box_set_timeout")
+        self.timeout_s = float(seconds)
+
+    def timed_out(self, clear=True):
+        """True when a device-side wait of this rank has timed out since the flag was last cleared (synchronous read)."""
+        flag = ctypes.c_int(0)
+        _lib.check(_lib.load().rn_peer_box_status(ctypes.c_void_p(self.box), ctypes.byref(flag), 1 if clear else 0), "rn_peer_box_status")
+        return bool(flag.value)
+
+    def check(self):
+        """Raises :class:`RnError` if a peer did not publish within the timeout (the losses / gradients of that step are NaN
+        and must be discarded).  Synchronous; call it wherever the step's losses are read on the host."""
+        if self.timed_out(clear=True):
+            raise _lib.RnError("peer mailbox: a rank did not publish its count / loss sums within %.1f s "
+                               "(RN_B200_PEER_TIMEOUT_S); the step's losses and gradients are invalid" % self.timeout_s)
 
     @classmethod
     def create(cls, group=None):

@@ -120,7 +120,7 @@ def smooth_l1(sigma=3.0):
 
 def detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None,
                      alpha=0.25, gamma=2.0, sigma=3.0, bce="tf2", want_grads=True, out=None, workspace=None,
-                     shared_state=False, peer_box=None, peer_lag=0, peer_publish=False):
+                     shared_state=False, peer_box=None, peer_lag=0, peer_publish=False, peer_losses=False):
     """Both losses, forward + backward, in ONE launch of K2 (``rn_loss_fwd_bwd``).
 
     All tensors are float32 CUDA: ``y_true_reg`` (B,N,5), ``y_true_cls`` (B,N,C+1) in the order
@@ -136,7 +136,10 @@ def detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None
     the kernel then takes the sum of the published counts as the normaliser (``normalizer`` is ignored);
     ``peer_lag=1`` selects the step published before the latest one (pipelined schedule, see ``pipeline``).
     ``peer_publish=True`` (``peer_box.bind(count)`` done once): fused publish -- this launch sends the rank's count
-    itself and completes the step, ``publish`` is not called for it."""
+    itself and completes the step, ``publish`` is not called for it.
+    ``peer_losses=True``: the two loss sums travel through the mailbox as well (the kernel's last CTA sends, collects and
+    adds them in rank order), so ``losses`` is the loss of the whole merged batch on every rank -- what the reference's
+    ``multi_gpu_model`` computes (``RetinaNet.py:106-112``, ``model/losses.py:44, :90``).  One such launch per step."""
     device = cls_pred.device
     C = cls_pred.shape[-1]
     R = cls_pred.numel() // C
@@ -158,7 +161,11 @@ def detection_losses(y_true_reg, y_true_cls, reg_pred, cls_pred, normalizer=None
             if peer_lag or peer_box.bound is None:
                 raise ValueError("peer_publish needs peer_box.bind(count) and is not combinable with peer_lag")
             flags |= _lib.RN_LOSS_PEER_PUBLISH
+        if peer_losses:
+            flags |= _lib.RN_LOSS_PEER_LOSSES
     else:
+        if peer_losses:
+            raise ValueError("peer_losses needs peer_box")
         npos = _norm_tensor(normalizer, device)
         npos_ptr = _lib.ptr(npos)
     _lib.check(_lib.load().rn_loss_fwd_bwd(_lib.ptr(y_true_cls), _lib.ptr(cls_pred), _lib.ptr(y_true_reg),

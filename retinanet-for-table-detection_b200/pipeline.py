@@ -89,6 +89,7 @@ class TargetLossStep(object):
         self._chunk_events = None
         self._losses_host = None
         self._done_event = None
+        self._gt_event = None                  # the last H2D copy of the pinned GT block (guards its reuse by the host)
 
     def _bind_inorder(self):
         """Fused publish, in-order schedule: every step's loss launch sends ``npos_total``."""
@@ -99,9 +100,16 @@ class TargetLossStep(object):
 
     # ---- inputs ---------------------------------------------------------------------------------
     def load_annotations(self, image_group, annotations_group):
-        """Pack the ragged GT list (reference format) and copy it to the static device block (async)."""
+        """Pack the ragged GT list (reference format) and copy it to the static device block (async).  The steps are
+        asynchronous graph replays, so the host may run ahead: the pinned block is only rewritten once the previous copy
+        out of it has executed."""
+        if self._gt_event is not None:
+            self._gt_event.synchronize()
         _anchors.pack_annotations(image_group, annotations_group, self.C, out=self._gt_views)   # straight into the pinned block
         self.gt_dev.copy_(self.gt_host, non_blocking=True)
+        if self._gt_event is None:
+            self._gt_event = torch.cuda.Event()
+        self._gt_event.record(torch.cuda.current_stream(self.device))
         return self.gt_host.numel()
 
     def load_predictions(self, cls_pred, reg_pred):
@@ -117,15 +125,22 @@ class TargetLossStep(object):
         if self.peer is not None and not self.peer_fused:
             self.peer.publish(self.npos_total, self.device)     # this rank's count -> every rank's mailbox
 
-    def _exchange(self):
+    def _exchange(self, npos_total=None):
         """Several ranks without the peer mailbox: the count is all-reduced between the two kernels."""
         if self.peer is None and _dist.world()[1] > 1:
-            torch.distributed.all_reduce(self.npos_total)
+            torch.distributed.all_reduce(self.npos_total if npos_total is None else npos_total)
+
+    def _reduce_losses(self):
+        """Several ranks without the peer mailbox: every rank's sums are already divided by the global normaliser, so
+        the merged batch's losses are their plain sum (with the mailbox K2's last CTA does this itself)."""
+        if self.peer is None and _dist.world()[1] > 1:
+            torch.distributed.all_reduce(self.losses[:2])
 
     def _losses(self):
         _losses.detection_losses(self.y_reg, self.y_cls, self.reg_pred, self.cls_pred, normalizer=self.npos_total,
                                  out=(self.losses, self.grad_cls, self.grad_reg), workspace=self.loss_ws,
-                                 peer_box=self.peer, peer_publish=self.peer_fused, **self.loss_kw)
+                                 peer_box=self.peer, peer_publish=self.peer_fused, peer_losses=self.peer is not None,
+                                 **self.loss_kw)
 
     def _capture(self, fn):
         g = torch.cuda.CUDAGraph()
@@ -163,6 +178,8 @@ class TargetLossStep(object):
         bufs = [(self.y_reg, self.y_cls, self.npos, self.npos_total),
                 (torch.empty_like(self.y_reg), torch.empty_like(self.y_cls), second[:self.B], second[self.B:].view(torch.float32))]
 
+        no_box = self.peer is None and _dist.world()[1] > 1    # several ranks, no mailbox: all_reduce between the graphs
+
         def targets(i):
             y_reg, y_cls, npos, npos_total = bufs[i]
             _anchors.anchor_targets_device(self.spec, self.d_boxes, self.d_labels, self.d_counts, self.d_hw, self.C,
@@ -178,7 +195,7 @@ class TargetLossStep(object):
             _losses.detection_losses(y_reg, y_cls, self.reg_pred, self.cls_pred, normalizer=npos_total,
                                      out=(self.losses, self.grad_cls, self.grad_reg), workspace=self.loss_ws,
                                      peer_box=self.peer, peer_lag=0 if self.peer_fused else 1,
-                                     peer_publish=self.peer_fused, **self.loss_kw)
+                                     peer_publish=self.peer_fused, peer_losses=self.peer is not None, **self.loss_kw)
         if self.peer_fused:
             # the loss launch completing step t sends value[t & 1]: bind the two count buffers so that the warm-up's
             # losses(0) (step t0 = steps() + 1) reads buffer 0 and the following steps alternate 1, 0, 1, ...
@@ -192,12 +209,15 @@ class TargetLossStep(object):
         s.wait_stream(torch.cuda.current_stream(d))
         with torch.cuda.stream(s):
             targets(0)
+            self._exchange(bufs[0][3])
             if self.peer_fused:
                 losses(0)
                 targets(1)
             else:
                 targets(1)
+                self._exchange(bufs[1][3])
                 losses(0)
+            self._reduce_losses()
         torch.cuda.current_stream(d).wait_stream(s)
         torch.cuda.synchronize(d)
         side = (torch.cuda.Stream(d), torch.cuda.Stream(d))
@@ -218,10 +238,17 @@ class TargetLossStep(object):
         if self.use_graph:
             ga = [self._capture(lambda i=i: targets(i)) for i in range(2)]
             gb = [self._capture(lambda i=i: losses(i)) for i in range(2)]
-            gc = [self._capture(lambda i=i: both(i, 1 - i)) for i in range(2)]          # index = the NEXT batch's buffer
-            run_a, run_b, run_ab = (lambda i: ga[i].replay()), (lambda i: gb[i].replay()), (lambda i: gc[i].replay())
+            # the two-branch graph is only legal when nothing has to happen between K1 and K2 on the host
+            gc = None if no_box else [self._capture(lambda i=i: both(i, 1 - i)) for i in range(2)]   # index = the NEXT batch's buffer
+            run_a, run_b = (lambda i: ga[i].replay()), (lambda i: gb[i].replay())
+            run_ab = None if no_box else (lambda i: gc[i].replay())
         else:
-            run_a, run_b, run_ab = targets, losses, (lambda i: both(i, 1 - i))
+            run_a, run_b, run_ab = targets, losses, (None if no_box else (lambda i: both(i, 1 - i)))
+        if no_box:
+            # the count of the NEXT batch is all-reduced right behind its K1, one call before the K2 that divides by it
+            plain_a, plain_b = run_a, run_b
+            run_a = lambda i: (plain_a(i), self._exchange(bufs[i][3]))
+            run_b = lambda i: (plain_b(i), self._reduce_losses())
         # after the warm-up the latest published batch sits in buffer 1 (lag 0); prime: it becomes "current"
         self._pipe = dict(bufs=bufs, run_a=run_a, run_b=run_b, run_ab=run_ab, cur=1)
 
@@ -233,6 +260,9 @@ class TargetLossStep(object):
         if overlap and self.peer is not None and not self.peer_fused:
             raise ValueError("overlap=True with several ranks needs the fused publish (the separate publish kernel would "
                              "bump the step counter while K2 of the previous batch reads it)")
+        if overlap and self.peer is None and _dist.world()[1] > 1:
+            raise ValueError("overlap=True with several ranks needs the peer mailbox: without it the positive count is "
+                             "all-reduced on the host side between K1 and K2, which a two-branch graph cannot contain")
         if self._pipe is None:
             self._pipe_setup()
         pp = self._pipe
@@ -339,7 +369,10 @@ class TargetLossStep(object):
                                      out=(self._chunk_losses[i], sl(self.grad_cls), sl(self.grad_reg)),
                                      workspace=self.loss_ws, peer_box=self.peer,
                                      peer_publish=self.peer_fused and i == 0,     # the step's first launch sends the count
+                                     peer_losses=self.peer is not None and chunks == 1,   # one launch per step: sums via the mailbox
                                      **self.loss_kw)
+        if _dist.world()[1] > 1 and not (self.peer is not None and chunks == 1):
+            torch.distributed.all_reduce(self._chunk_losses[:, :2])       # page chunks / no mailbox: the merged batch's losses
         self._losses_host.copy_(self._chunk_losses, non_blocking=True)
         self._done_event.record(compute)
 
@@ -347,6 +380,8 @@ class TargetLossStep(object):
         self._done_event.synchronize()
         out = self._losses_host.sum(dim=0)
         out[2] = self._losses_host[0, 2]                    # the normaliser is the same in every row
+        if self.peer is not None and bool(torch.isnan(out[2])):
+            self.peer.check()                               # a peer never published: raise instead of returning NaN losses
         return out
 
     def run(self, events=None):
@@ -374,9 +409,17 @@ class TargetLossStep(object):
             self._graphs[1].replay()
         else:
             self._losses()
+        self._reduce_losses()
         if events is not None:
             events[2].record()
         return self.losses
+
+    def check(self):
+        """Raises when a peer did not deliver its count / loss sums within the mailbox timeout (the step's losses are NaN).
+        Synchronous."""
+        if self.peer is not None:
+            torch.cuda.synchronize(self.device)
+            self.peer.check()
 
 
 class HostStepPipeline(object):
