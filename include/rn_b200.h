@@ -265,6 +265,10 @@ int rn_peer_box_create(int world, void** box_out, void* ipc_handle_out64);
 int rn_peer_box_open(const void* ipc_handle64, void** peer_box_out);
 int rn_peer_box_close(void* peer_box);
 int rn_peer_box_destroy(void* box);
+/* records every rank's mailbox pointer (as mapped into this process, boxes_of_all_ranks[rank] == local_box) and this rank in
+ * the local mailbox: what the device-side SENDS of a loss launch need (RN_LOSS_PEER_LOSSES, RN_LOSS_PEER_PUBLISH).  Call it
+ * once after the peers' mailboxes have been opened.  Synchronous. */
+int rn_peer_box_connect(void* local_box, void* const* boxes_of_all_ranks /* host, (world) */, int rank, int world);
 /* records in the local mailbox what RN_LOSS_PEER_PUBLISH needs: every rank's mailbox pointer (as mapped into this
  * process, boxes_of_all_ranks[rank] == local_box), this rank, and the device floats it publishes: the loss launch that
  * completes step t (steps count from 1, rn_peer_box_step() + 1 is the next) sends value_even_dev for even t and

@@ -15,7 +15,7 @@ anchors = np.asarray(rn.anchors_for_shape(HW + (3,)))
 _, anns = synthetic.training_batch(3, batch=B)
 cls, reg = synthetic.inference_predictions(3, B, anchors, anns, classes=1)
 cls_d, reg_d = torch.from_numpy(cls).cuda(), torch.from_numpy(reg).cuda()
-names = ["bisection select", "gather", "bitonic sort", "group fetch/decode", "(a) suppression tests", "(b) resolve", "-", "-"]
+names = ["bisection select", "gather", "bitonic sort", "group fetch/decode", "(a) windows + in-batch tests", "(b) resolve + eager", "sweep between rounds"]
 rn._lib.load().rn_debug_nms_timing(1)
 for topk in (0, 1000):
     head = rn.DetectionHead(pre_nms_top_k=topk)
@@ -24,6 +24,7 @@ for topk in (0, 1000):
     torch.cuda.synchronize()
     ws = [v for k, v in rn._lib._scratch.items() if k[0] == "filter"][0]
     t = ws[:64].view(torch.int64).cpu().numpy().astype(np.float64)
-    print("pre_nms_top_k=%d: ticks per segment (thread 0): total %.0f" % (topk, t.sum() / B))
+    slowest, t = t[7], t[:7]
+    print("pre_nms_top_k=%d: ticks per segment (thread 0): mean %.0f, slowest CTA %.0f" % (topk, t.sum() / B, slowest))
     for n, v in zip(names, t):
-        print("   %-16s %8.0f  %5.1f%%" % (n, v / B, 100 * v / t.sum()))
+        print("   %-30s %8.0f  %5.1f%%" % (n, v / B, 100 * v / t.sum()))

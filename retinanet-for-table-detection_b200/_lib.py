@@ -70,6 +70,7 @@ SIGNATURES = {
     "rn_peer_box_open": (c_int, [c_void_p, POINTER(c_void_p)]),
     "rn_peer_box_close": (c_int, [c_void_p]),
     "rn_peer_box_destroy": (c_int, [c_void_p]),
+    "rn_peer_box_connect": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int]),
     "rn_peer_box_bind": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, _P, _P]),
     "rn_peer_box_set_timeout": (c_int, [c_void_p, c_double]),
     "rn_peer_box_status": (c_int, [c_void_p, POINTER(c_int), c_int]),

@@ -174,26 +174,18 @@ __global__ void __launch_bounds__(K3_THREADS) k_threshold_keys(const K3Params p)
 }
 
 // The class-specific path (the reference's default) when page rows are 16-byte aligned: a warp-autonomous stream.
-// grid = (CTAs per page, pages), about SMs x 8 CTAs in total; a CTA owns a contiguous slice of one page's scores, its 8 warps
-// interleave warp-tiles (32 lanes x one float4 = 128 consecutive scores) of the slice, each with the loads of its next two
-// tiles already in flight while it handles the current one -- no block barrier anywhere.  Survivors are ranked inside the
-// warp with three ballots (a lane has 0..4 of them) and collected in a warp-private shared-memory buffer; ONE global atomic
-// per flush reserves their slab slots (same-address atomics are what limits this kernel otherwise: one per warp-tile made
-// it 4x slower), and the keys leave with coalesced stores.  C > 1: candidates of a warp feed different slabs, one atomic each.
+// grid = (CTAs per page, pages), about SMs x 4 CTAs in total; a CTA owns a contiguous slice of one page's scores, its 8 warps
+// interleave warp-tiles (32 lanes x 4 float4 = 512 consecutive scores) of the slice, each with the four loads of its next
+// tile already in flight while it handles the current one -- no block barrier anywhere.  Survivors are ranked inside the
+// warp with five ballots (a lane has 0..16 of them) and collected in a warp-private shared-memory buffer; ONE global atomic
+// per flush reserves their slab slots and the keys leave with coalesced stores.  (Measured on the way here: one global atomic
+// per 128 scores serialises on the page's counter -- 69 us; 128-score tiles are instruction bound -- 143 warp-instructions
+// per tile, 23 us.)  C > 1: the candidates of a warp feed different slabs, one atomic each.
 // The slab order is arbitrary by design: keys are unique, the NMS kernel orders them.
-constexpr int K3S_TILE = 128;                               // scores per warp-tile
-constexpr int K3S_CTAS_PER_SM = 8;
-constexpr int K3S_BUF = 192;                                // keys a warp buffers before it flushes (a tile adds <= 128)
-
-__device__ __forceinline__ float4 k3s_load(const float* src, int t, int t_end, int lane, int total) {
-    const float ninf = __int_as_float(0xff800000);
-    float4 v = make_float4(ninf, ninf, ninf, ninf);         // out of range: never above any threshold
-    if (t < t_end) {
-        const int e = t * K3S_TILE + lane * 4;
-        if (e < total) v = rn_ldg_stream4(src + e);         // total % 4 == 0: all four or none
-    }
-    return v;
-}
+constexpr int K3S_VEC = 4;                                  // float4 per lane and tile
+constexpr int K3S_TILE = 128 * K3S_VEC;                     // scores per warp-tile
+constexpr int K3S_CTAS_PER_SM = 4;
+constexpr int K3S_BUF = 256;                                // keys a warp buffers before it flushes
 
 __device__ __forceinline__ void k3s_flush(const K3Params& p, int page, const unsigned long long* buf, int n, int lane) {
     __syncwarp();
@@ -213,40 +205,70 @@ __global__ void __launch_bounds__(K3_THREADS, K3S_CTAS_PER_SM) k_threshold_keys_
     const float* src = p.cls + (size_t)page * total;
     const int t_begin = blockIdx.x * tiles_per_cta, t_end = min(tiles_per_page, t_begin + tiles_per_cta);
     unsigned long long* buf = s_buf[warp];
+    const float ninf = __int_as_float(0xff800000);          // out of range: never above any threshold
     int fill = 0;                                           // warp-uniform
-    int t = t_begin + warp;
-    float4 v0 = k3s_load(src, t, t_end, lane, total);
-    float4 v1 = k3s_load(src, t + K3_THREADS / 32, t_end, lane, total);
-    for (; t < t_end; t += K3_THREADS / 32) {
-        const float4 cur = v0;
-        v0 = v1;
-        v1 = k3s_load(src, t + 2 * (K3_THREADS / 32), t_end, lane, total);      // two tiles ahead
-        const unsigned hits = (cur.x > p.thr ? 1u : 0u) | (cur.y > p.thr ? 2u : 0u) | (cur.z > p.thr ? 4u : 0u) | (cur.w > p.thr ? 8u : 0u);
-        if (!__any_sync(0xffffffffu, hits != 0u)) continue;  // warp-uniform
-        const int e0 = t * K3S_TILE + lane * 4;
-        const float sc[4] = {cur.x, cur.y, cur.z, cur.w};
-        if (p.C == 1) {
-            // exclusive prefix of the lanes' survivor counts (0..4 = 3 bits): three ballots, no shuffles
-            const unsigned mine = (unsigned)__popc(hits);
-            const unsigned b0 = __ballot_sync(0xffffffffu, mine & 1u), b1 = __ballot_sync(0xffffffffu, mine & 2u),
-                           b2 = __ballot_sync(0xffffffffu, mine & 4u);
-            const unsigned lt = (1u << lane) - 1u;
-            const int tot = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-            if (fill + tot > K3S_BUF) { k3s_flush(p, page, buf, fill, lane); fill = 0; }
-            int at = fill + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+    float4 nx[K3S_VEC];
+    auto load = [&](int t) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (hits & (1u << j)) buf[at++] = make_key(sc[j], (unsigned)(e0 + j));
-            fill += tot;
+        for (int g = 0; g < K3S_VEC; ++g) {
+            nx[g] = make_float4(ninf, ninf, ninf, ninf);
+            if (t < t_end) {
+                const int e = t * K3S_TILE + g * 128 + lane * 4;
+                if (e < total) nx[g] = rn_ldg_stream4(src + e);     // total % 4 == 0: all four or none
+            }
+        }
+    };
+    int t = t_begin + warp;
+    load(t);
+    for (; t < t_end; t += K3_THREADS / 32) {
+        float sc[K3S_VEC * 4];
+#pragma unroll
+        for (int g = 0; g < K3S_VEC; ++g) { sc[4 * g] = nx[g].x; sc[4 * g + 1] = nx[g].y; sc[4 * g + 2] = nx[g].z; sc[4 * g + 3] = nx[g].w; }
+        load(t + K3_THREADS / 32);                          // the next tile's loads are in flight while this one is handled
+        unsigned hits = 0u;                                 // bit 4 g + k: score k of float4 g
+#pragma unroll
+        for (int i = 0; i < K3S_VEC * 4; ++i) hits |= (sc[i] > p.thr) ? (1u << i) : 0u;
+        if (!__any_sync(0xffffffffu, hits != 0u)) continue;  // warp-uniform
+        const int e0 = t * K3S_TILE + lane * 4;              // element of sc[4 g + k]: e0 + 128 g + k
+        if (p.C == 1) {
+            // exclusive prefix of the lanes' survivor counts (0..16 = 5 bits): five ballots, no shuffles
+            const unsigned mine = (unsigned)__popc(hits), lt = (1u << lane) - 1u;
+            int at = 0, tot = 0;
+#pragma unroll
+            for (int bit = 0; bit < 5; ++bit) {
+                const unsigned bb = __ballot_sync(0xffffffffu, (mine >> bit) & 1u);
+                at += __popc(bb & lt) << bit;
+                tot += __popc(bb) << bit;
+            }
+            if (fill + tot > K3S_BUF) { k3s_flush(p, page, buf, fill, lane); fill = 0; }
+            if (tot > K3S_BUF) {
+                // a dense tile: slots reserved for it alone, keys stored straight from the registers
+                int base = 0;
+                if (lane == 0) base = atomicAdd(p.sl.counts + page, tot);
+                at += __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+                for (int i = 0; i < K3S_VEC * 4; ++i) {
+                    if (hits & (1u << i)) {
+                        if (at < p.sl.cap) p.sl.keys[(size_t)page * p.sl.cap + at] = make_key(sc[i], (unsigned)(e0 + 128 * (i >> 2) + (i & 3)));
+                        ++at;
+                    }
+                }
+            } else {
+                at += fill;
+#pragma unroll
+                for (int i = 0; i < K3S_VEC * 4; ++i)
+                    if (hits & (1u << i)) buf[at++] = make_key(sc[i], (unsigned)(e0 + 128 * (i >> 2) + (i & 3)));
+                fill += tot;
+            }
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (hits & (1u << j)) {
-                    const int e = e0 + j;
+            for (int i = 0; i < K3S_VEC * 4; ++i) {
+                if (hits & (1u << i)) {
+                    const int e = e0 + 128 * (i >> 2) + (i & 3);
                     const int n = rn_div(e, p.C, p.inv_c);
                     const int seg = page * p.C + (e - n * p.C);
                     const long long slot = atomicAdd(p.sl.counts + seg, 1);
-                    if (slot < p.sl.cap) p.sl.keys[(size_t)seg * p.sl.cap + slot] = make_key(sc[j], (unsigned)n);
+                    if (slot < p.sl.cap) p.sl.keys[(size_t)seg * p.sl.cap + slot] = make_key(sc[i], (unsigned)n);
                 }
             }
         }
@@ -475,10 +497,11 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
 
     // optional phase timing (rn_debug_nms_timing(1)): thread 0 accumulates clock64() deltas per phase
     long long t_mark = p.timing ? clock64() : 0;
+    const long long t_start = t_mark;
 #define RN_PHASE(k) do { if (p.timing && tid == 0) { const long long now = clock64(); atomicAdd(p.timing + (k), (unsigned long long)(now - t_mark)); t_mark = now; } } while (0)
     unsigned long long upper = ~0ull;   // keys >= upper have been visited (no key equals ~0: its score bits would be a NaN's)
     int visited = 0, nsel = 0, round = 0, bis = 0;
-    if (tid == 0) { s_nsel = 0; s_kmax = 0u; }
+    if (tid == 0) { s_nsel = 0; s_kmax = 0u; s_loaded = 0; }
     if (tid < 4) s_cnt[0][tid] = 0u;
     __syncthreads();
     // The slab's keys are read ONCE into registers (8 per thread) when the slab has <= 8192 candidates -- the
@@ -502,8 +525,100 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     // every key's score word lies in [key_floor_hi, kmax]: the first bracket of the bisection
     const unsigned long long top = in_regs ? (((unsigned long long)s_kmax + 1ull) << 32) : 0ull;   // 0: no bound known (also on overflow)
 
+    // ---------------- K4: a threshold key that keeps between `lo` and `hi` of the unvisited keys (more than `hi` are left) ------
+    // c(x) = #{unvisited k >= x} falls from the number left (> hi) at x = L to 0 (< lo) at x = H; keys are unique, so
+    // c steps by one and some x has lo <= c(x) <= hi.  Each pass evaluates c at the three quartile points of [L, H)
+    // and either accepts one of them or keeps the quarter that brackets the window.  While the bracket spans at
+    // least four values of the keys' upper (score) word the pivots are multiples of 2^32, so a 32-bit compare of
+    // that word decides k >= pivot; only ties in the score ever need the 64-bit form.  Called by all threads.
+    auto find_threshold = [&](const int lo, const int hi) -> unsigned long long {
+        unsigned long long thr_key = 0ull;
+        unsigned long long L = (unsigned long long)p.key_floor_hi << 32, H = upper;
+        if (top != 0ull && top < H) H = top;
+        for (int pass = 0; pass < 96; ++pass, ++bis) {
+            const int set = bis % 3;                          // `bis` runs on across calls: the rotation never restarts on a used set
+            if (tid < 4) s_cnt[(bis + 1) % 3][tid] = 0u;      // the next pass's set (last read two barriers ago)
+            const unsigned long long span = H - L;
+            const bool wide = in_regs && (span >> 34) != 0ull;
+            unsigned long long q1, q2, q3;
+            unsigned c1 = 0u, c2 = 0u, c3 = 0u;
+            if (wide) {
+                const unsigned long long Lh = L >> 32, sh = span >> 32;
+                const unsigned long long h1 = Lh + (sh >> 2), h2 = Lh + (sh >> 1), h3 = h2 + (sh >> 2);
+                q1 = h1 << 32; q2 = h2 << 32; q3 = h3 << 32;
+#pragma unroll
+                for (int t = 0; t < KPT; ++t) count3_hi((unsigned)(rk[t] >> 32), (unsigned)h1, (unsigned)h2, (unsigned)h3, c1, c2, c3);
+            } else {
+                q1 = L + (span >> 2); q2 = L + (span >> 1); q3 = q2 + (span >> 2);
+                if (in_regs) {
+#pragma unroll
+                    for (int t = 0; t < KPT; ++t) count3(rk[t], q1, q2, q3, c1, c2, c3);
+                } else {
+                    for (int i = tid; i < cnt; i += NMS_THREADS) {
+                        const unsigned long long k = __ldcg(keys + i);
+                        if (k < upper) count3(k, q1, q2, q3, c1, c2, c3);
+                    }
+                }
+            }
+            c1 = __reduce_add_sync(0xffffffffu, c1);
+            c2 = __reduce_add_sync(0xffffffffu, c2);
+            c3 = __reduce_add_sync(0xffffffffu, c3);
+            if (lane == 0) {
+                if (c1) atomicAdd(&s_cnt[set][0], c1);
+                if (c2) atomicAdd(&s_cnt[set][1], c2);
+                if (c3) atomicAdd(&s_cnt[set][2], c3);
+            }
+            __syncthreads();
+            const int n1 = (int)s_cnt[set][0], n2 = (int)s_cnt[set][1], n3 = (int)s_cnt[set][2];   // n1 >= n2 >= n3
+            if (n1 >= lo && n1 <= hi) { thr_key = q1; ++bis; break; }
+            if (n2 >= lo && n2 <= hi) { thr_key = q2; ++bis; break; }
+            if (n3 >= lo && n3 <= hi) { thr_key = q3; ++bis; break; }
+            if (n1 < lo) H = q1;                         // c(L) > hi, c(q1) < lo
+            else if (n2 < lo) { L = q1; H = q2; }        // n1 > hi
+            else if (n3 < lo) { L = q2; H = q3; }
+            else L = q3;                                 // n3 > hi
+            thr_key = L;                                 // (only used if the pass limit is ever hit: more than `hi` keys, the gather truncates)
+        }
+        return thr_key;
+    };
+
     while (visited < limit && nsel < p.max_det) {
-        // ---------------- K4: a threshold key that keeps between `lo` and `hi` of the unvisited keys ----------------
+        // ---------------- a round after the first: sweep before sorting ------------------------------------------------
+        // The first chunk did not yield max_det selections.  When that is because most of it was suppressed by a FEW boxes
+        // (clusters of high-scoring anchors around each table), what follows in score order is mostly more of the same:
+        // the next <= 2048 candidates are tested against the selected boxes right where they sit -- in the registers, no
+        // sort, no order needed: suppression by an already selected box does not depend on the order -- and the suppressed
+        // ones are struck out (they count as visited), so that the rounds below sort only what can still be selected.
+        if (round > 0 && p.nms && in_regs && limit == cnt && nsel > 0 && nsel * 4 < p.max_det && cnt - visited > 512) {
+            unsigned long long thr_s = 0ull;
+            if (cnt - visited > NMS_CHUNK) thr_s = find_threshold(NMS_CHUNK - (NMS_CHUNK >> 2), NMS_CHUNK);
+#pragma unroll
+            for (int t = 0; t < KPT; ++t)                   // the rows are requested first, read (from L2) below
+                if (rk[t] != 0ull && rk[t] >= thr_s)
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const float4*>(p.src.rows) + (size_t)page * p.src.N + key_idx(rk[t])));
+            int killed = 0;
+#pragma unroll
+            for (int t = 0; t < KPT; ++t) {
+                if (rk[t] != 0ull && rk[t] >= thr_s) {
+                    const int n = (int)key_idx(rk[t]);
+                    const float4 r = finish_box<DECODE>(p.src, n, fetch_row(p.src, page, n));
+                    float4 c;
+                    c.x = fminf(r.x, r.z); c.y = fminf(r.y, r.w); c.z = fmaxf(r.x, r.z); c.w = fmaxf(r.y, r.w);
+                    const float ca = (c.z - c.x) * (c.w - c.y);
+                    bool dead = false;
+                    for (int sI = 0; sI < nsel && !dead; ++sI) dead = iou_exceeds(c, ca, s_selbox[sI], s_selarea[sI], p.iou_thr);
+                    if (dead) { rk[t] = 0ull; ++killed; }
+                }
+            }
+            killed = __reduce_add_sync(0xffffffffu, killed);
+            if (lane == 0 && killed) atomicAdd(&s_loaded, killed);      // s_loaded is free between rounds (zero here)
+            __syncthreads();
+            visited += s_loaded;
+            __syncthreads();
+            if (tid == 0) s_loaded = 0;
+            RN_PHASE(6);
+            if (visited >= limit) break;
+        }
         // The first round takes (up to) a full chunk; later rounds are only reached when its candidates did not yield
         // max_det selections -- typically a few hundred more are needed -- so they start small and double.
         // (with pre_nms_top_k only `need` more candidates may be visited at all: the chunk is sized for them)
@@ -513,60 +628,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
         const int lo = min(hi - (hi >> 2), need);
         ++round;
         const int remaining = cnt - visited;
-        unsigned long long thr_key = 0ull;                   // remaining <= hi: everything that is left
-        if (remaining > hi) {
-            // c(x) = #{unvisited k >= x} falls from `remaining` (> hi) at x = L to 0 (< lo) at x = H; keys are unique, so
-            // c steps by one and some x has lo <= c(x) <= hi.  Each pass evaluates c at the three quartile points of [L, H)
-            // and either accepts one of them or keeps the quarter that brackets the window.  While the bracket spans at
-            // least four values of the keys' upper (score) word the pivots are multiples of 2^32, so a 32-bit compare of
-            // that word decides k >= pivot; only ties in the score ever need the 64-bit form.
-            unsigned long long L = (unsigned long long)p.key_floor_hi << 32, H = upper;
-            if (top != 0ull && top < H) H = top;
-            for (int pass = 0; pass < 96; ++pass, ++bis) {
-                const int set = bis % 3;                          // `bis` runs on across rounds: the rotation never restarts on a used set
-                if (tid < 4) s_cnt[(bis + 1) % 3][tid] = 0u;      // the next pass's set (last read two barriers ago)
-                const unsigned long long span = H - L;
-                const bool wide = in_regs && (span >> 34) != 0ull;
-                unsigned long long q1, q2, q3;
-                unsigned c1 = 0u, c2 = 0u, c3 = 0u;
-                if (wide) {
-                    const unsigned long long Lh = L >> 32, sh = span >> 32;
-                    const unsigned long long h1 = Lh + (sh >> 2), h2 = Lh + (sh >> 1), h3 = h2 + (sh >> 2);
-                    q1 = h1 << 32; q2 = h2 << 32; q3 = h3 << 32;
-#pragma unroll
-                    for (int t = 0; t < KPT; ++t) count3_hi((unsigned)(rk[t] >> 32), (unsigned)h1, (unsigned)h2, (unsigned)h3, c1, c2, c3);
-                } else {
-                    q1 = L + (span >> 2); q2 = L + (span >> 1); q3 = q2 + (span >> 2);
-                    if (in_regs) {
-#pragma unroll
-                        for (int t = 0; t < KPT; ++t) count3(rk[t], q1, q2, q3, c1, c2, c3);
-                    } else {
-                        for (int i = tid; i < cnt; i += NMS_THREADS) {
-                            const unsigned long long k = __ldcg(keys + i);
-                            if (k < upper) count3(k, q1, q2, q3, c1, c2, c3);
-                        }
-                    }
-                }
-                c1 = __reduce_add_sync(0xffffffffu, c1);
-                c2 = __reduce_add_sync(0xffffffffu, c2);
-                c3 = __reduce_add_sync(0xffffffffu, c3);
-                if (lane == 0) {
-                    if (c1) atomicAdd(&s_cnt[set][0], c1);
-                    if (c2) atomicAdd(&s_cnt[set][1], c2);
-                    if (c3) atomicAdd(&s_cnt[set][2], c3);
-                }
-                __syncthreads();
-                const int n1 = (int)s_cnt[set][0], n2 = (int)s_cnt[set][1], n3 = (int)s_cnt[set][2];   // n1 >= n2 >= n3
-                if (n1 >= lo && n1 <= hi) { thr_key = q1; ++bis; break; }
-                if (n2 >= lo && n2 <= hi) { thr_key = q2; ++bis; break; }
-                if (n3 >= lo && n3 <= hi) { thr_key = q3; ++bis; break; }
-                if (n1 < lo) H = q1;                         // c(L) > hi, c(q1) < lo
-                else if (n2 < lo) { L = q1; H = q2; }        // n1 > hi
-                else if (n3 < lo) { L = q2; H = q3; }
-                else L = q3;                                 // n3 > hi
-                thr_key = L;                                 // (only used if the pass limit is ever hit: more than `hi` keys, the gather truncates)
-            }
-        }
+        const unsigned long long thr_key = remaining > hi ? find_threshold(lo, hi) : 0ull;     // 0: everything that is left
         RN_PHASE(0);
         // ---------------- gather the chunk into shared memory (one shared-memory atomic per warp and key slot) ----------
         if (tid == 0) s_loaded = 0;
@@ -727,10 +789,12 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
 #pragma unroll
             for (int t = 0; t < KPT; ++t) if (rk[t] >= upper) rk[t] = 0ull;     // visited
         }
+        if (tid == 0) s_loaded = 0;                         // (the sweep of the next round counts into it)
         __syncthreads();
         if (chunk_n == 0) break;                            // defensive: no progress is impossible while visited < limit
     }
     if (tid == 0) p.kept_count[seg] = nsel;
+    if (p.timing && tid == 0) atomicMax(p.timing + 7, (unsigned long long)(clock64() - t_start));   // the slowest CTA
 #undef RN_PHASE
 }
 
@@ -963,7 +1027,7 @@ int filter_common(K3Params kp, const BoxSource& src, bool decode, int nms, float
     if (rc) return rc;
     const long long page_tiles = ((long long)kp.N * C + K3S_TILE - 1) / K3S_TILE;
     if (kp.class_specific && kp.vec_ok) {
-        // about SMs x 8 CTAs over all pages, each CTA a contiguous slice of one page (at least one tile per warp)
+        // about SMs x 4 CTAs over all pages, each CTA a contiguous slice of one page (at least one tile per warp)
         long long per_page = (RN_NUM_SMS * K3S_CTAS_PER_SM + B - 1) / B;
         const long long most = (page_tiles + K3_THREADS / 32 - 1) / (K3_THREADS / 32);
         if (per_page > most) per_page = most;

@@ -117,6 +117,22 @@ extern "C" int rn_peer_box_bind(void* local_box, void* const* boxes_of_all_ranks
     return RN_OK;
 }
 
+extern "C" int rn_peer_box_connect(void* local_box, void* const* boxes_of_all_ranks, int rank, int world) {
+    RN_REQUIRE(local_box && boxes_of_all_ranks, "NULL pointer");
+    RN_REQUIRE(world >= 1 && world <= RN_MAX_WORLD && rank >= 0 && rank < world, "bad rank / world (%d / %d)", rank, world);
+    RN_REQUIRE(boxes_of_all_ranks[rank] == local_box, "boxes_of_all_ranks[rank] must be the local box");
+    RnPeerBox host = {};
+    for (int r = 0; r < world; ++r) {
+        RN_REQUIRE(boxes_of_all_ranks[r] != nullptr, "box of rank %d is NULL", r);
+        host.peers[r] = reinterpret_cast<RnPeerBox*>(boxes_of_all_ranks[r]);
+    }
+    cudaError_t e = cudaMemcpy(reinterpret_cast<char*>(local_box) + offsetof(RnPeerBox, rank), &rank, sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(reinterpret_cast<char*>(local_box) + offsetof(RnPeerBox, peers), host.peers, sizeof(host.peers), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "peer box connect: %s", cudaGetErrorString(e));
+    return RN_OK;
+}
+
 extern "C" int rn_peer_box_open(const void* ipc_handle64, void** peer_box_out) {
     RN_REQUIRE(ipc_handle64 && peer_box_out, "NULL pointer");
     cudaIpcMemHandle_t h;

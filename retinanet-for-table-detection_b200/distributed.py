@@ -117,6 +117,8 @@ class PeerCounter(object):
         self.rank, self.world, self.box, self.peers = rank, world, box, peers
         self._arr = (ctypes.c_void_p * world)(*peers)
         self.bound = None
+        # the device-side sends of a loss launch (loss sums, fused count publish) need the peers' pointers in the mailbox
+        _lib.check(_lib.load().rn_peer_box_connect(ctypes.c_void_p(self.box), self._arr, rank, world), "rn_peer_box_connect")
         # how long a device-side wait for a peer may last before it gives up (sticky error flag + NaN losses instead of a
         # hung GPU).  Rank skew of seconds is normal (checkpointing, evaluation callbacks, a stalled loader): default 30 s.
         self.set_timeout(float(os.environ.get("RN_B200_PEER_TIMEOUT_S", "30")))

@@ -120,3 +120,46 @@ def inference_predictions(config, batch, anchors, annotations_group, classes=Non
                           (g[2] - anchors[pick, 2]) / aw[pick], (g[3] - anchors[pick, 3]) / ah[pick]], axis=1) / 0.2
             reg[b, pick] = (t + rs.normal(0, 0.15, t.shape)).astype(np.float32)
     return cls, reg
+
+
+def inference_predictions_torch(config, batch, anchors, annotations_group, classes=None, first_page=0,
+                                planted_per_gt=200, device="cuda"):
+    """The distributions of :func:`inference_predictions` generated on the GPU with torch (seeded ``torch.Generator``;
+    not the same samples as the numpy version): used by ``bench.py`` for the large configurations, where the numpy
+    generator would take longer than the benchmark (C = 80: 257 M samples per 16 pages).  Returns device tensors
+    ``cls (B, N, C)``, ``reg (B, N, 4)`` float32."""
+    import torch
+    classes = classes or CONFIGS[config]['classes']
+    gen = torch.Generator(device=device)
+    gen.manual_seed(page_seed(config, first_page) + 700)
+    a = torch.as_tensor(np.asarray(anchors), dtype=torch.float64, device=device)
+    n = a.shape[0]
+    cls = torch.empty((batch, n, classes), dtype=torch.float32, device=device)
+    for b in range(batch):                                # page by page: the temporaries stay small
+        cls[b] = torch.sigmoid(torch.randn((n, classes), generator=gen, device=device, dtype=torch.float32) * 1.5 - 6.0)
+    reg = torch.randn((batch, n, 4), generator=gen, device=device, dtype=torch.float32) * 0.5
+    aw, ah = a[:, 2] - a[:, 0], a[:, 3] - a[:, 1]
+    area = aw * ah
+    for b in range(batch):
+        ann = annotations_group[b]
+        g = torch.as_tensor(np.asarray(ann['bboxes'], dtype=np.float64).reshape(-1, 4), device=device)
+        if g.shape[0] == 0:
+            continue
+        labs = torch.as_tensor(np.asarray(ann['labels']).astype(np.int64), device=device)
+        iw = (torch.minimum(a[:, None, 2], g[None, :, 2]) - torch.maximum(a[:, None, 0], g[None, :, 0])).clamp_(min=0)
+        ih = (torch.minimum(a[:, None, 3], g[None, :, 3]) - torch.maximum(a[:, None, 1], g[None, :, 1])).clamp_(min=0)
+        inter = iw * ih
+        iou = inter / (area[:, None] + ((g[:, 2] - g[:, 0]) * (g[:, 3] - g[:, 1]))[None, :] - inter)
+        r = torch.rand(iou.shape, generator=gen, device=device)
+        r = torch.where(iou > 0.3, r, torch.full_like(r, -1.0))
+        k = min(planted_per_gt, n)
+        val, pick = torch.topk(r, k, dim=0)               # (k, G): up to k random near anchors per table
+        ok = val > 0
+        gi = torch.arange(g.shape[0], device=device)[None, :].expand_as(pick)[ok]
+        pi = pick[ok]
+        score = (torch.rand(pi.shape, generator=gen, device=device) * 0.69 + 0.3).to(torch.float32)
+        cls[b, pi, labs[gi]] = score
+        t = torch.stack([(g[gi, 0] - a[pi, 0]) / aw[pi], (g[gi, 1] - a[pi, 1]) / ah[pi],
+                         (g[gi, 2] - a[pi, 2]) / aw[pi], (g[gi, 3] - a[pi, 3]) / ah[pi]], dim=1) / 0.2
+        reg[b, pi] = (t + torch.randn(t.shape, generator=gen, device=device, dtype=torch.float64) * 0.15).to(torch.float32)
+    return cls, reg
