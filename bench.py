@@ -1,11 +1,11 @@
 """Benchmark of the RetinaNet anchor + detection-head path on B200 (contract: see the task statement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3|4]
 
-Workload (BASELINE.json configs[1]): the training-target path on a batch of 16 pages of 800x1333, 1 class,
-<= 20 GT tables per page -- K1 (anchor generation + IoU matching + targets) then K2 (focal + smooth-L1
-forward and backward).  One "step" = one batch per GPU; per-GPU work is fixed as N grows (weak scaling),
-pages shard by image, the only exchange is the positive-anchor count (NVLink peer mailbox, or NCCL all-reduce).
+Headline workload (BASELINE.json configs[1], `--config 1`, the default): the training-target path on a batch of 16 pages of
+800x1333, 1 class, <= 20 GT tables per page -- K1 (anchor generation + IoU matching + targets) then K2 (focal + smooth-L1
+forward and backward).  One "step" = one batch per GPU; per-GPU work is fixed as N grows (weak scaling), pages shard by
+image, the only exchange is the positive-anchor count and the two loss sums (NVLink peer mailbox, or NCCL all-reduce).
 
 `value`  = pages/s with the batch's inputs resident in HBM (GT block + head outputs), CUDA events.  Every step launches
            one K1 and one K2 as two branches of one CUDA graph: K1 on the batch loaded now, K2 on the batch before it
@@ -16,11 +16,17 @@ pages shard by image, the only exchange is the positive-anchor count (NVLink pee
            kernels of step s (`e2e.synchronous` = one step at a time, TargetLossStep.run_from_host).
 `roofline` = K1, the dominant kernel of the step by time (instruction-issue bound): algorithmic bytes / its mean
            duration (CUDA events inside the timed region) against the measured HBM peak in MEASURED_PEAKS.json.
-`roofline_k2` = the same for K2, the HBM-bound loss kernel (north_star's 60 % target).
-`cpu_baseline` = the oracle (numpy port of the reference) on this host's cores, bounded sample.
-`inference` (extra) = BASELINE configs[2]: 64 pages, fused decode + clip + threshold + sort + NMS.
+`roofline_k2` / `roofline_k3` = the same for K2 (fused losses) and K3 (score threshold + key compaction), the HBM-bound
+           kernels north_star sets the 60 % target for; `nms` = the latency-bound sort + NMS kernel (us, candidates/s).
+`cpu_baseline` = the oracle (numpy port of the reference) on this host's cores, bounded sample; `inference.cpu_baseline`
+           the same for decode + filter.
+`inference` (extra) = BASELINE configs[2]: 64 pages/GPU, fused decode + clip + threshold + sort + NMS.
+`config3`, `config4` (extras) = BASELINE configs[3] (1600x2400, 4 pages/GPU) and configs[4] (80 classes, <= 100 GT,
+           16 pages/GPU): targets + losses + decode + NMS, per-kernel times and pages/s.
+`--config 2|3|4` makes that configuration the headline `value` instead (same JSON keys).
 """
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -35,7 +41,24 @@ if ROOT not in sys.path:
 
 import synthetic  # noqa: E402
 
-CFG = 2
+# BASELINE.json configs[k] -> synthetic.CONFIGS key, pages per GPU, what a step is
+BENCH_CONFIGS = {
+    1: dict(syn=2, pages=16, kind="train",
+            workload="configs[1]: training-target path, 16 pages/GPU of 800x1333, 1 class, <=20 GT, 200700 anchors/page",
+            metric="pages/sec (anchor targets + focal/smooth-L1 fwd+bwd) @800x1333"),
+    2: dict(syn=3, pages=64, kind="infer",
+            workload="configs[2]: inference post-processing, 64 pages/GPU of 800x1333, 1 class, score > 0.05, NMS 0.5, 300 detections",
+            metric="pages/sec (decode + clip + threshold + sort + NMS) @800x1333"),
+    3: dict(syn=4, pages=4, kind="full",
+            workload="configs[3]: high-res scans 1600x2400 (719523 anchors/page), 4 pages/GPU (32 over 8 GPUs), 1 class, <=20 GT: "
+                     "targets + losses + decode + NMS",
+            metric="pages/sec (targets + losses fwd+bwd + decode + NMS) @1600x2400"),
+    4: dict(syn=5, pages=16, kind="full",
+            workload="configs[4]: stress, 80 classes, <=100 GT/page, 16 pages/GPU (128 over 8 GPUs) of 800x1333: "
+                     "targets + losses + decode + per-class NMS",
+            metric="pages/sec (targets + losses fwd+bwd + decode + per-class NMS) @800x1333, 80 classes"),
+}
+CFG = 2                                            # synthetic key of the headline default (BASELINE configs[1])
 HW = synthetic.CONFIGS[CFG]['hw']
 PAGES_PER_GPU = synthetic.CONFIGS[CFG]['batch']
 GMAX = synthetic.CONFIGS[CFG]['gmax'] + 2          # +2: the adversarial snapped duplicates
@@ -43,8 +66,18 @@ CLASSES = 1
 E2E_GATHER = True                                  # smooth-L1 reads the positive anchors' regression rows straight from pinned host memory
 E2E_DEPTH = 2                                      # host-input steps in flight (HostStepPipeline slots)
 E2E_CHUNKS = 1                                     # page chunks of the overlapped host-input step
-METRIC = "pages/sec (anchor targets + focal/smooth-L1 fwd+bwd) @800x1333"
-WORKLOAD = "configs[1]: training-target path, 16 pages/GPU of 800x1333, 1 class, <=20 GT, 200700 anchors/page"
+METRIC = BENCH_CONFIGS[1]["metric"]
+WORKLOAD = BENCH_CONFIGS[1]["workload"]
+
+
+def static_config(k):
+    """The `config` object of the JSON line: static facts of BASELINE configs[k] only, so that both arms print the same."""
+    c = BENCH_CONFIGS[k]
+    s = synthetic.CONFIGS[c["syn"]]
+    return {"workload": c["workload"], "baseline_config": k, "pages_per_gpu": c["pages"], "image_hw": list(s["hw"]),
+            "anchors_per_page": synthetic.num_anchors(s["hw"]), "classes": s["classes"], "gt_max": s["gmax"],
+            "l2": "the tensors one step touches exceed the 126 MB L2 (training / full configurations), and the inference leg "
+                  "rotates three input sets (3 x 103 MB): no explicit flush"}
 
 
 def ncu_traffic(kernel):
@@ -67,7 +100,7 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------------------------
-# clocks sampler (NVML) -- runs during warm-up + timed region
+# clocks sampler (NVML) -- runs during warm-up + timed regions
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
@@ -96,10 +129,14 @@ class ClockSampler(threading.Thread):
                 self.samples.append((time.perf_counter(), sm, rs))
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
-    def summary(self, t0, t1):
-        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
+    def summary(self, windows):
+        """Samples that fall inside any of the (t0, t1) wall-clock windows of the timed regions."""
+        inside = [s for s in self.samples if any(t0 <= s[0] <= t1 for t0, t1 in windows)]
+        note = "samples taken inside the timed regions (2 ms period)"
+        if not inside:
+            inside, note = self.samples[-3:], "no sample fell inside a timed region: the last samples of the run"
         if not inside:
             return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": [], "samples": 0}
         bits = 0
@@ -107,11 +144,11 @@ class ClockSampler(threading.Thread):
             bits |= s[2]
         reasons = [n for b, n in self.REASONS.items() if bits & b and n != "gpu_idle"]
         return {"sm_mhz": float(np.median([s[1] for s in inside])), "sm_max_mhz": self.max_sm,
-                "reasons": reasons, "samples": len(inside)}
+                "reasons": reasons, "samples": len(inside), "note": note}
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle (numpy port of the reference) on the host cores
+# CPU baselines: the oracle (numpy port of the reference) on the host cores
 # ------------------------------------------------------------------------------------------------
 def _cpu_page(args):
     """One page of the training-target path on the CPU: targets + both losses forward and backward."""
@@ -131,6 +168,17 @@ def _cpu_page(args):
     return npos, float(lf), float(ls)
 
 
+def _cpu_detect_page(args):
+    """One page of the inference tail on the CPU: Anchors + RegressBoxes + ClipBoxes + FilterDetections (oracle)."""
+    page, = args
+    from oracle import layers_np as OLY
+    anchors = _cpu_page.anchors
+    ann = synthetic.gt_for_page(3, page)
+    cls, reg = synthetic.inference_predictions(3, 1, anchors, [ann], classes=1, first_page=page)
+    out = OLY.detect(HW, reg, cls)
+    return int((out[3] >= 0).sum())
+
+
 def _cpu_init():
     from oracle import anchors_np as OA
     _cpu_page.anchors = OA.anchors_for_shape(HW + (3,))
@@ -143,9 +191,9 @@ class CpuPool(object):
         self.cores = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
         self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init)
 
-    def run(self, pages):
+    def run(self, pages, fn=_cpu_page):
         t0 = time.perf_counter()
-        self.pool.map(_cpu_page, [(p,) for p in pages], chunksize=1)
+        self.pool.map(fn, [(p,) for p in pages], chunksize=1)
         return time.perf_counter() - t0
 
     def close(self):
@@ -153,20 +201,31 @@ class CpuPool(object):
         self.pool.join()
 
 
-def cpu_baseline_leg(budget_s=20.0):
-    pool = CpuPool()
-    try:
-        pool.run(range(min(pool.cores, PAGES_PER_GPU)))                 # warm-up (imports, anchors)
-        pages, elapsed, reps = 0, 0.0, 0
-        while elapsed < budget_s * 0.75 and reps < 400:
-            elapsed += pool.run(range(PAGES_PER_GPU))
-            pages += PAGES_PER_GPU
-            reps += 1
-        return {"value": pages / elapsed, "unit": "pages/s", "cores": pool.cores, "kind": "port",
-                "sample": "%d x the 16-page batch (targets + losses fwd+bwd per page), numpy oracle, "
-                          "multiprocessing.Pool(%d), %.1f s" % (reps, pool.cores, elapsed)}
-    finally:
-        pool.close()
+def cpu_baseline_leg(pool, budget_s=15.0):
+    pool.run(range(min(pool.cores, PAGES_PER_GPU)))                 # warm-up (imports, anchors)
+    pages, elapsed, reps = 0, 0.0, 0
+    while elapsed < budget_s and reps < 400:
+        elapsed += pool.run(range(PAGES_PER_GPU))
+        pages += PAGES_PER_GPU
+        reps += 1
+    return {"value": pages / elapsed, "unit": "pages/s", "cores": pool.cores, "kind": "port",
+            "sample": "%d x the 16-page batch (targets + losses fwd+bwd per page), numpy oracle, "
+                      "multiprocessing.Pool(%d), %.1f s" % (reps, pool.cores, elapsed)}
+
+
+def cpu_inference_leg(pool, budget_s=10.0):
+    """model/layers.py:177-264, :298-332 restated (oracle/layers_np.detect: fp32 decode + clip + threshold + stable sort +
+    greedy NMS per page), one page per task over the host cores.  The restated TF semantics are parity-unpinned."""
+    n = max(pool.cores, 16)
+    pool.run(range(min(pool.cores, n)), fn=_cpu_detect_page)
+    pages, elapsed, reps = 0, 0.0, 0
+    while elapsed < budget_s and reps < 200:
+        elapsed += pool.run(range(n), fn=_cpu_detect_page)
+        pages += n
+        reps += 1
+    return {"value": pages / elapsed, "unit": "pages/s", "cores": pool.cores, "kind": "port",
+            "sample": "%d x %d pages of configs[2] (decode + clip + threshold + sort + NMS per page), numpy oracle "
+                      "(restated TensorFlow semantics, parity unpinned), multiprocessing.Pool(%d), %.1f s" % (reps, n, pool.cores, elapsed)}
 
 
 def run_reference(args):
@@ -175,24 +234,32 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    k = args.config
+    if k not in (1, 2):
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU port is timed for configs[1] and configs[2] only "
+                          "(configs[3]/[4] take minutes per page on the host); run --config 1 or 2"}))
+        return
+    fn = _cpu_page if k == 1 else _cpu_detect_page
+    pages_full = BENCH_CONFIGS[k]["pages"]
     pool = CpuPool()
     try:
-        t_full = pool.run(range(PAGES_PER_GPU))                          # also warms the workers
+        t_full = pool.run(range(pages_full), fn=fn)                      # also warms the workers
         budget = 150.0
-        per_step = int(max(1, min(PAGES_PER_GPU, PAGES_PER_GPU * budget / max(1e-9, t_full * (args.steps + args.warmup)))))
+        per_step = int(max(1, min(pages_full, pages_full * budget / max(1e-9, t_full * (args.steps + args.warmup)))))
         for _ in range(args.warmup):
-            pool.run(range(per_step))
+            pool.run(range(per_step), fn=fn)
         t = 0.0
         for _ in range(args.steps):
-            t += pool.run(range(per_step))
+            t += pool.run(range(per_step), fn=fn)
         value = per_step * args.steps / t
-        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": args.gpus,
+        what = "model/anchors.py + model/losses.py (fwd+bwd)" if k == 1 else "model/layers.py decode + filter_detections (restated TF semantics)"
+        line = {"impl": "reference", "metric": BENCH_CONFIGS[k]["metric"], "value": value, "unit": "pages/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32",
-                "data": "synthetic", "config": {"workload": WORKLOAD, "pages_per_step": per_step},
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64 matching + f32 targets/losses" if k == 1 else "f32", "data": "synthetic", "config": static_config(k),
                 "cpu_baseline": {"value": value, "unit": "pages/s", "cores": pool.cores, "kind": "port",
-                                 "sample": "%d pages per step through multiprocessing.Pool(%d), numpy oracle port of "
-                                           "model/anchors.py + model/losses.py (fwd+bwd)" % (per_step, pool.cores)},
+                                 "sample": "%d pages per step through multiprocessing.Pool(%d), numpy oracle port of %s"
+                                           % (per_step, pool.cores, what)},
                 "e2e": {"value": value, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -201,26 +268,112 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-# our arm
+# helpers of our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    # stdout carries ONE JSON line: everything else written to fd 1 (NCCL prints its version banner there) goes to stderr
-    sys.stdout.flush()
-    json_out = os.fdopen(os.dup(1), "w")
-    os.dup2(2, 1)
-    import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
-    import retinanet_b200 as rn
-    rn._lib.load()
+class Ctx(object):
+    """Process-wide handles of one benchmark run."""
 
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.device = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.device)
+        import retinanet_b200 as rn
+        rn._lib.load()
+        self.rn = rn
+        self.windows = []                                   # wall-clock windows of the timed regions (clock samples)
+        self.warm = max(args.warmup, 3)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps, warm=None):
+        """W untimed calls, then `steps` calls between two CUDA events on the current stream, a barrier + device
+        synchronisation on both sides; returns the milliseconds of THIS rank (callers take the max over ranks)."""
+        torch = self.torch
+        for _ in range(self.warm if warm is None else warm):
+            fn()
+        self.barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        self.windows.append((t0, time.perf_counter()))
+        return e0.elapsed_time(e1)
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor([float(v) for v in values], dtype=self.torch.float64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.cpu()]
+
+    def gather_ranks(self, value):
+        t = self.torch.tensor([float(value)], dtype=self.torch.float64, device=self.device)
+        if self.world == 1:
+            return [float(value)]
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(x) for x in out]
+
+
+def filter_kernel_times(ctx, steps_eager, reps):
+    """us of k_threshold_keys, k_segment_nms, k_merge_topk inside ONE filter call: the library records four CUDA events
+    around them (rn_debug_filter_events).  `steps_eager`: DetectionStep(use_graph=False) objects cycled so that every call
+    reads inputs that are not in L2."""
+    torch, lib = ctx.torch, ctx.rn._lib.load()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    for e in evs:
+        e.record()                                          # creates the handles
+    torch.cuda.synchronize()
+    for st in steps_eager:
+        st.run()
+    torch.cuda.synchronize()
+    acc = np.zeros(3)
+    lib.rn_debug_filter_events(*[ctypes.c_void_p(e.cuda_event) for e in evs])
+    try:
+        for i in range(reps):
+            steps_eager[i % len(steps_eager)].run()
+            torch.cuda.synchronize()
+            acc += [evs[k].elapsed_time(evs[k + 1]) * 1e3 for k in range(3)]
+    finally:
+        lib.rn_debug_filter_events(None, None, None, None)
+    return acc / reps
+
+
+def h2d_ceiling(ctx, nbytes, reps=8):
+    """What the host -> device path of this box delivers to THIS rank while every rank copies at once (one pinned buffer of
+    the e2e step's size, one stream): the ceiling of the e2e number.  GB/s."""
+    torch = ctx.torch
+    src = torch.empty(int(nbytes), dtype=torch.uint8).pin_memory()
+    dst = torch.empty(int(nbytes), dtype=torch.uint8, device=ctx.device)
+    dst.copy_(src, non_blocking=True)
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    ctx.barrier()
+    return nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
+# ------------------------------------------------------------------------------------------------
+# leg 1: the training-target path (BASELINE configs[1])
+# ------------------------------------------------------------------------------------------------
+def leg_training(ctx):
+    args, torch, dist, rn, rank, world, device = ctx.args, ctx.torch, ctx.dist, ctx.rn, ctx.rank, ctx.world, ctx.device
     B, C = PAGES_PER_GPU, CLASSES
     anchors = rn.anchors_for_shape(HW + (3,))
     N = anchors.shape[0]
@@ -243,93 +396,71 @@ def run_ours(args):
     gt_bytes = step.load_annotations(images, anns)
     step.load_predictions(cls_host, reg_host)
     torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
-    sampler.start()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    steps = args.steps
 
     # ---- resident: `value` + per-kernel durations ----------------------------------------------------
     pipelined = world > 1 and step.peer is not None and args.pipelined
     run_step = step.run_pipelined if pipelined else step.run
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(ctx.warm):
         step.run()
     exchange = "none (1 rank)"
     if world > 1:
-        # the normaliser K2 used must be the all-reduced positive count, whichever way it was exchanged
+        # the normaliser K2 used must be the all-reduced positive count, whichever way it was exchanged, and the losses the
+        # merged batch's: identical on every rank
         check = step.npos_total.clone()
         if step.peer is None:
             check = check * 0 + step.losses[2]            # npos_total already holds the all-reduced count
         else:
             dist.all_reduce(check)
         assert float(check) == float(step.losses[2]) or float(check) < 1.0, (float(check), float(step.losses[2]))
-        exchange = ("NVLink peer mailbox, " + ("send + wait fused into K2 (CTA 0 stores the count into every rank's mailbox, all CTAs "
-                    "wait on local memory)" if step.peer_fused else "rn_peer_publish kernel + K2 prologue")) if step.peer is not None else "NCCL all_reduce"
-    # timed region 1 (`value`): K steps of the product call -- step.run() replays ONE graph per step (K1 [+ publish] + K2)
-    barrier()
-    t_wall0 = time.perf_counter()
-    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    v0.record()
-    for i in range(args.steps):
-        run_step()
-    v1.record()
-    barrier()
-    t_wall1 = time.perf_counter()
-    total_ms = v0.elapsed_time(v1)
-    # extra: the overlapped schedule (K1 of the next batch concurrently with K2 of this one, two graph branches)
+        mine_l = step.losses.clone()
+        lo_l, hi_l = mine_l.clone(), mine_l.clone()
+        dist.all_reduce(lo_l, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_l, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo_l, hi_l), ("losses differ between ranks", lo_l, hi_l)
+        exchange = ("NVLink peer mailbox: count at the start of K2 (CTA 0 stores it into every rank's mailbox, all CTAs wait on "
+                    "local memory), the two loss sums at its end (last CTA); " + ("send + wait fused into K2" if step.peer_fused
+                    else "rn_peer_publish kernel + K2 prologue")) if step.peer is not None else "NCCL all_reduce (count, then loss sums)"
+    # timed region 1: K steps of the product call -- step.run() replays ONE graph per step (K1 [+ publish] + K2)
+    total_ms = ctx.timed(run_step, steps, warm=0)
+    # the overlapped schedule (K1 of the next batch concurrently with K2 of this one, two graph branches)
     ov_ms, ov_match = float("nan"), None
     inorder_losses = step.losses.clone()
     if world == 1 or step.peer_fused:
         # (several ranks: K2 of batch s sends and collects the counts of batch s itself while K1 of batch s+1 runs beside
         # it -- fused publish -- so the exchange and the skew between ranks hide behind the longer kernel)
-        for _ in range(max(args.warmup, 3)):
-            step.run_pipelined(overlap=True)
-        barrier()
-        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        o0.record()
-        for i in range(args.steps):
-            step.run_pipelined(overlap=True)
-        o1.record()
-        barrier()
-        ov_ms = o0.elapsed_time(o1)
+        ov_ms = ctx.timed(lambda: step.run_pipelined(overlap=True), steps)
         ov_match = bool(torch.equal(step.losses, inorder_losses))     # same batch every step -> same bits as in order
-        t_wall1 = time.perf_counter()
     # timed region 2 (per-kernel durations for the rooflines): the same K steps with the two halves replayed
     # separately and CUDA events between them (costs one more graph launch per step, so it is not the `value`)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    barrier()
-    for i in range(args.steps):
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
         run_step(events=evs[i])
-    barrier()
+    ctx.barrier()
+    ctx.windows.append((t0, time.perf_counter()))
     split_ms = evs[0][0].elapsed_time(evs[-1][2])
-    k1_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    k2_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    k1_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
+    k2_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / steps
     losses = step.losses.cpu().numpy()
+    step.check()
 
     # ---- e2e: public API, host inputs every step -------------------------------------------------------
-    def e2e_step():
-        # public API with HOST inputs: ragged GT (Python dicts) packed + copied, head outputs copied from pinned
-        # memory chunk by chunk while K1 runs, K2 per chunk, 4 x 12 bytes of losses read back (synchronises)
-        return step.run_from_host(images, anns, cls_host, reg_host, chunks=E2E_CHUNKS, gather_reg_from_host=E2E_GATHER)
-    e2e_steps = 0 if args.no_e2e else args.steps
-    for _ in range(0 if args.no_e2e else max(args.warmup, 3)):
-        e2e_step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    sync_ms = e0.elapsed_time(e1) if e2e_steps else float("nan")
-    # the headline e2e: the same step through HostStepPipeline, two steps in flight (submit step s+1, then take the
-    # result of step s) -- every step still copies its inputs from pinned host memory and reads its losses back
-    e2e_ms = float("nan")
-    if e2e_steps:
+    sync_ms = e2e_ms = full_ms = float("nan")
+    ceiling = None
+    n_pos_rank = float(step.npos.sum().item())
+    h2d = gt_bytes + cls_host.numel() * 4 + (16 * n_pos_rank if E2E_GATHER else reg_host.numel() * 4)
+    if not args.no_e2e:
+        def e2e_step():
+            # public API with HOST inputs: ragged GT (Python dicts) packed + copied, head outputs copied from pinned
+            # memory while K1 runs, K2, 12 bytes of losses read back (synchronises)
+            return step.run_from_host(images, anns, cls_host, reg_host, chunks=E2E_CHUNKS, gather_reg_from_host=E2E_GATHER)
+        sync_ms = ctx.timed(e2e_step, steps)
+        # the headline e2e: the same step through HostStepPipeline, two steps in flight (submit step s+1, then take the
+        # result of step s) -- every step still copies its inputs from pinned host memory and reads its losses back
         pipe = rn.pipeline.HostStepPipeline(HW + (3,), B, GMAX, C, depth=E2E_DEPTH)
+        last = {}
 
         def pipe_steps(n):
             prev = None
@@ -338,41 +469,29 @@ def run_ours(args):
                 if prev is not None:
                     pipe.result(prev)
                 prev = k
-            return pipe.result(prev)
-        pipe_steps(max(args.warmup, 3))
-        barrier()
+            last["losses"] = pipe.result(prev)
+        pipe_steps(ctx.warm)
+        ctx.barrier()
+        t0 = time.perf_counter()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
-        pipe_losses = pipe_steps(e2e_steps)
+        pipe_steps(steps)
         p1.record()
-        barrier()
+        ctx.barrier()
+        ctx.windows.append((t0, time.perf_counter()))
         e2e_ms = p0.elapsed_time(p1)
         sync_losses = step.run_from_host(images, anns, cls_host, reg_host, chunks=E2E_CHUNKS, gather_reg_from_host=E2E_GATHER)
-        assert np.array_equal(pipe_losses.numpy(), sync_losses.numpy()), (pipe_losses, sync_losses)
+        assert np.array_equal(last["losses"].numpy(), sync_losses.numpy()), (last["losses"], sync_losses)
         del pipe
-    # bytes that cross PCIe per step: the GT block, the classification tensor, and -- with the gather -- only the
-    # 16-byte regression rows of the positive anchors (K2 reads them in place); the full-copy variant is timed too
-    n_pos_rank = float(step.npos.sum().item())
-    h2d = gt_bytes + cls_host.numel() * 4 + (16 * n_pos_rank if E2E_GATHER else reg_host.numel() * 4)
-    full_ms = float("nan")
-    if E2E_GATHER and not args.no_e2e:
-        full_step = lambda: step.run_from_host(images, anns, cls_host, reg_host, chunks=E2E_CHUNKS)
-        for _ in range(3):
-            full_step()
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(args.steps):
-            full_step()
-        f1.record()
-        barrier()
-        full_ms = f0.elapsed_time(f1)
-    sampler.stop_flag = True
+        if E2E_GATHER:
+            full_ms = ctx.timed(lambda: step.run_from_host(images, anns, cls_host, reg_host, chunks=E2E_CHUNKS), steps, warm=3)
+        ceiling = h2d_ceiling(ctx, int(h2d))
 
-    times = torch.tensor([total_ms, e2e_ms, k1_ms, k2_ms, split_ms, full_ms, sync_ms, ov_ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, k1_ms, k2_ms, split_ms, full_ms, sync_ms, ov_ms = [float(x) for x in times.cpu()]
+    total_ms, e2e_ms, k1_max, k2_ms, split_ms, full_ms, sync_ms, ov_ms = ctx.max_over_ranks(
+        [total_ms, e2e_ms, k1_ms, k2_ms, split_ms, full_ms, sync_ms, ov_ms])
+    k1_per_rank = ctx.gather_ranks(k1_ms * 1e3)
+    ceil_min = min(ctx.gather_ranks(ceiling)) if ceiling is not None else None
+    k1_ms = k1_max
     # `value`: the overlapped schedule (K1 of batch s+1 beside K2 of batch s: one K1 + one K2 per step, one graph launch)
     # unless --schedule in-order or the schedule is unavailable (several ranks without the peer mailbox)
     overlapped = args.schedule == "overlapped" and ov_ms == ov_ms and not pipelined
@@ -380,15 +499,18 @@ def run_ours(args):
 
     # ---- N2 (extra object): K2 fed by the per-level head outputs, sigmoid fused ---------------------------
     levels = None
-    if not args.no_inference:
+    if not args.no_extras:
         spec = step.spec
         rows = [int(h) * int(w) * spec.per_cell for h, w in spec.level_hw]
         rs = np.random.RandomState(77 + rank)
         cls_l = [torch.from_numpy(rs.normal(-4.6, 1.0, (B, n, 1)).astype(np.float32)).to(device) for n in rows]
         reg_l = [torch.from_numpy(rs.normal(0.0, 1.0, (B, n, 4)).astype(np.float32)).to(device) for n in rows]
         outs = (torch.empty(3, dtype=torch.float32, device=device), [torch.empty_like(c) for c in cls_l], [torch.empty_like(r) for r in reg_l])
-        run_levels = lambda: rn.detection_losses_levels(step.y_reg, step.y_cls, reg_l, cls_l, normalizer=step.npos_total,
-                                                        from_logits=True, out=outs, workspace=step.loss_ws)
+        one = rn.pipeline.TargetLossStep(HW + (3,), B, GMAX, C, peer_box=False)        # single-rank normaliser for this extra
+        one.load_annotations(images, anns)
+        one._targets()
+        run_levels = lambda: rn.detection_losses_levels(one.y_reg, one.y_cls, reg_l, cls_l, normalizer=one.npos_total,
+                                                        from_logits=True, out=outs, workspace=one.loss_ws)
         for _ in range(5):
             run_levels()
         torch.cuda.synchronize()
@@ -403,161 +525,161 @@ def run_ours(args):
         levels = {"kernel": "k_loss_c1_levels (per-level logits in, sigmoid fused, per-level gradients out)",
                   "us_per_launch": lv_us, "level_rows": rows,
                   "note": "back-to-back launches incl. launch overhead; replaces sigmoid + Concatenate(axis=1) + K2"}
+        del one
 
-    # ---- inference path (extra object) -----------------------------------------------------------------
-    inference = None
-    if not args.no_inference:
-        inference = bench_inference(rn, torch, device, rank, world, args)
-
+    out = None
     if rank == 0:
         peak, peak_src = measured_peak()
         # K2 algorithmic bytes: per anchor read labels 4(C+1) + probabilities 4C, write
         # gradients 4C + 16; the anchor state comes from the label row (shared_state: both target tensors are
         # K1's) so regression rows (20 B targets + 16 B prediction) are only read for positive anchors.
         # SURVEY 8(d) counts 12C + 56 = 68 B/anchor (every regression row read); given for comparison.
-        n_pos = float(losses[2])
+        n_pos = n_pos_rank
         k2_bytes = (12 * C + 20) * N * B + 36 * n_pos
         k2_bytes_survey = (12 * C + 56) * N * B
         k1_bytes = 4 * (5 + C + 1) * N * B            # 28 B/anchor at C=1
         achieved = k2_bytes / (k2_ms * 1e-3) / 1e9
-        line = {
-            "metric": METRIC, "value": world * B * args.steps / (value_ms * 1e-3), "unit": "pages/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": value_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64 matching + f32 targets/losses", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pages_per_gpu": B, "anchors_per_page": N, "classes": C,
-                       "l2": "working set per step ~%d MB (> 126 MB L2), no explicit flush" % ((k1_bytes + k2_bytes) // (1 << 20)),
-                       "cuda_graphs": True, "count_exchange": exchange, "sharding": sharding,
-                       "schedule": ("overlapped: every step launches K1 of batch s+1 and K2 of batch s as two branches of one "
-                                    "graph (TargetLossStep.run_pipelined(overlap=True), double-buffered targets; bit-identical "
-                                    "to in order)") if overlapped else
-                                   ("pipelined: K1 of batch s+1 enqueued ahead of K2 of batch s (double-buffered targets)"
-                                    if pipelined else "in order: K1(s), K2(s)")},
-            "in_order": {"pages_per_s": world * B * args.steps / (total_ms * 1e-3), "ms_per_step": total_ms / args.steps,
+        e2e_value = world * B * steps / (e2e_ms * 1e-3) if e2e_ms == e2e_ms else None
+        out = {
+            "metric": METRIC, "value": world * B * steps / (value_ms * 1e-3), "unit": "pages/s",
+            "ms_per_step": value_ms / steps, "dtype": "f64 matching + f32 targets/losses",
+            "run": {"cuda_graphs": True, "count_exchange": exchange, "sharding": sharding,
+                    "schedule": ("overlapped: every step launches K1 of batch s+1 and K2 of batch s as two branches of one "
+                                 "graph (TargetLossStep.run_pipelined(overlap=True), double-buffered targets; bit-identical "
+                                 "to in order)") if overlapped else
+                                ("pipelined: K1 of batch s+1 enqueued ahead of K2 of batch s (double-buffered targets)"
+                                 if pipelined else "in order: K1(s), K2(s)")},
+            "in_order": {"pages_per_s": world * B * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps,
                          "note": "TargetLossStep.run(): K1(s) then K2(s), one graph launch per step"},
-            "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "pages/s",
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 12 * E2E_CHUNKS, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_GBps": h2d / (e2e_ms / args.steps * 1e-3) / 1e9,
-                    "api": "HostStepPipeline.submit / result (%d steps in flight: the copy of step s+1 runs during K1 / K2 of "
-                           "step s; per step: GT packed + copied, classification tensor copied from pinned memory, K1, K2, "
-                           "loss rows read back)" % E2E_DEPTH,
-                    "synchronous": {"value": world * B * args.steps / (sync_ms * 1e-3), "ms_per_step": sync_ms / args.steps,
-                                    "api": "TargetLossStep.run_from_host (one step at a time, host waits for the losses)"},
-                    "regression_rows": ("positive anchors' rows read in place from pinned host memory (model/losses.py:72-74 "
-                                        "gathers exactly those); the (B,N,4) tensor is not copied") if E2E_GATHER else "copied",
-                    "full_copy": {"value": world * B * args.steps / (full_ms * 1e-3), "ms_per_step": full_ms / args.steps,
-                                  "h2d_bytes_per_step": int(gt_bytes + cls_host.numel() * 4 + reg_host.numel() * 4)}},
-            "gpu_launches": step.kernel_launches_per_step * args.steps,   # `value` region: K1 + K2 per step (+ publish when not fused into K2)
-            # the dominant kernel of the step by time is K1 (~74 %, profiles/*_launches_value_region.md): it is
-            # reported first although it is instruction-issue bound, not HBM bound; K2 (the HBM-bound loss kernel
-            # north_star sets the 60 % target for) follows
-            "roofline": {"kernel": "k_anchor_targets_tiles (K1 anchors + IoU/argmax matching + targets)", "bound": "hbm",
+            "e2e": None if e2e_value is None else {
+                "value": e2e_value, "unit": "pages/s",
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 12 * E2E_CHUNKS, "ms_per_step": e2e_ms / steps,
+                "h2d_GBps": h2d / (e2e_ms / steps * 1e-3) / 1e9,
+                "h2d_ceiling_GBps": ceil_min, "fraction_of_h2d_ceiling": (h2d / (e2e_ms / steps * 1e-3) / 1e9) / ceil_min if ceil_min else None,
+                "h2d_ceiling_note": "slowest rank's copy rate of one pinned buffer of the step's size while all %d ranks copy at once "
+                                    "(the host's PCIe / memory fabric is shared between the GPUs)" % world,
+                "results": "the three loss floats are read back per step; gradients and targets stay on the device",
+                "api": "HostStepPipeline.submit / result (%d steps in flight: the copy of step s+1 runs during K1 / K2 of "
+                       "step s; per step: GT packed + copied, classification tensor copied from pinned memory, K1, K2, "
+                       "loss rows read back)" % E2E_DEPTH,
+                "synchronous": {"value": world * B * steps / (sync_ms * 1e-3), "ms_per_step": sync_ms / steps,
+                                "api": "TargetLossStep.run_from_host (one step at a time, host waits for the losses)"},
+                "regression_rows": ("positive anchors' rows read in place from pinned host memory (model/losses.py:72-74 "
+                                    "gathers exactly those); the (B,N,4) tensor is not copied") if E2E_GATHER else "copied",
+                "full_copy": {"value": world * B * steps / (full_ms * 1e-3), "ms_per_step": full_ms / steps,
+                              "h2d_bytes_per_step": int(gt_bytes + cls_host.numel() * 4 + reg_host.numel() * 4)}},
+            "gpu_launches": step.kernel_launches_per_step * steps,   # `value` region: K1 + K2 per step (+ publish when not fused into K2)
+            # the dominant kernel of the step by time is K1: it is reported first although it is instruction-issue bound,
+            # not HBM bound; K2 (the HBM-bound loss kernel north_star sets the 60 % target for) follows
+            "roofline": {"kernel": "k_anchor_targets_tiles32 (K1 anchors + IoU/argmax matching + targets)", "bound": "hbm",
                          "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic("k_anchor_targets_tiles"),
+                         "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic("k_anchor_targets_tiles32"),
                          "peak_source": peak_src, "bytes_per_launch": k1_bytes, "bytes_per_anchor": k1_bytes / (N * B),
-                         "us_per_launch": k1_ms * 1e3, "share_of_step": k1_ms / (k1_ms + k2_ms),
+                         "us_per_launch": k1_ms * 1e3, "us_per_launch_by_rank": k1_per_rank, "share_of_step": k1_ms / (k1_ms + k2_ms),
                          "note": "write-only 28 B/anchor; limited by instruction issue (fp64 matching for every anchor x "
-                                 "overlapping GT; ncu: issue slots 74 % busy, DRAM 6 %), see DESIGN.md section 3"},
+                                 "overlapping GT; ncu: issue slots 67 % busy, DRAM 9 %), see DESIGN.md section 3"},
             "roofline_k2": {"kernel": "k_loss_c1_fast (K2 fused focal + smooth-L1 fwd+bwd)", "bound": "hbm",
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": ncu_traffic("k_loss_c1_fast"), "peak_source": peak_src, "bytes_per_launch": k2_bytes,
                             "bytes_per_anchor": k2_bytes / (N * B), "us_per_launch": k2_ms * 1e3,
                             "share_of_step": k2_ms / (k1_ms + k2_ms),
-                            "achieved_survey_bytes": k2_bytes_survey / (k2_ms * 1e-3) / 1e9},
-            "ms_per_step_split_graphs": split_ms / args.steps,
+                            "achieved_survey_bytes": k2_bytes_survey / (k2_ms * 1e-3) / 1e9,
+                            "note": "with several ranks the launch includes the wait for the slowest rank's count"},
+            "ms_per_step_split_graphs": split_ms / steps,
             "overlapped_schedule": None if ov_ms != ov_ms else {
-                "pages_per_s": world * B * args.steps / (ov_ms * 1e-3), "ms_per_step": ov_ms / args.steps,
+                "pages_per_s": world * B * steps / (ov_ms * 1e-3), "ms_per_step": ov_ms / steps,
                 "losses_equal_in_order": ov_match,
                 "note": "TargetLossStep.run_pipelined(overlap=True): K1 of batch s+1 and K2 of batch s as two branches of one graph"
-                        + ("; K2 sends and collects the ranks' positive counts itself (fused publish), hidden behind K1" if world > 1 else "")},
+                        + ("; K2 sends and collects the ranks' positive counts and loss sums itself, hidden behind K1" if world > 1 else "")},
             "kernels": {"K1_anchor_targets": {"us": k1_ms * 1e3, "algorithmic_bytes": k1_bytes,
                                               "GBps": k1_bytes / (k1_ms * 1e-3) / 1e9},
                         "K2_losses": {"us": k2_ms * 1e3, "algorithmic_bytes": k2_bytes, "GBps": achieved}},
-            "losses": {"focal": float(losses[0]), "smooth_l1": float(losses[1]), "normalizer": float(losses[2])},
-            "clocks": sampler.summary(t_wall0, t_wall1),
+            "losses": {"focal": float(losses[0]), "smooth_l1": float(losses[1]), "normalizer": float(losses[2]),
+                       "scope": "the merged batch of all %d ranks (identical on every rank)" % world},
         }
-        if inference is not None:
-            line["inference"] = inference
         if levels is not None:
             levels["GBps"] = k2_bytes / (levels["us_per_launch"] * 1e-6) / 1e9
-            line["per_level_heads"] = levels
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_leg()
-        json_out.write(json.dumps(line) + "\n")
-        json_out.flush()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+            out["per_level_heads"] = levels
+    del step
+    torch.cuda.empty_cache()
+    return out
 
 
-def bench_inference(rn, torch, device, rank, world, args):
-    """BASELINE configs[2]: 64 pages/GPU, score > 0.05, NMS 0.5, 300 detections, fused head."""
-    import torch.distributed as dist
-    cfg, B = 3, synthetic.CONFIGS[3]['batch']
+# ------------------------------------------------------------------------------------------------
+# leg 2: the inference tail (BASELINE configs[2])
+# ------------------------------------------------------------------------------------------------
+def leg_inference(ctx):
+    args, torch, rn, rank, world, device = ctx.args, ctx.torch, ctx.rn, ctx.rank, ctx.world, ctx.device
+    cfg, B = 3, BENCH_CONFIGS[2]["pages"]
     anchors = np.asarray(rn.anchors_for_shape(HW + (3,)))
     N = anchors.shape[0]
+    SETS = 3                                                # input sets in rotation: 3 x (51 + 51 MB) > 126 MB L2
     _, anns = synthetic.training_batch(cfg, batch=B, first_page=rank * B)
     cls_np, reg_np = synthetic.inference_predictions(cfg, B, anchors, anns, classes=1, first_page=rank * B)
     cls_host, reg_host = torch.from_numpy(cls_np).pin_memory(), torch.from_numpy(reg_np).pin_memory()
-    cls_d, reg_d = cls_host.to(device), reg_host.to(device)
-    shape = (B,) + HW + (3,)
+    steps = max(5, min(args.steps, 50))
     out = {}
+    peak, peak_src = measured_peak()
     for tag, topk in (("reference_semantics", 0), ("pre_nms_top_k_1000", 1000)):
         head = rn.DetectionHead(pre_nms_top_k=topk)
-        for _ in range(3):
-            head([shape, reg_d, cls_d])
-        steps = max(5, min(args.steps, 50))
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ms = float("inf")
-        for _ in range(3):                                  # best of 3 timing loops (this leg is an extra, not the headline)
-            e0.record()
-            for _ in range(steps):
-                res = head([shape, reg_d, cls_d])
-            e1.record()
-            torch.cuda.synchronize()
-            ms = min(ms, e0.elapsed_time(e1) / steps)
-        # two batches in flight on two streams (serving loop): k_segment_nms runs one CTA per (page, class), i.e. 64
-        # of the 148 SMs per batch, so a second independent batch fills the other SMs.  Workspaces are per stream.
+        dets = [rn.pipeline.DetectionStep(HW, B, 1, head=head) for _ in range(SETS)]
+        for k, d in enumerate(dets):
+            # the same pages in every set, rolled by k pages: identical work per batch, different addresses
+            d.load_predictions(torch.roll(cls_host, k, 0).to(device), torch.roll(reg_host, k, 0).to(device))
+        it = {"i": 0}
+
+        def one():
+            dets[it["i"] % SETS].run()
+            it["i"] += 1
+        ms = min(ctx.timed(one, steps), ctx.timed(one, steps, warm=0), ctx.timed(one, steps, warm=0)) / steps
+        res = [t.clone() for t in dets[0].run()]
+        dets[0].check()
+        # two batches in flight on two streams (a serving loop): k_segment_nms runs one CTA per (page, class), i.e. 64
+        # of the 148 SMs per batch, so a second independent batch fills the other SMs
         streams = [torch.cuda.Stream(device) for _ in range(2)]
-        for st in streams:
+        pair = [dets[0], dets[1]]
+        for st, d in zip(streams, pair):
             st.wait_stream(torch.cuda.current_stream(device))
             with torch.cuda.stream(st):
-                head([shape, reg_d, cls_d])
+                d.run()
         torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for st in streams:
             st.wait_stream(torch.cuda.current_stream(device))
         for i in range(2 * steps):
             with torch.cuda.stream(streams[i % 2]):
-                res2 = head([shape, reg_d, cls_d])
+                pair[i % 2].run()
         for st in streams:
             torch.cuda.current_stream(device).wait_stream(st)
         e1.record()
         torch.cuda.synchronize()
         ms_2s = e0.elapsed_time(e1) / (2 * steps)
-        assert torch.equal(res2[1], res[1])
-        # e2e: host head outputs in, detections out
-        # (a) both tensors copied; (b) scores copied, the candidates' regression rows read in place from pinned memory
+        assert torch.equal(dets[0].scores, res[1])
+        # per-kernel durations: eager calls (no graph) with the library's event hook, the same rotation of inputs
+        eager = [rn.pipeline.DetectionStep(HW, B, 1, head=head, use_graph=False) for _ in range(SETS)]
+        for e, d in zip(eager, dets):
+            e.cls_pred, e.reg_pred = d.cls_pred, d.reg_pred
+        k3_us, nms_us, merge_us = filter_kernel_times(ctx, eager, reps=max(6, min(steps, 30)))
+        del eager
+        # e2e: host head outputs in, detections out.  (a) both tensors copied; (b) scores copied, the visited candidates'
+        # regression rows read in place from pinned memory; (c) the same with two batches in flight
         e0.record()
         for _ in range(steps):
-            r = head([shape, reg_host.to(device, non_blocking=True), cls_host.to(device, non_blocking=True)])
+            r = head([(B,) + HW + (3,), reg_host.to(device, non_blocking=True), cls_host.to(device, non_blocking=True)])
             host = [t.cpu() for t in r]
         e1.record()
         torch.cuda.synchronize()
         ms_e2e_copy = e0.elapsed_time(e1) / steps
-        r = head([shape, reg_host, cls_host.to(device, non_blocking=True)])
+        r = head([(B,) + HW + (3,), reg_host, cls_host.to(device, non_blocking=True)])
         assert torch.equal(r[0], res[0]) and torch.equal(r[1], res[1])
         e0.record()
         for _ in range(steps):
-            r = head([shape, reg_host, cls_host.to(device, non_blocking=True)])
+            r = head([(B,) + HW + (3,), reg_host, cls_host.to(device, non_blocking=True)])
             host = [t.cpu() for t in r]
         e1.record()
         torch.cuda.synchronize()
         ms_e2e_sync = e0.elapsed_time(e1) / steps
-        # the same with two batches in flight (HostDetectionPipeline: per-slot stream, device score buffer, pinned results)
         pipe = rn.pipeline.HostDetectionPipeline(head, B, HW, depth=2)
 
         def pipe_batches(n):
@@ -570,27 +692,182 @@ def bench_inference(rn, torch, device, rank, world, args):
             return pipe.result(prev)
         got = pipe_batches(3)
         assert torch.equal(got[0], res[0].cpu()) and torch.equal(got[1], res[1].cpu())
-        torch.cuda.synchronize()
-        e0.record()
-        pipe_batches(steps)
-        e1.record()
-        torch.cuda.synchronize()
-        ms_e2e = e0.elapsed_time(e1) / steps
+        ms_e2e = ctx.timed(lambda: pipe_batches(steps), 1, warm=0) / steps
         del pipe
-        t = torch.tensor([ms, ms_e2e, ms_2s, ms_e2e_copy, ms_e2e_sync], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_2s, ms_e2e_copy, ms_e2e_sync = [float(x) for x in t.cpu()]
+        ms, ms_e2e, ms_2s, ms_e2e_copy, ms_e2e_sync, k3_us, nms_us, merge_us = ctx.max_over_ranks(
+            [ms, ms_e2e, ms_2s, ms_e2e_copy, ms_e2e_sync, k3_us, nms_us, merge_us])
         ndet = int((res[1] >= 0).sum().item())
+        cands = float((cls_np > 0.05).sum())
+        k3_bytes = 4.0 * N * B + 8.0 * cands                # scores read + one 64-bit key written per candidate
         out[tag] = {"pages_per_s": world * B / (ms * 1e-3), "ms_per_batch": ms,
+                    "api": "pipeline.DetectionStep.run(): K3 + K4/K5 + merge as one CUDA graph, one stream, %d input sets in rotation" % SETS,
                     "pages_per_s_two_streams": world * B / (ms_2s * 1e-3),
+                    "kernels_us": {"k_threshold_keys": k3_us, "k_segment_nms": nms_us, "k_merge_topk": merge_us,
+                                   "note": "CUDA events recorded by the library around the three kernels of one (eager) call"},
                     "e2e_pages_per_s": world * B / (ms_e2e * 1e-3), "e2e_api": "HostDetectionPipeline.submit / result, 2 batches in flight",
+                    "e2e_h2d_bytes_per_batch": int(cls_host.numel() * 4), "e2e_d2h_bytes_per_batch": int(B * 300 * 24),
                     "e2e_one_batch_at_a_time_pages_per_s": world * B / (ms_e2e_sync * 1e-3),
                     "e2e_full_copy_pages_per_s": world * B / (ms_e2e_copy * 1e-3),
                     "detections_per_page": ndet / B}
-    out["workload"] = "configs[2]: %d pages/GPU of 800x1333, 1 class, thr 0.05, NMS 0.5, 300 detections" % B
-    out["candidates_per_page"] = float((cls_np > 0.05).sum()) / B
+        if topk == 0:
+            ach = k3_bytes / (k3_us * 1e-6) / 1e9
+            out["roofline_k3"] = {"kernel": "k_threshold_keys_stream (K3 score threshold + key compaction)", "bound": "hbm",
+                                  "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                  "traffic": ncu_traffic("k_threshold_keys_stream"), "peak_source": peak_src,
+                                  "bytes_per_launch": k3_bytes, "bytes_formula": "4*C*N*B scores read + 8 per candidate (key written)",
+                                  "us_per_launch": k3_us,
+                                  "achieved_survey_bytes": 20.0 * N * B / (k3_us * 1e-6) / 1e9,
+                                  "survey_bytes_note": "SURVEY 8(d) counts 20 B/anchor (every regression row read); the kernel reads "
+                                                       "none of them -- rows are fetched by the NMS kernel for visited candidates only -- "
+                                                       "so that figure is NOT a fraction of anything"}
+            out["nms"] = {"kernel": "k_segment_nms (bisection select + bitonic sort + lazy decode + greedy NMS), one CTA per (page, class)",
+                          "us_per_launch": nms_us, "candidates_per_s": cands / (nms_us * 1e-6), "candidates_per_page": cands / B,
+                          "bound": "latency / instruction issue (no bandwidth target, SURVEY 8d)", "merge_us": merge_us}
+        del dets
+        torch.cuda.empty_cache()
+    out["workload"] = BENCH_CONFIGS[2]["workload"]
+    out["parity"] = "bit-exact against oracle/layers_np.py, a restatement of tf.image.non_max_suppression / tf.nn.top_k: parity UNPINNED (no TensorFlow here)"
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# leg 3: a full configuration (BASELINE configs[3] / configs[4]): targets + losses + decode + NMS
+# ------------------------------------------------------------------------------------------------
+def leg_full(ctx, k):
+    args, torch, rn, rank, world, device = ctx.args, ctx.torch, ctx.rn, ctx.rank, ctx.world, ctx.device
+    bc = BENCH_CONFIGS[k]
+    syn = bc["syn"]
+    sc = synthetic.CONFIGS[syn]
+    hw, C, B = sc["hw"], sc["classes"], bc["pages"]
+    gmax = sc["gmax"] + 2
+    anchors = np.asarray(rn.anchors_for_shape(hw + (3,)))
+    N = anchors.shape[0]
+    images, anns = synthetic.training_batch(syn, batch=B, anchors=anchors, first_page=rank * B)
+    # head outputs of a trained model (low-score background + clusters around each table), generated on the GPU;
+    # the same tensors feed the losses and the detection tail
+    cls_d, reg_d = synthetic.inference_predictions_torch(syn, B, anchors, anns, classes=C, first_page=rank * B, device=device)
+    step = rn.pipeline.TargetLossStep(hw + (3,), B, gmax, C)
+    step.load_annotations(images, anns)
+    step.cls_pred, step.reg_pred = cls_d, reg_d
+    step.grad_cls, step.grad_reg = torch.empty_like(cls_d), torch.empty_like(reg_d)
+    det = rn.pipeline.DetectionStep(hw, B, C)
+    det.cls_pred, det.reg_pred = cls_d, reg_d
+    steps = max(3, min(args.steps, 20))
+
+    def one():
+        step.run()
+        det.run()
+    ms = ctx.timed(one, steps) / steps
+    det.check()
+    step.check()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    ctx.barrier()
+    for i in range(steps):
+        step.run(events=evs[i])
+    ctx.barrier()
+    k1_us = sum(e[0].elapsed_time(e[1]) for e in evs) / steps * 1e3
+    k2_us = sum(e[1].elapsed_time(e[2]) for e in evs) / steps * 1e3
+    eager = rn.pipeline.DetectionStep(hw, B, C, use_graph=False)
+    eager.cls_pred, eager.reg_pred = cls_d, reg_d
+    k3_us, nms_us, merge_us = filter_kernel_times(ctx, [eager], reps=max(3, min(steps, 10)))
+    ms, k1_us, k2_us, k3_us, nms_us, merge_us = ctx.max_over_ranks([ms, k1_us, k2_us, k3_us, nms_us, merge_us])
+    n_pos = float(step.npos.sum().item())
+    cands = float((cls_d > 0.05).sum().item())
+    ndet = float((det.scores >= 0).sum().item())
+    losses = step.losses.cpu().numpy()
+    peak, _ = measured_peak()
+    k1_bytes = 4.0 * (5 + C + 1) * N * B
+    k2_bytes = (12.0 * C + 20) * N * B + 36 * n_pos
+    k3_bytes = 4.0 * C * N * B + 8.0 * cands
+    out = {"workload": bc["workload"], "pages_per_s": world * B / (ms * 1e-3), "ms_per_step": ms,
+           "step": "TargetLossStep.run() (K1 + K2, one graph) then DetectionStep.run() (K3 + NMS + merge, one graph), same stream",
+           "anchors_per_page": N, "classes": C, "pages_per_gpu": B, "gt_per_page_max": sc["gmax"],
+           "kernels_us": {"K1_anchor_targets": k1_us, "K2_losses": k2_us, "K3_threshold_keys": k3_us, "K4K5_segment_nms": nms_us,
+                          "merge_topk": merge_us},
+           "hbm_fraction": {"K1": k1_bytes / (k1_us * 1e-6) / 1e9 / peak, "K2": k2_bytes / (k2_us * 1e-6) / 1e9 / peak,
+                            "K3": k3_bytes / (k3_us * 1e-6) / 1e9 / peak,
+                            "bytes": {"K1": k1_bytes, "K2": k2_bytes, "K3": k3_bytes}},
+           "candidates_per_page": cands / B, "detections_per_page": ndet / B, "positives_per_page": n_pos / B,
+           "losses": {"focal": float(losses[0]), "smooth_l1": float(losses[1]), "normalizer": float(losses[2])},
+           "data": "synthetic (torch generator on the device; distributions of SURVEY 8d)"}
+    del step, det, eager, cls_d, reg_d
+    torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    # stdout carries ONE JSON line: everything else written to fd 1 (NCCL prints its version banner there) goes to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    ctx = Ctx(args)
+    sampler = ClockSampler(ctx.local)
+    sampler.start()
+    k = args.config
+    train = leg_training(ctx) if (k == 1 or not args.no_extras) else None
+    infer = leg_inference(ctx) if (k == 2 or not args.no_extras) else None
+    full = {}
+    for f in (3, 4):
+        if k == f or not args.no_extras:
+            full[f] = leg_full(ctx, f)
+    sampler.stop_flag = True
+    if ctx.rank == 0:
+        world, steps = ctx.world, args.steps
+        line = {"metric": BENCH_CONFIGS[k]["metric"], "value": None, "unit": "pages/s", "n_gpus": world, "steps": steps,
+                "warmup": ctx.warm, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": None, "data": "synthetic", "config": static_config(k)}
+        if k == 1:
+            line.update(train)
+            if infer is not None:
+                line["roofline_k3"] = infer.pop("roofline_k3")
+                line["nms"] = infer.pop("nms")
+                line["inference"] = infer
+        elif k == 2:
+            ref = infer["reference_semantics"]
+            line.update({"value": ref["pages_per_s"], "ms_per_step": ref["ms_per_batch"], "dtype": "f32",
+                         "e2e": {"value": ref["e2e_pages_per_s"], "unit": "pages/s", "h2d_bytes_per_step": ref["e2e_h2d_bytes_per_batch"],
+                                 "d2h_bytes_per_step": ref["e2e_d2h_bytes_per_batch"], "api": ref["e2e_api"]},
+                         "gpu_launches": 3 * max(5, min(steps, 50)), "roofline": infer["roofline_k3"], "nms": infer["nms"],
+                         "inference": infer})
+            if train is not None:
+                line["training"] = train
+        else:
+            f = full[k]
+            dom = max(f["kernels_us"], key=lambda n: f["kernels_us"][n])
+            line.update({"value": f["pages_per_s"], "ms_per_step": f["ms_per_step"],
+                         "dtype": "f64 matching + f32 targets/losses/decode", "gpu_launches": 5 * max(3, min(steps, 20)),
+                         "e2e": None, "roofline": {"kernel": dom, "bound": "hbm", "us_per_launch": f["kernels_us"][dom],
+                                                   "frac": f["hbm_fraction"].get(dom[:2]), "unit": "GB/s"},
+                         "full": f})
+        for f in (3, 4):
+            if f in full and f != k:
+                line["config%d" % f] = full[f]
+        line["clocks"] = sampler.summary(ctx.windows)
+        if world == 1 and not args.no_cpu:
+            pool = CpuPool()
+            try:
+                if k == 1 or not args.no_extras:
+                    cb = cpu_baseline_leg(pool)
+                    if k == 1:
+                        line["cpu_baseline"] = cb
+                    else:
+                        line.setdefault("training", {})["cpu_baseline"] = cb
+                if k == 2 or not args.no_extras:
+                    cb = cpu_inference_leg(pool)
+                    if k == 2:
+                        line["cpu_baseline"] = cb
+                    else:
+                        line.setdefault("inference", {})["cpu_baseline"] = cb
+            finally:
+                pool.close()
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
+    if ctx.world > 1:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
 
 
 def main():
@@ -599,7 +876,11 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-inference", action="store_true")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4],
+                    help="which BASELINE.json configs[k] is the headline `value` (default 1: the training-target path the metric "
+                         "is quoted on); the other configurations are emitted as extra objects unless --no-extras")
+    ap.add_argument("--no-extras", "--no-inference", dest="no_extras", action="store_true",
+                    help="only the headline configuration (no inference / config3 / config4 / per-level objects)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--contiguous-shards", action="store_true", help="several ranks: rank r takes pages [16r, 16r+16) instead of the load-aware deal")
     ap.add_argument("--schedule", default="overlapped", choices=["overlapped", "in-order"],

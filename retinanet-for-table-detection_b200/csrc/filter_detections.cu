@@ -197,6 +197,19 @@ __device__ __forceinline__ void k3s_flush(const K3Params& p, int page, const uns
     __syncwarp();
 }
 
+// sc[i] for a run-time i in [0, 16) without dynamic register indexing (which would put the array in local memory): a
+// binary tree of 15 selects
+__device__ __forceinline__ float k3s_pick(const float (&sc)[16], int i) {
+    float a[8], b[4], c[2];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = (i & 1) ? sc[2 * k + 1] : sc[2 * k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) b[k] = (i & 2) ? a[2 * k + 1] : a[2 * k];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) c[k] = (i & 4) ? b[2 * k + 1] : b[2 * k];
+    return (i & 8) ? c[1] : c[0];
+}
+
 __global__ void __launch_bounds__(K3_THREADS, K3S_CTAS_PER_SM) k_threshold_keys_stream(const K3Params p, int tiles_per_page, int tiles_per_cta) {
     __shared__ unsigned long long s_buf[K3_THREADS / 32][K3S_BUF];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -246,30 +259,29 @@ __global__ void __launch_bounds__(K3_THREADS, K3S_CTAS_PER_SM) k_threshold_keys_
                 int base = 0;
                 if (lane == 0) base = atomicAdd(p.sl.counts + page, tot);
                 at += __shfl_sync(0xffffffffu, base, 0);
-#pragma unroll
-                for (int i = 0; i < K3S_VEC * 4; ++i) {
-                    if (hits & (1u << i)) {
-                        if (at < p.sl.cap) p.sl.keys[(size_t)page * p.sl.cap + at] = make_key(sc[i], (unsigned)(e0 + 128 * (i >> 2) + (i & 3)));
-                        ++at;
-                    }
+                for (unsigned h = hits; h != 0u; h &= h - 1u) {
+                    const int i = __ffs(h) - 1;
+                    if (at < p.sl.cap) p.sl.keys[(size_t)page * p.sl.cap + at] = make_key(k3s_pick(sc, i), (unsigned)(e0 + 128 * (i >> 2) + (i & 3)));
+                    ++at;
                 }
             } else {
+                // survivors are sparse (~0.4 per lane and tile): a divergent loop over the set bits costs far fewer issue slots
+                // than 16 predicated store blocks
                 at += fill;
-#pragma unroll
-                for (int i = 0; i < K3S_VEC * 4; ++i)
-                    if (hits & (1u << i)) buf[at++] = make_key(sc[i], (unsigned)(e0 + 128 * (i >> 2) + (i & 3)));
+                for (unsigned h = hits; h != 0u; h &= h - 1u) {
+                    const int i = __ffs(h) - 1;
+                    buf[at++] = make_key(k3s_pick(sc, i), (unsigned)(e0 + 128 * (i >> 2) + (i & 3)));
+                }
                 fill += tot;
             }
         } else {
-#pragma unroll
-            for (int i = 0; i < K3S_VEC * 4; ++i) {
-                if (hits & (1u << i)) {
-                    const int e = e0 + 128 * (i >> 2) + (i & 3);
-                    const int n = rn_div(e, p.C, p.inv_c);
-                    const int seg = page * p.C + (e - n * p.C);
-                    const long long slot = atomicAdd(p.sl.counts + seg, 1);
-                    if (slot < p.sl.cap) p.sl.keys[(size_t)seg * p.sl.cap + slot] = make_key(sc[i], (unsigned)n);
-                }
+            for (unsigned h = hits; h != 0u; h &= h - 1u) {
+                const int i = __ffs(h) - 1;
+                const int e = e0 + 128 * (i >> 2) + (i & 3);
+                const int n = rn_div(e, p.C, p.inv_c);
+                const int seg = page * p.C + (e - n * p.C);
+                const long long slot = atomicAdd(p.sl.counts + seg, 1);
+                if (slot < p.sl.cap) p.sl.keys[(size_t)seg * p.sl.cap + slot] = make_key(k3s_pick(sc, i), (unsigned)n);
             }
         }
     }
@@ -709,8 +721,11 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                 const int alive_total = __shfl_sync(0xffffffffu, incl, NMS_GROUP / 32 - 1);
                 if (alive_total == 0) {                     // block-uniform: every warp reads the same words
                     if (gdone >= gn) break;
+                    // ... and no wider than ~6 k pair tests at opening: a candidate of an open window is tested against every
+                    // later selection as well, so what is opened but never consumed (behind the stopping point) is pure waste
                     const int room = p.max_det - nsel;
-                    int wn = min(gn - gdone, (room + (room >> 2) + 47) & ~31);      // a multiple of 32 unless it ends the group
+                    const int by_cost = max(32, (6144 / max(nsel, 24)) & ~31);
+                    const int wn = min(gn - gdone, min(by_cost, (room + (room >> 2) + 47) & ~31));   // a multiple of 32 unless it ends the group
                     __syncthreads();                        // everybody has read the (empty) alive words
                     if (tid < NMS_GROUP / 32) {
                         const int left = gdone + wn - tid * 32, skip = gdone - tid * 32;    // gdone is a multiple of 32

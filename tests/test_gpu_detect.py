@@ -183,3 +183,41 @@ def test_randomized_filter_detections(rn, seed):
     layer = rn.FilterDetections(**kw)
     b, s, l = layer([torch.tensor(boxes, device="cuda"), torch.tensor(cls, device="cuda")])
     assert same(layer.last_indices, want[3]) and same(l, want[2]) and same(s, want[1]) and same(b, want[0])
+
+
+@pytest.mark.parametrize("members,bg,max_out", [(500, 1000, 300), (700, 1100, 1000), (760, 400, 40)])
+def test_heavy_clusters_sweep_between_rounds(rn, members, bg, max_out):
+    """Ten tight clusters of high-scoring boxes (thousands of candidates suppressed by ten selections) in front of a
+    background of small boxes: the first sorted chunk yields only a few selections, so the kernel strikes out the
+    suppressed part of what follows in its registers before the next round (the sweep between rounds) -- the result must
+    still be the greedy order of the oracle and of torchvision, bit for bit."""
+    import torchvision
+    rs = np.random.RandomState(members + bg)
+    centers = rs.uniform(200, 1800, (10, 2))
+    size = rs.uniform(150, 300, (10, 2))
+    which = rs.randint(0, 10, 10 * members)
+    c = centers[which] + rs.normal(0, 4, (which.size, 2))
+    wh = size[which] * rs.uniform(0.93, 1.07, (which.size, 2))
+    cl = np.concatenate([c - wh / 2, c + wh / 2], 1)
+    bc = rs.uniform(0, 2000, (bg, 2))
+    bwh = rs.uniform(8, 30, (bg, 2))
+    bb = np.concatenate([bc - bwh / 2, bc + bwh / 2], 1)
+    b = np.concatenate([cl, bb], 0).astype(np.float32)
+    s = np.concatenate([rs.uniform(0.5, 0.99, cl.shape[0]), rs.uniform(0.05, 0.3, bg)]).astype(np.float32)
+    perm = rs.permutation(b.shape[0])
+    b, s = b[perm], s[perm]
+    assert b.shape[0] <= 8192                               # keys held in registers: the sweep is possible
+    want = L.non_max_suppression(b, s, max_out, 0.5)
+    got = rn.layers.non_max_suppression(b, s, max_out, 0.5).cpu().numpy()
+    assert np.array_equal(got, want)
+    tv = torchvision.ops.nms(torch.from_numpy(b), torch.from_numpy(s), 0.5)[:max_out].numpy()
+    assert np.array_equal(got, tv)
+    # the same boxes through the layer (threshold + per-class slabs; scores of the clusters in class 1, background in class 0)
+    cls = np.zeros((1, b.shape[0], 2), np.float32)
+    hi = s >= 0.5
+    cls[0, hi, 1] = s[hi]
+    cls[0, ~hi, 0] = s[~hi]
+    wantf = L.filter_detections_batch(b[None], cls, max_detections=max_out)
+    layer = rn.FilterDetections(max_detections=max_out)
+    fb, fs, fl = layer([torch.tensor(b[None], device="cuda"), torch.tensor(cls, device="cuda")])
+    assert same(layer.last_indices, wantf[3]) and same(fl, wantf[2]) and same(fs, wantf[1]) and same(fb, wantf[0])
