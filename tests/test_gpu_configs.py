@@ -55,8 +55,9 @@ def test_full_batch_of_config(rn, cfg, B, pages):
     # the loss is a sum over pages: per-page launches with the batch normaliser add up, gradients are bit-equal
     norm = torch.tensor([losses[2]], device="cuda")
     acc = np.zeros(2)
+    page = lambda t, b: t[b:b + 1].clone()                  # (page slices of an odd-sized page are not 16-byte aligned)
     for b in range(B):
-        lb, gcb, grb = rn.detection_losses(step.y_reg[b:b + 1], step.y_cls[b:b + 1], reg_d[b:b + 1], cls_d[b:b + 1],
+        lb, gcb, grb = rn.detection_losses(page(step.y_reg, b), page(step.y_cls, b), page(reg_d, b), page(cls_d, b),
                                            normalizer=norm, shared_state=True)
         acc += lb.cpu().numpy()[:2].astype(np.float64)
         if b in pages:
@@ -71,7 +72,7 @@ def test_full_batch_of_config(rn, cfg, B, pages):
         cls_b, reg_b = cls_d[b:b + 1].cpu().numpy(), reg_d[b:b + 1].cpu().numpy()
         wf, wgf = OL.focal()(olab, cls_b, return_grad=True, normalizer=float(losses[2]))
         ws, wgs = OL.smooth_l1()(oreg, reg_b, return_grad=True, normalizer=float(losses[2]))
-        lb = rn.detection_losses(step.y_reg[b:b + 1], step.y_cls[b:b + 1], reg_d[b:b + 1], cls_d[b:b + 1], normalizer=norm)[0].cpu().numpy()
+        lb = rn.detection_losses(page(step.y_reg, b), page(step.y_cls, b), page(reg_d, b), page(cls_d, b), normalizer=norm)[0].cpu().numpy()
         assert close(lb[0], wf) and close(lb[1], ws)
         assert np.allclose(step.grad_cls[b].cpu().numpy(), wgf[0], rtol=1e-5, atol=1e-7 * float(np.abs(wgf).max()))
         assert np.allclose(step.grad_reg[b].cpu().numpy(), wgs[0], rtol=1e-5, atol=1e-9)
