@@ -670,8 +670,19 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
 // ------------------------------------------------------------------------------------------------
 constexpr int K32_G = 32;
 constexpr int K32_A = 9;
+#ifndef RN_K1_XT
+#define RN_K1_XT 2
+#endif
+constexpr int K32_XT = RN_K1_XT;       // x tiles (of 32 columns) a CTA walks: everything that depends on (anchor type, rows, table)
+                                       // only -- intersection heights, the y-target table, the border mask, the tile decode and the
+                                       // staged tables -- is computed once for all of them
 
-template <bool C1, bool AM>
+// dynamic shared memory of k_anchor_targets_tiles32: staged regression rows, staged label rows, intersection heights, y-target table
+static size_t k32_dyn_smem(int A) {
+    return kt_dyn_smem(A) + (K32_XT > 1 ? (size_t)A * KT_ROWS * 32 * sizeof(float2) : 0);
+}
+
+template <bool C1, bool AM, int XT>
 __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const K1Params p, const K1Tiles tl) {
     extern __shared__ __align__(16) float s_dyn[];
     __shared__ double s_gx1[K32_G], s_gy1[K32_G], s_gx2[K32_G], s_gy2[K32_G], s_ga[K32_G];
@@ -705,9 +716,8 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
     const int ty = rn_div(t, tiles_x, inv_tiles_x);
     const int tx = t - ty * tiles_x;
     const double stride = (double)istride;
-    const int cx0 = tx * 32, cy0 = ty * KT_ROWS;
-    const int ncols = min(32, W - cx0), nrows = min(KT_ROWS, H - cy0);
-    const bool valid_x = lane < ncols;
+    const int cxt = tx * (32 * XT), cy0 = ty * KT_ROWS;     // first column of the CTA's XT tiles
+    const int ncols_all = min(32 * XT, W - cxt), nrows = min(KT_ROWS, H - cy0);
     int G = p.gt_count[b];
     G = max(0, min(G, min(p.Gmax, K32_G)));
 
@@ -721,12 +731,9 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
         s_glab[tid] = __ldg(p.gt_labels + (size_t)b * p.Gmax + tid);
     }
 
-    // ---- geometry: base box (warp-uniform), column extent (per thread), row extents (warp-uniform) -----
+    // ---- geometry that does not depend on the column: base box (warp-uniform), row extents (warp-uniform) -----
     const double* bs = p.base + ((size_t)level * A + a) * 4;
     const double b0 = __ldg(bs), b1 = __ldg(bs + 1), b2 = __ldg(bs + 2), b3 = __ldg(bs + 3);
-    const double sx = ((double)(cx0 + lane) + 0.5) * stride;
-    const double ax1 = b0 + sx, ax2 = b2 + sx;
-    const double aw = ax2 - ax1;
     if (lane < KT_ROWS) {
         const double sy = ((double)(cy0 + lane) + 0.5) * stride;
         const double y1 = b1 + sy, y2 = b3 + sy;
@@ -734,78 +741,52 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
     }
     __syncthreads();                                        // staged tables, row geometry, s_npos
     const double (*row)[3] = s_row[a];
-    const bool match_x = valid_x && (aw > 0.0);
-    const double wx1 = b0 + ((double)cx0 + 0.5) * stride, wx2 = b2 + ((double)(cx0 + ncols - 1) + 0.5) * stride;
 
-    // ---- matching: lane j prepares table j's intersection heights with the warp's rows, then the live tables are
-    //      walked in GT order with warp-uniform control flow (first maximum wins) -------------------------------
-    float best[KT_ROWS];
-    int arg[KT_ROWS];
-#pragma unroll
-    for (int r = 0; r < KT_ROWS; ++r) { best[r] = 0.0f; arg[r] = 0; }   // all-zero IoU row -> argmax 0
+    // ---- lane j prepares table j's intersection heights with the warp's rows (the y half of every overlap is the same for
+    //      all columns) and finds out which of the XT tiles the table reaches ------------------------------------------
     double* ihw = s_ih + (size_t)a * (KT_ROWS * 32);       // this warp's [KT_ROWS][32] intersection heights
-    unsigned rows_hit = 0u;
+    unsigned rows_hit = 0u, reach = 0u;                     // reach: bit h = the table's x range meets tile h's anchors
     if (lane < G) {
         const double gx1 = s_gx1[lane], gy1 = s_gy1[lane], gx2 = s_gx2[lane], gy2 = s_gy2[lane];
-        // empty tables and tables outside the warp's x range have zero intersection with all its anchors
-        if ((gx2 > gx1) && (gy2 > gy1) && (gx2 > wx1) && (gx1 < wx2)) {
+        if ((gx2 > gx1) && (gy2 > gy1)) {                   // empty tables have zero intersection with everything
 #pragma unroll
-            for (int r = 0; r < KT_ROWS; ++r) {
-                const double y1 = row[r][0], y2 = row[r][1], hh = row[r][2];
-                ihw[r * 32 + lane] = dmin(y2, gy2) - dmax(y1, gy1);
-                if (r < nrows && gy2 > y1 && gy1 < y2 && hh > 0.0) rows_hit |= 1u << r;
+            for (int h = 0; h < XT; ++h) {
+                const int c0 = cxt + 32 * h, nc = min(32, W - c0);
+                if (nc > 0) {
+                    // exact bounding box of the warp's anchors in tile h (first / last valid column)
+                    const double wx1 = b0 + ((double)c0 + 0.5) * stride, wx2 = b2 + ((double)(c0 + nc - 1) + 0.5) * stride;
+                    if ((gx2 > wx1) && (gx1 < wx2)) reach |= 1u << h;
+                }
+            }
+            if (reach) {
+#pragma unroll
+                for (int r = 0; r < KT_ROWS; ++r) {
+                    const double y1 = row[r][0], y2 = row[r][1], hh = row[r][2];
+                    ihw[r * 32 + lane] = dmin(y2, gy2) - dmax(y1, gy1);
+                    if (r < nrows && gy2 > y1 && gy1 < y2 && hh > 0.0) rows_hit |= 1u << r;
+                }
             }
         }
     }
     __syncwarp();                                           // the intersection heights are visible to the whole warp
-    unsigned live = __ballot_sync(0xffffffffu, rows_hit != 0u);
-    const unsigned cand = live | 1u;                        // possible argmax tables of this warp: table 0 (nothing overlaps) + live
-    while (live) {                                          // warp-uniform, ascending GT order
-        const int m = __ffs(live) - 1;
-        live &= live - 1u;
-        const unsigned rmask = __shfl_sync(0xffffffffu, rows_hit, m);
-        const double g1 = s_gx1[m], g2 = s_gx2[m];
-        if (match_x && g2 > ax1 && g1 < ax2) {
-            const double iw = dmin(ax2, g2) - dmax(ax1, g1);
-            const double ga = s_ga[m];
-            if (rmask == (1u << KT_ROWS) - 1u) {
-                // every row of the tile overlaps (the common case inside a table): no per-row branches, so
-                // pairs of reciprocal chains (MUFU -> DFMA -> DFMA -> DMUL) overlap each other
+    unsigned live_h[XT];
+    unsigned cand = 1u;                                     // possible argmax tables of this warp: table 0 (nothing overlaps) + live
 #pragma unroll
-                for (int r = 0; r < KT_ROWS; r += 2) {
-                    const double i0 = iw * ihw[r * 32 + m], i1 = iw * ihw[(r + 1) * 32 + m];
-                    const double u0 = aw * row[r][2] + ga - i0, u1 = aw * row[r + 1][2] + ga - i1;
-                    float iou0, iou1;
-                    iou_pair(i0, u0, i1, u1, iou0, iou1);
-                    if (iou0 > best[r]) { best[r] = iou0; arg[r] = m; }
-                    if (iou1 > best[r + 1]) { best[r + 1] = iou1; arg[r + 1] = m; }
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < KT_ROWS; ++r) {
-                    if (rmask & (1u << r)) {
-                        const double inter = iw * ihw[r * 32 + m];
-                        const double uni = aw * row[r][2] + ga - inter;
-                        const double q = inter * rcp_fast(uni);
-                        const float iou = f32_rounding_safe(q) ? (float)q : iou_exact(inter, uni);
-                        if (iou > best[r]) { best[r] = iou; arg[r] = m; }
-                    }
-                }
-            }
-        }
+    for (int h = 0; h < XT; ++h) {
+        live_h[h] = __ballot_sync(0xffffffffu, rows_hit != 0u && ((reach >> h) & 1u));
+        cand |= live_h[h];
     }
-    __syncwarp();                                           // the intersection heights are dead: their space becomes the y-target table
 
     // ---- y targets per (row, candidate table), computed by the warp once ---------------------------------
     // 5/width, 5/height for the regression fast path: the base box's stand in for the anchor's own (they
     // differ by rounding only) when that is far inside the fast path's tolerance (see the wrapper)
-    const double bw = __ldg(bs + 2) - __ldg(bs), bh = __ldg(bs + 3) - __ldg(bs + 1);     // re-read: not kept live across the matching loop
+    const double bw = b2 - b0, bh = b3 - b1;
     const bool table_ok = (bw > 0.0) && (bh > 0.0) && (p.max_coord < 4096.0 * fmin(bw, bh));
-    const double r5w = 5.0 * rcp_fast(table_ok ? bw : aw);
-    float2* tyw = reinterpret_cast<float2*>(ihw);           // [KT_ROWS][32]: {t1, t3} of (row, table)
+    // XT == 1: the table takes over the intersection heights' space once the matching is done; XT > 1: its own space
+    float2* tyw = XT > 1 ? reinterpret_cast<float2*>(s_ih + (size_t)A * (KT_ROWS * 32)) + (size_t)a * (KT_ROWS * 32)
+                         : reinterpret_cast<float2*>(ihw);  // [KT_ROWS][32]: {t1, t3} of (row, table)
     unsigned out_y = 0u;                                    // bit r: the centres of tile row r lie below the page
-    bool out_x = false;
-    {
+    auto make_y_table = [&]() {
         const int r = lane & (KT_ROWS - 1);
         const double y1 = row[r][0], y2 = row[r][1], hh = row[r][2];
         if (G > 0) {
@@ -820,82 +801,144 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
                 tyw[r * 32 + m] = make_float2(t1, t3);
             }
         }
-        if (p.img_hw) {
-            out_y = __ballot_sync(0xffffffffu, (lane < KT_ROWS) && (((y1 + y2) / 2.0) >= (double)p.img_hw[2 * b]));
-            out_x = ((ax1 + ax2) / 2.0) >= (double)p.img_hw[2 * b + 1];
-        }
+        if (p.img_hw) out_y = __ballot_sync(0xffffffffu, (lane < KT_ROWS) && (((y1 + y2) / 2.0) >= (double)p.img_hw[2 * b]));
         __syncwarp();                                       // the table is complete and visible to the whole warp
-    }
+    };
+    if (XT > 1) make_y_table();
 
-    // ---- state, regression targets, border rule, staging --------------------------------------------------
     int my_pos = 0;
-    // misalignment (in anchors, mod 4) of the tile's first anchor and of one feature-map row; unsigned wrap-around
-    // keeps the low two bits right.  Row r is staged shifted by ((al0 + r * alw) * 5) & 3 = (al0 + r * alw) & 3 floats
-    // (regression) and ((al0 + r * alw) * 2) & 3 floats (labels).
-    const unsigned al0 = ((unsigned)b * (unsigned)p.N + (unsigned)lstart + ((unsigned)cy0 * (unsigned)W + (unsigned)cx0) * (unsigned)A) & 3u;
-    const unsigned alw = ((unsigned)W * (unsigned)A) & 3u;
-    if (valid_x) {
-        const int k = lane * A + a;                         // reference order within the tile row
-        int prev = -1;                                      // the x targets depend on the column and the table only
-        float t0 = 0.f, t2 = 0.f;
-        unsigned posbits = 0u;
+#pragma unroll 1
+    for (int half = 0; half < XT; ++half) {
+        const int cx0 = cxt + 32 * half;
+        const int ncols = min(32, W - cx0);
+        if (ncols <= 0) break;                              // block-uniform
+        const bool valid_x = lane < ncols;
+        // ---- column extent (per thread) ----------------------------------------------------------------------------
+        const double sx = ((double)(cx0 + lane) + 0.5) * stride;
+        const double ax1 = b0 + sx, ax2 = b2 + sx;
+        const double aw = ax2 - ax1;
+        const bool match_x = valid_x && (aw > 0.0);
+
+        // ---- matching: the live tables are walked in GT order with warp-uniform control flow (first maximum wins) ------
+        float best[KT_ROWS];
+        int arg[KT_ROWS];
 #pragma unroll
-        for (int r = 0; r < KT_ROWS; ++r) {
-            if (r < nrows) {
-                float state = 0.0f, t1 = 0.f, t3 = 0.f;
-                if (G > 0) {
-                    const int m = arg[r];
-                    const bool is_pos = best[r] >= p.pos;
-                    const bool is_ign = (best[r] > p.neg) && !is_pos;
-                    state = is_pos ? 1.0f : (is_ign ? -1.0f : 0.0f);
-                    posbits |= is_pos ? (1u << r) : 0u;
-                    if (m != prev) {                        // x targets change with the table only
-                        prev = m;
-                        reg_target5_pair(s_gx1[m], ax1, s_gx2[m], ax2, aw, r5w, t0, t2);
+        for (int r = 0; r < KT_ROWS; ++r) { best[r] = 0.0f; arg[r] = 0; }   // all-zero IoU row -> argmax 0
+        unsigned live = live_h[0];
+#pragma unroll
+        for (int h = 1; h < XT; ++h) if (half == h) live = live_h[h];
+        while (live) {                                      // warp-uniform, ascending GT order
+            const int m = __ffs(live) - 1;
+            live &= live - 1u;
+            const unsigned rmask = __shfl_sync(0xffffffffu, rows_hit, m);
+            const double g1 = s_gx1[m], g2 = s_gx2[m];
+            if (match_x && g2 > ax1 && g1 < ax2) {
+                const double iw = dmin(ax2, g2) - dmax(ax1, g1);
+                const double ga = s_ga[m];
+                if (rmask == (1u << KT_ROWS) - 1u) {
+                    // every row of the tile overlaps (the common case inside a table): no per-row branches, so
+                    // pairs of reciprocal chains (MUFU -> DFMA -> DFMA -> DMUL) overlap each other
+#pragma unroll
+                    for (int r = 0; r < KT_ROWS; r += 2) {
+                        const double i0 = iw * ihw[r * 32 + m], i1 = iw * ihw[(r + 1) * 32 + m];
+                        const double u0 = aw * row[r][2] + ga - i0, u1 = aw * row[r + 1][2] + ga - i1;
+                        float iou0, iou1;
+                        iou_pair(i0, u0, i1, u1, iou0, iou1);
+                        if (iou0 > best[r]) { best[r] = iou0; arg[r] = m; }
+                        if (iou1 > best[r + 1]) { best[r + 1] = iou1; arg[r + 1] = m; }
                     }
-                    const float2 ty2 = tyw[r * 32 + m];
-                    t1 = ty2.x; t3 = ty2.y;
-                }
-                if (out_x || ((out_y >> r) & 1u)) state = -1.0f;
-                const unsigned al = al0 + r * alw;          // first anchor of the staged row, mod 4 in the low bits
-                float* sr = s_reg + r * reg_stride + (int)(al & 3u) + k * 5;
-                sr[0] = t0; sr[1] = t1; sr[2] = t2; sr[3] = t3; sr[4] = state;
-                if (C1) {
-                    *reinterpret_cast<float2*>(s_lab + r * lab_stride + (int)((al & 1u) * 2u) + k * 2) = make_float2(0.0f, state);
                 } else {
-                    s_state[r * 32 * A + k] = state;
-                    s_hot[r * 32 * A + k] = -1;
+#pragma unroll
+                    for (int r = 0; r < KT_ROWS; ++r) {
+                        if (rmask & (1u << r)) {
+                            const double inter = iw * ihw[r * 32 + m];
+                            const double uni = aw * row[r][2] + ga - inter;
+                            const double q = inter * rcp_fast(uni);
+                            const float iou = f32_rounding_safe(q) ? (float)q : iou_exact(inter, uni);
+                            if (iou > best[r]) { best[r] = iou; arg[r] = m; }
+                        }
+                    }
                 }
-                my_pos += (state == 1.0f);
-                if (AM && p.argmax)
-                    p.argmax[(size_t)b * p.N + lstart + ((size_t)(cy0 + r) * W + cx0 + lane) * A + a] = arg[r];
             }
         }
-        if (posbits) {                                      // positives are ~0.2 % of the anchors
+        if (XT == 1) {
+            __syncwarp();                                   // the intersection heights are dead: their space becomes the y-target table
+            make_y_table();
+        }
+        const double r5w = 5.0 * rcp_fast(table_ok ? bw : aw);
+        const bool out_x = p.img_hw ? (((ax1 + ax2) / 2.0) >= (double)p.img_hw[2 * b + 1]) : false;
+
+        // ---- state, regression targets, border rule, staging --------------------------------------------------
+        // misalignment (in anchors, mod 4) of the tile's first anchor and of one feature-map row; unsigned wrap-around
+        // keeps the low two bits right.  Row r is staged shifted by ((al0 + r * alw) * 5) & 3 = (al0 + r * alw) & 3 floats
+        // (regression) and ((al0 + r * alw) * 2) & 3 floats (labels).
+        const unsigned al0 = ((unsigned)b * (unsigned)p.N + (unsigned)lstart + ((unsigned)cy0 * (unsigned)W + (unsigned)cx0) * (unsigned)A) & 3u;
+        const unsigned alw = ((unsigned)W * (unsigned)A) & 3u;
+        if (XT > 1 && half > 0) __syncthreads();            // the previous tile's staged rows have been read by the copy engine
+        if (valid_x) {
+            const int k = lane * A + a;                     // reference order within the tile row
+            int prev = -1;                                  // the x targets depend on the column and the table only
+            float t0 = 0.f, t2 = 0.f;
+            unsigned posbits = 0u;
 #pragma unroll
             for (int r = 0; r < KT_ROWS; ++r) {
-                if (posbits & (1u << r)) {
-                    const int hot = s_glab[arg[r]];
+                if (r < nrows) {
+                    float state = 0.0f, t1 = 0.f, t3 = 0.f;
+                    if (G > 0) {
+                        const int m = arg[r];
+                        const bool is_pos = best[r] >= p.pos;
+                        const bool is_ign = (best[r] > p.neg) && !is_pos;
+                        state = is_pos ? 1.0f : (is_ign ? -1.0f : 0.0f);
+                        posbits |= is_pos ? (1u << r) : 0u;
+                        if (m != prev) {                    // x targets change with the table only
+                            prev = m;
+                            reg_target5_pair(s_gx1[m], ax1, s_gx2[m], ax2, aw, r5w, t0, t2);
+                        }
+                        const float2 ty2 = tyw[r * 32 + m];
+                        t1 = ty2.x; t3 = ty2.y;
+                    }
+                    if (out_x || ((out_y >> r) & 1u)) state = -1.0f;
+                    const unsigned al = al0 + r * alw;      // first anchor of the staged row, mod 4 in the low bits
+                    float* sr = s_reg + r * reg_stride + (int)(al & 3u) + k * 5;
+                    sr[0] = t0; sr[1] = t1; sr[2] = t2; sr[3] = t3; sr[4] = state;
                     if (C1) {
-                        if (hot == 0) s_lab[r * lab_stride + (int)(((al0 + r * alw) & 1u) * 2u) + k * 2] = 1.0f;
+                        *reinterpret_cast<float2*>(s_lab + r * lab_stride + (int)((al & 1u) * 2u) + k * 2) = make_float2(0.0f, state);
                     } else {
-                        s_hot[r * 32 * A + k] = hot;
+                        s_state[r * 32 * A + k] = state;
+                        s_hot[r * 32 * A + k] = -1;
+                    }
+                    my_pos += (state == 1.0f);
+                    if (AM && p.argmax)
+                        p.argmax[(size_t)b * p.N + lstart + ((size_t)(cy0 + r) * W + cx0 + lane) * A + a] = arg[r];
+                }
+            }
+            if (posbits) {                                  // positives are ~0.2 % of the anchors
+#pragma unroll
+                for (int r = 0; r < KT_ROWS; ++r) {
+                    if (posbits & (1u << r)) {
+                        const int hot = s_glab[arg[r]];
+                        if (C1) {
+                            if (hot == 0) s_lab[r * lab_stride + (int)(((al0 + r * alw) & 1u) * 2u) + k * 2] = 1.0f;
+                        } else {
+                            s_hot[r * 32 * A + k] = hot;
+                        }
                     }
                 }
             }
         }
+        const bool last = (half == XT - 1) || (W - (cx0 + 32) <= 0);       // block-uniform
+        if (last && (p.npos || p.npos_total)) {
+            my_pos = rn_warp_sum(my_pos);
+            if (lane == 0 && my_pos) atomicAdd(&s_npos, my_pos);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the staged rows are read by the TMA engine below
+        __syncthreads();
+        if (last && tid == 0 && s_npos) {
+            if (p.npos) atomicAdd(p.npos + b, s_npos);
+            if (p.npos_total) atomicAdd(p.npos_total, (float)s_npos);   // integer-valued: exact, order-independent
+        }
+        tile_write_out<C1>(p, s_reg, s_lab, s_state, s_hot, b, lstart, cy0, cx0, W, A, ncols, nrows, reg_stride, lab_stride, tid, nthreads);
     }
-    if (p.npos || p.npos_total) {
-        my_pos = rn_warp_sum(my_pos);
-        if (lane == 0 && my_pos) atomicAdd(&s_npos, my_pos);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the staged rows are read by the TMA engine below
-    __syncthreads();
-    if (tid == 0 && s_npos) {
-        if (p.npos) atomicAdd(p.npos + b, s_npos);
-        if (p.npos_total) atomicAdd(p.npos_total, (float)s_npos);   // integer-valued: exact, order-independent
-    }
-    tile_write_out<C1>(p, s_reg, s_lab, s_state, s_hot, b, lstart, cy0, cx0, W, A, ncols, nrows, reg_stride, lab_stride, tid, nthreads);
 }
 
 __global__ void k_anchors_f64(const RnLevels lv, const double* base, int N, double* out) {
@@ -951,9 +994,9 @@ static int k1_opt_in_shared_memory() {
     if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<KT_MAX_A, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
     if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles<9, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles32<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles32<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles32<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles32<true, false, K32_XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k32_dyn_smem(9));
+    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles32<true, true, K32_XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k32_dyn_smem(9));
+    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles32<false, true, K32_XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k32_dyn_smem(9));
     if (ae != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
     if (bit) done.fetch_or(bit, std::memory_order_release);
     return RN_OK;
@@ -1051,9 +1094,23 @@ extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* leve
         // <= 9 anchor types and <= 32 tables per page (the table-detection case): the y-target-table kernel; the common
         // instantiation (one class, no argmax tensor) is specialised; everything else goes through the general tile kernel
         if (tiles > 0 && A <= K32_A && Gmax <= K32_G) {
-            if (C != 1) k_anchor_targets_tiles32<false, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
-            else if (argmax_out) k_anchor_targets_tiles32<true, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
-            else k_anchor_targets_tiles32<true, false><<<tgrid, 32 * A, dyn, s>>>(p, tl);
+            // (a CTA of this kernel walks K32_XT x tiles: its own tile table)
+            K1Tiles t2 = tl;
+            int n2 = 0;
+            for (int l = 0; l < num_levels; ++l) {
+                const int h = level_hw[2 * l], w = level_hw[2 * l + 1];
+                const int tx = (w + 32 * K32_XT - 1) / (32 * K32_XT);
+                t2.tile_start[l] = n2;
+                t2.tiles_x[l] = tx > 0 ? tx : 1;
+                t2.inv_tiles_x[l] = 1.0f / (float)t2.tiles_x[l];
+                n2 += tx * ((h + KT_ROWS - 1) / KT_ROWS);
+            }
+            for (int l = num_levels; l <= RN_MAX_LEVELS; ++l) t2.tile_start[l] = n2;
+            const dim3 g2((unsigned)n2, (unsigned)B);
+            const size_t dyn2 = k32_dyn_smem(A);
+            if (C != 1) k_anchor_targets_tiles32<false, true, K32_XT><<<g2, 32 * A, dyn2, s>>>(p, t2);
+            else if (argmax_out) k_anchor_targets_tiles32<true, true, K32_XT><<<g2, 32 * A, dyn2, s>>>(p, t2);
+            else k_anchor_targets_tiles32<true, false, K32_XT><<<g2, 32 * A, dyn2, s>>>(p, t2);
         } else if (tiles > 0 && A <= 9) {
             if (C == 1) k_anchor_targets_tiles<9, 3, true, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
             else k_anchor_targets_tiles<9, 3, false, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);

@@ -372,7 +372,9 @@ class TargetLossStep(object):
                                      peer_losses=self.peer is not None and chunks == 1,   # one launch per step: sums via the mailbox
                                      **self.loss_kw)
         if _dist.world()[1] > 1 and not (self.peer is not None and chunks == 1):
-            torch.distributed.all_reduce(self._chunk_losses[:, :2])       # page chunks / no mailbox: the merged batch's losses
+            merged = self._chunk_losses[:, :2].contiguous()                # page chunks / no mailbox: the merged batch's losses
+            torch.distributed.all_reduce(merged)
+            self._chunk_losses[:, :2] = merged
         self._losses_host.copy_(self._chunk_losses, non_blocking=True)
         self._done_event.record(compute)
 
