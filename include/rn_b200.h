@@ -236,6 +236,19 @@ int rn_rescale_cut(const float* boxes, const float* scores, const float* image_s
                    float min_score, float* boxes_out, int* count_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * N4  the page-image producer (DetectTablesUtils.py:183-262, preProcessTrainValImages / preProcessSampleImages):
+ *     cv2.cvtColor(BGR2GRAY) -> cv2.adaptiveThreshold(255, ADAPTIVE_THRESH_GAUSSIAN_C, THRESH_BINARY, 11, 2) ->
+ *     cv2.distanceTransform(DIST_L2 | DIST_L1 | DIST_C, maskSize 5) -> merge -> the 8-bit image imwrite encodes.
+ *   bgr_dev (B, H, W, 3) uint8 (cv2.imread order), out_dev (B, H, W, 3) uint8: channel 0 = 5x5 chamfer "L2", 1 = L1, 2 = C,
+ *   each rounded half-to-even and saturated at 255; binary_out_dev (B, H, W) uint8 or NULL: the thresholded page.
+ *   Bit-exact against OpenCV 4.13 for page widths that are a multiple of 8 (its scalar tail columns round the blur
+ *   differently); W < 65535, H * W < 2^31.
+ * ------------------------------------------------------------------------------------------- */
+size_t rn_preprocess_workspace_bytes(int B, int H, int W);
+int rn_preprocess_pages(const unsigned char* bgr_dev, int B, int H, int W, unsigned char* out_dev,
+                        unsigned char* binary_out_dev, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * C1  the path's only exchange step: the batch-global positive-anchor count of the two losses
  *     (model/losses.py:40-44, :88-90; with keras.utils.multi_gpu_model the loss sees the merged
  *     batch, RetinaNet.py:106-112), exchanged over NVLink peer memory between the ranks of one node.

@@ -10,12 +10,13 @@ detection-head path, drop-in for the functions and layers of the reference's ``m
 ``layers``   Anchors, RegressBoxes, ClipBoxes, FilterDetections, filter_detections, DetectionHead  (K3-K5)
 ``generator``   filter_annotations, compute_inputs, compute_targets   (csv_generator.py batching around K1)
 ``postprocess`` rescale_and_cut, read_annotations_csv, write_detections_csv  (RetinaNet.py post-step, CSV formats)
+``preprocess``  preprocess_pages (DetectTablesUtils.py: grey -> adaptive threshold -> three distance transforms -> uint8 page)
 
 All arithmetic runs in hand-written CUDA kernels behind the C-ABI of ``include/rn_b200.h``
 (``librn_b200.so``, built by ``build.py``); there is no CPU fallback.
 """
 from . import _lib  # noqa: F401
-from . import anchors, distributed, generator, layers, losses, pipeline, postprocess, utils  # noqa: F401
+from . import anchors, distributed, generator, layers, losses, pipeline, postprocess, preprocess, utils  # noqa: F401
 from .anchors import (AnchorParameters, AnchorParameters_default, anchor_targets_bbox,  # noqa: F401
                       anchors_for_shape, bbox_transform, compute_gt_annotations, generate_anchors, guess_shapes)
 from .layers import (Anchors, ClipBoxes, DetectionHead, FilterDetections, RegressBoxes,  # noqa: F401

@@ -1,0 +1,175 @@
+// N4: the page-image producer (reference DetectTablesUtils.py:183-262, preProcessTrainValImages / preProcessSampleImages):
+//
+//     gray   = cv2.cvtColor(img, COLOR_BGR2GRAY)
+//     binary = cv2.adaptiveThreshold(gray, 255, ADAPTIVE_THRESH_GAUSSIAN_C, THRESH_BINARY, 11, 2)
+//     page   = imwrite(merge(distanceTransform(binary, DIST_L2, 5), distanceTransform(binary, DIST_L1, 5),
+//                            distanceTransform(binary, DIST_C, 5)))                     -> uint8 (H, W, 3)
+//
+// as three kernels over a batch of pages (OpenCV's arithmetic restated: see oracle/preprocess_np.py, pinned against cv2):
+//
+//   k_gray_threshold   one pass over the BGR bytes: 15-bit fixed-point grey, the separable 11-tap float Gaussian in shared
+//                      memory IN OPENCV'S EVALUATION ORDER (row pass left to right with fused multiply-adds, column pass
+//                      symmetric with fused multiply-adds: a blurred mean that lands on x.5 flips a pixel, so the order is
+//                      part of the result), round-half-even mean, threshold.  HBM: 3 B/pixel read, 1 B/pixel written.
+//   k_row_distance     per page row, one warp: g(x) = distance to the nearest zero pixel of the row (ballot + clz / ffs
+//                      scans forward and backward).  1 B/pixel read, 2 B/pixel written.
+//   k_distance_u8      per pixel: all three metrics are monotone in dx, so the nearest zero of a row is the only one that
+//                      matters: DT(x, y) = min over y' of D(g(x, y'), |y - y'|), swept outward from the pixel's own row and
+//                      stopped as soon as |y - y'| exceeds the best L1 distance found (every metric is >= |y - y'|) or 255
+//                      (the output saturates).  The 5x5 "L2" of OpenCV is the CHAMFER distance (moves 1, 1.4f, 2.1969f) in
+//                      closed form; L1 = dx + dy; C = max(dx, dy).  Output: round-half-even, saturated uint8, the bytes
+//                      imwrite encodes.  Reads g from L2 (2 B/pixel/row visited), writes 3 B/pixel.
+#include "rn_common.cuh"
+
+namespace {
+
+constexpr int PT_W = 64, PT_H = 32;                         // output tile of k_gray_threshold
+constexpr int PT_R = 5;                                     // kernel radius (11 taps)
+constexpr int PT_THREADS = 256;
+constexpr unsigned short NO_ZERO = 0xFFFF;
+
+// cv2.getGaussianKernel(11, -1, CV_32F) (sigma = 0.3 * ((11 - 1) * 0.5 - 1) + 0.8 = 2.0), bit patterns
+__constant__ unsigned c_gauss11[11] = {0x3c10612bu, 0x3cde5c35u, 0x3d855a85u, 0x3df92326u, 0x3e353f0fu, 0x3e4d6105u,
+                                       0x3e353f0fu, 0x3df92326u, 0x3d855a85u, 0x3cde5c35u, 0x3c10612bu};
+
+__global__ void __launch_bounds__(PT_THREADS) k_gray_threshold(const unsigned char* __restrict__ bgr, int H, int W,
+                                                                unsigned char* __restrict__ binary) {
+    __shared__ float s_gray[PT_H + 2 * PT_R][PT_W + 2 * PT_R];     // grey levels of the tile + halo (replicated border)
+    __shared__ float s_row[PT_H + 2 * PT_R][PT_W];                 // row pass
+    const int page = blockIdx.z;
+    const unsigned char* src = bgr + (size_t)page * H * W * 3;
+    unsigned char* dst = binary + (size_t)page * H * W;
+    const int x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H;
+    const int tid = threadIdx.x;
+    float k[11];
+#pragma unroll
+    for (int j = 0; j < 11; ++j) k[j] = __uint_as_float(c_gauss11[j]);
+    // grey = (B * 3735 + G * 19235 + R * 9798 + 2^14) >> 15   (OpenCV's 8-bit BGR2GRAY)
+    for (int i = tid; i < (PT_H + 2 * PT_R) * (PT_W + 2 * PT_R); i += PT_THREADS) {
+        const int ly = i / (PT_W + 2 * PT_R), lx = i - ly * (PT_W + 2 * PT_R);
+        const int y = min(max(y0 + ly - PT_R, 0), H - 1), x = min(max(x0 + lx - PT_R, 0), W - 1);     // BORDER_REPLICATE
+        const unsigned char* px = src + ((size_t)y * W + x) * 3;
+        const int g = (px[0] * 3735 + px[1] * 19235 + px[2] * 9798 + (1 << 14)) >> 15;
+        s_gray[ly][lx] = (float)g;
+    }
+    __syncthreads();
+    // row pass, left to right: acc = k0 * p0; acc = fma(p_j, k_j, acc)
+    for (int i = tid; i < (PT_H + 2 * PT_R) * PT_W; i += PT_THREADS) {
+        const int ly = i / PT_W, lx = i - ly * PT_W;
+        float acc = k[0] * s_gray[ly][lx];
+#pragma unroll
+        for (int j = 1; j < 11; ++j) acc = fmaf(s_gray[ly][lx + j], k[j], acc);
+        s_row[ly][lx] = acc;
+    }
+    __syncthreads();
+    // column pass, symmetric: acc = k5 * c; acc = fma(p_{+j} + p_{-j}, k_{5+j}, acc); then the threshold
+    for (int i = tid; i < PT_H * PT_W; i += PT_THREADS) {
+        const int ly = i / PT_W, lx = i - ly * PT_W;
+        const int y = y0 + ly, x = x0 + lx;
+        if (y < H && x < W) {
+            float acc = k[5] * s_row[ly + PT_R][lx];
+#pragma unroll
+            for (int j = 1; j <= PT_R; ++j) acc = fmaf(s_row[ly + PT_R + j][lx] + s_row[ly + PT_R - j][lx], k[5 + j], acc);
+            const int mean = min(max(__float2int_rn(acc), 0), 255);         // saturate_cast<uchar>(cvRound(.))
+            const int g = (int)s_gray[ly + PT_R][lx + PT_R];
+            dst[(size_t)y * W + x] = (g - mean > -2) ? 255 : 0;             // THRESH_BINARY with delta 2
+        }
+    }
+}
+
+// one warp per page row
+__global__ void __launch_bounds__(256) k_row_distance(const unsigned char* __restrict__ binary, int rows_total, int W,
+                                                       unsigned short* __restrict__ g) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows_total) return;
+    const unsigned char* src = binary + (size_t)row * W;
+    unsigned short* out = g + (size_t)row * W;
+    int carry = -(1 << 20);                                 // position of the last zero seen so far (none yet)
+    for (int c0 = 0; c0 < W; c0 += 32) {
+        const int x = c0 + lane;
+        const unsigned m = __ballot_sync(0xffffffffu, x < W && src[x] == 0);
+        const unsigned upto = m & (0xffffffffu >> (31 - lane));            // zeros at or before this lane
+        const int last = upto ? c0 + 31 - __clz(upto) : carry;
+        if (x < W) out[x] = (unsigned short)min(x - last, (int)NO_ZERO);
+        if (m) carry = c0 + 31 - __clz(m);
+    }
+    carry = 1 << 20;                                        // position of the next zero to the right (none yet)
+    for (int c0 = ((W - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
+        const int x = c0 + lane;
+        const unsigned m = __ballot_sync(0xffffffffu, x < W && src[x] == 0);
+        const unsigned from = m & (0xffffffffu << lane);                   // zeros at or after this lane
+        const int next = from ? c0 + __ffs(from) - 1 : carry;
+        if (x < W) out[x] = (unsigned short)min((int)out[x], min(next - x, (int)NO_ZERO));
+        if (m) carry = c0 + __ffs(m) - 1;
+    }
+}
+
+// candidates of one row at vertical distance dy with in-row distance gx
+__device__ __forceinline__ void dt_candidates(int gx, int dy, float& l2, int& l1, int& cc) {
+    const int M = max(gx, dy), m = min(gx, dy);
+    const float c = 2.1969f, b = 1.4f;                      // OpenCV's 5x5 DIST_L2 mask: moves 1, 1.4f, 2.1969f
+    const float d = (M >= 2 * m) ? c * (float)m + (float)(M - 2 * m) : c * (float)(M - m) + b * (float)(2 * m - M);
+    l2 = fminf(l2, d);
+    l1 = min(l1, gx + dy);
+    cc = min(cc, M);
+}
+
+__global__ void __launch_bounds__(256) k_distance_u8(const unsigned short* __restrict__ g, int H, int W,
+                                                      unsigned char* __restrict__ out) {
+    const int page = blockIdx.z;
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= W || y >= H) return;
+    const unsigned short* gp = g + (size_t)page * H * W + x;
+    float l2 = 1e9f;
+    int l1 = 1 << 28, cc = 1 << 28;
+    for (int dy = 0; dy <= 255 && dy < l1; ++dy) {          // every metric is >= dy; beyond 255 the output saturates anyway
+        if (y - dy >= 0) {
+            const int gx = gp[(size_t)(y - dy) * W];
+            if (gx != NO_ZERO) dt_candidates(gx, dy, l2, l1, cc);
+        }
+        if (dy > 0 && y + dy < H) {
+            const int gx = gp[(size_t)(y + dy) * W];
+            if (gx != NO_ZERO) dt_candidates(gx, dy, l2, l1, cc);
+        }
+    }
+    unsigned char* o = out + ((size_t)page * H * W + (size_t)y * W + x) * 3;
+    o[0] = (unsigned char)min(__float2int_rn(fminf(l2, 1000.0f)), 255);     // saturate_cast<uchar>(cvRound(.)), merge order b, g, r
+    o[1] = (unsigned char)min(l1, 255);
+    o[2] = (unsigned char)min(cc, 255);
+}
+
+size_t pp_align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" size_t rn_preprocess_workspace_bytes(int B, int H, int W) {
+    if (B < 1 || H < 1 || W < 1) return 0;
+    const size_t px = (size_t)B * H * W;
+    return pp_align256(px) + pp_align256(px * sizeof(unsigned short));
+}
+
+extern "C" int rn_preprocess_pages(const unsigned char* bgr_dev, int B, int H, int W, unsigned char* out_dev,
+                                   unsigned char* binary_out_dev, void* workspace, size_t workspace_bytes, void* stream) {
+    RN_REQUIRE(bgr_dev && out_dev && workspace, "NULL pointer");
+    RN_REQUIRE(B >= 1 && B <= 65535 && H >= 1 && W >= 1, "bad shape");
+    RN_REQUIRE(W < 65535 && (long long)H * W < (1ll << 31), "page too large (W < 65535, H * W < 2^31)");
+    if (workspace_bytes < rn_preprocess_workspace_bytes(B, H, W)) return rn_fail(RN_ERR_WORKSPACE, "preprocess workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t px = (size_t)B * H * W;
+    unsigned char* binary = binary_out_dev ? binary_out_dev : reinterpret_cast<unsigned char*>(workspace);
+    unsigned short* g = reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(workspace) + pp_align256(px));
+    const dim3 tiles((unsigned)((W + PT_W - 1) / PT_W), (unsigned)((H + PT_H - 1) / PT_H), (unsigned)B);
+    RN_REQUIRE(tiles.y <= 65535, "page too tall");
+    k_gray_threshold<<<tiles, PT_THREADS, 0, s>>>(bgr_dev, H, W, binary);
+    int rc = rn_check_launch("k_gray_threshold");
+    if (rc) return rc;
+    const long long rows = (long long)B * H;
+    RN_REQUIRE(rows < (1ll << 31), "too many rows");
+    k_row_distance<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(binary, (int)rows, W, g);
+    rc = rn_check_launch("k_row_distance");
+    if (rc) return rc;
+    const dim3 grid((unsigned)((W + 63) / 64), (unsigned)((H + 3) / 4), (unsigned)B);
+    RN_REQUIRE(grid.y <= 65535, "page too tall");
+    k_distance_u8<<<grid, 256, 0, s>>>(g, H, W, out_dev);
+    return rn_check_launch("k_distance_u8");
+}
