@@ -15,7 +15,7 @@ anchors = np.asarray(rn.anchors_for_shape(HW + (3,)))
 _, anns = synthetic.training_batch(3, batch=B)
 cls, reg = synthetic.inference_predictions(3, B, anchors, anns, classes=1)
 cls_d, reg_d = torch.from_numpy(cls).cuda(), torch.from_numpy(reg).cuda()
-names = ["bisection select", "gather", "bitonic sort", "group fetch/decode", "(a) windows + in-batch tests", "(b) resolve + eager", "sweep between rounds"]
+names = ["bisection select", "gather", "sort (radix on score words; bitonic on ties)", "group fetch/decode", "(a) windows + in-batch tests", "(b) resolve + eager", "sweep between rounds"]
 rn._lib.load().rn_debug_nms_timing(1)
 for topk in (0, 1000):
     head = rn.DetectionHead(pre_nms_top_k=topk)

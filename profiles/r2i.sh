@@ -6,6 +6,10 @@ mkdir -p $OUT
 timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/r2i_pytest.log 2>&1
 echo "pytest_exit=$?" | tee -a $OUT/r2i_pytest.log
 grep -v "^frame" $OUT/r2i_pytest.log | tail -25
+timeout 300 python profiles/nms_phases.py > $OUT/r2i_nms_phases.log 2>&1
+cat $OUT/r2i_nms_phases.log
+timeout 300 python profiles/time_inference.py > $OUT/r2i_time_inference.log 2>&1
+cat $OUT/r2i_time_inference.log
 timeout 600 python - > $OUT/r2i_preprocess_time.log 2>&1 <<'PY'
 import sys, time, numpy as np, torch
 sys.path.insert(0, ".")

@@ -442,6 +442,92 @@ __device__ __forceinline__ void sort_chunk_desc(unsigned long long* s_key, unsig
     __syncthreads();
 }
 
+// LSD radix sort of the chunk by the keys' upper (score) word, descending, 7 bits per pass over the bits in which the chunk's
+// score words can differ at all (they lie in [lo_hi, hi_hi]: ~26 bits = 4 passes for probabilities above a threshold).  A
+// thread holds the elements at positions tid and tid + 1024; per pass: a 64 x 128 histogram (64 groups of 32 consecutive
+// positions; __match_any_sync ranks the members of a group that share a digit and one of them writes the count), a scan per
+// digit over the groups, a scan over the digits, and a stable scatter into the second buffer.  ~90 instructions per thread
+// and pass instead of ~50 per stage of a 66-stage bitonic network.  The lower (anchor) word is NOT sorted: equal scores are
+// rare, so the caller checks the order of neighbours with equal score words afterwards (return value) and only then falls
+// back to the bitonic network.  n2p: padded size (power of two >= 128, padding keys are 0 and sort last).
+constexpr int RDX_BITS = 7, RDX_BINS = 1 << RDX_BITS, RDX_GROUPS = NMS_CHUNK / 32;
+
+template <bool SLOT>
+__device__ __forceinline__ bool radix_sort_desc(unsigned long long* s_key, unsigned* s_slot, unsigned long long* s_key2, unsigned* s_slot2,
+                                                unsigned short* s_hist, unsigned* s_base, unsigned* s_ws, const int n2p, const int loaded,
+                                                const unsigned lo_hi, const unsigned hi_hi, const int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const bool one = tid < n2p, two = n2p > NMS_THREADS;     // warp-uniform: n2p is a multiple of 32
+    unsigned long long k0 = one ? s_key[tid] : 0ull, k1 = two ? s_key[tid + NMS_THREADS] : 0ull;
+    unsigned v0 = 0u, v1 = 0u;
+    if (SLOT) { v0 = one ? s_slot[tid] : 0u; v1 = two ? s_slot[tid + NMS_THREADS] : 0u; }
+    const unsigned diff = lo_hi ^ hi_hi;
+    const int topbit = diff ? 31 - __clz(diff) : -1;         // the score words agree above this bit
+    const unsigned lt = (1u << lane) - 1u;
+    for (int shift = 0; shift <= topbit; shift += RDX_BITS) {
+        for (int i = tid; i < RDX_GROUPS * RDX_BINS / 2; i += NMS_THREADS) reinterpret_cast<unsigned*>(s_hist)[i] = 0u;
+        __syncthreads();
+        // digit, inverted so that bin 0 holds the largest scores; rank among the group members with the same digit
+        unsigned d0 = 0u, d1 = 0u, r0 = 0u, r1 = 0u;
+        if (one) {
+            d0 = (RDX_BINS - 1) - (((unsigned)(k0 >> 32) >> shift) & (RDX_BINS - 1));
+            const unsigned peers = __match_any_sync(0xffffffffu, d0);
+            r0 = __popc(peers & lt);
+            if (r0 == 0u) s_hist[warp * RDX_BINS + d0] = (unsigned short)__popc(peers);
+        }
+        if (two) {
+            d1 = (RDX_BINS - 1) - (((unsigned)(k1 >> 32) >> shift) & (RDX_BINS - 1));
+            const unsigned peers = __match_any_sync(0xffffffffu, d1);
+            r1 = __popc(peers & lt);
+            if (r1 == 0u) s_hist[(warp + 32) * RDX_BINS + d1] = (unsigned short)__popc(peers);
+        }
+        __syncthreads();
+        // per digit: exclusive scan over the groups (in place), then over the digits
+        unsigned tot = 0u;
+        if (tid < RDX_BINS) {
+#pragma unroll 8
+            for (int g = 0; g < RDX_GROUPS; ++g) {
+                const unsigned c = s_hist[g * RDX_BINS + tid];
+                s_hist[g * RDX_BINS + tid] = (unsigned short)tot;
+                tot += c;
+            }
+        }
+        unsigned incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (tid < RDX_BINS && lane == 31) s_ws[warp] = incl;
+        __syncthreads();
+        if (tid < RDX_BINS) {
+            unsigned off = 0u;
+            for (int w = 0; w < warp; ++w) off += s_ws[w];
+            s_base[tid] = off + incl - tot;
+        }
+        __syncthreads();
+        if (one) {
+            const unsigned pos = s_base[d0] + s_hist[warp * RDX_BINS + d0] + r0;
+            s_key2[pos] = k0;
+            if (SLOT) s_slot2[pos] = v0;
+        }
+        if (two) {
+            const unsigned pos = s_base[d1] + s_hist[(warp + 32) * RDX_BINS + d1] + r1;
+            s_key2[pos] = k1;
+            if (SLOT) s_slot2[pos] = v1;
+        }
+        __syncthreads();
+        if (one) { k0 = s_key2[tid]; if (SLOT) v0 = s_slot2[tid]; }
+        if (two) { k1 = s_key2[tid + NMS_THREADS]; if (SLOT) v1 = s_slot2[tid + NMS_THREADS]; }
+    }
+    if (one) { s_key[tid] = k0; if (SLOT) s_slot[tid] = v0; }
+    if (two) { s_key[tid + NMS_THREADS] = k1; if (SLOT) s_slot[tid + NMS_THREADS] = v1; }
+    __syncthreads();
+    bool bad = false;                                       // equal score words in the wrong (anchor) order?
+    for (int i = tid; i + 1 < loaded; i += NMS_THREADS) {
+        const unsigned long long a = s_key[i], b = s_key[i + 1];
+        bad = bad || (((a >> 32) == (b >> 32)) && (a < b));
+    }
+    return __syncthreads_or(bad ? 1 : 0) != 0;
+}
+
 // ---- bisection helpers: #{keys >= pivot} for three pivots at once -------------------------------------------------
 // keys held in registers: visited keys have been zeroed, so "unvisited" needs no test (every pivot is >= 1)
 __device__ __forceinline__ void count3_hi(unsigned khi, unsigned q1, unsigned q2, unsigned q3, unsigned& c1, unsigned& c2, unsigned& c3) {
@@ -483,7 +569,11 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // dynamic: selected boxes (normalised corners) + areas, sized by max_det
     float4* s_selbox = reinterpret_cast<float4*>(smem_raw);
-    float* s_selarea = reinterpret_cast<float*>(s_selbox + p.max_det);
+    unsigned long long* s_key2 = reinterpret_cast<unsigned long long*>(s_selbox + p.max_det);   // radix sort: second key buffer,
+    unsigned short* s_hist = reinterpret_cast<unsigned short*>(s_key2 + NMS_CHUNK);              // group x digit histogram,
+    unsigned* s_slot2 = reinterpret_cast<unsigned*>(s_hist + RDX_GROUPS * RDX_BINS);             // second payload buffer (SLOT)
+    float* s_selarea = reinterpret_cast<float*>(s_slot2 + (SLOT ? NMS_CHUNK : 0));
+    __shared__ unsigned s_base[RDX_BINS], s_ws[4];
 
     __shared__ unsigned long long s_key[NMS_CHUNK];
     __shared__ unsigned s_slot[SLOT ? NMS_CHUNK : 1];
@@ -683,7 +773,12 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
         __syncthreads();
         RN_PHASE(1);
         // ---------------- bitonic network, descending (keys are unique) ----------------------------
-        sort_chunk_desc<SLOT>(s_key, s_slot, n2p, tid);
+        {
+            const unsigned long long hb = (top != 0ull && top < upper) ? top : upper;      // the chunk's keys are below this
+            const unsigned lo_hi = thr_key ? (unsigned)(thr_key >> 32) : p.key_floor_hi, hi_hi = (unsigned)(hb >> 32);
+            if (n2p <= 128 || radix_sort_desc<SLOT>(s_key, s_slot, s_key2, s_slot2, s_hist, s_base, s_ws, n2p, loaded, lo_hi, hi_hi, tid))
+                sort_chunk_desc<SLOT>(s_key, s_slot, n2p, tid);     // tiny chunks, or equal scores met in the wrong anchor order
+        }
         const int chunk_n = min(loaded, limit - visited);
         RN_PHASE(2);
         // ---------------- K5: greedy NMS over the ordered chunk -------------------------------------------
@@ -944,7 +1039,10 @@ unsigned host_f2ord(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-size_t nms_dynamic_smem(int max_det) { return (size_t)max_det * (sizeof(float4) + sizeof(float)); }
+size_t nms_dynamic_smem(int max_det) {      // selected boxes + areas, the radix sort's second buffers and histogram
+    return (size_t)max_det * (sizeof(float4) + sizeof(float)) + (size_t)NMS_CHUNK * (sizeof(unsigned long long) + sizeof(unsigned)) +
+           (size_t)RDX_GROUPS * RDX_BINS * sizeof(unsigned short);
+}
 
 std::atomic<int> g_phase_timing{0};
 // measurement hook (rn_debug_filter_events): four cudaEvent_t recorded around the three kernels of a filter call
@@ -1043,7 +1141,9 @@ int filter_common(K3Params kp, const BoxSource& src, bool decode, int nms, float
     const long long page_tiles = ((long long)kp.N * C + K3S_TILE - 1) / K3S_TILE;
     if (kp.class_specific && kp.vec_ok) {
         // about SMs x 4 CTAs over all pages, each CTA a contiguous slice of one page (at least one tile per warp)
-        long long per_page = (RN_NUM_SMS * K3S_CTAS_PER_SM + B - 1) / B;
+        // ONE wave: no more CTAs than the GPU holds at once (640 CTAs on 592 slots ran a second, nearly empty wave: 16 us
+        // instead of 12)
+        long long per_page = (RN_NUM_SMS * K3S_CTAS_PER_SM) / B;
         const long long most = (page_tiles + K3_THREADS / 32 - 1) / (K3_THREADS / 32);
         if (per_page > most) per_page = most;
         if (per_page < 1) per_page = 1;
