@@ -94,6 +94,10 @@ def distance_transforms_u8(binary, reach=256):
     Rows further than `reach` away cannot lower a distance below 256 (every metric is >= dy), i.e. cannot change the
     8-bit result."""
     H, W = binary.shape
+    if not (binary == 0).any():
+        # no dark pixel at all: OpenCV leaves FLT_MAX everywhere, and the 8-bit conversion of imwrite (cvRound overflows to
+        # INT_MIN, which saturates to 0) turns that into a BLACK page, not a white one
+        return np.zeros((H, W, 3), np.uint8)
     g = row_distance(binary)
     big = np.float64(1e9)
     best = [np.full((H, W), big), np.full((H, W), big), np.full((H, W), big)]

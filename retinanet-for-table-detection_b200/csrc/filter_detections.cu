@@ -520,12 +520,27 @@ __device__ __forceinline__ bool radix_sort_desc(unsigned long long* s_key, unsig
     if (one) { s_key[tid] = k0; if (SLOT) s_slot[tid] = v0; }
     if (two) { s_key[tid + NMS_THREADS] = k1; if (SLOT) s_slot[tid + NMS_THREADS] = v1; }
     __syncthreads();
-    bool bad = false;                                       // equal score words in the wrong (anchor) order?
-    for (int i = tid; i + 1 < loaded; i += NMS_THREADS) {
-        const unsigned long long a = s_key[i], b = s_key[i + 1];
-        bad = bad || (((a >> 32) == (b >> 32)) && (a < b));
+    // Equal score words (~1 pair per page among thousands of fp32 scores) may sit in the wrong anchor order: a few rounds of
+    // odd-even transposition restricted to such pairs repair short runs; a run that is still unsorted after them (quantised
+    // scores) sends the caller to the bitonic network.
+    for (int iter = 0; iter < 6; ++iter) {
+        bool swapped = false;
+#pragma unroll
+        for (int phase = 0; phase < 2; ++phase) {
+            const int i = 2 * tid + phase;
+            if (i + 1 < loaded) {
+                const unsigned long long a = s_key[i], b = s_key[i + 1];
+                if (((a >> 32) == (b >> 32)) && (a < b)) {
+                    s_key[i] = b; s_key[i + 1] = a;
+                    if (SLOT) { const unsigned t = s_slot[i]; s_slot[i] = s_slot[i + 1]; s_slot[i + 1] = t; }
+                    swapped = true;
+                }
+            }
+            __syncthreads();
+        }
+        if (!__syncthreads_or(swapped ? 1 : 0)) return false;       // a whole round without a swap: ordered
     }
-    return __syncthreads_or(bad ? 1 : 0) != 0;
+    return true;
 }
 
 // ---- bisection helpers: #{keys >= pivot} for three pivots at once -------------------------------------------------
