@@ -1,16 +1,14 @@
 #!/bin/bash
-# round 2, capture j: radix sort with tie repair, N4 blank pages + register-blocked blur + unrolled sweep, default bench
+# round 2, capture k: select-based merge (C > 1), N4 conflict-free blur, K1 page-cost calibration of the new kernel
 set -u
 OUT=gpurun_out
 mkdir -p $OUT
-timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/r2j_pytest.log 2>&1
-echo "pytest_exit=$?" | tee -a $OUT/r2j_pytest.log
-grep -v "^frame" $OUT/r2j_pytest.log | tail -25
-timeout 300 python profiles/nms_phases.py > $OUT/r2j_nms_phases.log 2>&1
-cat $OUT/r2j_nms_phases.log
-timeout 300 python profiles/time_inference.py > $OUT/r2j_time_inference.log 2>&1
-cat $OUT/r2j_time_inference.log
-timeout 600 python - > $OUT/r2j_preprocess_time.log 2>&1 <<'PY'
+timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/r2k_pytest.log 2>&1
+echo "pytest_exit=$?" | tee -a $OUT/r2k_pytest.log
+grep -v "^frame" $OUT/r2k_pytest.log | tail -12
+timeout 600 python profiles/k1_page_cost.py > $OUT/r2k_k1_page_cost.log 2>&1
+tail -4 $OUT/r2k_k1_page_cost.log
+timeout 600 python - > $OUT/r2k_preprocess_time.log 2>&1 <<'PY'
 import sys, time, numpy as np, torch
 sys.path.insert(0, ".")
 import retinanet_b200 as rn
@@ -32,8 +30,8 @@ t0 = time.perf_counter(); cv2_pipeline(imgs[0]); t1 = time.perf_counter()
 print("N4: %d pages of %dx%d in %.3f ms = %.0f pages/s; bytes 3 in + 3 out per pixel -> %.0f GB/s algorithmic; OpenCV one page on one core %.1f ms"
       % (B, H, W, ms, B / ms * 1e3, B * H * W * 6 / ms / 1e6, (t1 - t0) * 1e3))
 PY
-cat $OUT/r2j_preprocess_time.log
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $OUT/r2j_preprocess_launches.csv python - > /dev/null 2>&1 <<'PY'
+cat $OUT/r2k_preprocess_time.log | tail -2
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $OUT/r2k_preprocess_launches.csv python - > /dev/null 2>&1 <<'PY'
 import sys, numpy as np, torch
 sys.path.insert(0, ".")
 import retinanet_b200 as rn
@@ -44,18 +42,15 @@ for _ in range(2):
     rn.preprocess.preprocess_pages(dev)
 torch.cuda.synchronize()
 PY
-grep -i "k_gray\|k_row\|k_distance" $OUT/r2j_preprocess_launches.csv | cut -d, -f5,12- | tail -6
-timeout 900 python bench.py > $OUT/r2j_bench.json 2> $OUT/r2j_bench.err
+grep -i "k_gray\|k_row\|k_distance" $OUT/r2k_preprocess_launches.csv | awk -F'","' '{print $1, $NF}' | tail -3
+timeout 900 python bench.py --no-cpu > $OUT/r2k_bench.json 2> $OUT/r2k_bench.err
 echo "bench_exit=$?"
-tail -3 $OUT/r2j_bench.err
 python - <<'PY'
 import json
 try:
-    d = json.load(open("gpurun_out/r2j_bench.json"))
-    print({k: d[k] for k in ("value", "ms_per_step")}, "K1", d["roofline"]["us_per_launch"], d["roofline"]["frac"], "K2", d["roofline_k2"]["us_per_launch"], d["roofline_k2"]["frac"])
-    print("K3", d["roofline_k3"]["us_per_launch"], d["roofline_k3"]["frac"], "NMS", d["nms"]["us_per_launch"], "merge", d["nms"]["merge_us"])
-    print("e2e", d["e2e"]["value"], d["e2e"]["fraction_of_h2d_ceiling"])
-    print("inference", {k: v for k, v in d["inference"]["reference_semantics"].items() if not isinstance(v, (dict, str))})
+    d = json.load(open("gpurun_out/r2k_bench.json"))
+    print({k: d[k] for k in ("value", "ms_per_step")}, "K1", d["roofline"]["us_per_launch"], "K2", d["roofline_k2"]["us_per_launch"], "K3", d["roofline_k3"]["us_per_launch"], d["roofline_k3"]["frac"], "NMS", d["nms"]["us_per_launch"])
+    print("inference", d["inference"]["reference_semantics"]["pages_per_s"], d["inference"]["reference_semantics"]["ms_per_batch"])
     for k in ("config3", "config4"):
         print(k, d[k]["pages_per_s"], d[k]["kernels_us"])
 except Exception as e:

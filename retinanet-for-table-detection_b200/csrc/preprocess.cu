@@ -34,8 +34,10 @@ __constant__ unsigned c_gauss11[11] = {0x3c10612bu, 0x3cde5c35u, 0x3d855a85u, 0x
 
 __global__ void __launch_bounds__(PT_THREADS) k_gray_threshold(const unsigned char* __restrict__ bgr, int H, int W,
                                                                 unsigned char* __restrict__ binary) {
-    __shared__ float s_gray[PT_H + 2 * PT_R][PT_W + 2 * PT_R + 2];     // grey levels of the tile + halo (replicated border)
-    __shared__ float s_row[PT_H + 2 * PT_R][PT_W];                     // row pass
+    // (odd row pitches: in the row pass the lanes of a warp walk DOWN a column of windows, so that neither its 14 window loads
+    // nor its 4 stores hit one bank twice)
+    __shared__ float s_gray[PT_H + 2 * PT_R][PT_W + 2 * PT_R + 3];     // grey levels of the tile + halo (replicated border)
+    __shared__ float s_row[PT_H + 2 * PT_R][PT_W + 1];                 // row pass
     const int page = blockIdx.z;
     const unsigned char* src = bgr + (size_t)page * H * W * 3;
     unsigned char* dst = binary + (size_t)page * H * W;
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_gray_threshold(const unsigned ch
     // row pass, left to right: acc = k0 * p0; acc = fma(p_j, k_j, acc).  A thread produces 4 consecutive outputs of a row
     // from a 14-element window held in registers (14 shared-memory loads instead of 44).
     for (int i = tid; i < (PT_H + 2 * PT_R) * (PT_W / 4); i += PT_THREADS) {
-        const int ly = i / (PT_W / 4), lx = (i - ly * (PT_W / 4)) * 4;
+        const int q = i / (PT_H + 2 * PT_R), ly = i - q * (PT_H + 2 * PT_R), lx = q * 4;
         float w[14];
 #pragma unroll
         for (int j = 0; j < 14; ++j) w[j] = s_gray[ly][lx + j];
@@ -146,20 +148,16 @@ __global__ void __launch_bounds__(256) k_distance_u8(const unsigned short* __res
     float l2 = 1e9f;
     int l1 = 1 << 28, cc = 1 << 28;
     // every metric is >= dy, so rows further away than the best L1 distance cannot matter; beyond 255 the output saturates
-    // anyway.  Four row pairs per round: their eight loads are in flight together (the sweep is latency bound otherwise).
-    for (int d0 = 0; d0 <= 255 && d0 < l1; d0 += 4) {
-        int up[4], dn[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int dy = d0 + j;
-            up[j] = (y - dy >= 0) ? (int)gp[(size_t)(y - dy) * W] : (int)NO_ZERO;
-            dn[j] = (dy > 0 && y + dy < H) ? (int)gp[(size_t)(y + dy) * W] : (int)NO_ZERO;
+    // anyway.  (A/B: fetching four row pairs per round to overlap their latencies was slower, 596 vs 456 us per 16 pages:
+    // on a text page most pixels are done after two or three rows.)
+    for (int dy = 0; dy <= 255 && dy < l1; ++dy) {
+        if (y - dy >= 0) {
+            const int gx = gp[(size_t)(y - dy) * W];
+            if (gx != NO_ZERO) dt_candidates(gx, dy, l2, l1, cc);
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int dy = d0 + j;
-            if (up[j] != NO_ZERO) dt_candidates(up[j], dy, l2, l1, cc);
-            if (dn[j] != NO_ZERO) dt_candidates(dn[j], dy, l2, l1, cc);
+        if (dy > 0 && y + dy < H) {
+            const int gx = gp[(size_t)(y + dy) * W];
+            if (gx != NO_ZERO) dt_candidates(gx, dy, l2, l1, cc);
         }
     }
     o[0] = (unsigned char)min(__float2int_rn(fminf(l2, 1000.0f)), 255);     // saturate_cast<uchar>(cvRound(.)), merge order b, g, r
