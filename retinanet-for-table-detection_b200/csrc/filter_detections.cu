@@ -1018,6 +1018,7 @@ __global__ void __launch_bounds__(256) k_merge_topk(const MergeParams p) {
 // gathered and ordered by one bitonic network.  ~10 us per page instead of max_det serial block-wide argmax rounds (237 us
 // at C = 80).  One CTA of 1024 threads per page; needs C * max_det * 8 bytes of shared memory (192 KB at C = 80, M = 300).
 constexpr int MERGE_THREADS = 1024;
+constexpr size_t MERGE_SMEM_MAX = 226 * 1024;             // of the 227 KB a CTA may have on sm_100 (80 classes x 300 need 203.5 KB)
 
 __device__ __forceinline__ int merge_count_ge(const unsigned long long* list, int n, unsigned long long pivot) {
     int lo = 0, hi = n;                                     // entries [0, lo) are >= pivot, [hi, n) are < pivot
@@ -1211,7 +1212,7 @@ int merge_opt_in_shared_memory() {
     if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
     const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
     if (bit && (done.load(std::memory_order_acquire) & bit)) return RN_OK;
-    e = cudaFuncSetAttribute(k_merge_topk_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(k_merge_topk_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MERGE_SMEM_MAX);
     if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (bit) done.fetch_or(bit, std::memory_order_release);
     return RN_OK;
@@ -1244,7 +1245,7 @@ int run_back_end(const FilterWs& w, const BoxSource& src, bool decode, int B, in
     mp.out_boxes = out_boxes; mp.out_scores = out_scores; mp.out_labels = out_labels; mp.out_indices = out_indices;
     mp.out_count = out_count;
     const size_t sel_smem = ((size_t)segs_per_page * max_det + NMS_CHUNK) * sizeof(unsigned long long);
-    if (segs_per_page > 1 && segs_per_page <= 65535 && sel_smem <= 200 * 1024) {
+    if (segs_per_page > 1 && segs_per_page <= 65535 && sel_smem <= MERGE_SMEM_MAX) {
         rc = merge_opt_in_shared_memory();
         if (rc) return rc;
         k_merge_topk_select<<<B, MERGE_THREADS, sel_smem, s>>>(mp);

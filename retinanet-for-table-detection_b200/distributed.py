@@ -79,9 +79,10 @@ def page_cost(annotations_group, image_hw, anchor_params=None, pyramid_levels=No
     return out
 
 
-# K1 on 16 copies of one 800x1333 page: 43.3 us + 3.68e-5 us per overlapping (anchor, table) pair of the page (32 pages,
-# rms error 1.5 us; profiles/k1_page_cost.py), i.e. the fixed per-anchor work of a page equals 5.9 pairs per anchor
-PAIRS_PER_FIXED = 5.9
+# K1 on 16 copies of one 800x1333 page: 35.9 us + 3.68e-5 us per overlapping (anchor, table) pair of the page (32 pages,
+# rms error 1.4 us; profiles/k1_page_cost.py, round-2 kernel: profiles/r2/r2k_k1_page_cost.log), i.e. the fixed per-anchor work
+# of a page equals 4.87 pairs per anchor (round-1 kernel: 43.3 us, 5.9)
+PAIRS_PER_FIXED = 4.87
 
 
 def global_positive_count(npos_per_page, group=None):
