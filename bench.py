@@ -77,7 +77,7 @@ def static_config(k):
     return {"workload": c["workload"], "baseline_config": k, "pages_per_gpu": c["pages"], "image_hw": list(s["hw"]),
             "anchors_per_page": synthetic.num_anchors(s["hw"]), "classes": s["classes"], "gt_max": s["gmax"],
             "l2": "the tensors one step touches exceed the 126 MB L2 (training / full configurations) and the inference leg rotates "
-                  "three input sets (3 x 103 MB); the per-kernel timings (rooflines) additionally overwrite a 512 MB buffer before "
+                  "three input sets (3 x 103 MB); the per-kernel timings (rooflines) additionally read a 512 MB buffer before "
                   "every timed call"}
 
 
@@ -342,13 +342,14 @@ def filter_kernel_times(ctx, steps_eager, reps):
         st.run()
     torch.cuda.synchronize()
     acc = np.zeros(3)
-    # before every timed call a 512 MB buffer is overwritten on the same stream: it flushes the 126 MB L2, and it keeps the GPU
-    # busy while the host enqueues the call's launches, so the events see the kernels back to back, not the host's launch gaps
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=ctx.device)
+    # before every timed call a 512 MB buffer is READ on the same stream (a reduction): it replaces the contents of the 126 MB
+    # L2 with clean lines (a write would leave dirty lines whose write-back competes with the timed kernel), and it keeps the
+    # GPU busy while the host enqueues the call's launches, so the events see the kernels back to back, not launch gaps
+    flush = torch.zeros(512 << 20, dtype=torch.uint8, device=ctx.device)
     lib.rn_debug_filter_events(*[ctypes.c_void_p(e.cuda_event) for e in evs])
     try:
         for i in range(reps):
-            flush.zero_()
+            flush.amax()
             steps_eager[i % len(steps_eager)].run()
             torch.cuda.synchronize()
             acc += [evs[k].elapsed_time(evs[k + 1]) * 1e3 for k in range(3)]
@@ -438,17 +439,23 @@ def leg_training(ctx):
         ov_match = bool(torch.equal(step.losses, inorder_losses))     # same batch every step -> same bits as in order
     # timed region 2 (per-kernel durations for the rooflines): the same K steps with the two halves replayed
     # separately and CUDA events between them (costs one more graph launch per step, so it is not the `value`)
-    # Before every split step a 512 MB buffer is overwritten on the same stream: the GPU is busy while the host enqueues the
-    # step's two graph launches, so the events bracket the kernels, not the host's launch gaps (and L2 is flushed).
+    # The two kernels are launched EAGERLY here (no graph-launch overhead between an event and its kernel), and before every
+    # split step a 512 MB buffer is read on the same stream (a reduction): the GPU is busy while the host enqueues the step's
+    # launches, so the events bracket the kernels, not the host's launch gaps, and L2 holds none of the step's tensors.
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=device)
+    flush = torch.zeros(512 << 20, dtype=torch.uint8, device=device)
+    graphs_on = step.use_graph
+    step.use_graph = False
+    for _ in range(3):
+        step.run(events=evs[0])
     ctx.barrier()
     t0 = time.perf_counter()
     for i in range(steps):
-        flush.zero_()
-        run_step(events=evs[i])
+        flush.amax()
+        step.run(events=evs[i])
     ctx.barrier()
     ctx.windows.append((t0, time.perf_counter()))
+    step.use_graph = graphs_on
     del flush
     split_ms = sum(e[0].elapsed_time(e[2]) for e in evs)
     k1_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
@@ -771,12 +778,15 @@ def leg_full(ctx, k):
     det.check()
     step.check()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=device)
+    flush = torch.zeros(512 << 20, dtype=torch.uint8, device=device)
+    step.use_graph = False                                  # eager launches: the events sit right at the kernels
+    step.run(events=evs[0])
     ctx.barrier()
     for i in range(steps):
-        flush.zero_()
+        flush.amax()
         step.run(events=evs[i])
     ctx.barrier()
+    step.use_graph = True
     del flush
     k1_us = sum(e[0].elapsed_time(e[1]) for e in evs) / steps * 1e3
     k2_us = sum(e[1].elapsed_time(e[2]) for e in evs) / steps * 1e3
