@@ -442,15 +442,15 @@ __device__ __forceinline__ void sort_chunk_desc(unsigned long long* s_key, unsig
     __syncthreads();
 }
 
-// LSD radix sort of the chunk by the keys' upper (score) word, descending, 7 bits per pass over the bits in which the chunk's
-// score words can differ at all (they lie in [lo_hi, hi_hi]: ~26 bits = 4 passes for probabilities above a threshold).  A
-// thread holds the elements at positions tid and tid + 1024; per pass: a 64 x 128 histogram (64 groups of 32 consecutive
+// LSD radix sort of the chunk by the keys' upper (score) word, descending, 8 bits per pass over the bits in which the chunk's
+// score words can differ at all (they lie in [lo_hi, hi_hi]: <= 24 bits = 3 passes for the scores of one chunk).  A
+// thread holds the elements at positions tid and tid + 1024; per pass: a 64 x 256 histogram (64 groups of 32 consecutive
 // positions; __match_any_sync ranks the members of a group that share a digit and one of them writes the count), a scan per
 // digit over the groups, a scan over the digits, and a stable scatter into the second buffer.  ~90 instructions per thread
 // and pass instead of ~50 per stage of a 66-stage bitonic network.  The lower (anchor) word is NOT sorted: equal scores are
 // rare, so the caller checks the order of neighbours with equal score words afterwards (return value) and only then falls
 // back to the bitonic network.  n2p: padded size (power of two >= 128, padding keys are 0 and sort last).
-constexpr int RDX_BITS = 7, RDX_BINS = 1 << RDX_BITS, RDX_GROUPS = NMS_CHUNK / 32;
+constexpr int RDX_BITS = 8, RDX_BINS = 1 << RDX_BITS, RDX_GROUPS = NMS_CHUNK / 32;
 
 template <bool SLOT>
 __device__ __forceinline__ bool radix_sort_desc(unsigned long long* s_key, unsigned* s_slot, unsigned long long* s_key2, unsigned* s_slot2,
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     unsigned short* s_hist = reinterpret_cast<unsigned short*>(s_key2 + NMS_CHUNK);              // group x digit histogram,
     unsigned* s_slot2 = reinterpret_cast<unsigned*>(s_hist + RDX_GROUPS * RDX_BINS);             // second payload buffer (SLOT)
     float* s_selarea = reinterpret_cast<float*>(s_slot2 + (SLOT ? NMS_CHUNK : 0));
-    __shared__ unsigned s_base[RDX_BINS], s_ws[4];
+    __shared__ unsigned s_base[RDX_BINS], s_ws[RDX_BINS / 32];
 
     __shared__ unsigned long long s_key[NMS_CHUNK];
     __shared__ unsigned s_slot[SLOT ? NMS_CHUNK : 1];
