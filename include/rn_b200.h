@@ -210,6 +210,10 @@ int rn_decode_filter_detections(const float* base_anchors_f32_dev, const int* le
                                 float* out_boxes, float* out_scores, int* out_labels, int* out_indices,
                                 int* status_out_dev, void* workspace, size_t workspace_bytes, void* stream);
 
+/* the `other` tensors of filter_detections (model/layers.py:247, :255): out[b, m, :] = other[b, indices[b, m], :] for the kept
+ * detections, -1 for the padding (indices < 0).  other (B, N, D) f32, indices (B, M) i32 (out_indices above), out (B, M, D). */
+int rn_gather_other(const float* other, const int* indices, int B, long long N, int M, int D, float* out, void* stream);
+
 /* tf.image.non_max_suppression (call site model/layers.py:211) for one box set:
  * out_indices (max_output) i32 in selection order, padded with -1; out_count_dev: 1 int32. */
 size_t rn_nms_workspace_bytes(long long K, int max_output);

@@ -60,6 +60,7 @@ SIGNATURES = {
     "rn_decode_filter_detections": (c_int, [_P, _HI, _HI, c_int, c_int, _P, _P, c_int, c_longlong, c_int,
                                             _HF, _HF, c_float, c_float, c_int, c_int, c_float, c_float, c_int,
                                             c_int, c_longlong, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "rn_gather_other": (c_int, [_P, _P, c_int, c_longlong, c_int, c_int, _P, _P]),
     "rn_nms_workspace_bytes": (c_size_t, [c_longlong, c_int]),
     "rn_nms": (c_int, [_P, _P, c_longlong, c_int, c_float, _P, _P, _P, c_size_t, _P]),
     "rn_debug_nms_timing": (c_int, [c_int]),

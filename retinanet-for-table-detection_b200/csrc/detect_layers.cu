@@ -133,3 +133,34 @@ extern "C" int rn_rescale_cut(const float* boxes, const float* scores, const flo
     k_rescale_cut<<<B, 256, 0, (cudaStream_t)stream>>>(boxes, scores, image_scale_dev, M, min_score, boxes_out, count_out);
     return rn_check_launch("rn_rescale_cut");
 }
+
+// ------------------------------------------------------------------------------------------------
+// `other` tensors of FilterDetections follow the selected anchors (model/layers.py:247, :255): tf.gather(o, indices) for the
+// kept detections, tf.pad(..., constant_values=-1) for the rest.  One 4-byte element per thread: rows are (B, N, D) with any
+// trailing size D.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) k_gather_other(const float* other, const int* idx, long long total, int N, int M, int D,
+                                                      float* out) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long row = e / D;                        // (b, m)
+        const int d = (int)(e - row * D);
+        const long long b = row / M;
+        const int n = __ldg(idx + row);
+        out[e] = n >= 0 ? __ldg(other + ((size_t)b * N + n) * D + d) : -1.0f;
+    }
+}
+
+}  // namespace
+
+extern "C" int rn_gather_other(const float* other, const int* indices, int B, long long N, int M, int D, float* out, void* stream) {
+    RN_REQUIRE(B >= 0 && N >= 0 && M >= 0 && D >= 1, "bad shape");
+    const long long total = (long long)B * M * D;
+    if (total == 0) return RN_OK;
+    RN_REQUIRE(other && indices && out, "NULL pointer");
+    RN_REQUIRE(N < (1ll << 31), "N too large");
+    const int blocks = (int)((total + 255) / 256 < (long long)RN_NUM_SMS * 8 ? (total + 255) / 256 : (long long)RN_NUM_SMS * 8);
+    k_gather_other<<<blocks, 256, 0, (cudaStream_t)stream>>>(other, indices, total, (int)N, M, D, out);
+    return rn_check_launch("rn_gather_other");
+}

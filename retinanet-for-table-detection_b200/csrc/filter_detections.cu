@@ -451,6 +451,8 @@ __device__ __forceinline__ void sort_chunk_desc(unsigned long long* s_key, unsig
 // rare, so the caller checks the order of neighbours with equal score words afterwards (return value) and only then falls
 // back to the bitonic network.  n2p: padded size (power of two >= 128, padding keys are 0 and sort last).
 constexpr int RDX_BITS = 8, RDX_BINS = 1 << RDX_BITS, RDX_GROUPS = NMS_CHUNK / 32;
+constexpr int RDX_PITCH = RDX_BINS + 2;                     // histogram row pitch (u16): the per-digit scans walk DOWN the rows, 2 per lane
+static_assert(RDX_GROUPS == 64 && RDX_BINS % 32 == 0, "the digit scan below assumes 64 groups (2 per lane)");
 
 template <bool SLOT>
 __device__ __forceinline__ bool radix_sort_desc(unsigned long long* s_key, unsigned* s_slot, unsigned long long* s_key2, unsigned* s_slot2,
@@ -465,7 +467,7 @@ __device__ __forceinline__ bool radix_sort_desc(unsigned long long* s_key, unsig
     const int topbit = diff ? 31 - __clz(diff) : -1;         // the score words agree above this bit
     const unsigned lt = (1u << lane) - 1u;
     for (int shift = 0; shift <= topbit; shift += RDX_BITS) {
-        for (int i = tid; i < RDX_GROUPS * RDX_BINS / 2; i += NMS_THREADS) reinterpret_cast<unsigned*>(s_hist)[i] = 0u;
+        for (int i = tid; i < RDX_GROUPS * RDX_PITCH / 2; i += NMS_THREADS) reinterpret_cast<unsigned*>(s_hist)[i] = 0u;
         __syncthreads();
         // digit, inverted so that bin 0 holds the largest scores; rank among the group members with the same digit
         unsigned d0 = 0u, d1 = 0u, r0 = 0u, r1 = 0u;
@@ -473,25 +475,31 @@ __device__ __forceinline__ bool radix_sort_desc(unsigned long long* s_key, unsig
             d0 = (RDX_BINS - 1) - (((unsigned)(k0 >> 32) >> shift) & (RDX_BINS - 1));
             const unsigned peers = __match_any_sync(0xffffffffu, d0);
             r0 = __popc(peers & lt);
-            if (r0 == 0u) s_hist[warp * RDX_BINS + d0] = (unsigned short)__popc(peers);
+            if (r0 == 0u) s_hist[warp * RDX_PITCH + d0] = (unsigned short)__popc(peers);
         }
         if (two) {
             d1 = (RDX_BINS - 1) - (((unsigned)(k1 >> 32) >> shift) & (RDX_BINS - 1));
             const unsigned peers = __match_any_sync(0xffffffffu, d1);
             r1 = __popc(peers & lt);
-            if (r1 == 0u) s_hist[(warp + 32) * RDX_BINS + d1] = (unsigned short)__popc(peers);
+            if (r1 == 0u) s_hist[(warp + 32) * RDX_PITCH + d1] = (unsigned short)__popc(peers);
         }
         __syncthreads();
-        // per digit: exclusive scan over the groups (in place), then over the digits
-        unsigned tot = 0u;
-        if (tid < RDX_BINS) {
-#pragma unroll 8
-            for (int g = 0; g < RDX_GROUPS; ++g) {
-                const unsigned c = s_hist[g * RDX_BINS + tid];
-                s_hist[g * RDX_BINS + tid] = (unsigned short)tot;
-                tot += c;
-            }
+        // per digit: exclusive scan over the 64 groups (in place) -- a warp takes 8 digits, a lane two groups, the scan is five
+        // shuffles (a thread-serial walk over the groups was a 64-step dependent chain per pass) -- then over the digits
+#pragma unroll
+        for (int dd = 0; dd < RDX_BINS / 32; ++dd) {
+            const int d = warp * (RDX_BINS / 32) + dd;
+            const unsigned a = s_hist[(2 * lane) * RDX_PITCH + d], b = s_hist[(2 * lane + 1) * RDX_PITCH + d];
+            unsigned inc = a + b;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+            const unsigned exc = inc - (a + b);
+            s_hist[(2 * lane) * RDX_PITCH + d] = (unsigned short)exc;
+            s_hist[(2 * lane + 1) * RDX_PITCH + d] = (unsigned short)(exc + a);
+            if (lane == 31) s_base[d] = inc;                 // the digit's total, turned into its base below
         }
+        __syncthreads();
+        const unsigned tot = tid < RDX_BINS ? s_base[tid] : 0u;
         unsigned incl = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
@@ -504,12 +512,12 @@ __device__ __forceinline__ bool radix_sort_desc(unsigned long long* s_key, unsig
         }
         __syncthreads();
         if (one) {
-            const unsigned pos = s_base[d0] + s_hist[warp * RDX_BINS + d0] + r0;
+            const unsigned pos = s_base[d0] + s_hist[warp * RDX_PITCH + d0] + r0;
             s_key2[pos] = k0;
             if (SLOT) s_slot2[pos] = v0;
         }
         if (two) {
-            const unsigned pos = s_base[d1] + s_hist[(warp + 32) * RDX_BINS + d1] + r1;
+            const unsigned pos = s_base[d1] + s_hist[(warp + 32) * RDX_PITCH + d1] + r1;
             s_key2[pos] = k1;
             if (SLOT) s_slot2[pos] = v1;
         }
@@ -586,7 +594,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     float4* s_selbox = reinterpret_cast<float4*>(smem_raw);
     unsigned long long* s_key2 = reinterpret_cast<unsigned long long*>(s_selbox + p.max_det);   // radix sort: second key buffer,
     unsigned short* s_hist = reinterpret_cast<unsigned short*>(s_key2 + NMS_CHUNK);              // group x digit histogram,
-    unsigned* s_slot2 = reinterpret_cast<unsigned*>(s_hist + RDX_GROUPS * RDX_BINS);             // second payload buffer (SLOT)
+    unsigned* s_slot2 = reinterpret_cast<unsigned*>(s_hist + RDX_GROUPS * RDX_PITCH);             // second payload buffer (SLOT)
     float* s_selarea = reinterpret_cast<float*>(s_slot2 + (SLOT ? NMS_CHUNK : 0));
     __shared__ unsigned s_base[RDX_BINS], s_ws[RDX_BINS / 32];
 
@@ -597,6 +605,8 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     __shared__ float s_garea[NMS_GROUP];
     __shared__ unsigned s_alive[NMS_GROUP / 32];   // bit set: candidate of the group neither consumed nor suppressed yet
     __shared__ unsigned s_vict[NMS_BATCH];    // per batch member: the later members it suppresses
+    __shared__ unsigned char s_bpos[NMS_BATCH];   // per batch member: its position in the group
+    __shared__ int s_alive_total;
     __shared__ unsigned s_cnt[3][4];          // pivot counts of the bisection, three rotating sets
     __shared__ unsigned s_kmax;
     __shared__ int s_loaded, s_nsel;
@@ -823,21 +833,30 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
             int gdone = 0;                                  // candidates of the group whose window has been opened
             while (nsel < p.max_det) {
                 __syncthreads();                            // the alive bits are final
-                // (a) the next <= 32 alive candidates, in order: every warp derives their positions from the 8 alive words
-                const unsigned aw = lane < NMS_GROUP / 32 ? s_alive[lane] : 0u;
-                int incl = __popc(aw);
+                // (a) the next <= 32 alive candidates, in order: one thread per candidate of the group ranks itself among the
+                //     alive ones (its warp's alive word + the population counts of the words before it) and the first 32 leave
+                //     their positions in shared memory
+                if (tid < NMS_GROUP) {
+                    const unsigned word = s_alive[warp];
+                    int before = 0;
 #pragma unroll
-                for (int o = 1; o < NMS_GROUP / 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-                const int alive_total = __shfl_sync(0xffffffffu, incl, NMS_GROUP / 32 - 1);
-                if (alive_total == 0) {                     // block-uniform: every warp reads the same words
+                    for (int w8 = 0; w8 < NMS_GROUP / 32 - 1; ++w8) before += (w8 < warp) ? __popc(s_alive[w8]) : 0;
+                    if ((word >> lane) & 1u) {
+                        const int rank = before + __popc(word & ((1u << lane) - 1u));
+                        if (rank < NMS_BATCH) s_bpos[rank] = (unsigned char)tid;
+                    }
+                    if (tid == NMS_GROUP - 1) s_alive_total = before + __popc(word);
+                }
+                __syncthreads();
+                const int alive_total = s_alive_total;
+                if (alive_total == 0) {                     // block-uniform
                     if (gdone >= gn) break;
                     // ... and no wider than ~6 k pair tests at opening: a candidate of an open window is tested against every
                     // later selection as well, so what is opened but never consumed (behind the stopping point) is pure waste
                     const int room = p.max_det - nsel;
                     const int by_cost = max(32, (6144 / max(nsel, 24)) & ~31);
                     const int wn = min(gn - gdone, min(by_cost, (room + (room >> 2) + 47) & ~31));   // a multiple of 32 unless it ends the group
-                    __syncthreads();                        // everybody has read the (empty) alive words
-                    if (tid < NMS_GROUP / 32) {
+                    if (tid < NMS_GROUP / 32) {             // (nobody reads the alive words between the barrier above and the next)
                         const int left = gdone + wn - tid * 32, skip = gdone - tid * 32;    // gdone is a multiple of 32
                         s_alive[tid] = (skip > 0 || left <= 0) ? 0u : (left >= 32 ? ~0u : (1u << left) - 1u);
                     }
@@ -848,14 +867,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                     continue;
                 }
                 const int bn = min(NMS_BATCH, alive_total);
-                int word = 0, before = 0;                   // lane l looks for the l-th alive candidate
-#pragma unroll
-                for (int w8 = 0; w8 < NMS_GROUP / 32 - 1; ++w8) {
-                    const int inc = __shfl_sync(0xffffffffu, incl, w8);
-                    if (inc <= lane) { word = w8 + 1; before = inc; }
-                }
-                const unsigned wbits = __shfl_sync(0xffffffffu, aw, word);
-                const int pos = lane < bn ? (word << 5) + (int)__fns(wbits, 0u, lane - before + 1) : 0;
+                const int pos = lane < bn ? (int)s_bpos[lane] : 0;
                 // warp w owns batch member w: one ballot over the later members gives row w of the in-batch suppression matrix
                 if (warp < bn) {                            // warp-uniform
                     unsigned vict = 0u;
@@ -1172,7 +1184,7 @@ unsigned host_f2ord(float f) {
 
 size_t nms_dynamic_smem(int max_det) {      // selected boxes + areas, the radix sort's second buffers and histogram
     return (size_t)max_det * (sizeof(float4) + sizeof(float)) + (size_t)NMS_CHUNK * (sizeof(unsigned long long) + sizeof(unsigned)) +
-           (size_t)RDX_GROUPS * RDX_BINS * sizeof(unsigned short);
+           (size_t)RDX_GROUPS * RDX_PITCH * sizeof(unsigned short);
 }
 
 std::atomic<int> g_phase_timing{0};

@@ -143,19 +143,24 @@ class ClipBoxes(_Layer):
 
 
 def _gather_other(other, indices, max_detections):
-    """``other`` tensors follow the selected anchors (model/layers.py:247,255): gather + pad with -1."""
+    """``other`` tensors follow the selected anchors (model/layers.py:247,255): gather + pad with -1 (``rn_gather_other``;
+    float32 like the reference's ``keras.backend.floatx()`` tensors)."""
     outs = []
     if not other:
         return outs
-    valid = indices >= 0
-    safe = indices.clamp(min=0).long()
+    lib = _lib.load()
+    B, M = int(indices.shape[0]), int(indices.shape[1])
     for o in other:
         o = o if isinstance(o, torch.Tensor) else torch.as_tensor(np.asarray(o))
-        o = o.to(indices.device)
-        idx = safe.view(safe.shape + (1,) * (o.dim() - 2)).expand(safe.shape + tuple(o.shape[2:]))
-        g = torch.gather(o, 1, idx)
-        mask = valid.view(valid.shape + (1,) * (o.dim() - 2))
-        outs.append(torch.where(mask, g, torch.full_like(g, -1)))
+        o = o.to(device=indices.device, dtype=torch.float32).contiguous()
+        if o.dim() < 2 or int(o.shape[0]) != B:
+            raise ValueError("other tensors must be (B, N, ...); got %s" % (tuple(o.shape),))
+        N = int(o.shape[1])
+        D = int(np.prod(o.shape[2:])) if o.dim() > 2 else 1
+        out = torch.empty((B, M) + tuple(o.shape[2:]), dtype=torch.float32, device=indices.device)
+        _lib.check(lib.rn_gather_other(_lib.ptr(o), _lib.ptr(indices), B, N, M, D, _lib.ptr(out), _lib.stream_ptr(indices.device)),
+                   "rn_gather_other")
+        outs.append(out)
     return outs
 
 
