@@ -573,36 +573,16 @@ __device__ __forceinline__ void count3(unsigned long long k, unsigned long long 
     c3 += (live && k >= q3) ? 1u : 0u;
 }
 
-// A coarse grid over the page (8 x 8 cells) remembers, per cell, WHICH selected boxes reach into it (one bit per selected box).
-// Two boxes can only suppress each other if they intersect, and intersecting boxes share at least one cell (the cell index is a
-// monotone function of the coordinate, so it is conservative for any extent, boxes outside the page included).  A candidate that
-// covers at most four cells therefore skips every selected box whose bit is in none of them -- on a text page a background
-// candidate is a 32-pixel anchor and the selected boxes near it are a handful out of hundreds.  Exact: only pairs with an empty
-// intersection are skipped, and those have IoU 0.
-constexpr int GRID = 8;
-
-struct CellGrid {
-    unsigned* bits;         // [GRID * GRID][words]
-    int words;              // ceil(max_det / 32)
-    float inv_cw, inv_ch;   // GRID / page extent; 0: no extent known, every box lies in cell (0, 0)
-};
-
-__device__ __forceinline__ int grid_cell(float v, float inv) { return min(GRID - 1, max(0, (int)(v * inv))); }
-
-// the selected box `index` reaches into these cells (called by the lane that selected it)
-__device__ __forceinline__ void grid_insert(const CellGrid& g, const float4 box, int index) {
-    const int x0 = grid_cell(box.x, g.inv_cw), x1 = grid_cell(box.z, g.inv_cw), y0 = grid_cell(box.y, g.inv_ch), y1 = grid_cell(box.w, g.inv_ch);
-    for (int y = y0; y <= y1; ++y)
-        for (int x = x0; x <= x1; ++x) atomicOr(&g.bits[(y * GRID + x) * g.words + (index >> 5)], 1u << (index & 31));
-}
-
 // The alive candidates [w0, w0 + wn) of the current group (wn <= 256, w0 a multiple of 32) are tested against the selected
 // boxes [s_lo, s_hi): NMS_THREADS / wp threads per candidate split the list (wp = wn rounded up to a power of two >= 32;
 // thread-serial loops over broadcast shared-memory reads: every lane does useful work), a hit clears the candidate's alive
 // bit (one shared-memory atomic per warp).  Callers separate this from the next read of the alive bits with a block barrier.
+// (Tried and dropped, r2o: an 8 x 8 grid of per-cell bit masks of the selected boxes, so that a candidate only tests the boxes
+// that share a cell with it -- exact, but the lookups and the insertion of table-sized boxes cost more than the tests they
+// saved: the NMS kernel went from 115 to 177 us per 64 pages.)
 __device__ __forceinline__ void suppress_window(const float4* s_gbox, const float* s_garea, unsigned* s_alive, int w0, int wn,
                                                 const float4* s_selbox, const float* s_selarea, int s_lo, int s_hi, float thr,
-                                                const CellGrid& g, int tid, int lane) {
+                                                int tid, int lane) {
     int wp = 32, sh = 5;
     while (wp < wn) { wp <<= 1; ++sh; }
     const int c = w0 + (tid & (wp - 1)), part = tid >> sh, parts = NMS_THREADS >> sh;
@@ -610,19 +590,8 @@ __device__ __forceinline__ void suppress_window(const float4* s_gbox, const floa
     if (c < w0 + wn && ((s_alive[c >> 5] >> (c & 31)) & 1u)) {
         const float4 cb = s_gbox[c];
         const float ca = s_garea[c];
-        const int x0 = grid_cell(cb.x, g.inv_cw), x1 = grid_cell(cb.z, g.inv_cw), y0 = grid_cell(cb.y, g.inv_ch), y1 = grid_cell(cb.w, g.inv_ch);
-        const bool few = (x1 - x0 + 1) * (y1 - y0 + 1) <= 4;          // else: test against everything (large boxes are rare and early)
-        int curw = -1;
-        unsigned near = ~0u;                                // bits of word `curw`: selected boxes that share a cell with the candidate
-        for (int s = s_lo + part; s < s_hi && !dead; s += parts) {
-            if (few && (s >> 5) != curw) {
-                curw = s >> 5;
-                near = 0u;
-                for (int y = y0; y <= y1; ++y)
-                    for (int x = x0; x <= x1; ++x) near |= g.bits[(y * GRID + x) * g.words + curw];
-            }
-            if ((near >> (s & 31)) & 1u) dead = iou_exceeds(cb, ca, s_selbox[s], s_selarea[s], thr);
-        }
+        for (int s = s_lo + part; s < s_hi && !dead; s += parts)
+            dead = iou_exceeds(cb, ca, s_selbox[s], s_selarea[s], thr);
     }
     const unsigned m = __ballot_sync(0xffffffffu, dead);
     if (m != 0u && lane == 0) atomicAnd(&s_alive[c >> 5], ~m);      // a warp's 32 candidates are one word of the bit set
@@ -637,12 +606,6 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     unsigned short* s_hist = reinterpret_cast<unsigned short*>(s_key2 + NMS_CHUNK);              // group x digit histogram,
     unsigned* s_slot2 = reinterpret_cast<unsigned*>(s_hist + RDX_GROUPS * RDX_PITCH);             // second payload buffer (SLOT)
     float* s_selarea = reinterpret_cast<float*>(s_slot2 + (SLOT ? NMS_CHUNK : 0));
-    CellGrid grid;
-    grid.bits = reinterpret_cast<unsigned*>(s_selarea + p.max_det);
-    grid.words = (p.max_det + 31) >> 5;
-    // page extent: the clip rectangle on the fused path; unknown otherwise (every box then falls into cell (0, 0): all tests run)
-    grid.inv_cw = (DECODE && p.src.clipW > 0.0f) ? (float)GRID / p.src.clipW : 0.0f;
-    grid.inv_ch = (DECODE && p.src.clipH > 0.0f) ? (float)GRID / p.src.clipH : 0.0f;
     __shared__ unsigned s_base[RDX_BINS], s_ws[RDX_BINS / 32];
     __shared__ unsigned short s_qoff[4][RDX_BINS];          // radix sort: per digit, the offsets of the four quarters of groups
 
@@ -677,7 +640,6 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     unsigned long long upper = ~0ull;   // keys >= upper have been visited (no key equals ~0: its score bits would be a NaN's)
     int visited = 0, nsel = 0, round = 0, bis = 0;
     if (tid == 0) { s_nsel = 0; s_kmax = 0u; s_loaded = 0; }
-    for (int i = threadIdx.x; i < GRID * GRID * grid.words; i += NMS_THREADS) grid.bits[i] = 0u;
     if (tid < 4) s_cnt[0][tid] = 0u;
     __syncthreads();
     // The slab's keys are read ONCE into registers (8 per thread) when the slab has <= 8192 candidates -- the
@@ -911,7 +873,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                     }
                     __syncthreads();
                     if (p.nms && nsel > 0)
-                        suppress_window(s_gbox, s_garea, s_alive, gdone, wn, s_selbox, s_selarea, 0, nsel, p.iou_thr, grid, tid, lane);
+                        suppress_window(s_gbox, s_garea, s_alive, gdone, wn, s_selbox, s_selarea, 0, nsel, p.iou_thr, tid, lane);
                     gdone += wn;
                     continue;
                 }
@@ -952,7 +914,6 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                         const int at_sel = nsel + __popc(keep & ((1u << lane) - 1u));
                         s_selbox[at_sel] = s_gbox[pos];
                         s_selarea[at_sel] = s_garea[pos];
-                        grid_insert(grid, s_gbox[pos], at_sel);
                         const size_t at = (size_t)seg * p.max_det + at_sel;
                         p.kept_key[at] = s_key[g0 + pos];
                         p.kept_box[at] = s_graw[pos];
@@ -965,7 +926,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                 nsel = s_nsel;
                 // (c) the new selections act on the rest of the open window at once
                 if (p.nms && nsel > n_old && nsel < p.max_det)
-                    suppress_window(s_gbox, s_garea, s_alive, 0, gdone, s_selbox, s_selarea, n_old, nsel, p.iou_thr, grid, tid, lane);
+                    suppress_window(s_gbox, s_garea, s_alive, 0, gdone, s_selbox, s_selarea, n_old, nsel, p.iou_thr, tid, lane);
                 RN_PHASE(5);
             }
             __syncthreads();                                // the group's arrays are rewritten next
@@ -1234,7 +1195,7 @@ unsigned host_f2ord(float f) {
 
 size_t nms_dynamic_smem(int max_det) {      // selected boxes + areas, the radix sort's second buffers and histogram
     return (size_t)max_det * (sizeof(float4) + sizeof(float)) + (size_t)NMS_CHUNK * (sizeof(unsigned long long) + sizeof(unsigned)) +
-           (size_t)RDX_GROUPS * RDX_PITCH * sizeof(unsigned short) + (size_t)GRID * GRID * ((max_det + 31) / 32) * sizeof(unsigned);
+           (size_t)RDX_GROUPS * RDX_PITCH * sizeof(unsigned short);
 }
 
 std::atomic<int> g_phase_timing{0};
