@@ -15,7 +15,7 @@ anchors = np.asarray(rn.anchors_for_shape(HW + (3,)))
 _, anns = synthetic.training_batch(3, batch=B)
 cls, reg = synthetic.inference_predictions(3, B, anchors, anns, classes=1)
 cls_d, reg_d = torch.from_numpy(cls).cuda(), torch.from_numpy(reg).cuda()
-names = ["bisection select", "gather", "sort (radix on score words; bitonic on ties)", "group fetch/decode", "(a) windows + in-batch tests", "(b) resolve + eager", "sweep between rounds"]
+names = ["bisection select", "gather", "sort (warp bitonic + merge levels)", "group fetch/decode", "(a) windows + in-batch tests", "(b) resolve + eager", "sweep between rounds", "rank the alive (per batch/window)", "open a window (vs all selected)"]
 rn._lib.load().rn_debug_nms_timing(1)
 for topk in (0, 1000):
     head = rn.DetectionHead(pre_nms_top_k=topk)
@@ -23,8 +23,10 @@ for topk in (0, 1000):
         head([(B,) + HW + (3,), reg_d, cls_d])
     torch.cuda.synchronize()
     ws = [v for k, v in rn._lib._scratch.items() if k[0] == "filter"][0]
-    t = ws[:64].view(torch.int64).cpu().numpy().astype(np.float64)
-    slowest, t = t[7], t[:7]
+    raw = ws[:128].view(torch.int64).cpu().numpy().astype(np.float64)
+    slowest, t = raw[7], np.concatenate([raw[:7], raw[8:10]])
     print("pre_nms_top_k=%d: ticks per segment (thread 0): mean %.0f, slowest CTA %.0f" % (topk, t.sum() / B, slowest))
     for n, v in zip(names, t):
         print("   %-30s %8.0f  %5.1f%%" % (n, v / B, 100 * v / t.sum()))
+    print("   per page: %.1f batches, %.1f windows, %.0f candidates sorted in %.2f rounds, %.0f selected, %.0f above the threshold"
+          % tuple(raw[k] / B for k in (10, 11, 12, 14, 13, 15)))

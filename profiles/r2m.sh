@@ -3,7 +3,7 @@ set -u
 OUT=gpurun_out
 mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/r2m_pytest.log 2>&1; echo "pytest_exit=$?"; grep -v "^frame" $OUT/r2m_pytest.log | tail -3
-timeout 300 python profiles/nms_phases.py > $OUT/r2m_nms_phases.log 2>&1; head -9 $OUT/r2m_nms_phases.log
+timeout 300 python profiles/nms_phases.py > $OUT/r2m_nms_phases.log 2>&1; head -13 $OUT/r2m_nms_phases.log
 python __graft_entry__.py --smoke > $OUT/r2m_smoke.log 2>&1; echo "smoke_exit=$?"; tail -2 $OUT/r2m_smoke.log
 timeout 900 python bench.py > $OUT/r2m_bench.json 2> $OUT/r2m_bench.err
 echo "bench_exit=$?"; tail -2 $OUT/r2m_bench.err

@@ -670,7 +670,10 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
 // ------------------------------------------------------------------------------------------------
 constexpr int K32_G = 32;
 constexpr int K32_A = 9;
-constexpr int K32_XT = 2;              // x tiles (of 32 columns) a CTA walks: everything that depends on (anchor type, rows, table)
+#ifndef RN_K32_XT
+#define RN_K32_XT 3
+#endif
+constexpr int K32_XT = RN_K32_XT;            // x tiles (of 32 columns) a CTA walks: everything that depends on (anchor type, rows, table)
                                        // only -- intersection heights, the y-target table, the border mask, the tile decode and the
                                        // staged tables -- is computed once for all of them.  (A/B on one box, profiles/r2h_sweep_k1.log:
                                        // 2 tiles 48.7 us / 31.0 M warp-instructions, 1 tile 51.3 us / 33.4 M, outputs bit-identical.)

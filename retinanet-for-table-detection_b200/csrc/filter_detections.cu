@@ -335,13 +335,15 @@ __device__ __forceinline__ float4 finish_box(const BoxSource& s, int n, const fl
 // ------------------------------------------------------------------------------------------------
 // K4 + K5
 // ------------------------------------------------------------------------------------------------
+struct IouTest { float thr, r; int plain; };    // see iou_exceeds()
+
 struct NmsParams {
     Slabs sl;
     BoxSource src;
     int S;                 // segments
     int segs_per_page;     // C (class specific) or 1
     int nms;
-    float iou_thr;
+    IouTest iou;           // threshold + the derived constants of iou_exceeds()
     int max_det;
     int pre_nms_top_k;
     unsigned key_floor_hi;         // every key's upper (score) word is >= this (the score threshold's image; 0 = unknown)
@@ -351,39 +353,48 @@ struct NmsParams {
     float4* kept_box;              // (S, max_det)
     int* kept_label;               // (S, max_det)
     int* status;                   // (pages) or nullptr
-    unsigned long long* timing;    // 8 phase counters (clock64 ticks of thread 0, summed over CTAs) or nullptr
+    unsigned long long* timing;    // 16 phase counters / event counts (clock64 ticks of thread 0, summed over CTAs) or nullptr
 };
 
-// TF non_max_suppression_op.cc IOU on corner-normalised boxes with precomputed areas: IoU = 0 when an area is not
-// positive, else inter / (area_a + area_b - inter); suppression iff IoU > thr (strict).  The quotient is only evaluated
-// when the product form cannot decide: inter > thr * union * (1 + 1e-4) implies RN(inter / union) > thr and
-// inter < thr * union * (1 - 1e-4) implies RN(inter / union) <= thr (fp32 rounding errors are ~1e-7), so the main path is
-// straight-line code without a divide and the outcome is bit-identical to always dividing.
-__device__ __noinline__ bool iou_exceeds_exact(float inter, float uni, float thr) { return inter / uni > thr; }
+// TF non_max_suppression_op.cc IOU on corner-normalised boxes: IoU = 0 when an area is not positive, else
+// inter / (area_a + area_b - inter); suppression iff IoU > thr (strict).
+//   IoU > thr  <=>  inter > thr (area_a + area_b - inter)  <=>  inter > R (area_a + area_b),  R = thr / (1 + thr),
+// so every box carries its WEIGHT w = R * area (+inf when the area is not positive: such a box never suppresses nor is
+// suppressed) and the test is inter > w_a + w_b: 4 min/max, 2 subtractions, one clamp, one product, one sum.  The fp32
+// quotient of the reference is only evaluated when that cannot decide: the IoU grows at least as fast (relatively) as
+// inter does, so inter > (w_a + w_b)(1 + 1e-4) implies RN(inter / union) > thr and inter < (w_a + w_b)(1 - 1e-4) implies
+// RN(inter / union) <= thr (the fp32 rounding errors of either side are ~1e-7) -- the outcome is bit-identical to always
+// dividing.  Thresholds outside [1e-3, 1e3] (and NaN) take the plain formula (`plain`: the weights are the areas then).
+__device__ __forceinline__ float box_area(const float4 c) { return (c.z - c.x) * (c.w - c.y); }
+__device__ __forceinline__ float box_weight(const float area, const IouTest t) {
+    return t.plain ? area : (area > 0.0f ? t.r * area : __int_as_float(0x7f800000));
+}
 
-__device__ __forceinline__ bool iou_exceeds(const float4 a, const float aa, const float4 b, const float ab, const float thr) {
-    if (thr < 0.0f) {                       // degenerate threshold (kernel-uniform): the plain formula
+__device__ __noinline__ bool iou_exceeds_exact(const float4 a, const float4 b, float inter, float thr) {
+    const float aa = box_area(a), ab = box_area(b);
+    return (aa > 0.0f && ab > 0.0f) && (inter / (aa + ab - inter) > thr);
+}
+
+__device__ __forceinline__ bool iou_exceeds(const float4 a, const float wa, const float4 b, const float wb, const IouTest t) {
+    if (t.plain) {                          // degenerate threshold (kernel-uniform): the plain formula on the areas
         float iou = 0.0f;
-        if (aa > 0.0f && ab > 0.0f) {
+        if (wa > 0.0f && wb > 0.0f) {
             const float iw = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.0f);
             const float ih = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.0f);
             const float inter = iw * ih;
-            iou = inter / (aa + ab - inter);
+            iou = inter / (wa + wb - inter);
         }
-        return iou > thr;
+        return iou > t.thr;
     }
-    const float iw = fminf(a.z, b.z) - fmaxf(a.x, b.x);
+    const float iw = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.0f);     // clamping ONE side is enough: inter <= 0 then
     const float ih = fminf(a.w, b.w) - fmaxf(a.y, b.y);
     const float inter = iw * ih;
-    const float uni = aa + ab - inter;
-    const float t = thr * uni;
-    const bool overlap = (iw > 0.0f) && (ih > 0.0f) && (aa > 0.0f) && (ab > 0.0f);
-    const bool sure = overlap && (inter > t * 1.0001f);
-    const bool maybe = overlap && !sure && (inter > t * 0.9999f);
-    if (maybe) return iou_exceeds_exact(inter, uni, thr);    // ~1e-4 of the overlapping pairs
+    const float rhs = wa + wb;                                            // > 0, or +inf
+    const bool sure = inter > rhs * 1.0001f;
+    const bool maybe = !sure && (inter > rhs * 0.9999f);
+    if (maybe) return iou_exceeds_exact(a, b, inter, t.thr);             // ~1e-4 of the overlapping pairs
     return sure;
 }
-
 
 // Descending bitonic sort of n (power of two, 128 <= n <= NMS_CHUNK) (key, slot) pairs in shared memory.
 // Each of the first n/2 threads keeps 2 adjacent elements in registers (all 1024 threads are busy at n = 2048, so
@@ -442,120 +453,124 @@ __device__ __forceinline__ void sort_chunk_desc(unsigned long long* s_key, unsig
     __syncthreads();
 }
 
-// LSD radix sort of the chunk by the keys' upper (score) word, descending, 8 bits per pass over the bits in which the chunk's
-// score words can differ at all (they lie in [lo_hi, hi_hi]: <= 24 bits = 3 passes for the scores of one chunk).  A
-// thread holds the elements at positions tid and tid + 1024; per pass: a 64 x 256 histogram (64 groups of 32 consecutive
-// positions; __match_any_sync ranks the members of a group that share a digit and one of them writes the count), a scan per
-// digit over the groups, a scan over the digits, and a stable scatter into the second buffer.  ~90 instructions per thread
-// and pass instead of ~50 per stage of a 66-stage bitonic network.  The lower (anchor) word is NOT sorted: equal scores are
-// rare, so the caller checks the order of neighbours with equal score words afterwards (return value) and only then falls
-// back to the bitonic network.  n2p: padded size (power of two >= 128, padding keys are 0 and sort last).
-constexpr int RDX_BITS = 8, RDX_BINS = 1 << RDX_BITS, RDX_GROUPS = NMS_CHUNK / 32;
-constexpr int RDX_PITCH = RDX_BINS + 2;                     // histogram row pitch (u16)
-static_assert(RDX_GROUPS == 64 && RDX_BINS * 4 == NMS_THREADS, "the scans below assume 256 digits x 4 quarters of 16 groups");
-
-template <bool SLOT>
-__device__ __forceinline__ bool radix_sort_desc(unsigned long long* s_key, unsigned* s_slot, unsigned long long* s_key2, unsigned* s_slot2,
-                                                unsigned short* s_hist, unsigned short (*s_qoff)[RDX_BINS], unsigned* s_base, unsigned* s_ws,
-                                                const int n2p, const int loaded,
-                                                const unsigned lo_hi, const unsigned hi_hi, const int tid) {
-    const int lane = tid & 31, warp = tid >> 5;
-    const bool one = tid < n2p, two = n2p > NMS_THREADS;     // warp-uniform: n2p is a multiple of 32
-    unsigned long long k0 = one ? s_key[tid] : 0ull, k1 = two ? s_key[tid + NMS_THREADS] : 0ull;
-    unsigned v0 = 0u, v1 = 0u;
-    if (SLOT) { v0 = one ? s_slot[tid] : 0u; v1 = two ? s_slot[tid + NMS_THREADS] : 0u; }
-    const unsigned diff = lo_hi ^ hi_hi;
-    const int topbit = diff ? 31 - __clz(diff) : -1;         // the score words agree above this bit
-    const unsigned lt = (1u << lane) - 1u;
-    for (int shift = 0; shift <= topbit; shift += RDX_BITS) {
-        for (int i = tid; i < RDX_GROUPS * RDX_PITCH / 2; i += NMS_THREADS) reinterpret_cast<unsigned*>(s_hist)[i] = 0u;
-        __syncthreads();
-        // digit, inverted so that bin 0 holds the largest scores; rank among the group members with the same digit
-        unsigned d0 = 0u, d1 = 0u, r0 = 0u, r1 = 0u;
-        if (one) {
-            d0 = (RDX_BINS - 1) - (((unsigned)(k0 >> 32) >> shift) & (RDX_BINS - 1));
-            const unsigned peers = __match_any_sync(0xffffffffu, d0);
-            r0 = __popc(peers & lt);
-            if (r0 == 0u) s_hist[warp * RDX_PITCH + d0] = (unsigned short)__popc(peers);
-        }
-        if (two) {
-            d1 = (RDX_BINS - 1) - (((unsigned)(k1 >> 32) >> shift) & (RDX_BINS - 1));
-            const unsigned peers = __match_any_sync(0xffffffffu, d1);
-            r1 = __popc(peers & lt);
-            if (r1 == 0u) s_hist[(warp + 32) * RDX_PITCH + d1] = (unsigned short)__popc(peers);
-        }
-        __syncthreads();
-        // per digit: exclusive scan over the 64 groups -- thread (digit, quarter) walks 16 groups in place, the quarters' sums
-        // become offsets that are added at scatter time (one 64-step walk per digit was a long dependent chain; a shuffle scan
-        // per digit cost all 32 warps 320 instructions) -- then the scan over the digits
-        {
-            const int d = tid & (RDX_BINS - 1), q = tid >> RDX_BITS;        // 1024 threads = 256 digits x 4 quarters
-            unsigned run = 0u;
-#pragma unroll 4
-            for (int g = q * (RDX_GROUPS / 4); g < (q + 1) * (RDX_GROUPS / 4); ++g) {
-                const unsigned c = s_hist[g * RDX_PITCH + d];
-                s_hist[g * RDX_PITCH + d] = (unsigned short)run;
-                run += c;
-            }
-            s_qoff[q][d] = (unsigned short)run;
-        }
-        __syncthreads();
-        unsigned tot = 0u;
-        if (tid < RDX_BINS) {
-            const unsigned a0 = s_qoff[0][tid], a1 = s_qoff[1][tid], a2 = s_qoff[2][tid], a3 = s_qoff[3][tid];
-            s_qoff[0][tid] = 0; s_qoff[1][tid] = (unsigned short)a0; s_qoff[2][tid] = (unsigned short)(a0 + a1);
-            s_qoff[3][tid] = (unsigned short)(a0 + a1 + a2);
-            tot = a0 + a1 + a2 + a3;
-        }
-        unsigned incl = tot;
+// How many of the 2^SH descending keys at `part` precede x in a merge: those > x, and for an element of a pair's SECOND run
+// (second = 1) also those == x (only the zero padding is ever equal).  y >= x is y > x - 1; for x = 0 everything precedes.
+// A branch-free binary search, fully unrolled: per step ONE 32-bit read of a key's score word at a compile-time offset, one
+// compare and one predicated add.  Equal score words (rare) do not decide: such a search is repeated on the full keys.
+__device__ __noinline__ int merge_rank_full(const unsigned long long* part, const int sh, const unsigned long long t) {
+    int c = 0;
+    for (int s = (1 << sh) >> 1; s >= 1; s >>= 1) if (part[c + s - 1] > t) c += s;
+    return c + (part[c] > t ? 1 : 0);
+}
+template <int SH>
+__device__ __forceinline__ int merge_rank(const unsigned long long* part, const unsigned long long x, const int second) {
+    if (second && x == 0ull) return 1 << SH;
+    const unsigned long long t = x - (unsigned long long)second;
+    const unsigned th = (unsigned)(t >> 32);
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(part) + 4;      // the keys' upper words
+    unsigned cb = 0u;                                       // the count, in bytes (8 per key)
+    bool tie = false;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        if (tid < RDX_BINS && lane == 31) s_ws[warp] = incl;
-        __syncthreads();
-        if (tid < RDX_BINS) {
-            unsigned off = 0u;
-            for (int w = 0; w < warp; ++w) off += s_ws[w];
-            s_base[tid] = off + incl - tot;
-        }
-        __syncthreads();
-        if (one) {
-            const unsigned pos = s_base[d0] + s_qoff[warp >> 4][d0] + s_hist[warp * RDX_PITCH + d0] + r0;
-            s_key2[pos] = k0;
-            if (SLOT) s_slot2[pos] = v0;
-        }
-        if (two) {
-            const unsigned pos = s_base[d1] + s_qoff[(warp + 32) >> 4][d1] + s_hist[(warp + 32) * RDX_PITCH + d1] + r1;
-            s_key2[pos] = k1;
-            if (SLOT) s_slot2[pos] = v1;
-        }
-        __syncthreads();
-        if (one) { k0 = s_key2[tid]; if (SLOT) v0 = s_slot2[tid]; }
-        if (two) { k1 = s_key2[tid + NMS_THREADS]; if (SLOT) v1 = s_slot2[tid + NMS_THREADS]; }
+    for (int s = (1 << SH) >> 1; s >= 1; s >>= 1) {
+        const unsigned y = *reinterpret_cast<const unsigned*>(base + cb + (s - 1) * 8);
+        tie |= (y == th);
+        if (y > th) cb += (unsigned)s * 8u;
     }
-    if (one) { s_key[tid] = k0; if (SLOT) s_slot[tid] = v0; }
-    if (two) { s_key[tid + NMS_THREADS] = k1; if (SLOT) s_slot[tid + NMS_THREADS] = v1; }
-    __syncthreads();
-    // Equal score words (~1 pair per page among thousands of fp32 scores) may sit in the wrong anchor order: a few rounds of
-    // odd-even transposition restricted to such pairs repair short runs; a run that is still unsorted after them (quantised
-    // scores) sends the caller to the bitonic network.
-    for (int iter = 0; iter < 6; ++iter) {
-        bool swapped = false;
+    {
+        const unsigned y = *reinterpret_cast<const unsigned*>(base + cb);
+        tie |= (y == th);
+        if (y > th) cb += 8u;
+    }
+    if (tie) return merge_rank_full(part, SH, t);
+    return (int)(cb >> 3);
+}
+
+// Merge sort of the chunk, descending, n2p a power of two in [128, NMS_CHUNK] (padding keys are 0 and end up last).
+//  1. every warp orders its 64 elements in registers (2 per lane: a bitonic network of 21 stages, 15 of them shuffles) --
+//     no barrier, all 32 warps busy;
+//  2. log2(n2p / 64) merge levels: an element's place in the merge of its run with the partner run is its index in its own
+//     run plus the number of partner elements that precede it -- a branch-free binary search (log2(run) + 1 shared-memory
+//     reads; a thread's two elements search in lockstep), then ONE store into the other buffer and ONE barrier per level.
+//     Keys are unique; the zero padding is not, so elements of the second run of a pair also count EQUAL partners.
+// ~900 instructions per thread and 6 barriers for 2048 keys.  What it replaced (r2q): an LSD radix sort on the score words
+// (4 passes of 8 bits for a chunk whose scores span 0.1 .. 0.99, 7 barriers per pass, plus a repair pass for equal scores and a
+// bitonic fall-back) took 25 k cycles per chunk, the bitonic network alone 37 k.
+// The result is in s_key (s_slot); which buffer step 1 writes to is chosen so that the last level lands there.
+template <bool SLOT>
+__device__ __forceinline__ void merge_sort_desc(unsigned long long* s_key, unsigned* s_slot, unsigned long long* s_key2, unsigned* s_slot2,
+                                                const int n2p, const int tid) {
+    int levels = 0;
+    for (int r = 64; r < n2p; r <<= 1) ++levels;
+    unsigned long long* ka = (levels & 1) ? s_key2 : s_key;
+    unsigned long long* kb = (levels & 1) ? s_key : s_key2;
+    unsigned* va = (levels & 1) ? s_slot2 : s_slot;
+    unsigned* vb = (levels & 1) ? s_slot : s_slot2;
+    {
+        const bool act = tid < (n2p >> 1);               // warp-uniform: n2p / 2 is a multiple of 32
+        const int i0 = tid * 2;
+        unsigned long long k0 = 0ull, k1 = 0ull;
+        unsigned v0 = 0u, v1 = 0u;
+        if (act) {
+            k0 = s_key[i0]; k1 = s_key[i0 + 1];
+            if (SLOT) { v0 = s_slot[i0]; v1 = s_slot[i0 + 1]; }
 #pragma unroll
-        for (int phase = 0; phase < 2; ++phase) {
-            const int i = 2 * tid + phase;
-            if (i + 1 < loaded) {
-                const unsigned long long a = s_key[i], b = s_key[i + 1];
-                if (((a >> 32) == (b >> 32)) && (a < b)) {
-                    s_key[i] = b; s_key[i + 1] = a;
-                    if (SLOT) { const unsigned t = s_slot[i]; s_slot[i] = s_slot[i + 1]; s_slot[i + 1] = t; }
-                    swapped = true;
+            for (int k = 2; k <= 64; k <<= 1) {
+                const bool desc = (k == 64) || ((i0 & k) == 0);     // the last merge leaves every 64-run descending
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    if (j >= 2) {
+                        const int lm = j >> 1;
+                        const bool lower = ((i0 & j) == 0);
+                        const unsigned long long b0 = __shfl_xor_sync(0xffffffffu, k0, lm), b1 = __shfl_xor_sync(0xffffffffu, k1, lm);
+                        unsigned w0 = 0u, w1 = 0u;
+                        if (SLOT) { w0 = __shfl_xor_sync(0xffffffffu, v0, lm); w1 = __shfl_xor_sync(0xffffffffu, v1, lm); }
+                        ce_keep<SLOT>(k0, v0, b0, w0, lower == desc);
+                        ce_keep<SLOT>(k1, v1, b1, w1, lower == desc);
+                    } else {
+                        const bool sw = desc ? (k0 < k1) : (k0 > k1);
+                        if (sw) {
+                            const unsigned long long tk = k0; k0 = k1; k1 = tk;
+                            const unsigned tv = v0; v0 = v1; v1 = tv;
+                        }
+                    }
                 }
             }
-            __syncthreads();
         }
-        if (!__syncthreads_or(swapped ? 1 : 0)) return false;       // a whole round without a swap: ordered
+        __syncthreads();                                 // (s_key may be the destination: everybody has read it)
+        if (act) { ka[i0] = k0; ka[i0 + 1] = k1; if (SLOT) { va[i0] = v0; va[i0 + 1] = v1; } }
+        __syncthreads();
     }
-    return true;
+    const bool two = n2p > NMS_THREADS, one = tid < n2p;
+#pragma unroll 1
+    for (int sh = 6; (1 << sh) < n2p; ++sh) {
+        const int r = 1 << sh;
+        const int e0 = tid, e1 = tid + NMS_THREADS;
+        const unsigned long long x0 = one ? ka[e0] : 0ull, x1 = two ? ka[e1] : 0ull;
+        int c0 = 0, c1 = 0;
+        if (one) {
+            const int run0 = e0 >> sh, run1 = e1 >> sh;
+            const unsigned long long* p0 = ka + ((run0 ^ 1) << sh);
+            const unsigned long long* p1 = ka + ((run1 ^ 1) << sh);
+            switch (sh) {                                   // (block-uniform)
+                case 6: c0 = merge_rank<6>(p0, x0, run0 & 1); if (two) c1 = merge_rank<6>(p1, x1, run1 & 1); break;
+                case 7: c0 = merge_rank<7>(p0, x0, run0 & 1); if (two) c1 = merge_rank<7>(p1, x1, run1 & 1); break;
+                case 8: c0 = merge_rank<8>(p0, x0, run0 & 1); if (two) c1 = merge_rank<8>(p1, x1, run1 & 1); break;
+                case 9: c0 = merge_rank<9>(p0, x0, run0 & 1); if (two) c1 = merge_rank<9>(p1, x1, run1 & 1); break;
+                default: c0 = merge_rank<10>(p0, x0, run0 & 1); if (two) c1 = merge_rank<10>(p1, x1, run1 & 1); break;
+            }
+            const int at0 = ((run0 >> 1) << (sh + 1)) + (e0 & (r - 1)) + c0;
+            kb[at0] = x0;
+            if (SLOT) vb[at0] = va[e0];
+            if (two) {
+                const int at1 = ((run1 >> 1) << (sh + 1)) + (e1 & (r - 1)) + c1;
+                kb[at1] = x1;
+                if (SLOT) vb[at1] = va[e1];
+            }
+        }
+        __syncthreads();
+        unsigned long long* tk = ka; ka = kb; kb = tk;
+        unsigned* tv = va; va = vb; vb = tv;
+    }
 }
 
 // ---- bisection helpers: #{keys >= pivot} for three pivots at once -------------------------------------------------
@@ -581,10 +596,9 @@ __device__ __forceinline__ void count3(unsigned long long k, unsigned long long 
 // that share a cell with it -- exact, but the lookups and the insertion of table-sized boxes cost more than the tests they
 // saved: the NMS kernel went from 115 to 177 us per 64 pages.)
 __device__ __forceinline__ void suppress_window(const float4* s_gbox, const float* s_garea, unsigned* s_alive, int w0, int wn,
-                                                const float4* s_selbox, const float* s_selarea, int s_lo, int s_hi, float thr,
+                                                const float4* s_selbox, const float* s_selarea, int s_lo, int s_hi, const IouTest thr,
                                                 int tid, int lane) {
-    int wp = 32, sh = 5;
-    while (wp < wn) { wp <<= 1; ++sh; }
+    const int sh = max(5, 32 - __clz(wn - 1)), wp = 1 << sh;     // wn in [1, 256]
     const int c = w0 + (tid & (wp - 1)), part = tid >> sh, parts = NMS_THREADS >> sh;
     bool dead = false;
     if (c < w0 + wn && ((s_alive[c >> 5] >> (c & 31)) & 1u)) {
@@ -602,12 +616,9 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // dynamic: selected boxes (normalised corners) + areas, sized by max_det
     float4* s_selbox = reinterpret_cast<float4*>(smem_raw);
-    unsigned long long* s_key2 = reinterpret_cast<unsigned long long*>(s_selbox + p.max_det);   // radix sort: second key buffer,
-    unsigned short* s_hist = reinterpret_cast<unsigned short*>(s_key2 + NMS_CHUNK);              // group x digit histogram,
-    unsigned* s_slot2 = reinterpret_cast<unsigned*>(s_hist + RDX_GROUPS * RDX_PITCH);             // second payload buffer (SLOT)
+    unsigned long long* s_key2 = reinterpret_cast<unsigned long long*>(s_selbox + p.max_det);   // merge sort: second key buffer,
+    unsigned* s_slot2 = reinterpret_cast<unsigned*>(s_key2 + NMS_CHUNK);                         // second payload buffer (SLOT)
     float* s_selarea = reinterpret_cast<float*>(s_slot2 + (SLOT ? NMS_CHUNK : 0));
-    __shared__ unsigned s_base[RDX_BINS], s_ws[RDX_BINS / 32];
-    __shared__ unsigned short s_qoff[4][RDX_BINS];          // radix sort: per digit, the offsets of the four quarters of groups
 
     __shared__ unsigned long long s_key[NMS_CHUNK];
     __shared__ unsigned s_slot[SLOT ? NMS_CHUNK : 1];
@@ -636,6 +647,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     // optional phase timing (rn_debug_nms_timing(1)): thread 0 accumulates clock64() deltas per phase
     long long t_mark = p.timing ? clock64() : 0;
     const long long t_start = t_mark;
+#define RN_COUNT(k, v) do { if (p.timing && tid == 0) atomicAdd(p.timing + (k), (unsigned long long)(v)); } while (0)
 #define RN_PHASE(k) do { if (p.timing && tid == 0) { const long long now = clock64(); atomicAdd(p.timing + (k), (unsigned long long)(now - t_mark)); t_mark = now; } } while (0)
     unsigned long long upper = ~0ull;   // keys >= upper have been visited (no key equals ~0: its score bits would be a NaN's)
     int visited = 0, nsel = 0, round = 0, bis = 0;
@@ -742,9 +754,9 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                     const float4 r = finish_box<DECODE>(p.src, n, fetch_row(p.src, page, n));
                     float4 c;
                     c.x = fminf(r.x, r.z); c.y = fminf(r.y, r.w); c.z = fmaxf(r.x, r.z); c.w = fmaxf(r.y, r.w);
-                    const float ca = (c.z - c.x) * (c.w - c.y);
+                    const float ca = box_weight(box_area(c), p.iou);
                     bool dead = false;
-                    for (int sI = 0; sI < nsel && !dead; ++sI) dead = iou_exceeds(c, ca, s_selbox[sI], s_selarea[sI], p.iou_thr);
+                    for (int sI = 0; sI < nsel && !dead; ++sI) dead = iou_exceeds(c, ca, s_selbox[sI], s_selarea[sI], p.iou);
                     if (dead) { rk[t] = 0ull; ++killed; }
                 }
             }
@@ -808,15 +820,12 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
         for (int i = loaded + tid; i < n2p; i += NMS_THREADS) { s_key[i] = 0ull; if (SLOT) s_slot[i] = 0u; }
         __syncthreads();
         RN_PHASE(1);
-        // ---------------- bitonic network, descending (keys are unique) ----------------------------
-        {
-            const unsigned long long hb = (top != 0ull && top < upper) ? top : upper;      // the chunk's keys are below this
-            const unsigned lo_hi = thr_key ? (unsigned)(thr_key >> 32) : p.key_floor_hi, hi_hi = (unsigned)(hb >> 32);
-            if (n2p <= 128 || radix_sort_desc<SLOT>(s_key, s_slot, s_key2, s_slot2, s_hist, s_qoff, s_base, s_ws, n2p, loaded, lo_hi, hi_hi, tid))
-                sort_chunk_desc<SLOT>(s_key, s_slot, n2p, tid);     // tiny chunks, or equal scores met in the wrong anchor order
-        }
+        // ---------------- order the chunk, descending (keys are unique) ----------------------------
+        merge_sort_desc<SLOT>(s_key, s_slot, s_key2, s_slot2, n2p, tid);
         const int chunk_n = min(loaded, limit - visited);
         RN_PHASE(2);
+        RN_COUNT(12, loaded);
+        RN_COUNT(14, 1);
         // ---------------- K5: greedy NMS over the ordered chunk -------------------------------------------
         // boxes arrive one group (256 candidates) ahead: the row is requested here, decoded when its group starts
         float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -829,7 +838,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                     float4 c;
                     c.x = fminf(r.x, r.z); c.y = fminf(r.y, r.w); c.z = fmaxf(r.x, r.z); c.w = fmaxf(r.y, r.w);
                     s_graw[tid] = r; s_gbox[tid] = c;
-                    s_garea[tid] = (c.z - c.x) * (c.w - c.y);
+                    s_garea[tid] = box_weight(box_area(c), p.iou);
                 }
                 const int nx = g0 + NMS_GROUP + tid;
                 if (nx < chunk_n) nxt = fetch_row(p.src, page, (int)key_idx(s_key[nx]));
@@ -859,13 +868,14 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                     if (tid == NMS_GROUP - 1) s_alive_total = before + __popc(word);
                 }
                 __syncthreads();
+                RN_PHASE(8);
                 const int alive_total = s_alive_total;
                 if (alive_total == 0) {                     // block-uniform
                     if (gdone >= gn) break;
                     // ... and no wider than ~6 k pair tests at opening: a candidate of an open window is tested against every
                     // later selection as well, so what is opened but never consumed (behind the stopping point) is pure waste
                     const int room = p.max_det - nsel;
-                    const int by_cost = max(32, (6144 / max(nsel, 24)) & ~31);
+                    const int by_cost = max(32, (int)(__fdividef(6144.0f, (float)max(nsel, 24)) + 0.01f) & ~31);
                     const int wn = min(gn - gdone, min(by_cost, (room + (room >> 2) + 47) & ~31));   // a multiple of 32 unless it ends the group
                     if (tid < NMS_GROUP / 32) {             // (nobody reads the alive words between the barrier above and the next)
                         const int left = gdone + wn - tid * 32, skip = gdone - tid * 32;    // gdone is a multiple of 32
@@ -873,10 +883,13 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                     }
                     __syncthreads();
                     if (p.nms && nsel > 0)
-                        suppress_window(s_gbox, s_garea, s_alive, gdone, wn, s_selbox, s_selarea, 0, nsel, p.iou_thr, tid, lane);
+                        suppress_window(s_gbox, s_garea, s_alive, gdone, wn, s_selbox, s_selarea, 0, nsel, p.iou, tid, lane);
                     gdone += wn;
+                    RN_PHASE(9);
+                    RN_COUNT(11, 1);
                     continue;
                 }
+                RN_COUNT(10, 1);
                 const int bn = min(NMS_BATCH, alive_total);
                 const int pos = lane < bn ? (int)s_bpos[lane] : 0;
                 // warp w owns batch member w: one ballot over the later members gives row w of the in-batch suppression matrix
@@ -885,7 +898,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                     if (p.nms) {
                         const int mine = __shfl_sync(0xffffffffu, pos, warp);
                         const bool hit = (lane > warp) && (lane < bn) &&
-                                         iou_exceeds(s_gbox[mine], s_garea[mine], s_gbox[pos], s_garea[pos], p.iou_thr);
+                                         iou_exceeds(s_gbox[mine], s_garea[mine], s_gbox[pos], s_garea[pos], p.iou);
                         vict = __ballot_sync(0xffffffffu, hit);
                     }
                     if (lane == 0) s_vict[warp] = vict;
@@ -926,7 +939,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                 nsel = s_nsel;
                 // (c) the new selections act on the rest of the open window at once
                 if (p.nms && nsel > n_old && nsel < p.max_det)
-                    suppress_window(s_gbox, s_garea, s_alive, 0, gdone, s_selbox, s_selarea, n_old, nsel, p.iou_thr, tid, lane);
+                    suppress_window(s_gbox, s_garea, s_alive, 0, gdone, s_selbox, s_selarea, n_old, nsel, p.iou, tid, lane);
                 RN_PHASE(5);
             }
             __syncthreads();                                // the group's arrays are rewritten next
@@ -942,8 +955,11 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
         if (chunk_n == 0) break;                            // defensive: no progress is impossible while visited < limit
     }
     if (tid == 0) p.kept_count[seg] = nsel;
+    RN_COUNT(13, nsel);
+    RN_COUNT(15, cnt);
     if (p.timing && tid == 0) atomicMax(p.timing + 7, (unsigned long long)(clock64() - t_start));   // the slowest CTA
 #undef RN_PHASE
+#undef RN_COUNT
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1173,7 +1189,7 @@ FilterWs carve(void* ws, int B, int S, long long cap, int max_det, bool agnostic
     size_t off = 0;
     char* base = reinterpret_cast<char*>(ws);
     auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align256(bytes); return p; };
-    w.timing = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * 8));   // first 64 bytes
+    w.timing = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * 16));  // first 128 bytes
     w.counts = reinterpret_cast<int*>(take(sizeof(int) * S));
     w.kept_count = reinterpret_cast<int*>(take(sizeof(int) * S));
     w.status = reinterpret_cast<int*>(take(sizeof(int) * B));
@@ -1193,9 +1209,8 @@ unsigned host_f2ord(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-size_t nms_dynamic_smem(int max_det) {      // selected boxes + areas, the radix sort's second buffers and histogram
-    return (size_t)max_det * (sizeof(float4) + sizeof(float)) + (size_t)NMS_CHUNK * (sizeof(unsigned long long) + sizeof(unsigned)) +
-           (size_t)RDX_GROUPS * RDX_PITCH * sizeof(unsigned short);
+size_t nms_dynamic_smem(int max_det) {      // selected boxes + weights, the merge sort's second buffers
+    return (size_t)max_det * (sizeof(float4) + sizeof(float)) + (size_t)NMS_CHUNK * (sizeof(unsigned long long) + sizeof(unsigned));
 }
 
 std::atomic<int> g_phase_timing{0};
@@ -1248,7 +1263,8 @@ int run_back_end(const FilterWs& w, const BoxSource& src, bool decode, int B, in
     NmsParams np;
     np.sl.counts = w.counts; np.sl.keys = w.keys; np.sl.labels = w.labels; np.sl.cap = cap;
     np.src = src;
-    np.S = S; np.segs_per_page = segs_per_page; np.nms = nms; np.iou_thr = nms_thr;
+    np.S = S; np.segs_per_page = segs_per_page; np.nms = nms; np.iou.thr = nms_thr; np.iou.plain = !(nms_thr >= 1e-3f && nms_thr <= 1e3f);
+    np.iou.r = np.iou.plain ? 0.0f : (float)((double)nms_thr / (1.0 + (double)nms_thr));
     np.max_det = max_det; np.pre_nms_top_k = pre_nms_top_k; np.key_floor_hi = key_floor_hi;
     np.kept_count = w.kept_count; np.kept_key = w.kept_key; np.kept_box = w.kept_box; np.kept_label = w.kept_label;
     np.status = status;
