@@ -15,7 +15,8 @@ anchors = np.asarray(rn.anchors_for_shape(HW + (3,)))
 _, anns = synthetic.training_batch(3, batch=B)
 cls, reg = synthetic.inference_predictions(3, B, anchors, anns, classes=1)
 cls_d, reg_d = torch.from_numpy(cls).cuda(), torch.from_numpy(reg).cuda()
-names = ["bisection select", "gather", "sort (warp bitonic + merge levels)", "group fetch/decode", "(a) windows + in-batch tests", "(b) resolve + eager", "sweep between rounds", "rank the alive (per batch/window)", "open a window (vs all selected)"]
+names = [  # phases end at block barriers: thread 0's clock is the block's
+         "bisection select", "gather", "sort (warp bitonic + merge levels)", "group fetch/decode", "in-batch tests", "resolve (warp 0)", "sweep between rounds", "rank the alive (per batch/window)", "open a window (vs all selected)", "eager (new selections vs open window)"]
 rn._lib.load().rn_debug_nms_timing(1)
 for topk in (0, 1000):
     head = rn.DetectionHead(pre_nms_top_k=topk)
@@ -23,10 +24,18 @@ for topk in (0, 1000):
         head([(B,) + HW + (3,), reg_d, cls_d])
     torch.cuda.synchronize()
     ws = [v for k, v in rn._lib._scratch.items() if k[0] == "filter"][0]
-    raw = ws[:128].view(torch.int64).cpu().numpy().astype(np.float64)
-    slowest, t = raw[7], np.concatenate([raw[:7], raw[8:10]])
+    full = ws[:2048].view(torch.int64).cpu().numpy()
+    raw = ws[:256].view(torch.int64).cpu().numpy().astype(np.float64)
+    slowest, t = raw[7], np.concatenate([raw[:7], raw[8:10], raw[17:18]])
     print("pre_nms_top_k=%d: ticks per segment (thread 0): mean %.0f, slowest CTA %.0f" % (topk, t.sum() / B, slowest))
     for n, v in zip(names, t):
         print("   %-30s %8.0f  %5.1f%%" % (n, v / B, 100 * v / t.sum()))
-    print("   per page: %.1f batches, %.1f windows, %.0f candidates sorted in %.2f rounds, %.0f selected, %.0f above the threshold"
-          % tuple(raw[k] / B for k in (10, 11, 12, 14, 13, 15)))
+    print("   per page: %.1f batches, %.1f windows (%.0f candidates opened), %.0f candidates sorted in %.2f rounds, %.0f selected, %.0f above the threshold"
+          % tuple(raw[k] / B for k in (10, 11, 16, 12, 14, 13, 15)))
+    if topk == 0:
+        print("   first 56 pages: ticks, above threshold, sorted, opened, rounds, batches, windows")
+        rec = full[32:].reshape(56, 4)
+        for i in np.argsort(-rec[:, 0]):
+            r = rec[i]
+            print("   page %2d %7d  %5d %5d %5d  %d  %3d %3d" % (i, r[0], r[1] & 0xffffffff, r[1] >> 32, r[2] & 0xffffffff, r[2] >> 32,
+                                                                 r[3] & 0xffffffff, r[3] >> 32))

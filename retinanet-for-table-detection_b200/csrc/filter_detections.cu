@@ -353,7 +353,7 @@ struct NmsParams {
     float4* kept_box;              // (S, max_det)
     int* kept_label;               // (S, max_det)
     int* status;                   // (pages) or nullptr
-    unsigned long long* timing;    // 16 phase counters / event counts (clock64 ticks of thread 0, summed over CTAs) or nullptr
+    unsigned long long* timing;    // 32 phase counters / event counts (clock64 ticks of thread 0, summed over CTAs) + 56 segment records, or nullptr
 };
 
 // TF non_max_suppression_op.cc IOU on corner-normalised boxes: IoU = 0 when an area is not positive, else
@@ -588,15 +588,40 @@ __device__ __forceinline__ void count3(unsigned long long k, unsigned long long 
     c3 += (live && k >= q3) ? 1u : 0u;
 }
 
+// A selected box as the suppression loops read it: corners + weight in ONE 32-byte record (one address register, two reads)
+struct __align__(16) SelRec { float4 box; float w; float pad[3]; };
+
+// shared-memory access by 32-bit shared address.  The base of an array carved out of the dynamic shared memory is a value the
+// compiler re-derives wherever it is used (S2UR SR_CgaCtaId + 4 uniform instructions, inside the loops); pinned in a register
+// once (smem_pin) and advanced by hand, the loops below carry one address and nothing else.
+__device__ __forceinline__ unsigned smem_pin(const void* p) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ float4 lds128(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+template <int IMM>
+__device__ __forceinline__ float lds32f(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1 + %2];" : "=f"(v) : "r"(a), "n"(IMM));
+    return v;
+}
+
 // The alive candidates [w0, w0 + wn) of the current group (wn <= 256, w0 a multiple of 32) are tested against the selected
 // boxes [s_lo, s_hi): NMS_THREADS / wp threads per candidate split the list (wp = wn rounded up to a power of two >= 32;
 // thread-serial loops over broadcast shared-memory reads: every lane does useful work), a hit clears the candidate's alive
 // bit (one shared-memory atomic per warp).  Callers separate this from the next read of the alive bits with a block barrier.
+// The loop is 17 instructions per test: two reads, the 13 of the test with ONE compare (inter > 0.9999 (w_a + w_b): a hit or
+// a near-hit, rare) and the loop's own three.
 // (Tried and dropped, r2o: an 8 x 8 grid of per-cell bit masks of the selected boxes, so that a candidate only tests the boxes
 // that share a cell with it -- exact, but the lookups and the insertion of table-sized boxes cost more than the tests they
 // saved: the NMS kernel went from 115 to 177 us per 64 pages.)
 __device__ __forceinline__ void suppress_window(const float4* s_gbox, const float* s_garea, unsigned* s_alive, int w0, int wn,
-                                                const float4* s_selbox, const float* s_selarea, int s_lo, int s_hi, const IouTest thr,
+                                                const SelRec* s_sel, int s_lo, int s_hi, const IouTest thr,
                                                 int tid, int lane) {
     const int sh = max(5, 32 - __clz(wn - 1)), wp = 1 << sh;     // wn in [1, 256]
     const int c = w0 + (tid & (wp - 1)), part = tid >> sh, parts = NMS_THREADS >> sh;
@@ -604,8 +629,25 @@ __device__ __forceinline__ void suppress_window(const float4* s_gbox, const floa
     if (c < w0 + wn && ((s_alive[c >> 5] >> (c & 31)) & 1u)) {
         const float4 cb = s_gbox[c];
         const float ca = s_garea[c];
-        for (int s = s_lo + part; s < s_hi && !dead; s += parts)
-            dead = iou_exceeds(cb, ca, s_selbox[s], s_selarea[s], thr);
+        if (thr.plain) {
+            for (int s = s_lo + part; s < s_hi && !dead; s += parts) dead = iou_exceeds(cb, ca, s_sel[s].box, s_sel[s].w, thr);
+        } else {
+            const unsigned base = smem_pin(s_sel);
+            unsigned at = base + (unsigned)(s_lo + part) * (unsigned)sizeof(SelRec);
+            const unsigned end = base + (unsigned)s_hi * (unsigned)sizeof(SelRec), step = (unsigned)parts * (unsigned)sizeof(SelRec);
+            while (at < end) {
+                const float4 b = lds128(at);
+                const float wb = lds32f<16>(at);
+                at += step;
+                const float iw = fmaxf(fminf(cb.z, b.z) - fmaxf(cb.x, b.x), 0.0f);
+                const float ih = fminf(cb.w, b.w) - fmaxf(cb.y, b.y);
+                const float inter = iw * ih;
+                const float rhs = ca + wb;
+                if (inter > rhs * 0.9999f) {                // a hit, or too close to call without the quotient
+                    if (inter > rhs * 1.0001f || iou_exceeds_exact(cb, b, inter, thr.thr)) { dead = true; break; }
+                }
+            }
+        }
     }
     const unsigned m = __ballot_sync(0xffffffffu, dead);
     if (m != 0u && lane == 0) atomicAnd(&s_alive[c >> 5], ~m);      // a warp's 32 candidates are one word of the bit set
@@ -615,10 +657,9 @@ template <bool DECODE, bool SLOT>
 __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // dynamic: selected boxes (normalised corners) + areas, sized by max_det
-    float4* s_selbox = reinterpret_cast<float4*>(smem_raw);
-    unsigned long long* s_key2 = reinterpret_cast<unsigned long long*>(s_selbox + p.max_det);   // merge sort: second key buffer,
+    SelRec* s_sel = reinterpret_cast<SelRec*>(smem_raw);
+    unsigned long long* s_key2 = reinterpret_cast<unsigned long long*>(s_sel + p.max_det);      // merge sort: second key buffer,
     unsigned* s_slot2 = reinterpret_cast<unsigned*>(s_key2 + NMS_CHUNK);                         // second payload buffer (SLOT)
-    float* s_selarea = reinterpret_cast<float*>(s_slot2 + (SLOT ? NMS_CHUNK : 0));
 
     __shared__ unsigned long long s_key[NMS_CHUNK];
     __shared__ unsigned s_slot[SLOT ? NMS_CHUNK : 1];
@@ -647,7 +688,9 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     // optional phase timing (rn_debug_nms_timing(1)): thread 0 accumulates clock64() deltas per phase
     long long t_mark = p.timing ? clock64() : 0;
     const long long t_start = t_mark;
-#define RN_COUNT(k, v) do { if (p.timing && tid == 0) atomicAdd(p.timing + (k), (unsigned long long)(v)); } while (0)
+    __shared__ unsigned s_dbg[16];      // (phase timing only: this segment's event counts)
+    if (p.timing && tid < 16) s_dbg[tid] = 0u;
+#define RN_COUNT(k, v) do { if (p.timing && tid == 0) { atomicAdd(p.timing + (k), (unsigned long long)(v)); s_dbg[(k) - 10] += (unsigned)(v); } } while (0)
 #define RN_PHASE(k) do { if (p.timing && tid == 0) { const long long now = clock64(); atomicAdd(p.timing + (k), (unsigned long long)(now - t_mark)); t_mark = now; } } while (0)
     unsigned long long upper = ~0ull;   // keys >= upper have been visited (no key equals ~0: its score bits would be a NaN's)
     int visited = 0, nsel = 0, round = 0, bis = 0;
@@ -756,7 +799,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                     c.x = fminf(r.x, r.z); c.y = fminf(r.y, r.w); c.z = fmaxf(r.x, r.z); c.w = fmaxf(r.y, r.w);
                     const float ca = box_weight(box_area(c), p.iou);
                     bool dead = false;
-                    for (int sI = 0; sI < nsel && !dead; ++sI) dead = iou_exceeds(c, ca, s_selbox[sI], s_selarea[sI], p.iou);
+                    for (int sI = 0; sI < nsel && !dead; ++sI) dead = iou_exceeds(c, ca, s_sel[sI].box, s_sel[sI].w, p.iou);
                     if (dead) { rk[t] = 0ull; ++killed; }
                 }
             }
@@ -845,14 +888,15 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                 if (tid < NMS_GROUP / 32) s_alive[tid] = 0u;
             }
             __syncthreads();
-            RN_PHASE(3);
             // The group is opened window by window: a window's candidates are first tested against everything selected so
             // far (what an earlier selection suppresses leaves before its order is ever looked at), then consumed 32 alive
             // candidates at a time.  A window is no wider than what can still be needed -- about (max_det - nsel) more
             // selections -- so candidates behind the stopping point are (almost) never tested.
             int gdone = 0;                                  // candidates of the group whose window has been opened
+            int tail = 3;                                   // (phase timing: what the barrier below completes)
             while (nsel < p.max_det) {
                 __syncthreads();                            // the alive bits are final
+                RN_PHASE(tail);
                 // (a) the next <= 32 alive candidates, in order: one thread per candidate of the group ranks itself among the
                 //     alive ones (its warp's alive word + the population counts of the words before it) and the first 32 leave
                 //     their positions in shared memory
@@ -883,10 +927,11 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                     }
                     __syncthreads();
                     if (p.nms && nsel > 0)
-                        suppress_window(s_gbox, s_garea, s_alive, gdone, wn, s_selbox, s_selarea, 0, nsel, p.iou, tid, lane);
+                        suppress_window(s_gbox, s_garea, s_alive, gdone, wn, s_sel, 0, nsel, p.iou, tid, lane);
                     gdone += wn;
-                    RN_PHASE(9);
+                    tail = 9;
                     RN_COUNT(11, 1);
+                    RN_COUNT(16, wn);
                     continue;
                 }
                 RN_COUNT(10, 1);
@@ -925,8 +970,8 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                     while (extra-- > 0) keep &= ~(0x80000000u >> __clz(keep));
                     if ((keep >> lane) & 1u) {
                         const int at_sel = nsel + __popc(keep & ((1u << lane) - 1u));
-                        s_selbox[at_sel] = s_gbox[pos];
-                        s_selarea[at_sel] = s_garea[pos];
+                        s_sel[at_sel].box = s_gbox[pos];
+                        s_sel[at_sel].w = s_garea[pos];
                         const size_t at = (size_t)seg * p.max_det + at_sel;
                         p.kept_key[at] = s_key[g0 + pos];
                         p.kept_box[at] = s_graw[pos];
@@ -936,11 +981,12 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                     if (lane == 0) s_nsel = nsel + __popc(keep);
                 }
                 __syncthreads();
+                RN_PHASE(5);
                 nsel = s_nsel;
                 // (c) the new selections act on the rest of the open window at once
                 if (p.nms && nsel > n_old && nsel < p.max_det)
-                    suppress_window(s_gbox, s_garea, s_alive, 0, gdone, s_selbox, s_selarea, n_old, nsel, p.iou, tid, lane);
-                RN_PHASE(5);
+                    suppress_window(s_gbox, s_garea, s_alive, 0, gdone, s_sel, n_old, nsel, p.iou, tid, lane);
+                tail = 17;
             }
             __syncthreads();                                // the group's arrays are rewritten next
         }
@@ -957,7 +1003,17 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     if (tid == 0) p.kept_count[seg] = nsel;
     RN_COUNT(13, nsel);
     RN_COUNT(15, cnt);
-    if (p.timing && tid == 0) atomicMax(p.timing + 7, (unsigned long long)(clock64() - t_start));   // the slowest CTA
+    if (p.timing && tid == 0) {
+        const unsigned long long ticks = (unsigned long long)(clock64() - t_start);
+        atomicMax(p.timing + 7, ticks);                     // the slowest CTA
+        if (seg < 56) {                                     // the first segments' own records: ticks, counts 10..16
+            unsigned long long* rec = p.timing + 32 + 4 * seg;
+            rec[0] = ticks;
+            rec[1] = (unsigned long long)s_dbg[5] | ((unsigned long long)s_dbg[2] << 32);     // above threshold | sorted
+            rec[2] = (unsigned long long)s_dbg[6] | ((unsigned long long)s_dbg[4] << 32);     // opened | rounds
+            rec[3] = (unsigned long long)s_dbg[0] | ((unsigned long long)s_dbg[1] << 32);     // batches | windows
+        }
+    }
 #undef RN_PHASE
 #undef RN_COUNT
 }
@@ -1189,7 +1245,7 @@ FilterWs carve(void* ws, int B, int S, long long cap, int max_det, bool agnostic
     size_t off = 0;
     char* base = reinterpret_cast<char*>(ws);
     auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align256(bytes); return p; };
-    w.timing = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * 16));  // first 128 bytes
+    w.timing = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * 256));  // first 2 KB
     w.counts = reinterpret_cast<int*>(take(sizeof(int) * S));
     w.kept_count = reinterpret_cast<int*>(take(sizeof(int) * S));
     w.status = reinterpret_cast<int*>(take(sizeof(int) * B));
@@ -1210,7 +1266,7 @@ unsigned host_f2ord(float f) {
 }
 
 size_t nms_dynamic_smem(int max_det) {      // selected boxes + weights, the merge sort's second buffers
-    return (size_t)max_det * (sizeof(float4) + sizeof(float)) + (size_t)NMS_CHUNK * (sizeof(unsigned long long) + sizeof(unsigned));
+    return (size_t)max_det * sizeof(SelRec) + (size_t)NMS_CHUNK * (sizeof(unsigned long long) + sizeof(unsigned));
 }
 
 std::atomic<int> g_phase_timing{0};
