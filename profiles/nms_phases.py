@@ -16,7 +16,7 @@ _, anns = synthetic.training_batch(3, batch=B)
 cls, reg = synthetic.inference_predictions(3, B, anchors, anns, classes=1)
 cls_d, reg_d = torch.from_numpy(cls).cuda(), torch.from_numpy(reg).cuda()
 names = [  # phases end at block barriers: thread 0's clock is the block's
-         "bisection select", "gather", "sort (warp bitonic + merge levels)", "group fetch/decode", "in-batch tests", "resolve (warp 0)", "sweep between rounds", "rank the alive (per batch/window)", "open a window (vs all selected)", "eager (new selections vs open window)"]
+         "bisection select", "gather", "sort (warp bitonic + merge levels)", "group fetch/decode", "pairs (conflict matrix of the batch)", "resolve (warp 0)", "sweep between rounds", "rank the alive (per batch/window)", "apply (new selections vs open windows + next window vs all)", "-"]
 rn._lib.load().rn_debug_nms_timing(1)
 for topk in (0, 1000):
     head = rn.DetectionHead(pre_nms_top_k=topk)

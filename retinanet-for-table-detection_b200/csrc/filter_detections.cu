@@ -30,7 +30,7 @@ constexpr int NMS_THREADS = 1024;
 constexpr int NMS_WARPS = NMS_THREADS / 32;
 constexpr int NMS_CHUNK = 2048;    // candidates ordered per round (shared-memory capacity of the sorted chunk)
 constexpr int NMS_GROUP = 256;     // boxes fetched / decoded per step, one group ahead of the greedy loop
-constexpr int NMS_BATCH = 32;      // candidates resolved per greedy step: warp i <-> candidate i
+constexpr int NMS_BATCH = 64;      // candidates resolved per greedy step: warp w <-> candidates w and w + 32
 constexpr int MAX_DET_LIMIT = 1024;
 
 struct Norm4 { float mean[4]; float std[4]; };
@@ -653,6 +653,22 @@ __device__ __forceinline__ void suppress_window(const float4* s_gbox, const floa
     if (m != 0u && lane == 0) atomicAnd(&s_alive[c >> 5], ~m);      // a warp's 32 candidates are one word of the bit set
 }
 
+// alive word `w` of a group when the window [from, from + wn) opens (from is a multiple of 32)
+__device__ __forceinline__ unsigned window_bits(int w, int from, int wn) {
+    const int left = from + wn - w * 32, skip = from - w * 32;
+    return (skip > 0 || left <= 0) ? 0u : (left >= 32 ? ~0u : (1u << left) - 1u);
+}
+// The next window of a group of gn candidates of which gdone are open: no wider than what can still be needed (about
+// max_det - nsel more selections) and no wider than ~6 k pair tests at opening -- a candidate of an open window is tested
+// against every later selection as well, so what is opened but never consumed (behind the stopping point) is pure waste.
+// A multiple of 32 unless it ends the group; 0 when the group is open to its end.
+__device__ __forceinline__ int next_window(int nsel, int gdone, int gn, int max_det) {
+    if (gdone >= gn) return 0;
+    const int room = max_det - nsel;
+    const int by_cost = max(NMS_BATCH, (int)(__fdividef(6144.0f, (float)max(nsel, 24)) + 0.01f) & ~31);
+    return min(gn - gdone, min(by_cost, (room + (room >> 2) + 47) & ~31));
+}
+
 template <bool DECODE, bool SLOT>
 __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -667,9 +683,9 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     __shared__ float4 s_graw[NMS_GROUP];      // ... as decoded / stored
     __shared__ float s_garea[NMS_GROUP];
     __shared__ unsigned s_alive[NMS_GROUP / 32];   // bit set: candidate of the group neither consumed nor suppressed yet
-    __shared__ unsigned s_vict[NMS_BATCH];    // per batch member: the later members it suppresses
+    __shared__ uint2 s_conf[NMS_BATCH];       // per batch member: the members it conflicts with (IoU > thr), 64 bits
     __shared__ unsigned char s_bpos[NMS_BATCH];   // per batch member: its position in the group
-    __shared__ int s_alive_total;
+    __shared__ int s_alive_total, s_open;
     __shared__ unsigned s_cnt[3][4];          // pivot counts of the bisection, three rotating sets
     __shared__ unsigned s_kmax;
     __shared__ int s_loaded, s_nsel;
@@ -885,21 +901,38 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                 }
                 const int nx = g0 + NMS_GROUP + tid;
                 if (nx < chunk_n) nxt = fetch_row(p.src, page, (int)key_idx(s_key[nx]));
-                if (tid < NMS_GROUP / 32) s_alive[tid] = 0u;
             }
-            __syncthreads();
             // The group is opened window by window: a window's candidates are first tested against everything selected so
-            // far (what an earlier selection suppresses leaves before its order is ever looked at), then consumed 32 alive
+            // far (what an earlier selection suppresses leaves before its order is ever looked at), then consumed 64 alive
             // candidates at a time.  A window is no wider than what can still be needed -- about (max_det - nsel) more
-            // selections -- so candidates behind the stopping point are (almost) never tested.
+            // selections -- so candidates behind the stopping point are (almost) never tested.  One greedy step is four
+            // phases between block barriers:
+            //   apply    all threads: the step's new selections against the open windows' alive candidates, and -- when the
+            //            open windows are about to run dry -- the next window against everything selected
+            //   rank     the first 64 alive candidates, in order (the batch)
+            //   pairs    the 64 x 64 conflict matrix of the batch (warp w: rows w and w + 32, one ballot per half row)
+            //   resolve  warp 0: greedy order by fixpoint iteration in registers, the survivors join the selected list, the batch
+            //            is consumed, and the next window (if any) is declared
             int gdone = 0;                                  // candidates of the group whose window has been opened
-            int tail = 3;                                   // (phase timing: what the barrier below completes)
-            while (nsel < p.max_det) {
+            int n_old = nsel;                               // selections [n_old, nsel) have not met the open windows yet
+            int open_wn = next_window(nsel, 0, gn, p.max_det);      // (uniform) the window the next apply phase opens
+            if (tid < NMS_GROUP / 32) s_alive[tid] = window_bits(tid, 0, open_wn);
+            __syncthreads();
+            RN_PHASE(3);
+            while (true) {
+                // ---- apply
+                if (p.nms) {
+                    if (nsel > n_old && gdone > 0)
+                        suppress_window(s_gbox, s_garea, s_alive, 0, gdone, s_sel, n_old, nsel, p.iou, tid, lane);
+                    if (open_wn > 0 && nsel > 0)
+                        suppress_window(s_gbox, s_garea, s_alive, gdone, open_wn, s_sel, 0, nsel, p.iou, tid, lane);
+                }
+                if (open_wn > 0) { RN_COUNT(11, 1); RN_COUNT(16, open_wn); }
+                gdone += open_wn;
                 __syncthreads();                            // the alive bits are final
-                RN_PHASE(tail);
-                // (a) the next <= 32 alive candidates, in order: one thread per candidate of the group ranks itself among the
-                //     alive ones (its warp's alive word + the population counts of the words before it) and the first 32 leave
-                //     their positions in shared memory
+                RN_PHASE(9);
+                // ---- rank: one thread per candidate of the group ranks itself among the alive ones (its warp's alive word +
+                //      the population counts of the words before it); the first 64 leave their positions in shared memory
                 if (tid < NMS_GROUP) {
                     const unsigned word = s_alive[warp];
                     int before = 0;
@@ -914,79 +947,97 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                 __syncthreads();
                 RN_PHASE(8);
                 const int alive_total = s_alive_total;
-                if (alive_total == 0) {                     // block-uniform
-                    if (gdone >= gn) break;
-                    // ... and no wider than ~6 k pair tests at opening: a candidate of an open window is tested against every
-                    // later selection as well, so what is opened but never consumed (behind the stopping point) is pure waste
-                    const int room = p.max_det - nsel;
-                    const int by_cost = max(32, (int)(__fdividef(6144.0f, (float)max(nsel, 24)) + 0.01f) & ~31);
-                    const int wn = min(gn - gdone, min(by_cost, (room + (room >> 2) + 47) & ~31));   // a multiple of 32 unless it ends the group
-                    if (tid < NMS_GROUP / 32) {             // (nobody reads the alive words between the barrier above and the next)
-                        const int left = gdone + wn - tid * 32, skip = gdone - tid * 32;    // gdone is a multiple of 32
-                        s_alive[tid] = (skip > 0 || left <= 0) ? 0u : (left >= 32 ? ~0u : (1u << left) - 1u);
-                    }
-                    __syncthreads();
-                    if (p.nms && nsel > 0)
-                        suppress_window(s_gbox, s_garea, s_alive, gdone, wn, s_sel, 0, nsel, p.iou, tid, lane);
-                    gdone += wn;
-                    tail = 9;
-                    RN_COUNT(11, 1);
-                    RN_COUNT(16, wn);
-                    continue;
-                }
-                RN_COUNT(10, 1);
+                if (alive_total == 0 && gdone >= gn) break; // block-uniform: the group is used up
                 const int bn = min(NMS_BATCH, alive_total);
-                const int pos = lane < bn ? (int)s_bpos[lane] : 0;
-                // warp w owns batch member w: one ballot over the later members gives row w of the in-batch suppression matrix
-                if (warp < bn) {                            // warp-uniform
-                    unsigned vict = 0u;
+                // ---- pairs: row i of the conflict matrix = the members j != i with IoU(i, j) > thr
+                if (bn > 0) {
+                    RN_COUNT(10, 1);
                     if (p.nms) {
-                        const int mine = __shfl_sync(0xffffffffu, pos, warp);
-                        const bool hit = (lane > warp) && (lane < bn) &&
-                                         iou_exceeds(s_gbox[mine], s_garea[mine], s_gbox[pos], s_garea[pos], p.iou);
-                        vict = __ballot_sync(0xffffffffu, hit);
-                    }
-                    if (lane == 0) s_vict[warp] = vict;
-                }
-                __syncthreads();
-                RN_PHASE(4);
-                // (b) one warp resolves the greedy order in registers; the survivors join the selected list
-                const int n_old = nsel;
-                if (warp == 0) {
-                    const unsigned vict = (lane < bn) ? s_vict[lane] : 0u;
-                    const unsigned rem = bn >= 32 ? ~0u : (1u << bn) - 1u;      // every batch member is alive
-                    unsigned keep = rem;
-                    if (__any_sync(0xffffffffu, vict != 0u)) {   // conflicts inside the batch: walk it
-                        keep = 0u;
-                        unsigned r = rem;
-                        while (r) {                         // warp-uniform
-                            const int i = __ffs(r) - 1;
-                            keep |= 1u << i;
-                            r &= ~(1u << i);
-                            r &= ~__shfl_sync(0xffffffffu, vict, i);
+                        const int pos_lo = lane < bn ? (int)s_bpos[lane] : 0, pos_hi = lane + 32 < bn ? (int)s_bpos[lane + 32] : 0;
+                        const float4 b_lo = s_gbox[pos_lo], b_hi = s_gbox[pos_hi];
+                        const float w_lo = s_garea[pos_lo], w_hi = s_garea[pos_hi];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int i = warp + 32 * h;
+                            if (i < bn) {                   // warp-uniform
+                                const int mine = (int)s_bpos[i];
+                                const float4 mb = s_gbox[mine];
+                                const float mw = s_garea[mine];
+                                const bool hit_lo = (lane != i) && (lane < bn) && iou_exceeds(mb, mw, b_lo, w_lo, p.iou);
+                                const bool hit_hi = (lane + 32 != i) && (lane + 32 < bn) && iou_exceeds(mb, mw, b_hi, w_hi, p.iou);
+                                const unsigned c_lo = __ballot_sync(0xffffffffu, hit_lo), c_hi = __ballot_sync(0xffffffffu, hit_hi);
+                                if (lane == 0) s_conf[i] = make_uint2(c_lo, c_hi);
+                            }
                         }
                     }
-                    int extra = __popc(keep) - (p.max_det - nsel);       // TF stops at max_output_size: the first ones in order
-                    while (extra-- > 0) keep &= ~(0x80000000u >> __clz(keep));
-                    if ((keep >> lane) & 1u) {
-                        const int at_sel = nsel + __popc(keep & ((1u << lane) - 1u));
-                        s_sel[at_sel].box = s_gbox[pos];
-                        s_sel[at_sel].w = s_garea[pos];
-                        const size_t at = (size_t)seg * p.max_det + at_sel;
-                        p.kept_key[at] = s_key[g0 + pos];
-                        p.kept_box[at] = s_graw[pos];
-                        p.kept_label[at] = (SLOT && labels) ? labels[s_slot[g0 + pos]] : seg_label;
+                    __syncthreads();
+                }
+                RN_PHASE(4);
+                // ---- resolve (warp 0).  Lane l owns members l and l + 32.  A member is KEPT once every earlier member that
+                //      conflicts with it is known to be suppressed, SUPPRESSED once one of them is known to be kept; each round
+                //      settles at least the first unsettled member, usually almost all of them (2-3 rounds).
+                n_old = nsel;
+                if (warp == 0) {
+                    unsigned k_lo = 0u, k_hi = 0u;          // the kept members (uniform)
+                    if (bn > 0) {
+                        const unsigned v_lo = bn >= 32 ? ~0u : (1u << bn) - 1u;
+                        const unsigned v_hi = bn >= 64 ? ~0u : (bn > 32 ? (1u << (bn - 32)) - 1u : 0u);
+                        k_lo = v_lo; k_hi = v_hi;
+                        if (p.nms) {
+                            const uint2 ca = (lane < bn) ? s_conf[lane] : make_uint2(0u, 0u);
+                            const uint2 cb = (lane + 32 < bn) ? s_conf[lane + 32] : make_uint2(0u, 0u);
+                            const unsigned below = (1u << lane) - 1u;
+                            // earlier members in conflict: member l has only low ones, member l + 32 all low ones and some high
+                            const unsigned ha = ca.x & below, hb_lo = cb.x, hb_hi = cb.y & below;
+                            if (__any_sync(0xffffffffu, (ha | hb_lo | hb_hi) != 0u)) {
+                                unsigned s_lo = 0u, s_hi = 0u;      // the suppressed members (uniform)
+                                k_lo = 0u; k_hi = 0u;
+                                while (((k_lo | s_lo) != v_lo) || ((k_hi | s_hi) != v_hi)) {       // warp-uniform
+                                    const bool a_open = (lane < bn) && !(((k_lo | s_lo) >> lane) & 1u);
+                                    const bool b_open = (lane + 32 < bn) && !(((k_hi | s_hi) >> lane) & 1u);
+                                    const bool a_keep = a_open && (ha & ~s_lo) == 0u;
+                                    const bool a_supp = a_open && (ha & k_lo) != 0u;
+                                    const bool b_keep = b_open && (hb_lo & ~s_lo) == 0u && (hb_hi & ~s_hi) == 0u;
+                                    const bool b_supp = b_open && ((hb_lo & k_lo) != 0u || (hb_hi & k_hi) != 0u);
+                                    const unsigned nk_lo = __ballot_sync(0xffffffffu, a_keep), ns_lo = __ballot_sync(0xffffffffu, a_supp);
+                                    const unsigned nk_hi = __ballot_sync(0xffffffffu, b_keep), ns_hi = __ballot_sync(0xffffffffu, b_supp);
+                                    k_lo |= nk_lo; s_lo |= ns_lo; k_hi |= nk_hi; s_hi |= ns_hi;
+                                }
+                            }
+                        }
+                        int extra = __popc(k_lo) + __popc(k_hi) - (p.max_det - nsel);    // TF stops at max_output_size: the first ones in order
+                        while (extra-- > 0) { if (k_hi) k_hi &= ~(0x80000000u >> __clz(k_hi)); else k_lo &= ~(0x80000000u >> __clz(k_lo)); }
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const unsigned km = h ? k_hi : k_lo;
+                            const int m = lane + 32 * h;
+                            if (m < bn) {
+                                const int pos = (int)s_bpos[m];
+                                if ((km >> lane) & 1u) {
+                                    const int at_sel = nsel + (h ? __popc(k_lo) : 0) + __popc(km & ((1u << lane) - 1u));
+                                    s_sel[at_sel].box = s_gbox[pos];
+                                    s_sel[at_sel].w = s_garea[pos];
+                                    const size_t at = (size_t)seg * p.max_det + at_sel;
+                                    p.kept_key[at] = s_key[g0 + pos];
+                                    p.kept_box[at] = s_graw[pos];
+                                    p.kept_label[at] = (SLOT && labels) ? labels[s_slot[g0 + pos]] : seg_label;
+                                }
+                                atomicAnd(&s_alive[pos >> 5], ~(1u << (pos & 31)));      // the whole batch is consumed
+                            }
+                        }
                     }
-                    if (lane < bn) atomicAnd(&s_alive[pos >> 5], ~(1u << (pos & 31)));   // the whole batch is consumed
-                    if (lane == 0) s_nsel = nsel + __popc(keep);
+                    const int nsel_new = nsel + __popc(k_lo) + __popc(k_hi);
+                    // the next window: when fewer than a batch of opened candidates can be left (the apply phase may strike more)
+                    const int wn = (alive_total - bn < NMS_BATCH && nsel_new < p.max_det) ? next_window(nsel_new, gdone, gn, p.max_det) : 0;
+                    __syncwarp();
+                    if (lane < NMS_GROUP / 32 && wn > 0) s_alive[lane] |= window_bits(lane, gdone, wn);
+                    if (lane == 0) { s_nsel = nsel_new; s_open = wn; }
                 }
                 __syncthreads();
                 RN_PHASE(5);
                 nsel = s_nsel;
-                // (c) the new selections act on the rest of the open window at once
-                if (p.nms && nsel > n_old && nsel < p.max_det)
-                    suppress_window(s_gbox, s_garea, s_alive, 0, gdone, s_sel, n_old, nsel, p.iou, tid, lane);
-                tail = 17;
+                open_wn = s_open;
+                if (nsel >= p.max_det) break;
             }
             __syncthreads();                                // the group's arrays are rewritten next
         }
