@@ -16,7 +16,7 @@ _, anns = synthetic.training_batch(3, batch=B)
 cls, reg = synthetic.inference_predictions(3, B, anchors, anns, classes=1)
 cls_d, reg_d = torch.from_numpy(cls).cuda(), torch.from_numpy(reg).cuda()
 names = [  # phases end at block barriers: thread 0's clock is the block's
-         "bisection select", "gather", "sort (warp bitonic + merge levels)", "group fetch/decode", "pairs (conflict matrix of the batch)", "resolve (warp 0)", "sweep between rounds", "rank the alive (per batch/window)", "apply (new selections vs open windows + next window vs all)", "-"]
+         "bisection select", "gather", "sort (warp bitonic + merge levels)", "group start (normalise, first window)", "pairs (conflict matrix of the batch)", "resolve (warp 0)", "sweep between rounds", "rank the alive (per batch/window)", "apply (new selections vs open windows + next window vs all)", "-", "chunk: read + decode all rows", "group: closing barrier"]
 rn._lib.load().rn_debug_nms_timing(1)
 for topk in (0, 1000):
     head = rn.DetectionHead(pre_nms_top_k=topk)
@@ -26,7 +26,7 @@ for topk in (0, 1000):
     ws = [v for k, v in rn._lib._scratch.items() if k[0] == "filter"][0]
     full = ws[:2048].view(torch.int64).cpu().numpy()
     raw = ws[:256].view(torch.int64).cpu().numpy().astype(np.float64)
-    slowest, t = raw[7], np.concatenate([raw[:7], raw[8:10], raw[17:18]])
+    slowest, t = raw[7], np.concatenate([raw[:7], raw[8:10], raw[17:20]])
     print("pre_nms_top_k=%d: ticks per segment (thread 0): mean %.0f, slowest CTA %.0f" % (topk, t.sum() / B, slowest))
     for n, v in zip(names, t):
         print("   %-30s %8.0f  %5.1f%%" % (n, v / B, 100 * v / t.sum()))

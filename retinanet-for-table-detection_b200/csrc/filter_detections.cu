@@ -30,6 +30,7 @@ constexpr int NMS_THREADS = 1024;
 constexpr int NMS_WARPS = NMS_THREADS / 32;
 constexpr int NMS_CHUNK = 2048;    // candidates ordered per round (shared-memory capacity of the sorted chunk)
 constexpr int NMS_GROUP = 256;     // boxes fetched / decoded per step, one group ahead of the greedy loop
+constexpr int NMS_BASE_MAX = 96;  // base anchors staged in shared memory (levels x anchors per cell; 45 by default)
 constexpr int NMS_BATCH = 64;      // candidates resolved per greedy step: warp w <-> candidates w and w + 32
 constexpr int MAX_DET_LIMIT = 1024;
 
@@ -311,14 +312,18 @@ __device__ __forceinline__ float4 fetch_row(const BoxSource& s, int page, int n)
 // row -> box.  Decode mode: fp32 anchor as the Anchors layer computes it (model/utils.py:51-80), a + (d * std + mean) * len
 // in the reference's order (model/utils.py:102-110), clip to [0, W] x [0, H] (model/layers.py:166-169).
 template <bool DECODE>
-__device__ __forceinline__ float4 finish_box(const BoxSource& s, int n, const float4 d) {
+__device__ __forceinline__ float4 finish_box(const BoxSource& s, int n, const float4 d, const float4* s_base = nullptr) {
     if (!DECODE) return d;
     int level, cx, cy, a;
     rn_locate(s.lv, n, level, cx, cy, a);
-    const float* bs = s.base32 + ((size_t)level * s.lv.anchors_per_cell + a) * 4;
+    const int bi = level * s.lv.anchors_per_cell + a;
+    // (s_base: the base anchors staged in shared memory -- a global read here sits in the middle of a group's dependent chain)
+    float4 ba;
+    if (s_base) ba = s_base[bi];
+    else { const float* bs = s.base32 + (size_t)bi * 4; ba = make_float4(__ldg(bs), __ldg(bs + 1), __ldg(bs + 2), __ldg(bs + 3)); }
     const float sx = ((float)cx + 0.5f) * (float)s.lv.stride[level];
     const float sy = ((float)cy + 0.5f) * (float)s.lv.stride[level];
-    const float ax1 = __ldg(bs) + sx, ay1 = __ldg(bs + 1) + sy, ax2 = __ldg(bs + 2) + sx, ay2 = __ldg(bs + 3) + sy;
+    const float ax1 = ba.x + sx, ay1 = ba.y + sy, ax2 = ba.z + sx, ay2 = ba.w + sy;
     const float w = ax2 - ax1, h = ay2 - ay1;
     float4 o;
     o.x = ax1 + (d.x * s.nm.std[0] + s.nm.mean[0]) * w;
@@ -675,17 +680,18 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     // dynamic: selected boxes (normalised corners) + areas, sized by max_det
     SelRec* s_sel = reinterpret_cast<SelRec*>(smem_raw);
     unsigned long long* s_key2 = reinterpret_cast<unsigned long long*>(s_sel + p.max_det);      // merge sort: second key buffer,
-    unsigned* s_slot2 = reinterpret_cast<unsigned*>(s_key2 + NMS_CHUNK);                         // second payload buffer (SLOT)
+    float4* s_raw = reinterpret_cast<float4*>(s_key2 + NMS_CHUNK);                               // the chunk's boxes as decoded / stored, in order
+    unsigned* s_slot2 = reinterpret_cast<unsigned*>(s_raw + NMS_CHUNK);                          // second payload buffer (SLOT)
 
     __shared__ unsigned long long s_key[NMS_CHUNK];
     __shared__ unsigned s_slot[SLOT ? NMS_CHUNK : 1];
     __shared__ float4 s_gbox[NMS_GROUP];      // the group's boxes, corner-normalised
-    __shared__ float4 s_graw[NMS_GROUP];      // ... as decoded / stored
     __shared__ float s_garea[NMS_GROUP];
     __shared__ unsigned s_alive[NMS_GROUP / 32];   // bit set: candidate of the group neither consumed nor suppressed yet
     __shared__ uint2 s_conf[NMS_BATCH];       // per batch member: the members it conflicts with (IoU > thr), 64 bits
     __shared__ unsigned char s_bpos[NMS_BATCH];   // per batch member: its position in the group
     __shared__ int s_alive_total, s_open;
+    __shared__ float4 s_banchor[NMS_BASE_MAX];   // decode mode: the base anchors (levels x anchors per cell), when they fit
     __shared__ unsigned s_cnt[3][4];          // pivot counts of the bisection, three rotating sets
     __shared__ unsigned s_kmax;
     __shared__ int s_loaded, s_nsel;
@@ -712,6 +718,12 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
     int visited = 0, nsel = 0, round = 0, bis = 0;
     if (tid == 0) { s_nsel = 0; s_kmax = 0u; s_loaded = 0; }
     if (tid < 4) s_cnt[0][tid] = 0u;
+    const int n_base = DECODE ? p.src.lv.num_levels * p.src.lv.anchors_per_cell : 0;
+    const float4* base_tab = (DECODE && n_base <= NMS_BASE_MAX) ? s_banchor : nullptr;
+    if (base_tab && tid < n_base) {
+        const float* bs = p.src.base32 + (size_t)tid * 4;
+        s_banchor[tid] = make_float4(__ldg(bs), __ldg(bs + 1), __ldg(bs + 2), __ldg(bs + 3));
+    }
     __syncthreads();
     // The slab's keys are read ONCE into registers (8 per thread) when the slab has <= 8192 candidates -- the
     // bisection passes and the gathers of every round then run out of registers (visited keys are zeroed there);
@@ -810,7 +822,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
             for (int t = 0; t < KPT; ++t) {
                 if (rk[t] != 0ull && rk[t] >= thr_s) {
                     const int n = (int)key_idx(rk[t]);
-                    const float4 r = finish_box<DECODE>(p.src, n, fetch_row(p.src, page, n));
+                    const float4 r = finish_box<DECODE>(p.src, n, fetch_row(p.src, page, n), base_tab);
                     float4 c;
                     c.x = fminf(r.x, r.z); c.y = fminf(r.y, r.w); c.z = fmaxf(r.x, r.z); c.w = fmaxf(r.y, r.w);
                     const float ca = box_weight(box_area(c), p.iou);
@@ -853,7 +865,12 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                     if (lane == 0) base = atomicAdd(&s_loaded, __popc(m));
                     base = __shfl_sync(0xffffffffu, base, 0);
                     const int at = base + __popc(m & ((1u << lane) - 1u));
-                    if (in && at < NMS_CHUNK) { s_key[at] = k; if (SLOT) s_slot[at] = (unsigned)(t * NMS_THREADS + tid); }
+                    if (in && at < NMS_CHUNK) {
+                        s_key[at] = k;
+                        if (SLOT) s_slot[at] = (unsigned)(t * NMS_THREADS + tid);
+                        // the chunk's rows start their way from DRAM to L2 now: the sort hides the latency of the first group's reads
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const float4*>(p.src.rows) + (size_t)page * p.src.N + key_idx(k)));
+                    }
                 }
             }
         } else {
@@ -886,21 +903,23 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
         RN_COUNT(12, loaded);
         RN_COUNT(14, 1);
         // ---------------- K5: greedy NMS over the ordered chunk -------------------------------------------
-        // boxes arrive one group (256 candidates) ahead: the row is requested here, decoded when its group starts
-        float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tid < NMS_GROUP && tid < chunk_n) nxt = fetch_row(p.src, page, (int)key_idx(s_key[tid]));
+        // The chunk's boxes: every candidate's row is read and decoded NOW, by all threads at once (two candidates per thread:
+        // one memory latency and one decode chain per round; the rows were requested from DRAM at gather time).  Decoding group by
+        // group, 256 threads at a time, put that chain -- ~1.6 k cycles -- in front of every group (r2v: 8 % of the kernel).
+        for (int e = tid; e < chunk_n; e += NMS_THREADS) {
+            const int n = (int)key_idx(s_key[e]);
+            s_raw[e] = finish_box<DECODE>(p.src, n, fetch_row(p.src, page, n), base_tab);
+        }
+        __syncthreads();
+        RN_PHASE(18);
         for (int g0 = 0; g0 < chunk_n && nsel < p.max_det; g0 += NMS_GROUP) {
             const int gn = min(NMS_GROUP, chunk_n - g0);
-            if (tid < NMS_GROUP) {
-                if (tid < gn) {
-                    const float4 r = finish_box<DECODE>(p.src, (int)key_idx(s_key[g0 + tid]), nxt);
-                    float4 c;
-                    c.x = fminf(r.x, r.z); c.y = fminf(r.y, r.w); c.z = fmaxf(r.x, r.z); c.w = fmaxf(r.y, r.w);
-                    s_graw[tid] = r; s_gbox[tid] = c;
-                    s_garea[tid] = box_weight(box_area(c), p.iou);
-                }
-                const int nx = g0 + NMS_GROUP + tid;
-                if (nx < chunk_n) nxt = fetch_row(p.src, page, (int)key_idx(s_key[nx]));
+            if (tid < gn) {
+                const float4 r = s_raw[g0 + tid];
+                float4 c;
+                c.x = fminf(r.x, r.z); c.y = fminf(r.y, r.w); c.z = fmaxf(r.x, r.z); c.w = fmaxf(r.y, r.w);
+                s_gbox[tid] = c;
+                s_garea[tid] = box_weight(box_area(c), p.iou);
             }
             // The group is opened window by window: a window's candidates are first tested against everything selected so
             // far (what an earlier selection suppresses leaves before its order is ever looked at), then consumed 64 alive
@@ -1019,7 +1038,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                                     s_sel[at_sel].w = s_garea[pos];
                                     const size_t at = (size_t)seg * p.max_det + at_sel;
                                     p.kept_key[at] = s_key[g0 + pos];
-                                    p.kept_box[at] = s_graw[pos];
+                                    p.kept_box[at] = s_raw[g0 + pos];
                                     p.kept_label[at] = (SLOT && labels) ? labels[s_slot[g0 + pos]] : seg_label;
                                 }
                                 atomicAnd(&s_alive[pos >> 5], ~(1u << (pos & 31)));      // the whole batch is consumed
@@ -1040,6 +1059,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) k_segment_nms(const NmsParams 
                 if (nsel >= p.max_det) break;
             }
             __syncthreads();                                // the group's arrays are rewritten next
+            RN_PHASE(19);
         }
         visited += chunk_n;
         upper = (chunk_n > 0) ? s_key[chunk_n - 1] : 0ull;
@@ -1317,7 +1337,7 @@ unsigned host_f2ord(float f) {
 }
 
 size_t nms_dynamic_smem(int max_det) {      // selected boxes + weights, the merge sort's second buffers
-    return (size_t)max_det * sizeof(SelRec) + (size_t)NMS_CHUNK * (sizeof(unsigned long long) + sizeof(unsigned));
+    return (size_t)max_det * sizeof(SelRec) + (size_t)NMS_CHUNK * (sizeof(unsigned long long) + sizeof(float4) + sizeof(unsigned));
 }
 
 std::atomic<int> g_phase_timing{0};
