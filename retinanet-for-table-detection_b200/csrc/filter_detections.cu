@@ -181,7 +181,8 @@ __global__ void __launch_bounds__(K3_THREADS) k_threshold_keys(const K3Params p)
 // warp with five ballots (a lane has 0..16 of them) and collected in a warp-private shared-memory buffer; ONE global atomic
 // per flush reserves their slab slots and the keys leave with coalesced stores.  (Measured on the way here: one global atomic
 // per 128 scores serialises on the page's counter -- 69 us; 128-score tiles are instruction bound -- 143 warp-instructions
-// per tile, 23 us.)  C > 1: the candidates of a warp feed different slabs, one atomic each.
+// per tile, 23 us; a two-deep cp.async ring per warp instead of registers -- two tiles, 128 KB per SM, in flight -- 19 us instead
+// of 17: the bytes in flight are not what limits it.)  C > 1: the candidates of a warp feed different slabs, one atomic each.
 // The slab order is arbitrary by design: keys are unique, the NMS kernel orders them.
 constexpr int K3S_VEC = 4;                                  // float4 per lane and tile
 constexpr int K3S_TILE = 128 * K3S_VEC;                     // scores per warp-tile
