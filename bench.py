@@ -737,7 +737,7 @@ def leg_inference(ctx):
                                   "survey_bytes_note": "SURVEY 8(d) counts 20 B/anchor (every regression row read); the kernel reads "
                                                        "none of them -- rows are fetched by the NMS kernel for visited candidates only -- "
                                                        "so that figure is NOT a fraction of anything"}
-            out["nms"] = {"kernel": "k_segment_nms (bisection select + bitonic sort + lazy decode + greedy NMS), one CTA per (page, class)",
+            out["nms"] = {"kernel": "k_segment_nms (bisection select + merge sort + decode + greedy NMS in steps of 64), one CTA per (page, class)",
                           "us_per_launch": nms_us, "candidates_per_s": cands / (nms_us * 1e-6), "candidates_per_page": cands / B,
                           "bound": "latency / instruction issue (no bandwidth target, SURVEY 8d)", "merge_us": merge_us}
         del dets
