@@ -74,6 +74,19 @@ int rn_anchor_targets(const double* base_anchors_dev, const int* level_hw, const
                       float* regression_out, float* labels_out, int* argmax_out, int* npos_out,
                       float* npos_total_out, void* stream);
 
+/* The same with a launch order for the pages: page_order_dev = a permutation of 0 .. B-1 (device int32) or NULL.  The
+ * kernel hands its CTAs out page by page, so the pages at the end of the order make the tail of the launch; callers that
+ * know the annotations put the heaviest pages (most / largest tables) first.  Results do not depend on the order; an
+ * array that is not a permutation leaves pages unwritten (not checked). */
+int rn_anchor_targets_ordered(const double* base_anchors_dev, const int* level_hw, const int* level_stride,
+                              int num_levels, int anchors_per_cell,
+                              const double* anchors_dev, long long num_anchors,
+                              const double* gt_boxes_dev, const int* gt_labels_dev, const int* gt_count_dev,
+                              const int* img_hw_dev, int B, int Gmax, int C,
+                              float neg_overlap, float pos_overlap,
+                              float* regression_out, float* labels_out, int* argmax_out, int* npos_out,
+                              float* npos_total_out, const int* page_order_dev, void* stream);
+
 /* anchors_for_shape (model/anchors.py:169-204) on the device: (N,4) float64. */
 int rn_anchors_f64(const double* base_anchors_dev, const int* level_hw, const int* level_stride,
                    int num_levels, int anchors_per_cell, double* anchors_out, void* stream);

@@ -25,7 +25,7 @@ images, anns = synthetic.training_batch(2, batch=B, anchors=np.asarray(anchors),
 cls, reg = synthetic.training_predictions(2, B, anchors.shape[0], classes=1)
 
 
-def measure(tag):
+def measure(tag, images=images, anns=anns):
     step = rn.pipeline.TargetLossStep(HW + (3,), B, 22, 1, peer_box=False)
     step.load_annotations(images, anns)
     step.load_predictions(torch.from_numpy(cls), torch.from_numpy(reg))
@@ -50,6 +50,14 @@ def measure(tag):
 
 
 measure("no-nccl")
+# the pages the benchmark gives this rank (dealt out by estimated cost, heaviest first), in that order and in page order
+g_images, g_anns = synthetic.training_batch(2, batch=max(world, 2) * B, anchors=np.asarray(anchors), first_page=0)
+cost = rn.distributed.page_cost(g_anns, HW)
+mine = rn.distributed.balanced_shards(cost, max(world, 2))[rank % max(world, 2)]
+print("rank %d shard cost %.1f  pages %s" % (rank, float(np.sum(np.asarray(cost)[mine])), list(mine)), flush=True)
+measure("shard", [g_images[i] for i in mine], [g_anns[i] for i in mine])
+srt = sorted(mine)
+measure("shard-sorted", [g_images[i] for i in srt], [g_anns[i] for i in srt])
 time.sleep(1.0)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))

@@ -43,3 +43,7 @@ for name, col in (("G", 0), ("area", 1), ("pairs", 2)):
     coef, res, _, _ = np.linalg.lstsq(A, r[:, 3], rcond=None)
     pred = A @ coef
     print("fit on %-5s: us = %.2f + %.4g * x   rms error %.2f us (of mean %.1f)" % (name, coef[0], coef[1], np.sqrt(np.mean((pred - r[:, 3]) ** 2)), r[:, 3].mean()))
+A = np.stack([np.ones(len(r)), r[:, 0], r[:, 2]], 1)
+coef, res, _, _ = np.linalg.lstsq(A, r[:, 3], rcond=None)
+pred = A @ coef
+print("fit on G + pairs: us = %.2f + %.4g * G + %.4g * pairs   rms error %.2f us" % (coef[0], coef[1], coef[2], np.sqrt(np.mean((pred - r[:, 3]) ** 2))))

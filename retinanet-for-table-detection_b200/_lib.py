@@ -39,6 +39,8 @@ SIGNATURES = {
     "rn_last_error": (c_char_p, []),
     "rn_anchor_targets": (c_int, [_P, _HI, _HI, c_int, c_int, _P, c_longlong, _P, _P, _P, _P, c_int, c_int, c_int,
                                   c_float, c_float, _P, _P, _P, _P, _P, _P]),
+    "rn_anchor_targets_ordered": (c_int, [_P, _HI, _HI, c_int, c_int, _P, c_longlong, _P, _P, _P, _P, c_int, c_int, c_int,
+                                          c_float, c_float, _P, _P, _P, _P, _P, _P, _P]),
     "rn_anchors_f64": (c_int, [_P, _HI, _HI, c_int, c_int, _P, _P]),
     "rn_compute_overlap": (c_int, [_P, c_longlong, _P, c_int, _P, _P]),
     "rn_bbox_transform": (c_int, [_P, _P, c_longlong, POINTER(c_double), POINTER(c_double), _P, _P]),

@@ -271,6 +271,19 @@ def pack_annotations(image_group, annotations_group, num_classes, out=None):
     return boxes, labels, counts, img_hw
 
 
+def page_launch_order(boxes, out=None):
+    """The order in which K1 should start the pages of a batch: heaviest first.  The kernel hands its CTAs out page by
+    page, so the pages at the end of the order make the tail of the launch; a page's cost grows with the number and the
+    size of its tables (``profiles/k1_page_cost.py``), and the summed table area of the packed ``(B, G, 4)`` block (padding
+    rows are zero) ranks the pages well enough for that.  Returns / fills a (B,) int32 permutation; stable, deterministic."""
+    area = (np.clip(boxes[:, :, 2] - boxes[:, :, 0], 0, None) * np.clip(boxes[:, :, 3] - boxes[:, :, 1], 0, None)).sum(axis=1)
+    order = np.argsort(-area, kind='stable').astype(np.int32)
+    if out is not None:
+        out[...] = order
+        return out
+    return order
+
+
 def upload_annotations(boxes, labels, counts, img_hw, device):
     """One pinned staging buffer, one async H2D copy; returns device views."""
     B, G = labels.shape
@@ -296,12 +309,13 @@ def upload_annotations(boxes, labels, counts, img_hw, device):
 
 def anchor_targets_device(anchors, d_boxes, d_labels, d_counts, d_hw, num_classes,
                           negative_overlap=0.4, positive_overlap=0.5, want_argmax=False, out=None,
-                          npos_total=None, npos_out=None):
+                          npos_total=None, npos_out=None, page_order=None):
     """Launch K1 on GT already resident on the device.  ``anchors``: an :class:`AnchorArray` /
     :class:`AnchorSpec` (generated in-kernel) or a CUDA float64 (N,4) tensor (explicit).
     ``npos_total``: optional 1-float CUDA tensor receiving the batch's positive count (loss normaliser);
     ``npos_out``: optional (B,) int32 tensor for the per-page counts (when it ends where ``npos_total`` starts the
-    library clears both with one memset).
+    library clears both with one memset); ``page_order``: optional (B,) int32 CUDA permutation, the order in which the
+    kernel starts the pages (:func:`page_launch_order`; the results do not depend on it).
     Returns ``(regression (B,N,5), labels (B,N,C+1), npos (B) int32, argmax (B,N) int32 | None)``."""
     lib = _lib.load()
     device = d_counts.device
@@ -326,13 +340,14 @@ def anchor_targets_device(anchors, d_boxes, d_labels, d_counts, d_hw, num_classe
     npos = torch.empty((B,), dtype=torch.int32, device=device) if npos_out is None else npos_out
     argmax = torch.empty((B, N), dtype=torch.int32, device=device) if want_argmax else None
     if N > 0:
-        _lib.check(lib.rn_anchor_targets(_lib.ptr(base), hw_p, st_p, levels, per_cell,
-                                         _lib.ptr(explicit), N,
-                                         _lib.ptr(d_boxes), _lib.ptr(d_labels), _lib.ptr(d_counts), _lib.ptr(d_hw),
-                                         B, G, num_classes, float(np.float32(negative_overlap)),
-                                         float(np.float32(positive_overlap)),
-                                         _lib.ptr(regression), _lib.ptr(labels), _lib.ptr(argmax), _lib.ptr(npos),
-                                         _lib.ptr(npos_total), _lib.stream_ptr(device)), "rn_anchor_targets")
+        _lib.check(lib.rn_anchor_targets_ordered(_lib.ptr(base), hw_p, st_p, levels, per_cell,
+                                                 _lib.ptr(explicit), N,
+                                                 _lib.ptr(d_boxes), _lib.ptr(d_labels), _lib.ptr(d_counts), _lib.ptr(d_hw),
+                                                 B, G, num_classes, float(np.float32(negative_overlap)),
+                                                 float(np.float32(positive_overlap)),
+                                                 _lib.ptr(regression), _lib.ptr(labels), _lib.ptr(argmax), _lib.ptr(npos),
+                                                 _lib.ptr(npos_total), _lib.ptr(page_order), _lib.stream_ptr(device)),
+                   "rn_anchor_targets_ordered")
     else:
         npos.zero_()
         if npos_total is not None:

@@ -36,6 +36,7 @@ struct K1Params {
     const int* gt_labels;    // (B, Gmax)
     const int* gt_count;     // (B)
     const int* img_hw;       // (B, 2) or nullptr
+    const int* page_order;   // (B) or nullptr: the page CTA row y works on
     int Gmax, C;
     float neg, pos;
     float* reg;              // (B, N, 5)
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_anchor_targets(const K1Params p)
     __shared__ int s_npos;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.y;
+    const int b = p.page_order ? __ldg(p.page_order + blockIdx.y) : (int)blockIdx.y;   // (heaviest pages first, see the wrapper)
     const int n0 = blockIdx.x * K1_THREADS;
     const int cnt = min(K1_THREADS, p.N - n0);
     const int n = n0 + tid;
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(32 * MAXA, MINB) k_anchor_targets_tiles(const 
     const int tid = threadIdx.x, lane = tid & 31, a = tid >> 5;
     const int A = p.lv.anchors_per_cell, L = p.lv.num_levels;
     const int nthreads = 32 * A;
-    const int b = blockIdx.y;
+    const int b = p.page_order ? __ldg(p.page_order + blockIdx.y) : (int)blockIdx.y;   // (heaviest pages first, see the wrapper)
     // staging rows are shifted by the destination's misalignment (start & 3 floats) so that 16-byte units of
     // shared memory map to 16-byte units of global memory: the write-out is LDS.128 + STG.128 per unit
     const int reg_stride = 32 * A * 5 + 4, lab_stride = 32 * A * 2 + 4;     // floats per staged tile row (multiples of 4)
@@ -695,7 +696,7 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
     const int tid = threadIdx.x, lane = tid & 31, a = tid >> 5;
     const int A = p.lv.anchors_per_cell, L = p.lv.num_levels;
     const int nthreads = 32 * A;
-    const int b = blockIdx.y;
+    const int b = p.page_order ? __ldg(p.page_order + blockIdx.y) : (int)blockIdx.y;   // (heaviest pages first, see the wrapper)
     const int reg_stride = 32 * A * 5 + 4, lab_stride = 32 * A * 2 + 4;     // floats per staged tile row (multiples of 4)
     float* s_reg = s_dyn;                                   // [KT_ROWS][reg_stride]
     float* s_lab = s_reg + KT_ROWS * reg_stride;            // C == 1: [KT_ROWS][lab_stride] {one-hot, state} pairs
@@ -1017,6 +1018,19 @@ extern "C" int rn_bbox_transform(const double* anchors_dev, const double* gt_box
     return rn_check_launch("rn_bbox_transform");
 }
 
+// page_order_dev: a permutation of 0 .. B-1 (device) or NULL.  CTAs are handed out page by page (blockIdx.y), so the pages
+// at the END of the order decide the tail of the launch: with the heaviest pages (most / largest tables) first the tail is
+// made of cheap CTAs.  Results do not depend on the order.  (16 pages of 800x1333 whose heaviest page came last: 56.7 us;
+// pages whose last three were light: 46 us for more total work -- profiles/r2/final_k1_order.log.)
+extern "C" int rn_anchor_targets_ordered(const double* base_anchors_dev, const int* level_hw, const int* level_stride,
+                                         int num_levels, int anchors_per_cell,
+                                         const double* anchors_dev, long long num_anchors,
+                                         const double* gt_boxes_dev, const int* gt_labels_dev, const int* gt_count_dev,
+                                         const int* img_hw_dev, int B, int Gmax, int C,
+                                         float neg_overlap, float pos_overlap,
+                                         float* regression_out, float* labels_out, int* argmax_out, int* npos_out,
+                                         float* npos_total_out, const int* page_order_dev, void* stream);
+
 extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* level_hw, const int* level_stride,
                                  int num_levels, int anchors_per_cell,
                                  const double* anchors_dev, long long num_anchors,
@@ -1025,6 +1039,19 @@ extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* leve
                                  float neg_overlap, float pos_overlap,
                                  float* regression_out, float* labels_out, int* argmax_out, int* npos_out,
                                  float* npos_total_out, void* stream) {
+    return rn_anchor_targets_ordered(base_anchors_dev, level_hw, level_stride, num_levels, anchors_per_cell, anchors_dev, num_anchors,
+                                     gt_boxes_dev, gt_labels_dev, gt_count_dev, img_hw_dev, B, Gmax, C, neg_overlap, pos_overlap,
+                                     regression_out, labels_out, argmax_out, npos_out, npos_total_out, nullptr, stream);
+}
+
+extern "C" int rn_anchor_targets_ordered(const double* base_anchors_dev, const int* level_hw, const int* level_stride,
+                                         int num_levels, int anchors_per_cell,
+                                         const double* anchors_dev, long long num_anchors,
+                                         const double* gt_boxes_dev, const int* gt_labels_dev, const int* gt_count_dev,
+                                         const int* img_hw_dev, int B, int Gmax, int C,
+                                         float neg_overlap, float pos_overlap,
+                                         float* regression_out, float* labels_out, int* argmax_out, int* npos_out,
+                                         float* npos_total_out, const int* page_order_dev, void* stream) {
     RN_REQUIRE(B >= 1 && B <= 65535, "B must be in [1, 65535] (got %d)", B);
     RN_REQUIRE(C >= 1, "C must be >= 1");
     RN_REQUIRE(Gmax >= 0, "Gmax must be >= 0");
@@ -1044,6 +1071,7 @@ extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* leve
     }
     p.base = base_anchors_dev; p.anchors = anchors_dev; p.N = (int)num_anchors;
     p.gt = gt_boxes_dev; p.gt_labels = gt_labels_dev; p.gt_count = gt_count_dev; p.img_hw = img_hw_dev;
+    p.page_order = page_order_dev;
     p.Gmax = Gmax; p.C = C; p.neg = neg_overlap; p.pos = pos_overlap;
     p.reg = regression_out; p.lab = labels_out; p.argmax = argmax_out; p.npos = npos_out;
     p.npos_total = npos_total_out;

@@ -40,21 +40,25 @@ class TargetLossStep(object):
         # both target tensors come from K1 in the same step, so their state columns are identical
         self.loss_kw = dict(alpha=alpha, gamma=gamma, sigma=sigma, bce=bce, shared_state=shared_state)
         d, B, G, N, C = self.device, self.B, self.G, self.N, self.C
-        # one staging block: boxes f64 | labels i32 | counts i32 | img_hw i32  (same layout as upload_annotations)
+        # one staging block: boxes f64 | labels i32 | counts i32 | img_hw i32  (same layout as upload_annotations) | page order i32
         self.nb, self.nl, self.nc, self.ni = B * G * 32, B * G * 4, B * 4, B * 8
-        total = self.nb + self.nl + self.nc + self.ni
+        total = self.nb + self.nl + self.nc + self.ni + B * 4
         self.gt_host = torch.zeros(total, dtype=torch.uint8, pin_memory=True)
         self.gt_dev = torch.zeros(total, dtype=torch.uint8, device=d)
         hv = self.gt_host.numpy()
         self._gt_views = (hv[:self.nb].view(np.float64).reshape(B, G, 4),
                           hv[self.nb:self.nb + self.nl].view(np.int32).reshape(B, G),
                           hv[self.nb + self.nl:self.nb + self.nl + self.nc].view(np.int32),
-                          hv[self.nb + self.nl + self.nc:].view(np.int32).reshape(B, 2))
+                          hv[self.nb + self.nl + self.nc:self.nb + self.nl + self.nc + self.ni].view(np.int32).reshape(B, 2))
+        self._order_view = hv[self.nb + self.nl + self.nc + self.ni:].view(np.int32)
+        self._order_view[:] = np.arange(B, dtype=np.int32)
         o = 0
         self.d_boxes = self.gt_dev[o:o + self.nb].view(torch.float64).view(B, G, 4); o += self.nb
         self.d_labels = self.gt_dev[o:o + self.nl].view(torch.int32).view(B, G); o += self.nl
         self.d_counts = self.gt_dev[o:o + self.nc].view(torch.int32); o += self.nc
-        self.d_hw = self.gt_dev[o:o + self.ni].view(torch.int32).view(B, 2)
+        self.d_hw = self.gt_dev[o:o + self.ni].view(torch.int32).view(B, 2); o += self.ni
+        self.d_order = self.gt_dev[o:o + B * 4].view(torch.int32)      # K1 starts the heaviest pages first (anchors.page_launch_order)
+        self.d_order.copy_(torch.arange(B, dtype=torch.int32))
         self.cls_pred = torch.zeros((B, N, C), dtype=torch.float32, device=d)
         self.reg_pred = torch.zeros((B, N, 4), dtype=torch.float32, device=d)
         self.y_reg = torch.empty((B, N, 5), dtype=torch.float32, device=d)
@@ -106,6 +110,7 @@ class TargetLossStep(object):
         if self._gt_event is not None:
             self._gt_event.synchronize()
         _anchors.pack_annotations(image_group, annotations_group, self.C, out=self._gt_views)   # straight into the pinned block
+        _anchors.page_launch_order(self._gt_views[0], out=self._order_view)
         self.gt_dev.copy_(self.gt_host, non_blocking=True)
         if self._gt_event is None:
             self._gt_event = torch.cuda.Event()
@@ -121,7 +126,7 @@ class TargetLossStep(object):
     def _targets(self):
         _anchors.anchor_targets_device(self.spec, self.d_boxes, self.d_labels, self.d_counts, self.d_hw, self.C,
                                        self.neg, self.pos, out=(self.y_reg, self.y_cls), npos_total=self.npos_total,
-                                       npos_out=self.npos)
+                                       npos_out=self.npos, page_order=self.d_order)
         if self.peer is not None and not self.peer_fused:
             self.peer.publish(self.npos_total, self.device)     # this rank's count -> every rank's mailbox
 
@@ -183,7 +188,8 @@ class TargetLossStep(object):
         def targets(i):
             y_reg, y_cls, npos, npos_total = bufs[i]
             _anchors.anchor_targets_device(self.spec, self.d_boxes, self.d_labels, self.d_counts, self.d_hw, self.C,
-                                           self.neg, self.pos, out=(y_reg, y_cls), npos_total=npos_total, npos_out=npos)
+                                           self.neg, self.pos, out=(y_reg, y_cls), npos_total=npos_total, npos_out=npos,
+                                           page_order=self.d_order)
             if self.peer is not None and not self.peer_fused:
                 self.peer.publish(npos_total, self.device)
 

@@ -234,3 +234,32 @@ def test_unaligned_output_tensors(rn, C, off_reg, off_lab):
     # nothing outside the views was touched
     assert float(big_r[:off_reg].sum()) == 7.0 * off_reg and float(big_r[off_reg + 2 * N * 5:].sum()) == 7.0 * (8 - off_reg)
     assert float(big_l[:off_lab].sum()) == 7.0 * off_lab and float(big_l[off_lab + 2 * N * (C + 1):].sum()) == 7.0 * (8 - off_lab)
+
+
+@pytest.mark.parametrize("C,hw", [(1, (400, 650)), (3, (131, 203))])
+def test_page_launch_order_does_not_change_results(rn, C, hw):
+    """rn_anchor_targets_ordered: the pages may be started in any order (heaviest first in the pipeline); targets, labels,
+    argmax indices and the per-page / total positive counts are the same bits as with the identity order and as the oracle's."""
+    anchors = rn.anchors_for_shape(hw + (3,))
+    oanchors = O.anchors_for_shape(hw + (3,))
+    B = 7
+    imgs = [synthetic.PageShape(hw + (3,))] * B
+    anns = [synthetic.gt_for_page(2, 60 + i, hw=hw, gmax=1 + 3 * i, classes=C) for i in range(B)]
+    want_reg, want_lab = O.anchor_targets_bbox(oanchors, imgs, anns, C)
+    boxes, labels, counts, img_hw = rn.anchors.pack_annotations(imgs, anns, C)
+    d = rn.anchors.upload_annotations(boxes, labels, counts, img_hw, torch.device("cuda"))
+    heavy_first = rn.anchors.page_launch_order(boxes)
+    assert sorted(heavy_first.tolist()) == list(range(B))
+    area = ((boxes[:, :, 2] - boxes[:, :, 0]) * (boxes[:, :, 3] - boxes[:, :, 1])).sum(axis=1)
+    assert all(area[heavy_first[i]] >= area[heavy_first[i + 1]] for i in range(B - 1))
+    results = []
+    for order in (None, heavy_first, heavy_first[::-1].copy(), np.roll(np.arange(B, dtype=np.int32), 3)):
+        d_order = None if order is None else torch.from_numpy(np.ascontiguousarray(order)).cuda()
+        total = torch.zeros(1, dtype=torch.float32, device="cuda")
+        reg, lab, npos, argmax = rn.anchors.anchor_targets_device(anchors.spec, *d, C, want_argmax=True, npos_total=total,
+                                                                 page_order=d_order)
+        results.append((reg.cpu().numpy(), lab.cpu().numpy(), npos.cpu().numpy(), argmax.cpu().numpy(), float(total.item())))
+    assert same(results[0][0], want_reg) and same(results[0][1], want_lab)
+    for r in results[1:]:
+        assert same(r[0], results[0][0]) and same(r[1], results[0][1])
+        assert (r[2] == results[0][2]).all() and (r[3] == results[0][3]).all() and r[4] == results[0][4]
