@@ -352,6 +352,15 @@ struct K1Tiles {
     float inv_tiles_x[RN_MAX_LEVELS];
 };
 
+// k_anchor_targets_tiles32: a 1-D grid, page slot by page slot.  The first `coarse_pages` page slots are cut into CTAs of
+// K32_XT x tiles (table `c`), the remaining ones -- the END of the launch -- into CTAs of one x tile (table `f`): three times
+// as many CTAs of a third of the duration, so the launch's drain (the time between the last CTA's start and the last CTA's
+// end, during which the GPU runs empty) shrinks with them.
+struct K1Tiles32 {
+    K1Tiles c, f;
+    int coarse_pages;
+};
+
 // MAXA bounds the block size (32 * A threads) so that the register budget can be set per instantiation:
 // <9, 3> is the RetinaNet default (288 threads, >= 3 CTAs per SM), <KT_MAX_A, 1> covers the rest
 // Write-out of a tile's staged rows when the output tensors are not 16-byte aligned: scalar stores (rows are staged
@@ -679,13 +688,29 @@ constexpr int K32_XT = RN_K32_XT;            // x tiles (of 32 columns) a CTA wa
                                        // staged tables -- is computed once for all of them.  (A/B on one box, profiles/r2h_sweep_k1.log:
                                        // 2 tiles 48.7 us / 31.0 M warp-instructions, 1 tile 51.3 us / 33.4 M, outputs bit-identical.)
 
+// page slots at the end of the launch that are cut into one-tile CTAs (see K1Tiles32).  A one-tile CTA repeats the per-CTA
+// work (tile decode, staged tables, intersection heights, y-target table: an empty one takes 3.6 us against 7.0 us for three
+// tiles), so only the very last page slot pays: A/B on one box (profiles/r2/r2q_sweep_k1_fine.log), 16 pages of 800 x 1333 /
+// 4 pages of 1600 x 2400: 0 fine pages 45.2 / 39.5 us, 1: 44.7 / 38.2, 2: 44.9 / 39.5, 3: 45.1 / 42.0, 4: 45.2 / 43.2, 6: 47.1 us.
+#ifndef RN_K32_FINE_PAGES
+#define RN_K32_FINE_PAGES 1
+#endif
+static int k32_fine_pages(int B) {
+    return K32_XT > 1 ? (RN_K32_FINE_PAGES < B ? RN_K32_FINE_PAGES : B) : 0;
+}
+
 // dynamic shared memory of k_anchor_targets_tiles32: staged regression rows, staged label rows, intersection heights, y-target table
 static size_t k32_dyn_smem(int A) {
     return kt_dyn_smem(A) + (K32_XT > 1 ? (size_t)A * KT_ROWS * 32 * sizeof(float2) : 0);
 }
 
+#ifdef RN_K1_TRACE
+// A/B build only (profiles/k1_cta_trace.py): per CTA {start, end} of %globaltimer, SM id, level -- what the launch's tail is made of
+__device__ unsigned long long g_k1_trace[4 * 16384];
+#endif
+
 template <bool C1, bool AM, int XT>
-__global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const K1Params p, const K1Tiles tl) {
+__global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const K1Params p, const K1Tiles32 tl) {
     extern __shared__ __align__(16) float s_dyn[];
     __shared__ double s_gx1[K32_G], s_gy1[K32_G], s_gx2[K32_G], s_gy2[K32_G], s_ga[K32_G];
     __shared__ int s_glab[K32_G];
@@ -696,7 +721,6 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
     const int tid = threadIdx.x, lane = tid & 31, a = tid >> 5;
     const int A = p.lv.anchors_per_cell, L = p.lv.num_levels;
     const int nthreads = 32 * A;
-    const int b = p.page_order ? __ldg(p.page_order + blockIdx.y) : (int)blockIdx.y;   // (heaviest pages first, see the wrapper)
     const int reg_stride = 32 * A * 5 + 4, lab_stride = 32 * A * 2 + 4;     // floats per staged tile row (multiples of 4)
     float* s_reg = s_dyn;                                   // [KT_ROWS][reg_stride]
     float* s_lab = s_reg + KT_ROWS * reg_stride;            // C == 1: [KT_ROWS][lab_stride] {one-hot, state} pairs
@@ -704,22 +728,39 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
     int* s_hot = reinterpret_cast<int*>(s_lab + KT_ROWS * 32 * A);
     double* s_ih = reinterpret_cast<double*>(s_lab + KT_ROWS * lab_stride);   // [A][KT_ROWS][32]; 8-byte aligned
     if (tid == 0) s_npos = 0;
+#ifdef RN_K1_TRACE
+    unsigned long long trace_t0 = 0;
+    if (tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(trace_t0));
+#endif
 
     // ---- tile -> (level, tile x, tile y): block-uniform (static indices only, see k_anchor_targets_tiles) ----
-    int level = 0, tstart = 0, tiles_x = tl.tiles_x[0], W = p.lv.w[0], H = p.lv.h[0], istride = p.lv.stride[0], lstart = p.lv.start[0];
-    float inv_tiles_x = tl.inv_tiles_x[0];
+    // CTA number -> (page slot, tile of the page, x tiles this CTA walks): coarse page slots first, fine ones at the end
+    const int n_coarse = tl.c.tile_start[RN_MAX_LEVELS], n_fine = tl.f.tile_start[RN_MAX_LEVELS];
+    const int split = tl.coarse_pages * n_coarse;
+    const bool fine = (int)blockIdx.x >= split;
+    const int xt = fine ? 1 : XT;                           // block-uniform
+    const int rest = fine ? (int)blockIdx.x - split : (int)blockIdx.x, per_page = fine ? n_fine : n_coarse;
+    const int slot_in = rest / per_page;
+    const int tile_id = rest - slot_in * per_page;
+    const int bslot = (fine ? tl.coarse_pages : 0) + slot_in;
+    const int b = p.page_order ? __ldg(p.page_order + bslot) : bslot;   // (heaviest pages first, see the wrapper)
+    int level = 0, tstart = 0, tiles_x = fine ? tl.f.tiles_x[0] : tl.c.tiles_x[0];
+    int W = p.lv.w[0], H = p.lv.h[0], istride = p.lv.stride[0], lstart = p.lv.start[0];
+    float inv_tiles_x = fine ? tl.f.inv_tiles_x[0] : tl.c.inv_tiles_x[0];
 #pragma unroll
-    for (int l = 1; l < RN_MAX_LEVELS; ++l)
-        if (l < L && (int)blockIdx.x >= tl.tile_start[l]) {
-            level = l; tstart = tl.tile_start[l]; tiles_x = tl.tiles_x[l]; inv_tiles_x = tl.inv_tiles_x[l];
+    for (int l = 1; l < RN_MAX_LEVELS; ++l) {
+        const int ts = fine ? tl.f.tile_start[l] : tl.c.tile_start[l];
+        if (l < L && tile_id >= ts) {
+            level = l; tstart = ts; tiles_x = fine ? tl.f.tiles_x[l] : tl.c.tiles_x[l]; inv_tiles_x = fine ? tl.f.inv_tiles_x[l] : tl.c.inv_tiles_x[l];
             W = p.lv.w[l]; H = p.lv.h[l]; istride = p.lv.stride[l]; lstart = p.lv.start[l];
         }
-    const int t = blockIdx.x - tstart;
+    }
+    const int t = tile_id - tstart;
     const int ty = rn_div(t, tiles_x, inv_tiles_x);
     const int tx = t - ty * tiles_x;
     const double stride = (double)istride;
-    const int cxt = tx * (32 * XT), cy0 = ty * KT_ROWS;     // first column of the CTA's XT tiles
-    const int ncols_all = min(32 * XT, W - cxt), nrows = min(KT_ROWS, H - cy0);
+    const int cxt = tx * (32 * xt), cy0 = ty * KT_ROWS;     // first column of the CTA's xt tiles
+    const int nrows = min(KT_ROWS, H - cy0);
     int G = p.gt_count[b];
     G = max(0, min(G, min(p.Gmax, K32_G)));
 
@@ -754,7 +795,7 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
 #pragma unroll
             for (int h = 0; h < XT; ++h) {
                 const int c0 = cxt + 32 * h, nc = min(32, W - c0);
-                if (nc > 0) {
+                if (h < xt && nc > 0) {
                     // exact bounding box of the warp's anchors in tile h (first / last valid column)
                     const double wx1 = b0 + ((double)c0 + 0.5) * stride, wx2 = b2 + ((double)(c0 + nc - 1) + 0.5) * stride;
                     if ((gx2 > wx1) && (gx1 < wx2)) reach |= 1u << h;
@@ -813,7 +854,7 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
     for (int half = 0; half < XT; ++half) {
         const int cx0 = cxt + 32 * half;
         const int ncols = min(32, W - cx0);
-        if (ncols <= 0) break;                              // block-uniform
+        if (half >= xt || ncols <= 0) break;                // block-uniform
         const bool valid_x = lane < ncols;
         // ---- column extent (per thread) ----------------------------------------------------------------------------
         const double sx = ((double)(cx0 + lane) + 0.5) * stride;
@@ -928,7 +969,7 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
                 }
             }
         }
-        const bool last = (half == XT - 1) || (W - (cx0 + 32) <= 0);       // block-uniform
+        const bool last = (half == xt - 1) || (W - (cx0 + 32) <= 0);       // block-uniform
         if (last && (p.npos || p.npos_total)) {
             my_pos = rn_warp_sum(my_pos);
             if (lane == 0 && my_pos) atomicAdd(&s_npos, my_pos);
@@ -941,6 +982,19 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
         }
         tile_write_out<C1>(p, s_reg, s_lab, s_state, s_hot, b, lstart, cy0, cx0, W, A, ncols, nrows, reg_stride, lab_stride, tid, nthreads);
     }
+#ifdef RN_K1_TRACE
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long t1; unsigned sm;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+        const unsigned id = blockIdx.x;
+        if (id < 16384) {
+            g_k1_trace[4 * id] = trace_t0; g_k1_trace[4 * id + 1] = t1; g_k1_trace[4 * id + 2] = sm;
+            g_k1_trace[4 * id + 3] = (unsigned long long)level | ((unsigned long long)b << 8) | ((unsigned long long)tile_id << 16);
+        }
+    }
+#endif
 }
 
 __global__ void k_anchors_f64(const RnLevels lv, const double* base, int N, double* out) {
@@ -1123,19 +1177,28 @@ extern "C" int rn_anchor_targets_ordered(const double* base_anchors_dev, const i
         // <= 9 anchor types and <= 32 tables per page (the table-detection case): the y-target-table kernel; the common
         // instantiation (one class, no argmax tensor) is specialised; everything else goes through the general tile kernel
         if (tiles > 0 && A <= K32_A && Gmax <= K32_G) {
-            // (a CTA of this kernel walks K32_XT x tiles: its own tile table)
-            K1Tiles t2 = tl;
-            int n2 = 0;
-            for (int l = 0; l < num_levels; ++l) {
-                const int h = level_hw[2 * l], w = level_hw[2 * l + 1];
-                const int tx = (w + 32 * K32_XT - 1) / (32 * K32_XT);
-                t2.tile_start[l] = n2;
-                t2.tiles_x[l] = tx > 0 ? tx : 1;
-                t2.inv_tiles_x[l] = 1.0f / (float)t2.tiles_x[l];
-                n2 += tx * ((h + KT_ROWS - 1) / KT_ROWS);
-            }
-            for (int l = num_levels; l <= RN_MAX_LEVELS; ++l) t2.tile_start[l] = n2;
-            const dim3 g2((unsigned)n2, (unsigned)B);
+            // (a CTA of this kernel walks K32_XT x tiles -- the first page slots -- or one -- the last ones: two tile tables)
+            K1Tiles32 t2;
+            auto fill = [&](K1Tiles& tt, int xt) {
+                int n = 0;
+                for (int l = 0; l < RN_MAX_LEVELS; ++l) { tt.tile_start[l] = 0; tt.tiles_x[l] = 1; tt.inv_tiles_x[l] = 1.0f; }
+                for (int l = 0; l < num_levels; ++l) {
+                    const int h = level_hw[2 * l], w = level_hw[2 * l + 1];
+                    const int tx = (w + 32 * xt - 1) / (32 * xt);
+                    tt.tile_start[l] = n;
+                    tt.tiles_x[l] = tx > 0 ? tx : 1;
+                    tt.inv_tiles_x[l] = 1.0f / (float)tt.tiles_x[l];
+                    n += tx * ((h + KT_ROWS - 1) / KT_ROWS);
+                }
+                for (int l = num_levels; l <= RN_MAX_LEVELS; ++l) tt.tile_start[l] = n;
+                return n;
+            };
+            const int n_coarse = fill(t2.c, K32_XT), n_fine = fill(t2.f, 1);
+            const int fine_pages = k32_fine_pages(B);
+            t2.coarse_pages = B - fine_pages;
+            const long long ctas = (long long)t2.coarse_pages * n_coarse + (long long)fine_pages * n_fine;
+            if (ctas > 0x7fffffffll) return rn_fail(RN_ERR_BAD_ARG, "rn_anchor_targets: %lld CTAs", ctas);
+            const dim3 g2((unsigned)ctas);
             const size_t dyn2 = k32_dyn_smem(A);
             if (C != 1) k_anchor_targets_tiles32<false, true, K32_XT><<<g2, 32 * A, dyn2, s>>>(p, t2);
             else if (argmax_out) k_anchor_targets_tiles32<true, true, K32_XT><<<g2, 32 * A, dyn2, s>>>(p, t2);
@@ -1177,3 +1240,9 @@ extern "C" int rn_compute_overlap(const double* boxes1_dev, long long M, const d
     k_compute_overlap<<<blocks, 256, 0, (cudaStream_t)stream>>>(boxes1_dev, M, boxes2_dev, G, iou_out);
     return rn_check_launch("rn_compute_overlap");
 }
+
+#ifdef RN_K1_TRACE
+extern "C" int rn_debug_k1_trace(unsigned long long* host_out, int ctas) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_k1_trace, sizeof(unsigned long long) * 4 * (size_t)ctas);
+}
+#endif
