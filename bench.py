@@ -271,6 +271,11 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # helpers of our arm
 # ------------------------------------------------------------------------------------------------
+TRAIN_NOTE = ("mean over a train of back-to-back launches of this kernel alone between ONE pair of CUDA events, operands "
+              "rotating over several sets (a tensor is touched again only after more than the 126 MB L2 of other traffic); "
+              "us_between_events_after_l2_flush = one launch between two events behind a 512 MB read, which adds 3-5 us of "
+              "front-end latency per interval and a cold instruction cache (round 2's earlier figure)")
+
 class Ctx(object):
     """Process-wide handles of one benchmark run."""
 
@@ -314,6 +319,31 @@ class Ctx(object):
         self.windows.append((t0, time.perf_counter()))
         return e0.elapsed_time(e1)
 
+    def train_us(self, launches, reps, host_us=12.0):
+        """Mean duration (us) of ONE launch inside a train of `reps` back-to-back launches: the callables of `launches` are
+        called in rotation (their operands together exceed the L2 several times, so no launch finds its inputs there), with
+        ONE pair of CUDA events around the whole train.  The interval between two events around a single short kernel
+        carries 3-5 us of front-end latency that is not the kernel's (ncu's gpu__time_duration of the same launches is that
+        much shorter); a train amortises it.  Before the first event the GPU is kept busy reading a 512 MB buffer long enough
+        for the host to enqueue the whole train (`host_us` per call), so the events bracket kernels, not launch gaps."""
+        torch = self.torch
+        if getattr(self, "_busy", None) is None:
+            self._busy = torch.zeros(512 << 20, dtype=torch.uint8, device=self.device)
+        for f in launches:
+            f()
+        self.barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(2 + int(reps * host_us / 150.0)):    # one read of the buffer takes ~250 us
+            self._busy.amax()
+        e0.record()
+        for i in range(reps):
+            launches[i % len(launches)]()
+        e1.record()
+        self.barrier()
+        self.windows.append((t0, time.perf_counter()))
+        return e0.elapsed_time(e1) * 1e3 / reps
+
     def max_over_ranks(self, values):
         t = self.torch.tensor([float(v) for v in values], dtype=self.torch.float64, device=self.device)
         if self.world > 1:
@@ -329,33 +359,28 @@ class Ctx(object):
         return [float(x) for x in out]
 
 
-def filter_kernel_times(ctx, steps_eager, reps):
-    """us of k_threshold_keys, k_segment_nms, k_merge_topk inside ONE filter call: the library records four CUDA events
-    around them (rn_debug_filter_events).  `steps_eager`: DetectionStep(use_graph=False) objects cycled so that every call
-    reads inputs that are not in L2."""
+def filter_kernel_times(ctx, dets, reps):
+    """us of k_threshold_keys (incl. the workspace reset in front of it), k_segment_nms, k_merge_topk: each stage of the filter
+    call timed ALONE as a train of back-to-back launches (Ctx.train_us).  `dets`: DetectionStep objects (CUDA graphs) whose
+    inputs together exceed the L2 several times, each with its own workspace holding the slabs / kept lists of a full call;
+    rn_debug_filter_stages(mask) makes the library launch one stage only, and the objects re-capture their graph under it."""
     torch, lib = ctx.torch, ctx.rn._lib.load()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    for e in evs:
-        e.record()                                          # creates the handles
+    for d in dets:
+        d.run()                                             # a full call: slabs and kept lists for the single-stage launches
     torch.cuda.synchronize()
-    for st in steps_eager:
-        st.run()
-    torch.cuda.synchronize()
-    acc = np.zeros(3)
-    # before every timed call a 512 MB buffer is READ on the same stream (a reduction): it replaces the contents of the 126 MB
-    # L2 with clean lines (a write would leave dirty lines whose write-back competes with the timed kernel), and it keeps the
-    # GPU busy while the host enqueues the call's launches, so the events see the kernels back to back, not launch gaps
-    flush = torch.zeros(512 << 20, dtype=torch.uint8, device=ctx.device)
-    lib.rn_debug_filter_events(*[ctypes.c_void_p(e.cuda_event) for e in evs])
+    out = []
     try:
-        for i in range(reps):
-            flush.amax()
-            steps_eager[i % len(steps_eager)].run()
-            torch.cuda.synchronize()
-            acc += [evs[k].elapsed_time(evs[k + 1]) * 1e3 for k in range(3)]
+        for mask in (1, 2, 4):
+            lib.rn_debug_filter_stages(mask)
+            for d in dets:
+                d._graph = None
+                d.run()                                     # captures this stage alone
+            out.append(ctx.train_us([d._graph.replay for d in dets], reps))
     finally:
-        lib.rn_debug_filter_events(None, None, None, None)
-    return acc / reps
+        lib.rn_debug_filter_stages(7)
+        for d in dets:
+            d._graph = None
+    return np.array(out)
 
 
 def h2d_ceiling(ctx, nbytes, reps=8):
@@ -458,10 +483,27 @@ def leg_training(ctx):
     step.use_graph = graphs_on
     del flush
     split_ms = sum(e[0].elapsed_time(e[2]) for e in evs)
-    k1_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
-    k2_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / steps
+    k1_ev_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
+    k2_ev_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / steps
     losses = step.losses.cpu().numpy()
     step.check()
+    # timed region 3 (the rooflines' durations): each kernel ALONE as a train of back-to-back launches, one pair of events
+    # around the train (Ctx.train_us).  Three objects with their own targets / head outputs / gradients in rotation: a K1
+    # launch writes 90 MB, a K2 launch reads and writes 103 MB, so a tensor is touched again only after ~200 MB of other
+    # traffic through the 126 MB L2.  No mailbox on these objects: K2 here is the kernel without the exchange wait.
+    rot = [rn.pipeline.TargetLossStep(HW + (3,), B, GMAX, C, peer_box=False) for _ in range(3)]
+    for r in rot:
+        r.load_annotations(images, anns)
+        r.load_predictions(cls_host, reg_host)
+        r._build_graphs()
+        r._graphs[0].replay()
+        r._graphs[1].replay()
+    torch.cuda.synchronize()
+    assert torch.equal(rot[0].y_cls, step.y_cls) and torch.equal(rot[0].grad_cls, step.grad_cls) or world > 1
+    reps_train = max(30, min(3 * steps, 150))
+    k1_ms = min(ctx.train_us([r._graphs[0].replay for r in rot], reps_train) for _ in range(2)) * 1e-3
+    k2_ms = min(ctx.train_us([r._graphs[1].replay for r in rot], reps_train) for _ in range(2)) * 1e-3
+    del rot
 
     # ---- e2e: public API, host inputs every step -------------------------------------------------------
     sync_ms = e2e_ms = full_ms = float("nan")
@@ -504,8 +546,8 @@ def leg_training(ctx):
             full_ms = ctx.timed(lambda: step.run_from_host(images, anns, cls_host, reg_host, chunks=E2E_CHUNKS), steps, warm=3)
         ceiling = h2d_ceiling(ctx, int(h2d))
 
-    total_ms, e2e_ms, k1_max, k2_ms, split_ms, full_ms, sync_ms, ov_ms = ctx.max_over_ranks(
-        [total_ms, e2e_ms, k1_ms, k2_ms, split_ms, full_ms, sync_ms, ov_ms])
+    total_ms, e2e_ms, k1_max, k2_ms, split_ms, full_ms, sync_ms, ov_ms, k1_ev_ms, k2_ev_ms = ctx.max_over_ranks(
+        [total_ms, e2e_ms, k1_ms, k2_ms, split_ms, full_ms, sync_ms, ov_ms, k1_ev_ms, k2_ev_ms])
     k1_per_rank = ctx.gather_ranks(k1_ms * 1e3)
     ceil_min = min(ctx.gather_ranks(ceiling)) if ceiling is not None else None
     k1_ms = k1_max
@@ -593,15 +635,18 @@ def leg_training(ctx):
                          "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic("k_anchor_targets_tiles32"),
                          "peak_source": peak_src, "bytes_per_launch": k1_bytes, "bytes_per_anchor": k1_bytes / (N * B),
                          "us_per_launch": k1_ms * 1e3, "us_per_launch_by_rank": k1_per_rank, "share_of_step": k1_ms / (k1_ms + k2_ms),
+                         "timing": TRAIN_NOTE, "us_between_events_after_l2_flush": k1_ev_ms * 1e3,
                          "note": "write-only 28 B/anchor; limited by instruction issue (fp64 matching for every anchor x "
-                                 "overlapping GT; ncu: issue slots 67 % busy, DRAM 9 %), see DESIGN.md section 3"},
+                                 "overlapping GT; ncu: issue slots 65 % busy, DRAM 10 %), see DESIGN.md section 3"},
             "roofline_k2": {"kernel": "k_loss_c1_fast (K2 fused focal + smooth-L1 fwd+bwd)", "bound": "hbm",
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": ncu_traffic("k_loss_c1_fast"), "peak_source": peak_src, "bytes_per_launch": k2_bytes,
                             "bytes_per_anchor": k2_bytes / (N * B), "us_per_launch": k2_ms * 1e3,
                             "share_of_step": k2_ms / (k1_ms + k2_ms),
                             "achieved_survey_bytes": k2_bytes_survey / (k2_ms * 1e-3) / 1e9,
-                            "note": "with several ranks the launch includes the wait for the slowest rank's count"},
+                            "timing": TRAIN_NOTE, "us_between_events_after_l2_flush": k2_ev_ms * 1e3,
+                            "note": "the kernel alone (rank-local normaliser); in the step with several ranks the launch also "
+                                    "holds the wait for the slowest rank's count: us_between_events_after_l2_flush"},
             "ms_per_step_split_graphs": split_ms / steps,
             "overlapped_schedule": None if ov_ms != ov_ms else {
                 "pages_per_s": world * B * steps / (ov_ms * 1e-3), "ms_per_step": ov_ms / steps,
@@ -673,12 +718,13 @@ def leg_inference(ctx):
         torch.cuda.synchronize()
         ms_2s = e0.elapsed_time(e1) / (2 * steps)
         assert torch.equal(dets[0].scores, res[1])
-        # per-kernel durations: eager calls (no graph) with the library's event hook, the same rotation of inputs
-        eager = [rn.pipeline.DetectionStep(HW, B, 1, head=head, use_graph=False) for _ in range(SETS)]
-        for e, d in zip(eager, dets):
-            e.cls_pred, e.reg_pred = d.cls_pred, d.reg_pred
-        k3_us, nms_us, merge_us = filter_kernel_times(ctx, eager, reps=max(6, min(steps, 30)))
-        del eager
+        # per-kernel durations: every stage alone as a train of back-to-back launches; six input sets in rotation here
+        # (6 x 51 MB of scores: a set is read again after 257 MB of other scores went through the 126 MB L2)
+        more = [rn.pipeline.DetectionStep(HW, B, 1, head=head) for _ in range(3)]
+        for k, d in enumerate(more):
+            d.load_predictions(torch.roll(cls_host, SETS + k, 0).to(device), torch.roll(reg_host, SETS + k, 0).to(device))
+        k3_us, nms_us, merge_us = filter_kernel_times(ctx, dets + more, reps=max(30, min(3 * steps, 120)))
+        del more
         # e2e: host head outputs in, detections out.  (a) both tensors copied; (b) scores copied, the visited candidates'
         # regression rows read in place from pinned memory; (c) the same with two batches in flight
         e0.record()
@@ -720,7 +766,8 @@ def leg_inference(ctx):
                     "api": "pipeline.DetectionStep.run(): K3 + K4/K5 + merge as one CUDA graph, one stream, %d input sets in rotation" % SETS,
                     "pages_per_s_two_streams": world * B / (ms_2s * 1e-3),
                     "kernels_us": {"k_threshold_keys": k3_us, "k_segment_nms": nms_us, "k_merge_topk": merge_us,
-                                   "note": "CUDA events recorded by the library around the three kernels of one (eager) call"},
+                                   "note": "each stage alone as a train of back-to-back launches (rn_debug_filter_stages), six input sets in rotation; "
+                                           "k_threshold_keys includes the workspace reset (one memset node) in front of it"},
                     "e2e_pages_per_s": world * B / (ms_e2e * 1e-3), "e2e_api": "HostDetectionPipeline.submit / result, 2 batches in flight",
                     "e2e_h2d_bytes_per_batch": int(cls_host.numel() * 4), "e2e_d2h_bytes_per_batch": int(B * 300 * 24),
                     "e2e_one_batch_at_a_time_pages_per_s": world * B / (ms_e2e_sync * 1e-3),
@@ -732,7 +779,7 @@ def leg_inference(ctx):
                                   "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                   "traffic": ncu_traffic("k_threshold_keys_stream"), "peak_source": peak_src,
                                   "bytes_per_launch": k3_bytes, "bytes_formula": "4*C*N*B scores read + 8 per candidate (key written)",
-                                  "us_per_launch": k3_us,
+                                  "us_per_launch": k3_us, "timing": TRAIN_NOTE,
                                   "achieved_survey_bytes": 20.0 * N * B / (k3_us * 1e-6) / 1e9,
                                   "survey_bytes_note": "SURVEY 8(d) counts 20 B/anchor (every regression row read); the kernel reads "
                                                        "none of them -- rows are fetched by the NMS kernel for visited candidates only -- "
@@ -777,22 +824,37 @@ def leg_full(ctx, k):
     ms = ctx.timed(one, steps) / steps
     det.check()
     step.check()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
-    flush = torch.zeros(512 << 20, dtype=torch.uint8, device=device)
-    step.use_graph = False                                  # eager launches: the events sit right at the kernels
-    step.run(events=evs[0])
-    ctx.barrier()
-    for i in range(steps):
-        flush.amax()
-        step.run(events=evs[i])
-    ctx.barrier()
-    step.use_graph = True
-    del flush
-    k1_us = sum(e[0].elapsed_time(e[1]) for e in evs) / steps * 1e3
-    k2_us = sum(e[1].elapsed_time(e[2]) for e in evs) / steps * 1e3
-    eager = rn.pipeline.DetectionStep(hw, B, C, use_graph=False)
-    eager.cls_pred, eager.reg_pred = cls_d, reg_d
-    k3_us, nms_us, merge_us = filter_kernel_times(ctx, [eager], reps=max(3, min(steps, 10)))
+    # per-kernel durations: each kernel alone as a train of back-to-back launches (Ctx.train_us).  configs[3]'s tensors are
+    # smaller than the L2 (K1 writes 81 MB, K2 moves 92 MB), so three objects with their own targets / gradients / score
+    # copies rotate; configs[4]'s are 1 - 3 GB per launch and need no rotation
+    small = (12.0 * C + 20) * N * B < 4.0 * (126 << 20)
+    rot = [step]
+    for _ in range(2 if small else 0):
+        r = rn.pipeline.TargetLossStep(hw + (3,), B, gmax, C, peer_box=False)
+        r.load_annotations(images, anns)
+        r.cls_pred, r.reg_pred = cls_d.clone(), reg_d.clone()
+        r.grad_cls, r.grad_reg = torch.empty_like(cls_d), torch.empty_like(reg_d)
+        rot.append(r)
+    if step.peer is not None:                               # the kernel alone: an object without the mailbox stands in for `step`
+        r = rn.pipeline.TargetLossStep(hw + (3,), B, gmax, C, peer_box=False)
+        r.load_annotations(images, anns)
+        r.cls_pred, r.reg_pred, r.grad_cls, r.grad_reg = cls_d, reg_d, step.grad_cls, step.grad_reg
+        rot[0] = r
+    for r in rot:
+        if r._graphs is None:
+            r._build_graphs()
+        r._graphs[0].replay()
+        r._graphs[1].replay()
+    reps_train = max(10, min(3 * steps, 60))
+    k1_us = ctx.train_us([r._graphs[0].replay for r in rot], reps_train)
+    k2_us = ctx.train_us([r._graphs[1].replay for r in rot], reps_train)
+    dets = [det]
+    for r in rot[1:] if small else []:
+        d = rn.pipeline.DetectionStep(hw, B, C)
+        d.cls_pred, d.reg_pred = r.cls_pred, r.reg_pred
+        dets.append(d)
+    k3_us, nms_us, merge_us = filter_kernel_times(ctx, dets, reps=reps_train)
+    del rot, dets
     ms, k1_us, k2_us, k3_us, nms_us, merge_us = ctx.max_over_ranks([ms, k1_us, k2_us, k3_us, nms_us, merge_us])
     n_pos = float(step.npos.sum().item())
     cands = float((cls_d > 0.05).sum().item())
@@ -813,7 +875,7 @@ def leg_full(ctx, k):
            "candidates_per_page": cands / B, "detections_per_page": ndet / B, "positives_per_page": n_pos / B,
            "losses": {"focal": float(losses[0]), "smooth_l1": float(losses[1]), "normalizer": float(losses[2])},
            "data": "synthetic (torch generator on the device; distributions of SURVEY 8d)"}
-    del step, det, eager, cls_d, reg_d
+    del step, det, cls_d, reg_d
     torch.cuda.empty_cache()
     return out
 

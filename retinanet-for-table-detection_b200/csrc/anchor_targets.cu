@@ -977,6 +977,7 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the staged rows are read by the TMA engine below
         __syncthreads();
         if (last && tid == 0 && s_npos) {
+            rn_grid_dependency_wait();                      // the counters are zeroed by the launch in front of this one
             if (p.npos) atomicAdd(p.npos + b, s_npos);
             if (p.npos_total) atomicAdd(p.npos_total, (float)s_npos);   // integer-valued: exact, order-independent
         }
@@ -1132,19 +1133,11 @@ extern "C" int rn_anchor_targets_ordered(const double* base_anchors_dev, const i
     p.vec_ok = rn_aligned16(regression_out) && rn_aligned16(labels_out);
     RN_REQUIRE((reinterpret_cast<uintptr_t>(labels_out) & 7u) == 0, "labels_out must be 8-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    if (npos_out && npos_total_out && reinterpret_cast<char*>(npos_total_out) == reinterpret_cast<char*>(npos_out + B)) {
-        // the two counters are adjacent (as TargetLossStep allocates them): one memset node instead of two
-        cudaError_t e = cudaMemsetAsync(npos_out, 0, sizeof(int) * (size_t)B + sizeof(float), s);
-        if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset npos: %s", cudaGetErrorString(e));
-    } else {
-        if (npos_out) {
-            cudaError_t e = cudaMemsetAsync(npos_out, 0, sizeof(int) * (size_t)B, s);
-            if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset npos: %s", cudaGetErrorString(e));
-        }
-        if (npos_total_out) {
-            cudaError_t e = cudaMemsetAsync(npos_total_out, 0, sizeof(float), s);
-            if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset npos_total: %s", cudaGetErrorString(e));
-        }
+    // the two counters are zeroed by ONE small kernel that lets K1 launch behind it at once (rn_common.cuh); K1 touches them at
+    // the very end of a CTA (k_anchor_targets_tiles32 waits for the reset there; the other kernels are launched plainly)
+    {
+        int rc0 = rn_reset_ints(npos_out, B, reinterpret_cast<int*>(npos_total_out), 1, s);
+        if (rc0) return rc0;
     }
     dim3 grid((unsigned)((num_anchors + K1_THREADS - 1) / K1_THREADS), (unsigned)B);
     if (anchors_dev) {
@@ -1200,9 +1193,9 @@ extern "C" int rn_anchor_targets_ordered(const double* base_anchors_dev, const i
             if (ctas > 0x7fffffffll) return rn_fail(RN_ERR_BAD_ARG, "rn_anchor_targets: %lld CTAs", ctas);
             const dim3 g2((unsigned)ctas);
             const size_t dyn2 = k32_dyn_smem(A);
-            if (C != 1) k_anchor_targets_tiles32<false, true, K32_XT><<<g2, 32 * A, dyn2, s>>>(p, t2);
-            else if (argmax_out) k_anchor_targets_tiles32<true, true, K32_XT><<<g2, 32 * A, dyn2, s>>>(p, t2);
-            else k_anchor_targets_tiles32<true, false, K32_XT><<<g2, 32 * A, dyn2, s>>>(p, t2);
+            if (C != 1) return rn_launch_dependent("rn_anchor_targets", k_anchor_targets_tiles32<false, true, K32_XT>, g2, dim3(32 * A), dyn2, s, p, t2);
+            else if (argmax_out) return rn_launch_dependent("rn_anchor_targets", k_anchor_targets_tiles32<true, true, K32_XT>, g2, dim3(32 * A), dyn2, s, p, t2);
+            else return rn_launch_dependent("rn_anchor_targets", k_anchor_targets_tiles32<true, false, K32_XT>, g2, dim3(32 * A), dyn2, s, p, t2);
         } else if (tiles > 0 && A <= 9) {
             if (C == 1) k_anchor_targets_tiles<9, 3, true, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);
             else k_anchor_targets_tiles<9, 3, false, true><<<tgrid, 32 * A, dyn, s>>>(p, tl);

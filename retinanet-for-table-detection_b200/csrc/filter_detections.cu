@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(K3_THREADS, K3S_CTAS_PER_SM) k_threshold_keys_
     };
     int t = t_begin + warp;
     load(t);
+    rn_grid_dependency_wait();                              // the slab counters are being zeroed by the launch in front (first loads already in flight)
     for (; t < t_end; t += K3_THREADS / 32) {
         float sc[K3S_VEC * 4];
 #pragma unroll
@@ -1344,6 +1345,11 @@ size_t nms_dynamic_smem(int max_det) {      // selected boxes + weights, the mer
 std::atomic<int> g_phase_timing{0};
 // measurement hook (rn_debug_filter_events): four cudaEvent_t recorded around the three kernels of a filter call
 std::atomic<void*> g_events[4];
+// measurement hook (rn_debug_filter_stages): which of the three stages a filter call launches -- bit 0: the workspace reset +
+// k_threshold_keys, bit 1: k_segment_nms, bit 2: k_merge_topk.  A stage run alone works on what an earlier full call left in
+// the workspace (the NMS kernel only reads the slabs, the merge only the kept lists), so every kernel can be timed as a train
+// of back-to-back launches without events in between.
+std::atomic<int> g_stages{7};
 
 int record_event(int k, cudaStream_t s) {
     void* ev = g_events[k].load(std::memory_order_relaxed);
@@ -1400,8 +1406,10 @@ int run_back_end(const FilterWs& w, const BoxSource& src, bool decode, int B, in
     const size_t dyn = nms_dynamic_smem(max_det);
     int rc = nms_opt_in_shared_memory();
     if (rc) return rc;
+    const int stages = g_stages.load(std::memory_order_relaxed);
     const bool slot = w.labels != nullptr;              // only class-agnostic filtering reads per-candidate labels
-    if (decode) { if (slot) k_segment_nms<true, true><<<S, NMS_THREADS, dyn, s>>>(np); else k_segment_nms<true, false><<<S, NMS_THREADS, dyn, s>>>(np); }
+    if (!(stages & 2)) { /* measurement: NMS stage skipped */ }
+    else if (decode) { if (slot) k_segment_nms<true, true><<<S, NMS_THREADS, dyn, s>>>(np); else k_segment_nms<true, false><<<S, NMS_THREADS, dyn, s>>>(np); }
     else { if (slot) k_segment_nms<false, true><<<S, NMS_THREADS, dyn, s>>>(np); else k_segment_nms<false, false><<<S, NMS_THREADS, dyn, s>>>(np); }
     rc = rn_check_launch("k_segment_nms");
     if (rc) return rc;
@@ -1412,7 +1420,9 @@ int run_back_end(const FilterWs& w, const BoxSource& src, bool decode, int B, in
     mp.out_boxes = out_boxes; mp.out_scores = out_scores; mp.out_labels = out_labels; mp.out_indices = out_indices;
     mp.out_count = out_count;
     const size_t sel_smem = ((size_t)segs_per_page * max_det + NMS_CHUNK) * sizeof(unsigned long long);
-    if (segs_per_page > 1 && segs_per_page <= 65535 && sel_smem <= MERGE_SMEM_MAX) {
+    if (!(stages & 4)) {
+        // measurement: merge stage skipped
+    } else if (segs_per_page > 1 && segs_per_page <= 65535 && sel_smem <= MERGE_SMEM_MAX) {
         rc = merge_opt_in_shared_memory();
         if (rc) return rc;
         k_merge_topk_select<<<B, MERGE_THREADS, sel_smem, s>>>(mp);
@@ -1442,12 +1452,13 @@ int filter_common(K3Params kp, const BoxSource& src, bool decode, int nms, float
     const int S = (int)S64;
     FilterWs w = carve(workspace, B, S, cand_cap, max_det, !kp.class_specific);
     if (workspace_bytes < w.bytes) return rn_fail(RN_ERR_WORKSPACE, "filter workspace too small: %zu < %zu", workspace_bytes, w.bytes);
-    // timing, counts, kept_count, status are contiguous at the front of the workspace
-    cudaError_t e = cudaMemsetAsync(w.timing, 0, (size_t)((char*)w.keys - (char*)w.timing), s);
-    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
-    if (status_out) {
-        e = cudaMemsetAsync(status_out, 0, sizeof(int) * (size_t)B, s);
-        if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+    const bool first_stage = (g_stages.load(std::memory_order_relaxed) & 1) != 0;    // (always, outside measurements)
+    // timing, counts, kept_count, status are contiguous at the front of the workspace: they and the caller's status words are
+    // zeroed by ONE small kernel that lets the threshold kernel launch behind it at once (rn_common.cuh)
+    if (first_stage) {
+        int rc0 = rn_reset_ints(reinterpret_cast<int*>(w.timing), (long long)(((char*)w.keys - (char*)w.timing) / sizeof(int)),
+                                status_out, B, s);
+        if (rc0) return rc0;
     }
     kp.sl.counts = w.counts; kp.sl.keys = w.keys; kp.sl.labels = w.labels; kp.sl.cap = cand_cap;
     RN_REQUIRE((long long)kp.N * C < (1ll << 31) - 4096, "N * C too large for one page");
@@ -1457,7 +1468,9 @@ int filter_common(K3Params kp, const BoxSource& src, bool decode, int nms, float
     int rc = record_event(0, s);
     if (rc) return rc;
     const long long page_tiles = ((long long)kp.N * C + K3S_TILE - 1) / K3S_TILE;
-    if (kp.class_specific && kp.vec_ok) {
+    if (!first_stage) {
+        // measurement: the slabs of an earlier call are reused
+    } else if (kp.class_specific && kp.vec_ok) {
         // about SMs x 4 CTAs over all pages, each CTA a contiguous slice of one page (at least one tile per warp)
         // ONE wave: no more CTAs than the GPU holds at once (640 CTAs on 592 slots ran a second, nearly empty wave: 16 us
         // instead of 12)
@@ -1467,7 +1480,8 @@ int filter_common(K3Params kp, const BoxSource& src, bool decode, int nms, float
         if (per_page < 1) per_page = 1;
         const int tiles_per_cta = (int)((page_tiles + per_page - 1) / per_page);
         const dim3 grid((unsigned)((page_tiles + tiles_per_cta - 1) / tiles_per_cta), (unsigned)B);
-        k_threshold_keys_stream<<<grid, K3_THREADS, 0, s>>>(kp, (int)page_tiles, tiles_per_cta);
+        int rc1 = rn_launch_dependent("k_threshold_keys_stream", k_threshold_keys_stream, grid, dim3(K3_THREADS), 0, s, kp, (int)page_tiles, tiles_per_cta);
+        if (rc1) return rc1;
     } else {
         // class-agnostic filtering (max over classes per anchor) or unaligned page rows: the tile-per-CTA kernel
         const long long tiles = kp.class_specific ? ((long long)kp.N * C + K3_TILE - 1) / K3_TILE
@@ -1487,6 +1501,11 @@ int filter_common(K3Params kp, const BoxSource& src, bool decode, int nms, float
 
 extern "C" int rn_debug_nms_timing(int enable) {
     g_phase_timing.store(enable ? 1 : 0, std::memory_order_relaxed);
+    return RN_OK;
+}
+
+extern "C" int rn_debug_filter_stages(int mask) {
+    g_stages.store(mask & 7, std::memory_order_relaxed);
     return RN_OK;
 }
 

@@ -125,3 +125,45 @@ __device__ __forceinline__ void rn_stg_stream4(float* p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+
+// ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (sm_90+): "reset, then the real kernel" without the launch latency in between.
+// k_rn_reset zeroes up to two small int ranges (counters, status words) and allows its dependents to launch at once; the
+// kernel behind it is launched with rn_launch_dependent (programmatic stream serialisation) so that its CTAs are placed and
+// run their prologue while the reset is still in flight, and calls rn_grid_dependency_wait() before it first touches what the
+// reset writes.  None of the other kernels triggers early, so a dependent launched behind one of them is ordered like a plain
+// launch.  Works eagerly and under stream capture (programmatic edges in the graph).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rn_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void rn_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+static __global__ void k_rn_reset(int* a, int na, int* b, int nb) {
+    rn_launch_dependents();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < na; i += gridDim.x * blockDim.x) a[i] = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x) b[i] = 0;
+}
+
+// zero `na` ints at a and `nb` ints at b (either may be empty) on the stream; one launch
+static inline int rn_reset_ints(int* a, long long na, int* b, long long nb, cudaStream_t s) {
+    if (a == nullptr) na = 0;
+    if (b == nullptr) nb = 0;
+    if (na + nb <= 0) return RN_OK;
+    const long long most = na > nb ? na : nb;
+    const int blocks = (int)(most > 256 * 64 ? 64 : (most + 255) / 256);
+    k_rn_reset<<<blocks, 256, 0, s>>>(a, (int)na, b, (int)nb);
+    return rn_check_launch("k_rn_reset");
+}
+
+template <typename... KArgs, typename... Args>
+static inline int rn_launch_dependent(const char* what, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                      cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return rn_check_launch(what);
+}
