@@ -87,6 +87,21 @@ int rn_anchor_targets_ordered(const double* base_anchors_dev, const int* level_h
                               float* regression_out, float* labels_out, int* argmax_out, int* npos_out,
                               float* npos_total_out, const int* page_order_dev, void* stream);
 
+/* The training step's form of the same targets (an EXTENSION; rn_anchor_targets stays the drop-in for anchor_targets_bbox):
+ * generated anchors, one class, <= 9 anchor types per cell, <= 32 tables per page.  labels_out, npos_out, npos_total_out are
+ * exactly what rn_anchor_targets writes; of regression_out (B, N, 5) ONLY the rows of anchors whose final state is 1 are
+ * written (bit-identical to rn_anchor_targets' rows), every other row is left untouched.  That is all the smooth-L1 loss
+ * ever reads when it takes the anchor state from the label tensor (model/losses.py:72-74 gathers the state == 1 rows;
+ * rn_loss_fwd_bwd with RN_LOSS_SHARED_STATE), and it takes 20 of the 28 bytes per anchor and the four fp64 quotients of
+ * every non-positive anchor out of the kernel. */
+int rn_anchor_targets_sparse(const double* base_anchors_dev, const int* level_hw, const int* level_stride,
+                             int num_levels, int anchors_per_cell, long long num_anchors,
+                             const double* gt_boxes_dev, const int* gt_labels_dev, const int* gt_count_dev,
+                             const int* img_hw_dev, int B, int Gmax,
+                             float neg_overlap, float pos_overlap,
+                             float* regression_out, float* labels_out, int* npos_out,
+                             float* npos_total_out, const int* page_order_dev, void* stream);
+
 /* anchors_for_shape (model/anchors.py:169-204) on the device: (N,4) float64. */
 int rn_anchors_f64(const double* base_anchors_dev, const int* level_hw, const int* level_stride,
                    int num_levels, int anchors_per_cell, double* anchors_out, void* stream);

@@ -41,6 +41,8 @@ SIGNATURES = {
                                   c_float, c_float, _P, _P, _P, _P, _P, _P]),
     "rn_anchor_targets_ordered": (c_int, [_P, _HI, _HI, c_int, c_int, _P, c_longlong, _P, _P, _P, _P, c_int, c_int, c_int,
                                           c_float, c_float, _P, _P, _P, _P, _P, _P, _P]),
+    "rn_anchor_targets_sparse": (c_int, [_P, _HI, _HI, c_int, c_int, c_longlong, _P, _P, _P, _P, c_int, c_int,
+                                         c_float, c_float, _P, _P, _P, _P, _P, _P]),
     "rn_anchors_f64": (c_int, [_P, _HI, _HI, c_int, c_int, _P, _P]),
     "rn_compute_overlap": (c_int, [_P, c_longlong, _P, c_int, _P, _P]),
     "rn_bbox_transform": (c_int, [_P, _P, c_longlong, POINTER(c_double), POINTER(c_double), _P, _P]),

@@ -309,13 +309,16 @@ def upload_annotations(boxes, labels, counts, img_hw, device):
 
 def anchor_targets_device(anchors, d_boxes, d_labels, d_counts, d_hw, num_classes,
                           negative_overlap=0.4, positive_overlap=0.5, want_argmax=False, out=None,
-                          npos_total=None, npos_out=None, page_order=None):
+                          npos_total=None, npos_out=None, page_order=None, sparse_regression=False):
     """Launch K1 on GT already resident on the device.  ``anchors``: an :class:`AnchorArray` /
     :class:`AnchorSpec` (generated in-kernel) or a CUDA float64 (N,4) tensor (explicit).
     ``npos_total``: optional 1-float CUDA tensor receiving the batch's positive count (loss normaliser);
     ``npos_out``: optional (B,) int32 tensor for the per-page counts (when it ends where ``npos_total`` starts the
     library clears both with one memset); ``page_order``: optional (B,) int32 CUDA permutation, the order in which the
     kernel starts the pages (:func:`page_launch_order`; the results do not depend on it).
+    ``sparse_regression`` (extension, ``rn_anchor_targets_sparse``): only the regression rows of state == 1 anchors are
+    written -- all a smooth-L1 loss that takes the state from the label tensor ever reads (model/losses.py:72-74); the
+    other rows of ``regression`` keep whatever they held.  Generated anchors, one class, no argmax.
     Returns ``(regression (B,N,5), labels (B,N,C+1), npos (B) int32, argmax (B,N) int32 | None)``."""
     lib = _lib.load()
     device = d_counts.device
@@ -333,13 +336,24 @@ def anchor_targets_device(anchors, d_boxes, d_labels, d_counts, d_hw, num_classe
         N = int(explicit.shape[0])
         base, hw_p, st_p, levels, per_cell = None, None, None, 0, 0
     if out is None:
-        regression = torch.empty((B, N, 5), dtype=torch.float32, device=device)
+        # (sparse: the rows that are not written read as zeros)
+        regression = (torch.zeros if sparse_regression else torch.empty)((B, N, 5), dtype=torch.float32, device=device)
         labels = torch.empty((B, N, num_classes + 1), dtype=torch.float32, device=device)
     else:
         regression, labels = out
     npos = torch.empty((B,), dtype=torch.int32, device=device) if npos_out is None else npos_out
     argmax = torch.empty((B, N), dtype=torch.int32, device=device) if want_argmax else None
-    if N > 0:
+    if sparse_regression:
+        if explicit is not None or num_classes != 1 or want_argmax:
+            raise ValueError("sparse_regression needs generated anchors, one class and no argmax tensor")
+        if N > 0:
+            _lib.check(lib.rn_anchor_targets_sparse(_lib.ptr(base), hw_p, st_p, levels, per_cell, N,
+                                                    _lib.ptr(d_boxes), _lib.ptr(d_labels), _lib.ptr(d_counts), _lib.ptr(d_hw),
+                                                    B, G, float(np.float32(negative_overlap)), float(np.float32(positive_overlap)),
+                                                    _lib.ptr(regression), _lib.ptr(labels), _lib.ptr(npos),
+                                                    _lib.ptr(npos_total), _lib.ptr(page_order), _lib.stream_ptr(device)),
+                       "rn_anchor_targets_sparse")
+    elif N > 0:
         _lib.check(lib.rn_anchor_targets_ordered(_lib.ptr(base), hw_p, st_p, levels, per_cell,
                                                  _lib.ptr(explicit), N,
                                                  _lib.ptr(d_boxes), _lib.ptr(d_labels), _lib.ptr(d_counts), _lib.ptr(d_hw),
@@ -348,7 +362,7 @@ def anchor_targets_device(anchors, d_boxes, d_labels, d_counts, d_hw, num_classe
                                                  _lib.ptr(regression), _lib.ptr(labels), _lib.ptr(argmax), _lib.ptr(npos),
                                                  _lib.ptr(npos_total), _lib.ptr(page_order), _lib.stream_ptr(device)),
                    "rn_anchor_targets_ordered")
-    else:
+    if N <= 0:
         npos.zero_()
         if npos_total is not None:
             npos_total.zero_()

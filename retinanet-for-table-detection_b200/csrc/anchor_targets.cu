@@ -45,6 +45,7 @@ struct K1Params {
     int* npos;               // (B) or nullptr
     float* npos_total;       // 1 float or nullptr
     int vec_ok;
+    int sparse_reg;          // k_anchor_targets_tiles32<.., SPARSE>: only the regression rows of state == 1 anchors are written
     double max_coord;        // upper bound of any anchor-centre coordinate (for the reciprocal table, see wrapper)
 };
 
@@ -384,7 +385,7 @@ __device__ __noinline__ void write_out_unaligned(float* reg, float* lab, int C, 
 
 // Write-out of a tile's staged rows (shared by the tile kernels).  Each tile row is one contiguous anchor range, staged
 // with the destination's 16-byte phase.
-template <bool C1>
+template <bool C1, bool NO_REG = false>   // NO_REG: the regression rows are not staged (sparse targets): label rows only
 __device__ __forceinline__ void tile_write_out(const K1Params& p, const float* s_reg, const float* s_lab, const float* s_state,
                                                const int* s_hot, int b, int lstart, int cy0, int cx0, int W, int A, int ncols,
                                                int nrows, int reg_stride, int lab_stride, int tid, int nthreads) {
@@ -398,7 +399,7 @@ __device__ __forceinline__ void tile_write_out(const K1Params& p, const float* s
         const int job = tid;                                // jobs [0, KT_ROWS): regression rows, [KT_ROWS, 2 KT_ROWS): label rows
         const bool lab_job = job >= KT_ROWS;
         const int r = lab_job ? job - KT_ROWS : job;
-        if (job < 2 * KT_ROWS && r < nrows && !(lab_job && !C1)) {
+        if (job < 2 * KT_ROWS && r < nrows && !(lab_job && !C1) && !(NO_REG && !lab_job)) {
             const int per = lab_job ? 2 : 5;
             const long long start = (tile_row0 + (long long)r * W * A) * per;
             const int len = cnt * per, shift = (int)(start & 3);
@@ -709,7 +710,11 @@ static size_t k32_dyn_smem(int A) {
 __device__ unsigned long long g_k1_trace[4 * 16384];
 #endif
 
-template <bool C1, bool AM, int XT>
+// SPARSE (C1 only): the training step's form.  The smooth-L1 loss reads the regression targets of state == 1 anchors only
+// (model/losses.py:72-74 gathers exactly those rows), so only THOSE rows of the (B, N, 5) tensor are written -- straight from
+// the rare-positive branch, with the exact IEEE expressions -- and neither the y-target table nor any other anchor's four
+// quotients are computed: 8 instead of 28 bytes per anchor leave the SM.  Labels, states, counts: unchanged.
+template <bool C1, bool AM, int XT, bool SPARSE = false>
 __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const K1Params p, const K1Tiles32 tl) {
     extern __shared__ __align__(16) float s_dyn[];
     __shared__ double s_gx1[K32_G], s_gy1[K32_G], s_gx2[K32_G], s_gy2[K32_G], s_ga[K32_G];
@@ -847,7 +852,11 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
         if (p.img_hw) out_y = __ballot_sync(0xffffffffu, (lane < KT_ROWS) && (((y1 + y2) / 2.0) >= (double)p.img_hw[2 * b]));
         __syncwarp();                                       // the table is complete and visible to the whole warp
     };
-    if (XT > 1) make_y_table();
+    if (XT > 1 && !SPARSE) make_y_table();
+    if (SPARSE && p.img_hw) {                               // (the border mask is a by-product of make_y_table)
+        const int r = lane & (KT_ROWS - 1);
+        out_y = __ballot_sync(0xffffffffu, (lane < KT_ROWS) && (((row[r][0] + row[r][1]) / 2.0) >= (double)p.img_hw[2 * b]));
+    }
 
     int my_pos = 0;
 #pragma unroll 1
@@ -904,7 +913,7 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
                 }
             }
         }
-        if (XT == 1) {
+        if (XT == 1 && !SPARSE) {
             __syncwarp();                                   // the intersection heights are dead: their space becomes the y-target table
             make_y_table();
         }
@@ -922,7 +931,7 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
             const int k = lane * A + a;                     // reference order within the tile row
             int prev = -1;                                  // the x targets depend on the column and the table only
             float t0 = 0.f, t2 = 0.f;
-            unsigned posbits = 0u;
+            unsigned posbits = 0u, fgbits = 0u;         // fgbits (SPARSE): rows whose FINAL state is 1 (positive and inside the page)
 #pragma unroll
             for (int r = 0; r < KT_ROWS; ++r) {
                 if (r < nrows) {
@@ -933,17 +942,23 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
                         const bool is_ign = (best[r] > p.neg) && !is_pos;
                         state = is_pos ? 1.0f : (is_ign ? -1.0f : 0.0f);
                         posbits |= is_pos ? (1u << r) : 0u;
-                        if (m != prev) {                    // x targets change with the table only
-                            prev = m;
-                            reg_target5_pair(s_gx1[m], ax1, s_gx2[m], ax2, aw, r5w, t0, t2);
+                        if (!SPARSE) {
+                            if (m != prev) {                // x targets change with the table only
+                                prev = m;
+                                reg_target5_pair(s_gx1[m], ax1, s_gx2[m], ax2, aw, r5w, t0, t2);
+                            }
+                            const float2 ty2 = tyw[r * 32 + m];
+                            t1 = ty2.x; t3 = ty2.y;
                         }
-                        const float2 ty2 = tyw[r * 32 + m];
-                        t1 = ty2.x; t3 = ty2.y;
                     }
                     if (out_x || ((out_y >> r) & 1u)) state = -1.0f;
                     const unsigned al = al0 + r * alw;      // first anchor of the staged row, mod 4 in the low bits
-                    float* sr = s_reg + r * reg_stride + (int)(al & 3u) + k * 5;
-                    sr[0] = t0; sr[1] = t1; sr[2] = t2; sr[3] = t3; sr[4] = state;
+                    if (!SPARSE) {
+                        float* sr = s_reg + r * reg_stride + (int)(al & 3u) + k * 5;
+                        sr[0] = t0; sr[1] = t1; sr[2] = t2; sr[3] = t3; sr[4] = state;
+                    } else if (state == 1.0f) {
+                        fgbits |= 1u << r;
+                    }
                     if (C1) {
                         *reinterpret_cast<float2*>(s_lab + r * lab_stride + (int)((al & 1u) * 2u) + k * 2) = make_float2(0.0f, state);
                     } else {
@@ -958,6 +973,17 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
             if (posbits) {                                  // positives are ~0.2 % of the anchors
 #pragma unroll
                 for (int r = 0; r < KT_ROWS; ++r) {
+                    if (SPARSE && (fgbits & (1u << r))) {
+                        // the anchor's regression row, straight to global memory: ((g - a) / len) / 0.2 in the reference's own
+                        // IEEE operations (model/anchors.py:300-311) -- what the dense path's fast quotients are certified to equal
+                        const int m = arg[r];
+                        float* dst = p.reg + ((size_t)b * p.N + lstart + ((size_t)(cy0 + r) * W + cx0 + lane) * A + a) * 5;
+                        dst[0] = reg_target_exact(s_gx1[m] - ax1, aw);
+                        dst[1] = reg_target_exact(s_gy1[m] - row[r][0], row[r][2]);
+                        dst[2] = reg_target_exact(s_gx2[m] - ax2, aw);
+                        dst[3] = reg_target_exact(s_gy2[m] - row[r][1], row[r][2]);
+                        dst[4] = 1.0f;
+                    }
                     if (posbits & (1u << r)) {
                         const int hot = s_glab[arg[r]];
                         if (C1) {
@@ -981,7 +1007,7 @@ __global__ void __launch_bounds__(32 * K32_A, 3) k_anchor_targets_tiles32(const 
             if (p.npos) atomicAdd(p.npos + b, s_npos);
             if (p.npos_total) atomicAdd(p.npos_total, (float)s_npos);   // integer-valued: exact, order-independent
         }
-        tile_write_out<C1>(p, s_reg, s_lab, s_state, s_hot, b, lstart, cy0, cx0, W, A, ncols, nrows, reg_stride, lab_stride, tid, nthreads);
+        tile_write_out<C1, SPARSE>(p, s_reg, s_lab, s_state, s_hot, b, lstart, cy0, cx0, W, A, ncols, nrows, reg_stride, lab_stride, tid, nthreads);
     }
 #ifdef RN_K1_TRACE
     __syncthreads();
@@ -1054,6 +1080,7 @@ static int k1_opt_in_shared_memory() {
     if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles32<true, false, K32_XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k32_dyn_smem(9));
     if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles32<true, true, K32_XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k32_dyn_smem(9));
     if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles32<false, true, K32_XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k32_dyn_smem(9));
+    if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_anchor_targets_tiles32<true, false, K32_XT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k32_dyn_smem(9));
     if (ae != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
     if (bit) done.fetch_or(bit, std::memory_order_release);
     return RN_OK;
@@ -1085,6 +1112,14 @@ extern "C" int rn_anchor_targets_ordered(const double* base_anchors_dev, const i
                                          float neg_overlap, float pos_overlap,
                                          float* regression_out, float* labels_out, int* argmax_out, int* npos_out,
                                          float* npos_total_out, const int* page_order_dev, void* stream);
+static int anchor_targets_impl(const double* base_anchors_dev, const int* level_hw, const int* level_stride,
+                               int num_levels, int anchors_per_cell,
+                               const double* anchors_dev, long long num_anchors,
+                               const double* gt_boxes_dev, const int* gt_labels_dev, const int* gt_count_dev,
+                               const int* img_hw_dev, int B, int Gmax, int C,
+                               float neg_overlap, float pos_overlap,
+                               float* regression_out, float* labels_out, int* argmax_out, int* npos_out,
+                               float* npos_total_out, const int* page_order_dev, unsigned flags, void* stream);
 
 extern "C" int rn_anchor_targets(const double* base_anchors_dev, const int* level_hw, const int* level_stride,
                                  int num_levels, int anchors_per_cell,
@@ -1107,6 +1142,33 @@ extern "C" int rn_anchor_targets_ordered(const double* base_anchors_dev, const i
                                          float neg_overlap, float pos_overlap,
                                          float* regression_out, float* labels_out, int* argmax_out, int* npos_out,
                                          float* npos_total_out, const int* page_order_dev, void* stream) {
+    return anchor_targets_impl(base_anchors_dev, level_hw, level_stride, num_levels, anchors_per_cell, anchors_dev, num_anchors,
+                               gt_boxes_dev, gt_labels_dev, gt_count_dev, img_hw_dev, B, Gmax, C, neg_overlap, pos_overlap,
+                               regression_out, labels_out, argmax_out, npos_out, npos_total_out, page_order_dev, 0u, stream);
+}
+
+extern "C" int rn_anchor_targets_sparse(const double* base_anchors_dev, const int* level_hw, const int* level_stride,
+                                        int num_levels, int anchors_per_cell, long long num_anchors,
+                                        const double* gt_boxes_dev, const int* gt_labels_dev, const int* gt_count_dev,
+                                        const int* img_hw_dev, int B, int Gmax,
+                                        float neg_overlap, float pos_overlap,
+                                        float* regression_out, float* labels_out, int* npos_out,
+                                        float* npos_total_out, const int* page_order_dev, void* stream) {
+    RN_REQUIRE(anchors_per_cell >= 1 && anchors_per_cell <= K32_A && Gmax <= K32_G,
+               "sparse regression targets: at most %d anchor types per cell and %d tables per page", K32_A, K32_G);
+    return anchor_targets_impl(base_anchors_dev, level_hw, level_stride, num_levels, anchors_per_cell, nullptr, num_anchors,
+                               gt_boxes_dev, gt_labels_dev, gt_count_dev, img_hw_dev, B, Gmax, 1, neg_overlap, pos_overlap,
+                               regression_out, labels_out, nullptr, npos_out, npos_total_out, page_order_dev, 1u, stream);
+}
+
+static int anchor_targets_impl(const double* base_anchors_dev, const int* level_hw, const int* level_stride,
+                               int num_levels, int anchors_per_cell,
+                               const double* anchors_dev, long long num_anchors,
+                               const double* gt_boxes_dev, const int* gt_labels_dev, const int* gt_count_dev,
+                               const int* img_hw_dev, int B, int Gmax, int C,
+                               float neg_overlap, float pos_overlap,
+                               float* regression_out, float* labels_out, int* argmax_out, int* npos_out,
+                               float* npos_total_out, const int* page_order_dev, unsigned flags, void* stream) {
     RN_REQUIRE(B >= 1 && B <= 65535, "B must be in [1, 65535] (got %d)", B);
     RN_REQUIRE(C >= 1, "C must be >= 1");
     RN_REQUIRE(Gmax >= 0, "Gmax must be >= 0");
@@ -1131,6 +1193,7 @@ extern "C" int rn_anchor_targets_ordered(const double* base_anchors_dev, const i
     p.reg = regression_out; p.lab = labels_out; p.argmax = argmax_out; p.npos = npos_out;
     p.npos_total = npos_total_out;
     p.vec_ok = rn_aligned16(regression_out) && rn_aligned16(labels_out);
+    p.sparse_reg = (flags & 1u) ? 1 : 0;
     RN_REQUIRE((reinterpret_cast<uintptr_t>(labels_out) & 7u) == 0, "labels_out must be 8-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     // the two counters are zeroed by ONE small kernel that lets K1 launch behind it at once (rn_common.cuh); K1 touches them at
@@ -1193,6 +1256,7 @@ extern "C" int rn_anchor_targets_ordered(const double* base_anchors_dev, const i
             if (ctas > 0x7fffffffll) return rn_fail(RN_ERR_BAD_ARG, "rn_anchor_targets: %lld CTAs", ctas);
             const dim3 g2((unsigned)ctas);
             const size_t dyn2 = k32_dyn_smem(A);
+            if (p.sparse_reg) return rn_launch_dependent("rn_anchor_targets", k_anchor_targets_tiles32<true, false, K32_XT, true>, g2, dim3(32 * A), dyn2, s, p, t2);
             if (C != 1) return rn_launch_dependent("rn_anchor_targets", k_anchor_targets_tiles32<false, true, K32_XT>, g2, dim3(32 * A), dyn2, s, p, t2);
             else if (argmax_out) return rn_launch_dependent("rn_anchor_targets", k_anchor_targets_tiles32<true, true, K32_XT>, g2, dim3(32 * A), dyn2, s, p, t2);
             else return rn_launch_dependent("rn_anchor_targets", k_anchor_targets_tiles32<true, false, K32_XT>, g2, dim3(32 * A), dyn2, s, p, t2);

@@ -31,12 +31,17 @@ from . import losses as _losses
 class TargetLossStep(object):
     def __init__(self, image_shape, batch, gmax, num_classes, anchor_params=None, pyramid_levels=None,
                  negative_overlap=0.4, positive_overlap=0.5, alpha=0.25, gamma=2.0, sigma=3.0, bce="tf2",
-                 use_graph=True, device=None, shared_state=True, peer_box=True):
+                 use_graph=True, device=None, shared_state=True, peer_box=True, sparse_targets=False):
         _lib.require_cuda()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.spec = _anchors.make_spec(image_shape, pyramid_levels, anchor_params, None)
         self.B, self.G, self.C, self.N = int(batch), max(1, int(gmax)), int(num_classes), self.spec.num_anchors
         self.neg, self.pos = negative_overlap, positive_overlap
+        # sparse_targets (extension): K1 writes the regression rows of positive anchors only -- the only ones K2 reads when it
+        # takes the anchor state from the label tensor (shared_state); y_reg is then NOT the reference's full tensor
+        self.sparse_targets = bool(sparse_targets)
+        if self.sparse_targets and not (shared_state and int(num_classes) == 1):
+            raise ValueError("sparse_targets needs shared_state=True and one class")
         # both target tensors come from K1 in the same step, so their state columns are identical
         self.loss_kw = dict(alpha=alpha, gamma=gamma, sigma=sigma, bce=bce, shared_state=shared_state)
         d, B, G, N, C = self.device, self.B, self.G, self.N, self.C
@@ -61,7 +66,7 @@ class TargetLossStep(object):
         self.d_order.copy_(torch.arange(B, dtype=torch.int32))
         self.cls_pred = torch.zeros((B, N, C), dtype=torch.float32, device=d)
         self.reg_pred = torch.zeros((B, N, 4), dtype=torch.float32, device=d)
-        self.y_reg = torch.empty((B, N, 5), dtype=torch.float32, device=d)
+        self.y_reg = (torch.zeros if self.sparse_targets else torch.empty)((B, N, 5), dtype=torch.float32, device=d)
         self.y_cls = torch.empty((B, N, C + 1), dtype=torch.float32, device=d)
         # per-page counts (B int32) and the batch total (1 float32) in one allocation: cleared by one memset node
         self._counts = torch.zeros(B + 1, dtype=torch.int32, device=d)
@@ -126,7 +131,7 @@ class TargetLossStep(object):
     def _targets(self):
         _anchors.anchor_targets_device(self.spec, self.d_boxes, self.d_labels, self.d_counts, self.d_hw, self.C,
                                        self.neg, self.pos, out=(self.y_reg, self.y_cls), npos_total=self.npos_total,
-                                       npos_out=self.npos, page_order=self.d_order)
+                                       npos_out=self.npos, page_order=self.d_order, sparse_regression=self.sparse_targets)
         if self.peer is not None and not self.peer_fused:
             self.peer.publish(self.npos_total, self.device)     # this rank's count -> every rank's mailbox
 
@@ -181,7 +186,7 @@ class TargetLossStep(object):
         d = self.device
         second = torch.zeros(self.B + 1, dtype=torch.int32, device=d)
         bufs = [(self.y_reg, self.y_cls, self.npos, self.npos_total),
-                (torch.empty_like(self.y_reg), torch.empty_like(self.y_cls), second[:self.B], second[self.B:].view(torch.float32))]
+                ((torch.zeros_like if self.sparse_targets else torch.empty_like)(self.y_reg), torch.empty_like(self.y_cls), second[:self.B], second[self.B:].view(torch.float32))]
 
         no_box = self.peer is None and _dist.world()[1] > 1    # several ranks, no mailbox: all_reduce between the graphs
 
@@ -189,7 +194,7 @@ class TargetLossStep(object):
             y_reg, y_cls, npos, npos_total = bufs[i]
             _anchors.anchor_targets_device(self.spec, self.d_boxes, self.d_labels, self.d_counts, self.d_hw, self.C,
                                            self.neg, self.pos, out=(y_reg, y_cls), npos_total=npos_total, npos_out=npos,
-                                           page_order=self.d_order)
+                                           page_order=self.d_order, sparse_regression=self.sparse_targets)
             if self.peer is not None and not self.peer_fused:
                 self.peer.publish(npos_total, self.device)
 

@@ -221,3 +221,35 @@ def test_heavy_clusters_sweep_between_rounds(rn, members, bg, max_out):
     layer = rn.FilterDetections(max_detections=max_out)
     fb, fs, fl = layer([torch.tensor(b[None], device="cuda"), torch.tensor(cls, device="cuda")])
     assert same(layer.last_indices, wantf[3]) and same(fl, wantf[2]) and same(fs, wantf[1]) and same(fb, wantf[0])
+
+
+def test_stages_launched_one_at_a_time_equal_the_full_call(rn):
+    """The measurement hook rn_debug_filter_stages (bench.py times every kernel of the filter call alone): K3, the NMS
+    kernel and the merge launched as three separate calls on one workspace -- eagerly and as re-captured CUDA graphs --
+    leave exactly the detections of the normal call; the default mask is restored."""
+    hw, B = (256, 320), 3
+    anchors = OA.anchors_for_shape(hw + (3,))
+    _, anns = synthetic.training_batch(3, batch=B)
+    anns = [synthetic.gt_for_page(2, i, hw=hw, gmax=6) for i in range(B)]
+    cls, reg = synthetic.inference_predictions(3, B, anchors, anns, classes=1)
+    lib = rn._lib.load()
+    for use_graph in (False, True):
+        det = rn.pipeline.DetectionStep(hw, B, 1, use_graph=use_graph)
+        det.load_predictions(torch.from_numpy(cls), torch.from_numpy(reg))
+        want = [t.clone() for t in det.run()]
+        torch.cuda.synchronize()
+        for t in det.out:
+            t.fill_(-7)
+        try:
+            for mask in (1, 2, 4):
+                lib.rn_debug_filter_stages(mask)
+                det._graph = None
+                det.run()
+                det.run()                                   # a stage may be repeated on what the earlier stages left
+        finally:
+            lib.rn_debug_filter_stages(7)
+            det._graph = None
+        torch.cuda.synchronize()
+        got = [det.boxes, det.scores, det.labels]
+        assert all(torch.equal(a, b) for a, b in zip(got, want))
+        assert all(torch.equal(a, b) for a, b in zip(det.run(), want))

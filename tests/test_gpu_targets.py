@@ -263,3 +263,64 @@ def test_page_launch_order_does_not_change_results(rn, C, hw):
     for r in results[1:]:
         assert same(r[0], results[0][0]) and same(r[1], results[0][1])
         assert (r[2] == results[0][2]).all() and (r[3] == results[0][3]).all() and r[4] == results[0][4]
+
+
+@pytest.mark.parametrize("hw,B,mixed", [((800, 1333), 6, False), ((256, 320), 5, True), ((1600, 2400), 2, False)])
+def test_sparse_regression_targets(rn, hw, B, mixed):
+    """rn_anchor_targets_sparse (extension for the training step): labels / counts are those of the dense call bit for
+    bit, the regression rows of state == 1 anchors are the dense call's rows bit for bit (the fast quotients of the dense
+    path are certified to equal the exact IEEE expression the sparse path evaluates), every other row keeps what the
+    tensor held -- and the losses and gradients computed from the two forms are identical."""
+    from retinanet_b200 import anchors as A
+    anchors = rn.anchors_for_shape(hw + (3,))
+    cfg = 2 if hw == (800, 1333) else 4
+    if mixed:
+        images = [synthetic.PageShape((hw[0] - 8 * (i % 3), hw[1] - 20 * (i % 2), 3)) for i in range(B)]   # border rule on
+        anns = [synthetic.gt_for_page(2, i, hw=hw, gmax=6) for i in range(B)]
+        anns[1] = {'bboxes': np.zeros((0, 4)), 'labels': np.zeros((0,))}                                   # an empty page
+    else:
+        images, anns = synthetic.training_batch(cfg, batch=B, anchors=np.asarray(anchors))
+    boxes, labels, counts, img_hw = A.pack_annotations(images, anns, 1)
+    d = A.upload_annotations(boxes, labels, counts, img_hw, torch.device("cuda"))
+    order = torch.from_numpy(A.page_launch_order(boxes)).cuda()
+    reg_d, lab_d, npos_d, _ = A.anchor_targets_device(anchors, *d, 1, page_order=order)
+    N = reg_d.shape[1]
+    sentinel = torch.full((B, N, 5), -123.0, dtype=torch.float32, device="cuda")
+    lab_s = torch.empty_like(lab_d)
+    tot = torch.zeros(1, dtype=torch.float32, device="cuda")
+    reg_s, lab_s, npos_s, _ = A.anchor_targets_device(anchors, *d, 1, out=(sentinel, lab_s), npos_total=tot, page_order=order,
+                                                      sparse_regression=True)
+    assert torch.equal(lab_s, lab_d) and torch.equal(npos_s, npos_d) and float(tot) == float(npos_d.sum())
+    fg = lab_d[:, :, 1] == 1.0
+    assert int(fg.sum()) == int(npos_d.sum()) and (int(fg.sum()) > 0 or mixed)
+    assert torch.equal(reg_s[fg], reg_d[fg])                          # positives: the dense rows, bit for bit
+    assert bool((reg_s[~fg] == -123.0).all())                         # everything else untouched
+    # the loss kernels read nothing else
+    cls, reg = synthetic.training_predictions(cfg, B, N, classes=1)
+    cls, reg = torch.tensor(cls, device="cuda"), torch.tensor(reg, device="cuda")
+    a = rn.detection_losses(reg_d, lab_d, reg, cls, normalizer=tot, shared_state=True)
+    b = rn.detection_losses(reg_s, lab_s, reg, cls, normalizer=tot, shared_state=True)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_sparse_targets_step_equals_dense_step(rn):
+    """TargetLossStep(sparse_targets=True): in-order and overlapped schedules give the dense step's losses and gradients."""
+    hw, B = (800, 1333), 4
+    anchors = rn.anchors_for_shape(hw + (3,))
+    images, anns = synthetic.training_batch(2, batch=B, anchors=np.asarray(anchors))
+    cls, reg = synthetic.training_predictions(2, B, anchors.shape[0], classes=1)
+    out = []
+    for sparse in (False, True):
+        step = rn.pipeline.TargetLossStep(hw + (3,), B, 22, 1, sparse_targets=sparse, peer_box=False)
+        step.load_annotations(images, anns)
+        step.load_predictions(torch.from_numpy(cls), torch.from_numpy(reg))
+        l0 = step.run().clone()
+        g0 = (step.grad_cls.clone(), step.grad_reg.clone())
+        for _ in range(3):
+            step.run_pipelined(overlap=True)
+        out.append((l0, g0, step.losses.clone(), step.grad_cls.clone(), step.grad_reg.clone()))
+    d, s = out
+    assert torch.equal(d[0], s[0]) and torch.equal(d[1][0], s[1][0]) and torch.equal(d[1][1], s[1][1])
+    assert torch.equal(d[2], s[2]) and torch.equal(d[3], s[3]) and torch.equal(d[4], s[4])
+    with pytest.raises(ValueError):
+        rn.pipeline.TargetLossStep(hw + (3,), B, 22, 3, sparse_targets=True, peer_box=False)
