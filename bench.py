@@ -504,6 +504,26 @@ def leg_training(ctx):
     k1_ms = min(ctx.train_us([r._graphs[0].replay for r in rot], reps_train) for _ in range(2)) * 1e-3
     k2_ms = min(ctx.train_us([r._graphs[1].replay for r in rot], reps_train) for _ in range(2)) * 1e-3
     del rot
+    # extra (never the `value`): the training step with SPARSE regression targets -- K1 writes the rows of positive anchors
+    # only, all K2 reads of that tensor (rn_anchor_targets_sparse; y_reg is then not the reference's full tensor)
+    sparse = None
+    if not args.no_extras:
+        rot = [rn.pipeline.TargetLossStep(HW + (3,), B, GMAX, C, peer_box=False, sparse_targets=True) for _ in range(3)]
+        for r in rot:
+            r.load_annotations(images, anns)
+            r.load_predictions(cls_host, reg_host)
+            r._build_graphs()
+        sp_k1 = min(ctx.train_us([r._graphs[0].replay for r in rot], reps_train) for _ in range(2))
+        sp_in = ctx.timed(rot[0].run, steps) / steps
+        sp_ov = ctx.timed(lambda: rot[0].run_pipelined(overlap=True), steps) / steps
+        sp_same = bool(torch.equal(rot[0].grad_reg, step.grad_reg) and torch.equal(rot[0].grad_cls, step.grad_cls)) if world == 1 else None
+        sp_k1, sp_in, sp_ov = ctx.max_over_ranks([sp_k1, sp_in, sp_ov])
+        sparse = {"what": "extension, NOT the drop-in anchor_targets_bbox and not the `value`: K1 writes labels + the regression rows of "
+                          "positive anchors only (rn_anchor_targets_sparse); K2 unchanged (it reads no other row)",
+                  "k1_us_per_launch": sp_k1, "k1_bytes_per_anchor": 8.0, "ms_per_step_in_order": sp_in, "ms_per_step_overlapped": sp_ov,
+                  "pages_per_s_overlapped": world * B / (sp_ov * 1e-3), "gradients_equal_dense_step": sp_same,
+                  "exchange": "none (rank-local normaliser)" if world > 1 else "none (1 rank)"}
+        del rot
 
     # ---- e2e: public API, host inputs every step -------------------------------------------------------
     sync_ms = e2e_ms = full_ms = float("nan")
@@ -662,6 +682,8 @@ def leg_training(ctx):
         if levels is not None:
             levels["GBps"] = k2_bytes / (levels["us_per_launch"] * 1e-6) / 1e9
             out["per_level_heads"] = levels
+        if sparse is not None:
+            out["sparse_targets_mode"] = sparse
     del step
     torch.cuda.empty_cache()
     return out
