@@ -789,7 +789,7 @@ def leg_inference(ctx):
                     "pages_per_s_two_streams": world * B / (ms_2s * 1e-3),
                     "kernels_us": {"k_threshold_keys": k3_us, "k_segment_nms": nms_us, "k_merge_topk": merge_us,
                                    "note": "each stage alone as a train of back-to-back launches (rn_debug_filter_stages), six input sets in rotation; "
-                                           "k_threshold_keys includes the workspace reset (one memset node) in front of it"},
+                                           "k_threshold_keys includes the reset kernel it is launched behind (programmatic dependent launch)"},
                     "e2e_pages_per_s": world * B / (ms_e2e * 1e-3), "e2e_api": "HostDetectionPipeline.submit / result, 2 batches in flight",
                     "e2e_h2d_bytes_per_batch": int(cls_host.numel() * 4), "e2e_d2h_bytes_per_batch": int(B * 300 * 24),
                     "e2e_one_batch_at_a_time_pages_per_s": world * B / (ms_e2e_sync * 1e-3),
