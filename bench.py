@@ -514,15 +514,24 @@ def leg_training(ctx):
             r.load_predictions(cls_host, reg_host)
             r._build_graphs()
         sp_k1 = min(ctx.train_us([r._graphs[0].replay for r in rot], reps_train) for _ in range(2))
-        sp_in = ctx.timed(rot[0].run, steps) / steps
-        sp_ov = ctx.timed(lambda: rot[0].run_pipelined(overlap=True), steps) / steps
-        sp_same = bool(torch.equal(rot[0].grad_reg, step.grad_reg) and torch.equal(rot[0].grad_cls, step.grad_cls)) if world == 1 else None
+        del rot
+        # the step itself: an object like `step` (with the mailbox when there are several ranks)
+        sp_step = rn.pipeline.TargetLossStep(HW + (3,), B, GMAX, C, sparse_targets=True)
+        sp_step.load_annotations(images, anns)
+        sp_step.load_predictions(cls_host, reg_host)
+        sp_in = ctx.timed(sp_step.run, steps) / steps
+        sp_ov = float("nan")
+        if world == 1 or sp_step.peer_fused:
+            sp_ov = ctx.timed(lambda: sp_step.run_pipelined(overlap=True), steps) / steps
+        sp_same = bool(torch.equal(sp_step.grad_reg, step.grad_reg) and torch.equal(sp_step.grad_cls, step.grad_cls))
+        sp_step.check()
+        rot = sp_step
         sp_k1, sp_in, sp_ov = ctx.max_over_ranks([sp_k1, sp_in, sp_ov])
         sparse = {"what": "extension, NOT the drop-in anchor_targets_bbox and not the `value`: K1 writes labels + the regression rows of "
                           "positive anchors only (rn_anchor_targets_sparse); K2 unchanged (it reads no other row)",
                   "k1_us_per_launch": sp_k1, "k1_bytes_per_anchor": 8.0, "ms_per_step_in_order": sp_in, "ms_per_step_overlapped": sp_ov,
-                  "pages_per_s_overlapped": world * B / (sp_ov * 1e-3), "gradients_equal_dense_step": sp_same,
-                  "exchange": "none (rank-local normaliser)" if world > 1 else "none (1 rank)"}
+                  "pages_per_s_overlapped": world * B / (sp_ov * 1e-3) if sp_ov == sp_ov else None, "gradients_equal_dense_step": sp_same,
+                  "exchange": exchange}
         del rot
 
     # ---- e2e: public API, host inputs every step -------------------------------------------------------
