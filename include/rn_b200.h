@@ -252,15 +252,11 @@ int rn_nms(const float* boxes /*(K,4)*/, const float* scores /*(K)*/, long long 
 /* profiling aid: when enabled, k_segment_nms adds its per-phase clock64() ticks (thread 0 of every CTA) to the first
  * 8 uint64 of the filter workspace (select, gather, sort, group fetch, suppression tests, resolve).  Off by default. */
 int rn_debug_nms_timing(int enable);
-/* measurement hook (process-wide, not for concurrent use): four cudaEvent_t handles that every following filter call records on
- * its stream before k_threshold_keys, after it, after k_segment_nms and after k_merge_topk; NULLs switch it off.  This is how
- * bench.py times the three kernels of one call individually (rn_nms records only the last two). */
-int rn_debug_filter_events(void* before_k3, void* after_k3, void* after_nms, void* after_merge);
 /* measurement hook (process-wide, not for concurrent use): which stages the following filter calls launch -- bit 0 the workspace
  * reset + k_threshold_keys, bit 1 k_segment_nms, bit 2 k_merge_topk; 7 = all (the default; anything else is for timing only).
  * A stage launched alone works on what an earlier full call left in the same workspace, so bench.py can time each kernel as a
  * train of back-to-back launches of that kernel alone (no event between kernels: the interval between two events around ONE
- * short kernel carries 3-5 us of front-end latency that is not the kernel's). */
+ * short kernel carries 3-5 us of front-end latency that is not the kernel's).  The mask applies to rn_nms' two kernels too. */
 int rn_debug_filter_stages(int mask);
 
 /* ---------------------------------------------------------------------------------------------

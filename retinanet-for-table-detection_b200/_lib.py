@@ -68,7 +68,6 @@ SIGNATURES = {
     "rn_nms_workspace_bytes": (c_size_t, [c_longlong, c_int]),
     "rn_nms": (c_int, [_P, _P, c_longlong, c_int, c_float, _P, _P, _P, c_size_t, _P]),
     "rn_debug_nms_timing": (c_int, [c_int]),
-    "rn_debug_filter_events": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "rn_debug_filter_stages": (c_int, [c_int]),
     "rn_rescale_cut": (c_int, [_P, _P, _P, c_int, c_int, c_float, _P, _P, _P]),
     "rn_preprocess_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

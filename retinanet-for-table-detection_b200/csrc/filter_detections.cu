@@ -1343,21 +1343,11 @@ size_t nms_dynamic_smem(int max_det) {      // selected boxes + weights, the mer
 }
 
 std::atomic<int> g_phase_timing{0};
-// measurement hook (rn_debug_filter_events): four cudaEvent_t recorded around the three kernels of a filter call
-std::atomic<void*> g_events[4];
 // measurement hook (rn_debug_filter_stages): which of the three stages a filter call launches -- bit 0: the workspace reset +
 // k_threshold_keys, bit 1: k_segment_nms, bit 2: k_merge_topk.  A stage run alone works on what an earlier full call left in
 // the workspace (the NMS kernel only reads the slabs, the merge only the kept lists), so every kernel can be timed as a train
 // of back-to-back launches without events in between.
 std::atomic<int> g_stages{7};
-
-int record_event(int k, cudaStream_t s) {
-    void* ev = g_events[k].load(std::memory_order_relaxed);
-    if (ev == nullptr) return RN_OK;
-    cudaError_t e = cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev), s);
-    if (e != cudaSuccess) return rn_fail(RN_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(e));
-    return RN_OK;
-}
 
 // static (~34 KB) + dynamic shared memory can exceed the 48 KB default: opt in once per DEVICE (bit per device ordinal)
 int nms_opt_in_shared_memory() {
@@ -1413,7 +1403,6 @@ int run_back_end(const FilterWs& w, const BoxSource& src, bool decode, int B, in
     else { if (slot) k_segment_nms<false, true><<<S, NMS_THREADS, dyn, s>>>(np); else k_segment_nms<false, false><<<S, NMS_THREADS, dyn, s>>>(np); }
     rc = rn_check_launch("k_segment_nms");
     if (rc) return rc;
-    if ((rc = record_event(2, s)) != RN_OK) return rc;
     MergeParams mp;
     mp.pages = B; mp.segs_per_page = segs_per_page; mp.max_det = max_det;
     mp.kept_count = w.kept_count; mp.kept_key = w.kept_key; mp.kept_box = w.kept_box; mp.kept_label = w.kept_label;
@@ -1429,9 +1418,7 @@ int run_back_end(const FilterWs& w, const BoxSource& src, bool decode, int B, in
     } else {
         k_merge_topk<<<B, 256, sizeof(int) * (size_t)segs_per_page, s>>>(mp);
     }
-    rc = rn_check_launch("k_merge_topk");
-    if (rc) return rc;
-    return record_event(3, s);
+    return rn_check_launch("k_merge_topk");
 }
 
 int filter_common(K3Params kp, const BoxSource& src, bool decode, int nms, float nms_thr, int max_det, int pre_nms_top_k,
@@ -1465,8 +1452,7 @@ int filter_common(K3Params kp, const BoxSource& src, bool decode, int nms, float
     RN_REQUIRE(B <= 65535, "B must be <= 65535");
     kp.inv_c = 1.0f / (float)C;
     kp.vec_ok = (((long long)kp.N * C) % 4 == 0) ? 1 : 0;
-    int rc = record_event(0, s);
-    if (rc) return rc;
+    int rc = RN_OK;
     const long long page_tiles = ((long long)kp.N * C + K3S_TILE - 1) / K3S_TILE;
     if (!first_stage) {
         // measurement: the slabs of an earlier call are reused
@@ -1491,7 +1477,6 @@ int filter_common(K3Params kp, const BoxSource& src, bool decode, int nms, float
     }
     rc = rn_check_launch("k_threshold_keys");
     if (rc) return rc;
-    if ((rc = record_event(1, s)) != RN_OK) return rc;
     return run_back_end(w, src, decode, B, S, spp, cand_cap, nms, nms_thr, max_det, pre_nms_top_k, host_f2ord(kp.thr),
                         out_boxes, out_scores, out_labels, out_indices, nullptr,
                         status_out ? status_out : w.status, s);
@@ -1506,11 +1491,6 @@ extern "C" int rn_debug_nms_timing(int enable) {
 
 extern "C" int rn_debug_filter_stages(int mask) {
     g_stages.store(mask & 7, std::memory_order_relaxed);
-    return RN_OK;
-}
-
-extern "C" int rn_debug_filter_events(void* before_k3, void* after_k3, void* after_nms, void* after_merge) {
-    g_events[0].store(before_k3); g_events[1].store(after_k3); g_events[2].store(after_nms); g_events[3].store(after_merge);
     return RN_OK;
 }
 

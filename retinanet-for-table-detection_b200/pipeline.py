@@ -235,7 +235,7 @@ class TargetLossStep(object):
         # HBM-bound kernel (and, with several ranks, the exchange it carries) finishes inside the long issue-bound one
         # (60.9 -> 59.7 us per step; profiles/r2/r2v_overlap_share_experiment.log also holds what did NOT help: K2 on
         # 1-4 CTAs per SM, K1 capped at 64 / 56 registers so that a K2 CTA fits beside three of K1's)
-        side = (torch.cuda.Stream(d), torch.cuda.Stream(d, priority=-1))
+        side = (torch.cuda.Stream(d), torch.cuda.Stream(d, priority=-1 if os.environ.get("RN_B200_K2_PRIORITY", "1") != "0" else 0))
 
         def both(nxt, cur):
             """K1 (+ publish) of the next batch and K2 of the current one on two streams: captured, they become two

@@ -163,3 +163,24 @@ def inference_predictions_torch(config, batch, anchors, annotations_group, class
                          (g[gi, 2] - a[pi, 2]) / aw[pi], (g[gi, 3] - a[pi, 3]) / ah[pi]], dim=1) / 0.2
         reg[b, pi] = (t + torch.randn(t.shape, generator=gen, device=device, dtype=torch.float64) * 0.15).to(torch.float32)
     return cls, reg
+
+
+def document_page(seed, H, W):
+    """A synthetic scanned page (uint8 BGR): paper-coloured noise, dark text lines, ruled table boxes, a grey photo block --
+    the input of the page preprocessing (DetectTablesUtils.py:183-262); the generator of tests/test_oracle_preprocess.py."""
+    rs = np.random.RandomState(seed)
+    img = np.clip(rs.normal(235, 6, (H, W, 3)), 0, 255)
+    for y in range(20, H - 20, 14):
+        if rs.uniform() < 0.8:
+            x0, x1 = int(rs.randint(10, W // 3)), int(rs.randint(W // 2, W - 10))
+            for x in range(x0, x1, 7):
+                if rs.uniform() < 0.75:
+                    img[y:y + int(rs.randint(4, 9)), x:x + int(rs.randint(2, 6))] = rs.uniform(10, 90)
+    for _ in range(3):
+        y0, x0 = int(rs.randint(0, H - 60)), int(rs.randint(0, W - 80))
+        h, w = int(rs.randint(30, 60)), int(rs.randint(40, 80))
+        img[y0:y0 + h, x0:x0 + 2] = 30; img[y0:y0 + h, x0 + w:x0 + w + 2] = 30
+        img[y0:y0 + 2, x0:x0 + w] = 30; img[y0 + h:y0 + h + 2, x0:x0 + w + 2] = 30
+    y0, x0 = int(rs.randint(0, H - 50)), int(rs.randint(0, W - 50))
+    img[y0:y0 + 48, x0:x0 + 48] = np.clip(rs.normal(128, 25, (48, 48, 3)), 0, 255)
+    return img.astype(np.uint8)
