@@ -656,7 +656,7 @@ def leg_training(ctx):
                                     "gathers exactly those); the (B,N,4) tensor is not copied") if E2E_GATHER else "copied",
                 "full_copy": {"value": world * B * steps / (full_ms * 1e-3), "ms_per_step": full_ms / steps,
                               "h2d_bytes_per_step": int(gt_bytes + cls_host.numel() * 4 + reg_host.numel() * 4)}},
-            "gpu_launches": step.kernel_launches_per_step * steps,   # `value` region: K1 + K2 per step (+ publish when not fused into K2)
+            "gpu_launches": step.kernel_launches_per_step * steps,   # `value` region: reset + K1 + K2 per step (+ publish when not fused into K2)
             # the dominant kernel of the step by time is K1: it is reported first although it is instruction-issue bound,
             # not HBM bound; K2 (the HBM-bound loss kernel north_star sets the 60 % target for) follows
             "roofline": {"kernel": "k_anchor_targets_tiles32 (K1 anchors + IoU/argmax matching + targets)", "bound": "hbm",
@@ -976,7 +976,7 @@ def run_ours(args):
             line.update({"value": ref["pages_per_s"], "ms_per_step": ref["ms_per_batch"], "dtype": "f32",
                          "e2e": {"value": ref["e2e_pages_per_s"], "unit": "pages/s", "h2d_bytes_per_step": ref["e2e_h2d_bytes_per_batch"],
                                  "d2h_bytes_per_step": ref["e2e_d2h_bytes_per_batch"], "api": ref["e2e_api"]},
-                         "gpu_launches": 3 * max(5, min(steps, 50)), "roofline": infer["roofline_k3"], "nms": infer["nms"],
+                         "gpu_launches": 4 * max(5, min(steps, 50)), "roofline": infer["roofline_k3"], "nms": infer["nms"],
                          "inference": infer})
             if train is not None:
                 line["training"] = train
@@ -984,7 +984,7 @@ def run_ours(args):
             f = full[k]
             dom = max(f["kernels_us"], key=lambda n: f["kernels_us"][n])
             line.update({"value": f["pages_per_s"], "ms_per_step": f["ms_per_step"],
-                         "dtype": "f64 matching + f32 targets/losses/decode", "gpu_launches": 5 * max(3, min(steps, 20)),
+                         "dtype": "f64 matching + f32 targets/losses/decode", "gpu_launches": 7 * max(3, min(steps, 20)),
                          "e2e": None, "roofline": {"kernel": dom, "bound": "hbm", "us_per_launch": f["kernels_us"][dom],
                                                    "frac": f["hbm_fraction"].get(dom[:2]), "unit": "GB/s"},
                          "full": f})

@@ -79,7 +79,7 @@ class TargetLossStep(object):
         self.use_graph = use_graph
         self._graphs = None
         self._fused = None
-        self.kernel_launches_per_step = 2      # K1 + K2 (memsets and NCCL are not ours)
+        self.kernel_launches_per_step = 3      # the counter reset K1 is launched behind, K1, K2 (NCCL is not ours)
         # run_from_host(): copy stream, per-chunk events, per-chunk loss rows
         rank, world = _dist.world()
         self.peer = _dist.PeerCounter.create() if peer_box else None   # NVLink mailbox; None with one rank / no peer access
@@ -527,7 +527,7 @@ class DetectionStep(object):
         self.workspace = torch.empty(max(256, self.head.workspace_bytes(self.B, self.hw, self.C)), dtype=torch.uint8, device=d)
         self.use_graph = use_graph
         self._graph = None
-        self.kernel_launches_per_step = 3       # k_threshold_keys, k_segment_nms, k_merge_topk
+        self.kernel_launches_per_step = 4       # the workspace reset, k_threshold_keys, k_segment_nms, k_merge_topk
 
     def load_predictions(self, cls_pred, reg_pred):
         self.cls_pred.copy_(cls_pred, non_blocking=True)

@@ -130,7 +130,7 @@ def test_peer_mailbox_one_rank(rn, monkeypatch, fused):
     monkeypatch.setenv("RN_B200_PEER_FUSED", fused)
     boxed = rn.pipeline.TargetLossStep(hw + (3,), B, 8, 1)
     assert boxed.peer is not None and boxed.peer_fused == (fused == "1")
-    assert boxed.kernel_launches_per_step == (2 if fused == "1" else 3)
+    assert boxed.kernel_launches_per_step == (3 if fused == "1" else 4)     # reset + K1 + K2 (+ the separate publish)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     for s in range(7):                                    # > RN_PEER_SLOTS steps
         anns = [synthetic.gt_for_page(2, 10 * s + i, hw=hw, gmax=6) for i in range(B)]
