@@ -104,3 +104,9 @@ def test_reference_sample_page():
     gray, th, out = cv2_pipeline(img)
     assert np.array_equal(P.adaptive_threshold(P.bgr_to_gray(img)), th)
     assert np.array_equal(P.distance_transforms_u8(th, reach=int(out.max()) + 2), out)
+
+
+def test_bench_page_generator_is_this_one():
+    """bench.py's N4 leg draws its pages from synthetic.document_page: the same generator as the parity tests'."""
+    import synthetic
+    assert np.array_equal(synthetic.document_page(5, 120, 96), document_page(5, 120, 96))
