@@ -313,8 +313,8 @@ def anchor_targets_device(anchors, d_boxes, d_labels, d_counts, d_hw, num_classe
     """Launch K1 on GT already resident on the device.  ``anchors``: an :class:`AnchorArray` /
     :class:`AnchorSpec` (generated in-kernel) or a CUDA float64 (N,4) tensor (explicit).
     ``npos_total``: optional 1-float CUDA tensor receiving the batch's positive count (loss normaliser);
-    ``npos_out``: optional (B,) int32 tensor for the per-page counts (when it ends where ``npos_total`` starts the
-    library clears both with one memset); ``page_order``: optional (B,) int32 CUDA permutation, the order in which the
+    ``npos_out``: optional (B,) int32 tensor for the per-page counts (both counters are cleared by one small kernel
+    that K1 is launched behind); ``page_order``: optional (B,) int32 CUDA permutation, the order in which the
     kernel starts the pages (:func:`page_launch_order`; the results do not depend on it).
     ``sparse_regression`` (extension, ``rn_anchor_targets_sparse``): only the regression rows of state == 1 anchors are
     written -- all a smooth-L1 loss that takes the state from the label tensor ever reads (model/losses.py:72-74); the

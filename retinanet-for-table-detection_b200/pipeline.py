@@ -68,7 +68,7 @@ class TargetLossStep(object):
         self.reg_pred = torch.zeros((B, N, 4), dtype=torch.float32, device=d)
         self.y_reg = (torch.zeros if self.sparse_targets else torch.empty)((B, N, 5), dtype=torch.float32, device=d)
         self.y_cls = torch.empty((B, N, C + 1), dtype=torch.float32, device=d)
-        # per-page counts (B int32) and the batch total (1 float32) in one allocation: cleared by one memset node
+        # per-page counts (B int32) and the batch total (1 float32) in one allocation (cleared by the reset kernel K1 is launched behind)
         self._counts = torch.zeros(B + 1, dtype=torch.int32, device=d)
         self.npos = self._counts[:B]
         self.npos_total = self._counts[B:].view(torch.float32)
