@@ -291,6 +291,106 @@ __global__ void __launch_bounds__(K3_THREADS, K3S_CTAS_PER_SM) k_threshold_keys_
     if (fill) k3s_flush(p, page, buf, fill, lane);
 }
 
+// The class-specific path for SEVERAL classes (C > 1, page rows 16-byte aligned).  Neighbouring scores belong to different
+// classes here, so the candidates of a tile feed up to C different slabs, and in the warp-autonomous kernel above every
+// candidate waits for the return of an atomic on its slab's counter: at C = 80, 5.4 M atomics per 16 pages on 1280 counters, a
+// few of which (the classes of a page's tables) take most of them -- same-address atomics serialise in L2.  ncu's source view
+// puts 80 % of that launch's stall samples on the atomic (394 us, 0.42 of the HBM peak).  This form collects the keys PER CLASS
+// in shared memory instead: a CTA walks its slice of a page in rounds of one 512-score tile per warp, the next round's tile
+// already in flight; survivors are appended to their class' list with shared-memory atomics; between two block barriers the
+// lists that are at least half full (after the last round: all) are flushed -- a warp owns every eighth list, its lanes issue
+// the atomics of all its due lists AT ONCE (one each, reserving the whole run), then the runs leave as coalesced stores.  A
+// list that overflows inside a round sends the surplus straight to the slab.
+constexpr int K3C_CAP = 32;                                 // keys per class list (one warp-wide store)
+constexpr int K3C_FLUSH = 16;                               // a list this full is flushed at the end of the round
+constexpr int K3C_MAX_C = 160;                              // C * (CAP * 8 + 4) + flags must fit the 48 KB default
+
+__global__ void __launch_bounds__(K3_THREADS, 4) k_threshold_keys_classes(const K3Params p, int tiles_per_page, int tiles_per_cta) {
+    extern __shared__ __align__(16) unsigned char k3c_smem[];
+    unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(k3c_smem);            // [C][CAP]
+    int* s_fill = reinterpret_cast<int*>(s_keys + (size_t)p.C * K3C_CAP);                   // [C] appended so far (may exceed CAP)
+    unsigned* s_need = reinterpret_cast<unsigned*>(s_fill + p.C);                            // [(C + 31) / 32] lists due this round
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int page = blockIdx.y, C = p.C;
+    const int total = p.N * C;
+    const float* src = p.cls + (size_t)page * total;
+    const int t_begin = blockIdx.x * tiles_per_cta, t_end = min(tiles_per_page, t_begin + tiles_per_cta);
+    const int nwords = (C + 31) >> 5;                       // <= 5
+    constexpr int STEP = K3_THREADS / 32;
+    const float ninf = __int_as_float(0xff800000);          // out of range: never above any threshold
+    float4 nx[K3S_VEC];
+    auto load = [&](int t) {
+#pragma unroll
+        for (int g = 0; g < K3S_VEC; ++g) {
+            nx[g] = make_float4(ninf, ninf, ninf, ninf);
+            if (t < t_end) {
+                const int e = t * K3S_TILE + g * 128 + lane * 4;
+                if (e < total) nx[g] = rn_ldg_stream4(src + e);     // total % 4 == 0: all four or none
+            }
+        }
+    };
+    load(t_begin + warp);
+    for (int i = threadIdx.x; i < C; i += K3_THREADS) s_fill[i] = 0;
+    for (int i = threadIdx.x; i < nwords; i += K3_THREADS) s_need[i] = 0u;
+    rn_grid_dependency_wait();                              // the slab counters are being zeroed by the launch in front
+    __syncthreads();
+    const unsigned own = 0x01010101u << warp;               // this warp's lists of a 32-list word: bits warp, warp + 8, ...
+    for (int t0 = t_begin; t0 < t_end; t0 += STEP) {        // block-uniform rounds
+        const int t = t0 + warp;
+        float sc[K3S_VEC * 4];
+#pragma unroll
+        for (int g = 0; g < K3S_VEC; ++g) { sc[4 * g] = nx[g].x; sc[4 * g + 1] = nx[g].y; sc[4 * g + 2] = nx[g].z; sc[4 * g + 3] = nx[g].w; }
+        load(t + STEP);                                     // the next round's tile is in flight through this round's barriers
+        unsigned hits = 0u;
+#pragma unroll
+        for (int i = 0; i < K3S_VEC * 4; ++i) hits |= (sc[i] > p.thr) ? (1u << i) : 0u;
+        const int e0 = t * K3S_TILE + lane * 4;
+        for (unsigned h = hits; h != 0u; h &= h - 1u) {
+            const int i = __ffs(h) - 1;
+            const int e = e0 + 128 * (i >> 2) + (i & 3);
+            const int n = rn_div(e, C, p.inv_c);
+            const int c = e - n * C;
+            const unsigned long long key = make_key(k3s_pick(sc, i), (unsigned)n);
+            const int slot = atomicAdd(&s_fill[c], 1);
+            if (slot < K3C_CAP) {
+                s_keys[(size_t)c * K3C_CAP + slot] = key;
+                if (slot == K3C_FLUSH - 1) atomicOr(&s_need[c >> 5], 1u << (c & 31));
+            } else {                                        // the list is full until the end of the round: straight to the slab
+                const int seg = page * C + c;
+                const long long gs = atomicAdd(p.sl.counts + seg, 1);
+                if (gs < p.sl.cap) p.sl.keys[(size_t)seg * p.sl.cap + gs] = key;
+            }
+        }
+        __syncthreads();                                    // the round's appends are complete
+        const bool last_round = t0 + STEP >= t_end;
+        // this warp's due lists: lane j < 4 * nwords looks at list (word j / 4, the (j % 4)-th of the warp's four bits)
+        int c_mine = -1, n_mine = 0, base_mine = 0;
+        if (lane < 4 * nwords) {
+            const int w = lane >> 2, b = warp + 8 * (lane & 3), c = w * 32 + b;
+            const bool due = last_round || ((s_need[w] >> b) & 1u);
+            if (due && c < C) {
+                n_mine = min(s_fill[c], K3C_CAP);
+                if (n_mine > 0) {
+                    c_mine = c;
+                    base_mine = atomicAdd(p.sl.counts + page * C + c, n_mine);      // all of the warp's due lists at once
+                }
+            }
+        }
+        unsigned due_lanes = __ballot_sync(0xffffffffu, c_mine >= 0);
+        for (; due_lanes != 0u; due_lanes &= due_lanes - 1u) {
+            const int j = __ffs(due_lanes) - 1;
+            const int c = __shfl_sync(0xffffffffu, c_mine, j), n = __shfl_sync(0xffffffffu, n_mine, j);
+            const int base = __shfl_sync(0xffffffffu, base_mine, j);
+            const size_t seg = (size_t)page * C + c;
+            if (lane < n && (long long)base + lane < p.sl.cap) p.sl.keys[seg * p.sl.cap + base + lane] = s_keys[(size_t)c * K3C_CAP + lane];
+        }
+        __syncwarp();
+        if (c_mine >= 0) s_fill[c_mine] = 0;
+        if (lane < nwords) atomicAnd(&s_need[lane], ~own);   // this warp's flags of every word
+        __syncthreads();                                    // flushed lists are empty, their flags cleared
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // where a candidate's box comes from: a dense (pages, N, 4) tensor, or the fused decode (Anchors + RegressBoxes + ClipBoxes)
 // ------------------------------------------------------------------------------------------------
@@ -1456,6 +1556,17 @@ int filter_common(K3Params kp, const BoxSource& src, bool decode, int nms, float
     const long long page_tiles = ((long long)kp.N * C + K3S_TILE - 1) / K3S_TILE;
     if (!first_stage) {
         // measurement: the slabs of an earlier call are reused
+    } else if (kp.class_specific && kp.vec_ok && C > 1 && C <= K3C_MAX_C) {
+        // several classes: keys collected per class in shared memory, flushed in runs (k_threshold_keys_classes)
+        long long per_page = (RN_NUM_SMS * K3S_CTAS_PER_SM) / B;
+        const long long most = (page_tiles + K3_THREADS / 32 - 1) / (K3_THREADS / 32);
+        if (per_page > most) per_page = most;
+        if (per_page < 1) per_page = 1;
+        const int tiles_per_cta = (int)((page_tiles + per_page - 1) / per_page);
+        const dim3 grid((unsigned)((page_tiles + tiles_per_cta - 1) / tiles_per_cta), (unsigned)B);
+        const size_t dyn = (size_t)C * (K3C_CAP * sizeof(unsigned long long) + sizeof(int)) + sizeof(unsigned) * (size_t)((C + 31) / 32);
+        int rc1 = rn_launch_dependent("k_threshold_keys_classes", k_threshold_keys_classes, grid, dim3(K3_THREADS), dyn, s, kp, (int)page_tiles, tiles_per_cta);
+        if (rc1) return rc1;
     } else if (kp.class_specific && kp.vec_ok) {
         // about SMs x 4 CTAs over all pages, each CTA a contiguous slice of one page (at least one tile per warp)
         // ONE wave: no more CTAs than the GPU holds at once (640 CTAs on 592 slots ran a second, nearly empty wave: 16 us
