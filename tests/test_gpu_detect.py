@@ -253,3 +253,28 @@ def test_stages_launched_one_at_a_time_equal_the_full_call(rn):
         got = [det.boxes, det.scores, det.labels]
         assert all(torch.equal(a, b) for a, b in zip(got, want))
         assert all(torch.equal(a, b) for a, b in zip(det.run(), want))
+
+
+@pytest.mark.parametrize("C,N,hot", [(2, 2000, False), (33, 1200, True), (80, 2048, True), (160, 800, False), (161, 800, False)])
+def test_several_classes_key_lists(rn, C, N, hot):
+    """k_threshold_keys_classes (class-specific filtering with several classes: keys collected per class in shared memory,
+    flushed in runs): one, two and five 32-list words, the largest C it takes and the first one it does not (C = 161: the
+    one-class stream kernel's general branch), a HOT class whose list overflows inside a round (its surplus goes straight to
+    the slab), lists that are only flushed after the last round, and a slab that is too small (raises)."""
+    rs = np.random.RandomState(9100 + C)
+    B = 2
+    cxy = rs.uniform(60, 900, (B, N, 2))
+    wh = rs.uniform(20, 90, (B, N, 2))
+    boxes = np.concatenate([cxy - wh / 2, cxy + wh / 2], axis=2).astype(np.float32)
+    cls = (rs.uniform(0, 1, (B, N, C)) ** 6).astype(np.float32)            # ~ 60 % below the 0.05 threshold
+    if hot:
+        cls[:, :, 1] = rs.uniform(0.06, 0.99, (B, N)).astype(np.float32)  # every anchor fires for class 1
+        cls[1, :, C - 1] = rs.uniform(0.5, 0.99, N).astype(np.float32)    # and, on page 1, for the last class
+    kw = dict(class_specific_filter=True, nms=True, score_threshold=0.05, max_detections=300, nms_threshold=0.5)
+    want = L.filter_detections_batch(boxes, cls, **kw)
+    layer = rn.FilterDetections(**kw)
+    b, s, l = layer([torch.tensor(boxes, device="cuda"), torch.tensor(cls, device="cuda")])
+    assert same(layer.last_indices, want[3]) and same(l, want[2]) and same(s, want[1]) and same(b, want[0])
+    if hot:
+        with pytest.raises(rn._lib.RnError):
+            rn.FilterDetections(cand_cap=64, **kw)([torch.tensor(boxes, device="cuda"), torch.tensor(cls, device="cuda")])
